@@ -1,0 +1,132 @@
+"""Generates the golden fixtures under tests/golden/ from the REFERENCE itself.
+
+Run in the build container only (needs /root/reference):  python tests/golden/make_golden.py
+It imports the reference's own folding/utils_ros/utils_ros.py with a stub
+``pyrosetta`` module (the only thing gen_rst needs from it is the import line)
+and the reference's utils_trX2dy/utils.py geometry with stub Bio/matplotlib.
+Nothing under tests/, bench.py or smoke() reads /root/reference at run time.
+
+Outputs
+  example_{NMR,Xray}.npz, example_seq.fasta   the reference's example inputs (data fixtures)
+  example_natives_ca.npz                       CA traces of example/apo.pdb, holo.pdb
+  gen_rst_example_NMR.npz                      a,b,p per type + sha256 of all text lines + every 7th table
+  gen_rst_random24.npz                         full tables for a random L=24 input (edge cases: p near cutoffs)
+  geometry_random.npz                          reference get_dihedrals/get_angles on random points
+"""
+import hashlib, os, shutil, sys, tempfile, types
+import numpy as np
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def load_reference_gen_rst():
+    sys.modules["pyrosetta"] = types.ModuleType("pyrosetta")
+    sys.path.insert(0, os.path.join(REF, "folding"))
+    from utils_ros import utils_ros  # noqa
+    return utils_ros
+
+
+def load_reference_geometry():
+    for name in ("Bio", "Bio.PDB", "matplotlib", "matplotlib.pyplot"):
+        sys.modules[name] = types.ModuleType(name)
+    sys.modules["Bio.PDB"].PDBParser = object
+    sys.modules["Bio.PDB"].PPBuilder = object
+    sys.modules["Bio"].PDB = sys.modules["Bio.PDB"]
+    sys.path.insert(0, REF)
+    import importlib
+    return importlib.import_module("utils_trX2dy.utils")
+
+
+def run_gen_rst(utils_ros, npz, seq, use_orient=True):
+    import json
+    params = json.load(open(os.path.join(REF, "folding/data/params.json")))
+    params["USE_ORIENT"] = use_orient
+    params["seq"] = seq
+    tmp = tempfile.TemporaryDirectory(prefix="/dev/shm/")
+    rst = utils_ros.gen_rst(npz, tmp, params)
+    res = {}
+    for name, recs in rst.items():
+        a = np.array([r[0] for r in recs], dtype=np.int32)
+        b = np.array([r[1] for r in recs], dtype=np.int32)
+        p = np.array([r[2] for r in recs], dtype=np.float32)
+        lines, texts = [], []
+        for r in recs:
+            toks = r[3].split()
+            fn = [t for t in toks if t.startswith(tmp.name)][0]
+            texts.append(open(fn).read())
+            lines.append(r[3].replace(tmp.name, "TMP"))
+        res[name] = dict(a=a, b=b, p=p, texts=texts, lines=lines)
+    tmp.cleanup()
+    return res
+
+
+def pack(res, every=1):
+    out = {}
+    for name, r in res.items():
+        out[f"{name}_a"], out[f"{name}_b"], out[f"{name}_p"] = r["a"], r["b"], r["p"]
+        h = hashlib.sha256()
+        for t in r["texts"]:
+            h.update(t.encode())
+        out[f"{name}_sha256"] = np.array(h.hexdigest())
+        hl = hashlib.sha256()
+        for t in r["lines"]:
+            hl.update(t.encode())
+        out[f"{name}_lines_sha256"] = np.array(hl.hexdigest())
+        idx = np.arange(0, len(r["texts"]), every)
+        out[f"{name}_sub_idx"] = idx
+        out[f"{name}_sub_text"] = np.array([r["texts"][k] for k in idx])
+        out[f"{name}_line0"] = np.array(r["lines"][0] if r["lines"] else "")
+    return out
+
+
+def ca_trace(pdb):
+    xyz = []
+    for ln in open(pdb):
+        if ln.startswith("ATOM") and ln[12:16].strip() == "CA":
+            xyz.append([float(ln[30:38]), float(ln[38:46]), float(ln[46:54])])
+    return np.array(xyz)
+
+
+def main():
+    ur = load_reference_gen_rst()
+    seq = "".join(l.strip() for l in open(f"{REF}/example/seq.fasta") if not l.startswith(">"))
+    for tag in ("NMR", "Xray"):
+        shutil.copy(f"{REF}/example/output/seq/pred_npz/seq_{tag}.npz", f"{HERE}/example_{tag}.npz")
+    shutil.copy(f"{REF}/example/seq.fasta", f"{HERE}/example_seq.fasta")
+    np.savez_compressed(f"{HERE}/example_natives_ca.npz", apo=ca_trace(f"{REF}/example/apo.pdb"),
+                        holo=ca_trace(f"{REF}/example/holo.pdb"))
+
+    npz = np.load(f"{HERE}/example_NMR.npz")
+    np.savez_compressed(f"{HERE}/gen_rst_example_NMR.npz", **pack(run_gen_rst(ur, npz, seq), every=7))
+
+    # random small input: Dirichlet rows, some rows pushed to the 'no contact' bin so
+    # that probabilities straddle the 0.05 / 0.55 / 0.65 cut-offs
+    rng = np.random.default_rng(24)
+    L = 24
+    def rand(nb, sym):
+        a = rng.dirichlet(np.full(nb, 0.3), size=(L, L)).astype(np.float32)
+        w = rng.uniform(0, 1, size=(L, L, 1)).astype(np.float32) ** 2
+        e0 = np.zeros(nb, dtype=np.float32); e0[0] = 1
+        a = (w * a + (1 - w) * e0).astype(np.float32)
+        if sym:
+            a = (0.5 * (a + a.transpose(1, 0, 2))).astype(np.float32)
+        return a
+    rnd = dict(dist=rand(37, True), omega=rand(25, True), theta=rand(25, False), phi=rand(13, False))
+    packed = pack(run_gen_rst(ur, rnd, "A" * L), every=1)
+    packed.update({f"in_{k}": v for k, v in rnd.items()})
+    np.savez_compressed(f"{HERE}/gen_rst_random24.npz", **packed)
+    packed = pack(run_gen_rst(ur, rnd, "A" * L, use_orient=False), every=1)
+    np.savez_compressed(f"{HERE}/gen_rst_random24_noorient.npz", **packed)
+
+    # geometry: the reference's numpy dihedral / angle on random points
+    ug = load_reference_geometry()
+    pts = rng.normal(size=(4, 64, 3)) * 5.0
+    np.savez_compressed(f"{HERE}/geometry_random.npz", pts=pts,
+                        dihedral=ug.get_dihedrals(pts[0].copy(), pts[1].copy(), pts[2].copy(), pts[3].copy()),
+                        angle=ug.get_angles(pts[0].copy(), pts[1].copy(), pts[2].copy()))
+    print("golden fixtures written to", HERE)
+
+
+if __name__ == "__main__":
+    main()
