@@ -1,0 +1,108 @@
+/* trx2dyn -- C ABI of the B200-native folding hot path of trRosettaX2-Dynamics.
+ *
+ * The reference exposes this path as a PROCESS boundary, not an FFI
+ * (utils_trX2dy/utils.py:484-505 shells out to folding/folding.py once per decoy);
+ * inside that process all arithmetic is PyRosetta.  Each entry point below names the
+ * reference call it replaces.  Plain C: opaque handles, caller-owned buffers, every
+ * function returns 0 on success and a negative trx_status on failure
+ * (trx_last_error() gives the message for the calling thread).  A handle is bound to
+ * one device and one stream; handles are thread-compatible, not thread-safe.
+ *
+ * Layouts.  "natural" host layout of backbone coordinates: [decoy][residue][atom][xyz]
+ * with atoms (N, CA, CB) for the restraint entry points and (N, CA, C, O, CB) for
+ * folded decoys.  Device-resident ("grouped") layout, used between kernels:
+ * [decoy/32][residue (padded to 16)][atom*3+xyz][decoy%32] so that the 32 lanes of a
+ * warp are 32 decoys and every load/store is one full line.
+ */
+#ifndef TRX2DYN_H
+#define TRX2DYN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRX_ABI_VERSION 1
+
+typedef enum {
+    TRX_OK = 0,
+    TRX_ERR_INVALID = -1,   /* bad argument */
+    TRX_ERR_CUDA = -2,      /* CUDA runtime error (message has the CUDA string) */
+    TRX_ERR_NOMEM = -3,
+    TRX_ERR_STATE = -4      /* call order / handle mismatch */
+} trx_status;
+
+typedef enum { TRX_F64 = 64, TRX_F32 = 32 } trx_precision;
+
+/* restraint types, in the order every array of 4 below uses */
+enum { TRX_DIST = 0, TRX_OMEGA = 1, TRX_THETA = 2, TRX_PHI = 3 };
+/* score terms, the order of every E[3] / w[3]:
+ * atom_pair_constraint, dihedral_constraint, angle_constraint */
+enum { TRX_APC = 0, TRX_DIH = 1, TRX_ANG = 2 };
+
+typedef struct trx_ctx trx_ctx;
+typedef struct trx_tables trx_tables;
+
+/* One restraint type of one target: n restraints on residue pairs (a[k], b[k])
+ * (0-based), all sharing the K spline knots x[K]; y[n][K] are the knot energies.
+ * Replaces: the per-restraint text files gen_rst writes (folding/utils_ros/
+ * utils_ros.py:68-73, 91-95, 110-114, 134-138) plus Rosetta's SplineFunc::read_data. */
+typedef struct {
+    int n;
+    const int32_t *a;
+    const int32_t *b;
+    int K;
+    const double *x;
+    const double *y;
+} trx_rst_set;
+
+int trx_abi_version(void);
+const char *trx_last_error(void);
+
+/* device: CUDA ordinal.  stream: a cudaStream_t (e.g. torch's current stream) or NULL
+ * for a stream the context creates and owns. */
+int trx_ctx_create(int device, void *stream, trx_ctx **out);
+int trx_ctx_destroy(trx_ctx *ctx);
+int trx_ctx_sync(trx_ctx *ctx);
+/* Per-kernel device timing (CUDA events on the context's stream around each launch).
+ * name: "restraints", "reduce", "nerf", "centroid", "torsion_grad", "lbfgs". */
+int trx_ctx_set_timing(trx_ctx *ctx, int enabled);
+int trx_ctx_get_timing(trx_ctx *ctx, const char *name, double *total_ms, long long *launches);
+int trx_ctx_reset_timing(trx_ctx *ctx);
+/* Number of kernels this library has launched on ctx since creation. */
+long long trx_ctx_launch_count(trx_ctx *ctx);
+
+/* Fit the clamped cubic splines (fp64, on device) and pack the tables + pair tiles.
+ * Replaces: add_rst -> ConstraintSetMover.apply (utils_ros.py:706-743), i.e. Rosetta
+ * parsing the .cst file and fitting one SplineFunc per line.  sets[t].n may be 0. */
+int trx_tables_create(trx_ctx *ctx, int L, const trx_rst_set sets[4], trx_tables **out);
+int trx_tables_destroy(trx_tables *t);
+/* counts[4] = restraints per type; *tiles = active 16x16 residue-pair tiles. */
+int trx_tables_info(const trx_tables *t, int *L, int counts[4], int *tiles);
+/* Copies the fitted second derivatives of type `type` back: y2[n][K] (for parity tests). */
+int trx_tables_get_y2(trx_tables *t, int type, double *y2);
+
+/* Restraint energies + analytic gradient for N decoys, host buffers in natural layout.
+ * xyz: [N][L][3 atoms N,CA,CB][3], double (TRX_F64) or float (TRX_F32).
+ * E: [N][3] unweighted term sums (always double).  grad (may be NULL): same layout and
+ * type as xyz, gradient of w[0]*E_apc + w[1]*E_dih + w[2]*E_ang.
+ * Replaces: ScoreFunction(pose) restricted to atom_pair_constraint, dihedral_constraint,
+ * angle_constraint and the matching derivative pass inside MinMover (folding.py:164-171). */
+int trx_energy_grad(trx_ctx *ctx, trx_tables *t, int N, int precision, const void *xyz,
+                    const double w[3], double *E, void *grad);
+
+/* Same, device-resident in the grouped layout (see top).  d_xyz: [ceil(N/32)][Lpad][9][32]
+ * with Lpad = trx_padded_length(L); d_E: [3][32*ceil(N/32)] double; d_grad like d_xyz. */
+int trx_energy_grad_device(trx_ctx *ctx, trx_tables *t, int N, int precision, const void *d_xyz,
+                           const double w[3], double *d_E, void *d_grad);
+int trx_padded_length(int L);
+/* natural <-> grouped conversion on device (n_atoms atoms per residue, same precision both sides) */
+int trx_to_grouped(trx_ctx *ctx, int N, int L, int n_atoms, int precision, const void *d_natural, void *d_grouped);
+int trx_from_grouped(trx_ctx *ctx, int N, int L, int n_atoms, int precision, const void *d_grouped, void *d_natural);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRX2DYN_H */

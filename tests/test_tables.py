@@ -1,0 +1,74 @@
+"""Product table builder (trx2dyn.tables) == oracle restatement, value for value."""
+import numpy as np
+import pytest
+
+import trx2dyn  # noqa: F401
+from trx2dyn import tables
+from oracle.tables_oracle import gen_rst_oracle, select_oracle, PARAMS
+from oracle.restraints_oracle import apply_end_rule
+
+
+def _inputs(golden_dir):
+    yield "example_NMR", np.load(f"{golden_dir}/example_NMR.npz")
+    yield "example_Xray", np.load(f"{golden_dir}/example_Xray.npz")
+    g = np.load(f"{golden_dir}/gen_rst_random24.npz")
+    yield "random24", {k: g[f"in_{k}"] for k in tables.TYPES}
+
+
+def test_params_file_matches_reference_constants():
+    assert tables.load_params() == {**PARAMS, "WDIR": "/dev/shm"}
+
+
+def test_gen_rst_equals_oracle(golden_dir):
+    params = tables.load_params()
+    for tag, npz in _inputs(golden_dir):
+        for orient in (True, False):
+            got = tables.gen_rst(npz, params, use_orient=orient)
+            want = gen_rst_oracle(npz, use_orient=orient)
+            assert list(got) == list(want)
+            for name in got:
+                for key in ("a", "b", "p", "x", "y"):
+                    np.testing.assert_array_equal(got[name][key], want[name][key], err_msg=f"{tag} {name} {key}")
+                assert got[name]["bin_size"] == want[name]["bin_size"]
+
+
+def test_round_decimals_ties_and_signs():
+    v = np.array([0.0005, 0.0015, 2.5e-4, -0.0004, -0.0005, 1.0005, 6.7025, -6.7035, 123.4565, 1e-9])
+    for nd in (3, 5):
+        want = np.array([float(("%%.%df" % nd) % x) for x in v])
+        got = tables.round_decimals(v, nd)
+        np.testing.assert_array_equal(got, want)
+        assert np.signbit(got).tolist() == np.signbit(want).tolist()
+    rng = np.random.default_rng(3)
+    v = rng.normal(size=20000) * 10
+    np.testing.assert_array_equal(tables.round_decimals(v, 3), np.array([float("%.3f" % x) for x in v]))
+    v32 = rng.normal(size=20000).astype(np.float32)
+    np.testing.assert_array_equal(tables.round_decimals(v32, 5), np.array([float("%.5f" % x) for x in v32]))
+
+
+@pytest.mark.parametrize("sep", [(1, 90), (1, 12), (12, 24), (24, 90), (3, 24)])
+def test_select_equals_oracle(golden_dir, sep):
+    params = tables.load_params()
+    npz = np.load(f"{golden_dir}/example_NMR.npz")
+    rst = tables.gen_rst(npz, params)
+    seq = open(f"{golden_dir}/example_seq.fasta").read().split("\n")[1]
+    for pcut, nogly in ((0.05, False), (0.15, True), (0.3, True)):
+        params["PCUT"] = pcut
+        got = tables.select(rst, sep[0], sep[1], params, seq, nogly)
+        want = select_oracle(gen_rst_oracle(npz), sep[0], sep[1], pcut, seq, nogly)
+        for name in got:
+            np.testing.assert_array_equal(got[name], want[name])
+
+
+def test_spline_knots_rules(golden_dir):
+    params = tables.load_params()
+    rst = tables.gen_rst(np.load(f"{golden_dir}/example_NMR.npz"), params)
+    for name in tables.TYPES:
+        for rule in ("H1", "H2"):
+            x, y = tables.spline_knots(rst[name]["x"], rst[name]["y"], rst[name]["bin_size"], rule)
+            xo, yo = apply_end_rule(rst[name]["x"], rst[name]["y"], rst[name]["bin_size"], rule)
+            np.testing.assert_array_equal(x, xo)
+            np.testing.assert_array_equal(y, yo)
+    act = tables.active_restraints(rst, tables.select(rst, 1, 90, params))
+    assert [len(act[t][0]) for t in tables.TYPES] == [3226, 2562, 5142, 2541]
+    assert [len(act[t][2]) for t in tables.TYPES] == [37, 30, 30, 18]

@@ -1,0 +1,170 @@
+"""ctypes binding of libtrx2dyn.so (include/trx2dyn.h).  No CPU fallback: loading or
+creating a context without the CUDA library / a B200 raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+F64, F32 = 64, 32
+_DT = {F64: np.float64, F32: np.float32}
+_lib = None
+
+
+class TrxError(RuntimeError):
+    pass
+
+
+class RstSet(C.Structure):
+    _fields_ = [("n", C.c_int), ("a", C.POINTER(C.c_int32)), ("b", C.POINTER(C.c_int32)),
+                ("K", C.c_int), ("x", C.POINTER(C.c_double)), ("y", C.POINTER(C.c_double))]
+
+
+def lib():
+    """Loads (building if sources are newer) the in-tree CUDA library."""
+    global _lib
+    if _lib is None:
+        path = _build.LIB
+        if _build.needs_build():
+            if not os.path.exists(_build.NVCC):
+                if not os.path.exists(path):
+                    raise TrxError("libtrx2dyn.so is missing and nvcc is not available; there is no CPU fallback")
+            else:
+                _build.build_library()
+        L = C.CDLL(path)
+        L.trx_last_error.restype = C.c_char_p
+        L.trx_ctx_launch_count.restype = C.c_longlong
+        L.trx_ctx_launch_count.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise TrxError("libtrx2dyn: %s (status %d)" % (lib().trx_last_error().decode(), rc))
+
+
+def _ptr(arr, ctype):
+    return arr.ctypes.data_as(C.POINTER(ctype))
+
+
+class Context:
+    def __init__(self, device=0, stream=None):
+        self._h = C.c_void_p()
+        check(lib().trx_ctx_create(C.c_int(device), C.c_void_p(stream or 0), C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().trx_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        check(lib().trx_ctx_sync(self._h))
+
+    def set_timing(self, on=True):
+        check(lib().trx_ctx_set_timing(self._h, C.c_int(1 if on else 0)))
+
+    def reset_timing(self):
+        check(lib().trx_ctx_reset_timing(self._h))
+
+    def timing(self, name):
+        ms, n = C.c_double(), C.c_longlong()
+        check(lib().trx_ctx_get_timing(self._h, name.encode(), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    @property
+    def launch_count(self):
+        return int(lib().trx_ctx_launch_count(self._h))
+
+
+class Tables:
+    """Device-resident spline tables of one target (one restraint set)."""
+
+    def __init__(self, ctx, L, active):
+        """active: {type: (a, b, x, y)} as tables.active_restraints returns."""
+        self.ctx, self.L = ctx, L
+        sets = (RstSet * 4)()
+        keep = []
+        for t, name in enumerate(("dist", "omega", "theta", "phi")):
+            if name in active and len(active[name][0]):
+                a, b, x, y = active[name]
+                a = np.ascontiguousarray(a, dtype=np.int32)
+                b = np.ascontiguousarray(b, dtype=np.int32)
+                x = np.ascontiguousarray(x, dtype=np.float64)
+                y = np.ascontiguousarray(y, dtype=np.float64)
+                if y.shape != (len(a), len(x)):
+                    raise ValueError("%s: y must be (n, K)" % name)
+                keep += [a, b, x, y]
+                sets[t] = RstSet(len(a), _ptr(a, C.c_int32), _ptr(b, C.c_int32), len(x), _ptr(x, C.c_double), _ptr(y, C.c_double))
+            else:
+                sets[t] = RstSet(0, None, None, 0, None, None)
+        self._h = C.c_void_p()
+        check(lib().trx_tables_create(ctx._h, C.c_int(L), sets, C.byref(self._h)))
+        self.counts = [int(s.n) for s in sets]
+        self.K = [int(s.K) for s in sets]
+
+    def close(self):
+        if self._h:
+            lib().trx_tables_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self):
+        L, tiles = C.c_int(), C.c_int()
+        counts = (C.c_int * 4)()
+        check(lib().trx_tables_info(self._h, C.byref(L), counts, C.byref(tiles)))
+        return dict(L=L.value, counts=list(counts), tiles=tiles.value)
+
+    def y2(self, t):
+        out = np.zeros((self.counts[t], self.K[t]))
+        if out.size:
+            check(lib().trx_tables_get_y2(self._h, C.c_int(t), _ptr(out, C.c_double)))
+        return out
+
+    def energy_grad(self, xyz, w=(1.0, 1.0, 1.0), precision=F64, want_grad=True):
+        """xyz (N, L, 3, 3) host array [decoy][res][N,CA,CB][xyz] -> (E (N,3) float64, grad like xyz)."""
+        dt = _DT[precision]
+        xyz = np.ascontiguousarray(xyz, dtype=dt)
+        N = xyz.shape[0]
+        if xyz.shape != (N, self.L, 3, 3):
+            raise ValueError("xyz must be (N, %d, 3, 3)" % self.L)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        E = np.zeros((N, 3))
+        grad = np.zeros_like(xyz) if want_grad else None
+        check(lib().trx_energy_grad(self.ctx._h, self._h, C.c_int(N), C.c_int(precision), C.c_void_p(xyz.ctypes.data),
+                                    _ptr(w, C.c_double), _ptr(E, C.c_double),
+                                    C.c_void_p(grad.ctypes.data) if want_grad else None))
+        return E, grad
+
+    def energy_grad_device(self, N, d_xyz, d_E, d_grad, w=(1.0, 1.0, 1.0), precision=F32):
+        """Device pointers (ints), grouped layout; asynchronous on the context's stream."""
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        check(lib().trx_energy_grad_device(self.ctx._h, self._h, C.c_int(N), C.c_int(precision), C.c_void_p(d_xyz),
+                                           _ptr(w, C.c_double), C.c_void_p(d_E), C.c_void_p(d_grad or 0)))
+
+
+def padded_length(L):
+    return int(lib().trx_padded_length(C.c_int(L)))
+
+
+def to_grouped(ctx, N, L, n_atoms, precision, d_nat, d_grp):
+    check(lib().trx_to_grouped(ctx._h, C.c_int(N), C.c_int(L), C.c_int(n_atoms), C.c_int(precision), C.c_void_p(d_nat), C.c_void_p(d_grp)))
+
+
+def from_grouped(ctx, N, L, n_atoms, precision, d_grp, d_nat):
+    check(lib().trx_from_grouped(ctx._h, C.c_int(N), C.c_int(L), C.c_int(n_atoms), C.c_int(precision), C.c_void_p(d_grp), C.c_void_p(d_nat)))

@@ -1,0 +1,109 @@
+// Internal declarations shared by the translation units of libtrx2dyn.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/trx2dyn.h"
+
+namespace trx {
+
+constexpr int LANES = 32;        // decoys per group: one warp lane per decoy
+constexpr int TILE = 16;         // residues per block row / block column
+constexpr int REC_ELEMS = TILE * 9 * LANES;  // one partial-gradient record (N,CA,CB x xyz)
+constexpr int MAXK = 40;         // max spline knots per restraint
+constexpr int K1_WARPS = 8;
+constexpr int K1_THREADS = K1_WARPS * 32;
+
+void set_error(const char *fmt, ...);
+
+#define TRX_CUDA(call)                                                                   \
+    do {                                                                                 \
+        cudaError_t _e = (call);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            ::trx::set_error("%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+            return TRX_ERR_CUDA;                                                         \
+        }                                                                                \
+    } while (0)
+
+#define TRX_REQUIRE(cond, ...)                 \
+    do {                                       \
+        if (!(cond)) {                         \
+            ::trx::set_error(__VA_ARGS__);     \
+            return TRX_ERR_INVALID;            \
+        }                                      \
+    } while (0)
+
+inline int padded_length(int L) { return (L + TILE - 1) / TILE * TILE; }
+inline int num_groups(int N) { return (N + LANES - 1) / LANES; }
+
+struct KernelTimer {
+    double total_ms = 0;
+    long long launches = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+};
+
+}  // namespace trx
+
+struct trx_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    bool timing = false;
+    long long launches = 0;
+    std::map<std::string, trx::KernelTimer> timers;
+    // scratch device buffers reused across calls, keyed by a tag
+    std::map<std::string, std::pair<void *, size_t>> scratch;
+
+    int get_scratch(const char *tag, size_t bytes, void **out);
+    void time_begin(const char *name);
+    void time_end(const char *name);
+    void collect_timers();
+};
+
+namespace trx {
+
+// Spline knot geometry of one restraint type, as the kernel keeps it in shared memory.
+template <typename T>
+struct KnotGeom {
+    T x[MAXK];      // knot abscissae
+    T rh[MAXK];     // 1/(x[k+1]-x[k])
+    T h2_6[MAXK];   // (x[k+1]-x[k])^2/6
+    T h_6[MAXK];    // (x[k+1]-x[k])/6
+    T gx0, ginv;    // interval guess: k = floor((x-gx0)*ginv)+goff
+    int goff;
+    int K;
+};
+
+// Work decomposition of the restraint kernel for a given number of decoy groups.
+struct Plan {
+    int groups = 0;
+    int nwork = 0;     // CTAs per decoy group
+    int nrec = 0;      // partial-gradient records per decoy group
+    int *d_work = nullptr;      // [nwork][4]: block row I, first tile, tile count, row record id
+    int *d_blk_ptr = nullptr;   // [nb+1] CSR over block -> records
+    int *d_blk_rec = nullptr;
+};
+
+}  // namespace trx
+
+struct trx_tables {
+    trx_ctx *ctx = nullptr;
+    int L = 0, Lpad = 0, nb = 0;
+    int n[4] = {0, 0, 0, 0};
+    int K[4] = {0, 0, 0, 0};
+    double *d_tab64[4] = {nullptr, nullptr, nullptr, nullptr};  // [n][K] (y, y2) double2
+    float *d_tab32[4] = {nullptr, nullptr, nullptr, nullptr};   // [n][K] (y, y2) float2
+    trx::KnotGeom<double> *d_geom64 = nullptr;                  // [4]
+    trx::KnotGeom<float> *d_geom32 = nullptr;                   // [4]
+    int ntiles = 0;
+    std::vector<int> tileI, tileJ;   // host copies, tiles sorted by (I, J)
+    int *d_tileJ = nullptr;          // [ntiles]
+    int *d_pairrec = nullptr;        // [ntiles][16][16][8]: mask, 6 restraint indices, pad
+    long long active_pairs = 0;
+    std::map<int, trx::Plan> plans;  // keyed by number of decoy groups
+    int get_plan(int groups, trx::Plan **out);
+};

@@ -1,0 +1,281 @@
+// Restraint tables: clamped cubic spline fit on device (fp64), knot geometry, and the
+// 16x16 residue-pair tiles the restraint kernel walks.
+//
+// What this replaces in the reference: add_rst writing minimize.cst and Rosetta's
+// ConstraintSetMover parsing one text file per restraint and fitting one SplineFunc
+// each (folding/utils_ros/utils_ros.py:706-743).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "internal.cuh"
+
+namespace trx {
+
+// Numerical-Recipes `spline`, clamped with zero slope at both ends (what Rosetta's
+// SplineGenerator(lbx,lby,0, ubx,uby,0) -> SimpleInterpolator computes).  One thread
+// per restraint; the scratch vector u lives in registers/local memory (K <= MAXK).
+__global__ void spline_fit_kernel(int n, int K, const double *__restrict__ x, const double *__restrict__ y,
+                                  double2 *__restrict__ tab64, float2 *__restrict__ tab32)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const double *yr = y + (size_t)r * K;
+    double u[MAXK], y2[MAXK];
+    y2[0] = -0.5;
+    u[0] = (3.0 / (x[1] - x[0])) * ((yr[1] - yr[0]) / (x[1] - x[0]) - 0.0);
+    for (int i = 1; i < K - 1; ++i) {
+        double sig = (x[i] - x[i - 1]) / (x[i + 1] - x[i - 1]);
+        double p = sig * y2[i - 1] + 2.0;
+        y2[i] = (sig - 1.0) / p;
+        double t = (yr[i + 1] - yr[i]) / (x[i + 1] - x[i]) - (yr[i] - yr[i - 1]) / (x[i] - x[i - 1]);
+        u[i] = (6.0 * t / (x[i + 1] - x[i - 1]) - sig * u[i - 1]) / p;
+    }
+    double un = (3.0 / (x[K - 1] - x[K - 2])) * (0.0 - (yr[K - 1] - yr[K - 2]) / (x[K - 1] - x[K - 2]));
+    y2[K - 1] = (un - 0.5 * u[K - 2]) / (0.5 * y2[K - 2] + 1.0);
+    for (int k = K - 2; k >= 0; --k) y2[k] = y2[k] * y2[k + 1] + u[k];
+    for (int k = 0; k < K; ++k) {
+        tab64[(size_t)r * K + k] = make_double2(yr[k], y2[k]);
+        tab32[(size_t)r * K + k] = make_float2((float)yr[k], (float)y2[k]);
+    }
+}
+
+template <typename T>
+static void fill_geom(KnotGeom<T> &g, int K, const double *x)
+{
+    memset(&g, 0, sizeof(g));
+    g.K = K;
+    if (K < 2) return;
+    for (int k = 0; k < K; ++k) g.x[k] = (T)x[k];
+    for (int k = 0; k + 1 < K; ++k) {
+        double h = x[k + 1] - x[k];
+        g.rh[k] = (T)(1.0 / h);
+        g.h2_6[k] = (T)(h * h / 6.0);
+        g.h_6[k] = (T)(h / 6.0);
+    }
+    // interval guess anchored on the longest run of (nearly) equal spacings -- the
+    // uniform part of the grid; the kernel corrects the guess against the true knots
+    int best = 0, bestlen = 0;
+    for (int k = 0; k + 1 < K;) {
+        double hk = x[k + 1] - x[k];
+        int m = k + 1;
+        while (m + 1 < K && std::fabs((x[m + 1] - x[m]) - hk) < 1e-2 * hk) ++m;
+        if (m - k > bestlen) { bestlen = m - k; best = k; }
+        k = m;
+    }
+    double h = x[best + 1] - x[best];
+    g.gx0 = (T)x[best];
+    g.ginv = (T)(1.0 / h);
+    g.goff = best;
+}
+
+}  // namespace trx
+
+using namespace trx;
+
+int trx_tables::get_plan(int groups, Plan **out)
+{
+    auto it = plans.find(groups);
+    if (it != plans.end()) { *out = &it->second; return TRX_OK; }
+    Plan p;
+    p.groups = groups;
+    // chunk tiles of one block row so that the grid has a few waves of CTAs
+    const long long want_ctas = 148LL * 3 * 4;
+    long long chunk = std::max(1LL, (long long)ntiles * groups / want_ctas);
+    chunk = std::min<long long>(chunk, std::max(1, nb));
+    std::vector<int> work;               // I, first tile, count, row record
+    std::vector<std::vector<int>> blk(nb);
+    int nrec = 0;
+    std::vector<int> tile_rec(ntiles);
+    for (int t = 0; t < ntiles; ++t) { tile_rec[t] = nrec++; blk[tileJ[t]].push_back(tile_rec[t]); }
+    int t0 = 0;
+    while (t0 < ntiles) {
+        int I = tileI[t0], t1 = t0;
+        while (t1 < ntiles && tileI[t1] == I) ++t1;
+        for (int s = t0; s < t1; s += (int)chunk) {
+            int cnt = std::min<int>((int)chunk, t1 - s);
+            int rr = nrec++;
+            blk[I].push_back(rr);
+            work.insert(work.end(), {I, s, cnt, rr});
+        }
+        t0 = t1;
+    }
+    p.nwork = (int)work.size() / 4;
+    p.nrec = nrec;
+    // longest work items first (they were emitted row by row; sort by tile count desc)
+    std::vector<int> order(p.nwork);
+    for (int i = 0; i < p.nwork; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return work[a * 4 + 2] > work[b * 4 + 2]; });
+    std::vector<int> sorted(work.size());
+    for (int i = 0; i < p.nwork; ++i) memcpy(&sorted[i * 4], &work[order[i] * 4], 4 * sizeof(int));
+    std::vector<int> ptr(nb + 1, 0), recs;
+    for (int b = 0; b < nb; ++b) { ptr[b + 1] = ptr[b] + (int)blk[b].size(); recs.insert(recs.end(), blk[b].begin(), blk[b].end()); }
+    if (recs.empty()) recs.push_back(0);
+    if (sorted.empty()) sorted.assign(4, 0);
+    // tile -> col record id is the identity by construction (tile_rec[t] == t)
+    TRX_CUDA(cudaMalloc(&p.d_work, sorted.size() * sizeof(int)));
+    TRX_CUDA(cudaMalloc(&p.d_blk_ptr, ptr.size() * sizeof(int)));
+    TRX_CUDA(cudaMalloc(&p.d_blk_rec, recs.size() * sizeof(int)));
+    TRX_CUDA(cudaMemcpy(p.d_work, sorted.data(), sorted.size() * sizeof(int), cudaMemcpyHostToDevice));
+    TRX_CUDA(cudaMemcpy(p.d_blk_ptr, ptr.data(), ptr.size() * sizeof(int), cudaMemcpyHostToDevice));
+    TRX_CUDA(cudaMemcpy(p.d_blk_rec, recs.data(), recs.size() * sizeof(int), cudaMemcpyHostToDevice));
+    plans[groups] = p;
+    *out = &plans[groups];
+    return TRX_OK;
+}
+
+extern "C" {
+
+int trx_tables_create(trx_ctx *ctx, int L, const trx_rst_set sets[4], trx_tables **out)
+{
+    TRX_REQUIRE(ctx && sets && out, "trx_tables_create: NULL argument");
+    TRX_REQUIRE(L >= 2 && L <= 4096, "trx_tables_create: L=%d out of range [2,4096]", L);
+    TRX_CUDA(cudaSetDevice(ctx->device));
+    for (int t = 0; t < 4; ++t) {
+        const trx_rst_set &s = sets[t];
+        TRX_REQUIRE(s.n >= 0, "trx_tables_create: sets[%d].n < 0", t);
+        if (s.n == 0) continue;
+        TRX_REQUIRE(s.a && s.b && s.x && s.y, "trx_tables_create: sets[%d] has NULL arrays", t);
+        TRX_REQUIRE(s.K >= 3 && s.K <= MAXK, "trx_tables_create: sets[%d].K=%d out of range [3,%d]", t, s.K, MAXK);
+        for (int k = 0; k + 1 < s.K; ++k)
+            TRX_REQUIRE(s.x[k + 1] > s.x[k], "trx_tables_create: sets[%d].x not strictly increasing at %d", t, k);
+        for (int r = 0; r < s.n; ++r)
+            TRX_REQUIRE(s.a[r] >= 0 && s.a[r] < L && s.b[r] >= 0 && s.b[r] < L && s.a[r] != s.b[r],
+                        "trx_tables_create: sets[%d] restraint %d has bad residues (%d,%d)", t, r, s.a[r], s.b[r]);
+    }
+    trx_tables *T = new trx_tables();
+    T->ctx = ctx;
+    T->L = L;
+    T->Lpad = padded_length(L);
+    T->nb = T->Lpad / TILE;
+    const int nb = T->nb;
+
+    // ---- spline fit on device
+    KnotGeom<double> g64[4];
+    KnotGeom<float> g32[4];
+    for (int t = 0; t < 4; ++t) {
+        const trx_rst_set &s = sets[t];
+        T->n[t] = s.n;
+        T->K[t] = s.n ? s.K : 0;
+        static const double dummy[2] = {0.0, 1.0};
+        fill_geom(g64[t], s.n ? s.K : 2, s.n ? s.x : dummy);
+        fill_geom(g32[t], s.n ? s.K : 2, s.n ? s.x : dummy);
+        if (s.n == 0) continue;
+        double *d_x = nullptr, *d_y = nullptr;
+        size_t ny = (size_t)s.n * s.K;
+        TRX_CUDA(cudaMalloc(&d_x, s.K * sizeof(double)));
+        TRX_CUDA(cudaMalloc(&d_y, ny * sizeof(double)));
+        TRX_CUDA(cudaMalloc(&T->d_tab64[t], ny * sizeof(double2)));
+        TRX_CUDA(cudaMalloc(&T->d_tab32[t], ny * sizeof(float2)));
+        TRX_CUDA(cudaMemcpyAsync(d_x, s.x, s.K * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        TRX_CUDA(cudaMemcpyAsync(d_y, s.y, ny * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->time_begin("spline_fit");
+        spline_fit_kernel<<<(s.n + 127) / 128, 128, 0, ctx->stream>>>(s.n, s.K, d_x, d_y, (double2 *)T->d_tab64[t],
+                                                                     (float2 *)T->d_tab32[t]);
+        ctx->time_end("spline_fit");
+        TRX_CUDA(cudaGetLastError());
+        TRX_CUDA(cudaStreamSynchronize(ctx->stream));
+        TRX_CUDA(cudaFree(d_x));
+        TRX_CUDA(cudaFree(d_y));
+    }
+    TRX_CUDA(cudaMalloc(&T->d_geom64, sizeof(g64)));
+    TRX_CUDA(cudaMalloc(&T->d_geom32, sizeof(g32)));
+    TRX_CUDA(cudaMemcpy(T->d_geom64, g64, sizeof(g64), cudaMemcpyHostToDevice));
+    TRX_CUDA(cudaMemcpy(T->d_geom32, g32, sizeof(g32), cudaMemcpyHostToDevice));
+
+    // ---- pair slots: for the unordered pair i<j the six restraints
+    //   0 dist(i,j) 1 omega(i,j) 2 theta(i,j) 3 theta(j,i) 4 phi(i,j) 5 phi(j,i)
+    // kept per active 16x16 tile as [r][c][8] ints: mask, 6 indices, pad
+    std::vector<int> tile_of((size_t)nb * nb, -1);
+    auto slot_of = [&](int type, int a, int b, int &i, int &j) -> int {
+        i = std::min(a, b);
+        j = std::max(a, b);
+        if (type == TRX_DIST) return 0;
+        if (type == TRX_OMEGA) return 1;
+        if (type == TRX_THETA) return a < b ? 2 : 3;
+        return a < b ? 4 : 5;
+    };
+    // pass 1: which tiles are active
+    for (int t = 0; t < 4; ++t)
+        for (int r = 0; r < sets[t].n; ++r) {
+            int i, j;
+            slot_of(t, sets[t].a[r], sets[t].b[r], i, j);
+            tile_of[(size_t)(i / TILE) * nb + j / TILE] = 0;
+        }
+    for (int I = 0; I < nb; ++I)
+        for (int J = I; J < nb; ++J)
+            if (tile_of[(size_t)I * nb + J] == 0) {
+                tile_of[(size_t)I * nb + J] = T->ntiles++;
+                T->tileI.push_back(I);
+                T->tileJ.push_back(J);
+            }
+    std::vector<int> rec((size_t)std::max(1, T->ntiles) * TILE * TILE * 8, -1);
+    for (size_t p = 0; p < rec.size(); p += 8) { rec[p] = 0; rec[p + 7] = 0; }
+    for (int t = 0; t < 4; ++t)
+        for (int r = 0; r < sets[t].n; ++r) {
+            int i, j;
+            int slot = slot_of(t, sets[t].a[r], sets[t].b[r], i, j);
+            int tile = tile_of[(size_t)(i / TILE) * nb + j / TILE];
+            size_t p = (((size_t)tile * TILE + i % TILE) * TILE + j % TILE) * 8;
+            if (rec[p + 1 + slot] != -1) {
+                set_error("trx_tables_create: duplicate restraint of type %d on pair (%d,%d)", t, sets[t].a[r], sets[t].b[r]);
+                trx_tables_destroy(T);
+                return TRX_ERR_INVALID;
+            }
+            if (rec[p] == 0) T->active_pairs++;
+            rec[p] |= 1 << slot;
+            rec[p + 1 + slot] = r;
+        }
+    std::vector<int> tj = T->tileJ;
+    if (tj.empty()) tj.push_back(0);
+    TRX_CUDA(cudaMalloc(&T->d_tileJ, tj.size() * sizeof(int)));
+    TRX_CUDA(cudaMalloc(&T->d_pairrec, rec.size() * sizeof(int)));
+    TRX_CUDA(cudaMemcpy(T->d_tileJ, tj.data(), tj.size() * sizeof(int), cudaMemcpyHostToDevice));
+    TRX_CUDA(cudaMemcpy(T->d_pairrec, rec.data(), rec.size() * sizeof(int), cudaMemcpyHostToDevice));
+    *out = T;
+    return TRX_OK;
+}
+
+int trx_tables_destroy(trx_tables *T)
+{
+    if (!T) return TRX_OK;
+    cudaSetDevice(T->ctx->device);
+    cudaStreamSynchronize(T->ctx->stream);
+    for (int t = 0; t < 4; ++t) {
+        if (T->d_tab64[t]) cudaFree(T->d_tab64[t]);
+        if (T->d_tab32[t]) cudaFree(T->d_tab32[t]);
+    }
+    if (T->d_geom64) cudaFree(T->d_geom64);
+    if (T->d_geom32) cudaFree(T->d_geom32);
+    if (T->d_tileJ) cudaFree(T->d_tileJ);
+    if (T->d_pairrec) cudaFree(T->d_pairrec);
+    for (auto &kv : T->plans) {
+        cudaFree(kv.second.d_work);
+        cudaFree(kv.second.d_blk_ptr);
+        cudaFree(kv.second.d_blk_rec);
+    }
+    delete T;
+    return TRX_OK;
+}
+
+int trx_tables_info(const trx_tables *T, int *L, int counts[4], int *tiles)
+{
+    TRX_REQUIRE(T, "trx_tables_info: tables is NULL");
+    if (L) *L = T->L;
+    if (counts) for (int t = 0; t < 4; ++t) counts[t] = T->n[t];
+    if (tiles) *tiles = T->ntiles;
+    return TRX_OK;
+}
+
+int trx_tables_get_y2(trx_tables *T, int type, double *y2)
+{
+    TRX_REQUIRE(T && y2 && type >= 0 && type < 4, "trx_tables_get_y2: bad argument");
+    size_t n = (size_t)T->n[type] * T->K[type];
+    if (n == 0) return TRX_OK;
+    std::vector<double> tmp(n * 2);
+    TRX_CUDA(cudaMemcpy(tmp.data(), T->d_tab64[type], n * 2 * sizeof(double), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; ++i) y2[i] = tmp[2 * i + 1];
+    return TRX_OK;
+}
+
+}  // extern "C"
