@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the folding hot path (contract: see DESIGN.md 'Measurement').
+
+Workload (BASELINE.json configs[2]): synthetic L=300 target, full dist+omega+theta+phi
+restraints, two-model mixing (half the decoys scored against each model's tables),
+4096 decoys per GPU, decoys sharded across GPUs with no data-path collective (weak scaling).
+
+One "step" = one pass of the hot path over the whole decoy batch.  With --mode restraint
+(stage available in every build) the pass is one restraint energy+gradient evaluation of
+every decoy (SURVEY 8d metric M2); with --mode fold it is a complete centroid fold of
+every decoy (metric M1, decoys/s).  The default is the most complete mode the library has.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--mode ...]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+L_TARGET = 300
+SEED = 300
+WEIGHTS = (5.0, 4.0, 4.0)  # folding/data/scorefxn.wts: atom_pair 5, dihedral 4, angle 4
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default=None, choices=["restraint", "fold"])
+    ap.add_argument("--decoys", type=int, default=4096, help="decoys per GPU")
+    ap.add_argument("--precision", type=int, default=32, choices=[32, 64])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 8 and r[4 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def build_workload(n_decoys, precision):
+    """Two table sets (two-model mixing) + decoy coordinates near the synthetic native."""
+    import trx2dyn  # noqa: F401
+    from trx2dyn import synth, tables
+    seq, npzs, nat = synth.target(L_TARGET, SEED, dense=False, two_model=True)
+    params = tables.load_params()
+    acts = []
+    for npz in npzs:
+        rst = tables.gen_rst(npz, params)
+        acts.append(tables.active_restraints(rst, tables.select(rst, 1, L_TARGET, params)))
+    rng = np.random.default_rng(SEED + 7)
+    sig = rng.uniform(0.3, 3.0, size=(n_decoys, 1, 1, 1))
+    xyz = nat[None, :, [0, 1, 3]] + rng.normal(size=(n_decoys, L_TARGET, 3, 3)) * sig
+    return seq, npzs, acts, xyz.astype(np.float32 if precision == 32 else np.float64)
+
+
+def oracle_sets(npzs):
+    from oracle.tables_oracle import gen_rst_oracle, select_oracle
+    from oracle import restraints_oracle as ro
+    sets = []
+    for npz in npzs:
+        rst = gen_rst_oracle(npz)
+        sets.append(ro.RestraintSetOracle(rst, select_oracle(rst, 1, L_TARGET, 0.05), "H1"))
+    return sets
+
+
+def cpu_restraint_rate(npzs, xyz, n_sample, threads):
+    """Oracle (CPU port of the same arithmetic) timed on a bounded sample of the workload."""
+    sets = oracle_sets(npzs)
+    half = n_sample // 2
+    xs = [np.ascontiguousarray(xyz[:half], dtype=np.float64), np.ascontiguousarray(xyz[half:n_sample], dtype=np.float64)]
+    sets[0].energy_grad_batch(xs[0][:threads], WEIGHTS, threads)  # warm
+    t0 = time.perf_counter()
+    for s, x in zip(sets, xs):
+        s.energy_grad_batch(x, WEIGHTS, threads)
+    dt = time.perf_counter() - t0
+    return n_sample / dt, dt
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path.  PyRosetta is absent
+    (un-vendored binary dependency), so this times the oracle port on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    steps = args.steps or 3
+    n_sample = max(2 * threads, 64)
+    _, npzs, _, xyz = build_workload(n_sample, 64)
+    for _ in range(min(args.warmup, 1)):
+        cpu_restraint_rate(npzs, xyz, n_sample, threads)
+    t = []
+    for _ in range(steps):
+        t.append(cpu_restraint_rate(npzs, xyz, n_sample, threads)[1])
+    val = n_sample / float(np.mean(t))
+    line = {"impl": "reference", "metric": "restraint_energy_grad_decoy_evals_per_sec_L300", "value": val,
+            "unit": "decoy-evals/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * float(np.mean(t)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "synthetic L=300 dist+omega+theta+phi, two-model mixing (configs[2])",
+                       "sample": "%d decoys per step" % n_sample},
+            "cpu_baseline": {"value": val, "unit": "decoy-evals/s", "cores": threads, "kind": "port",
+                             "sample": "%d decoys of the L=300 workload per step, oracle/restraints_oracle.c on %d pthreads (PyRosetta absent)" % (n_sample, threads)},
+            "e2e": {"value": val, "unit": "decoy-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import trx2dyn  # noqa: F401
+    from trx2dyn import capi
+
+    N, prec = args.decoys, args.precision
+    steps = args.steps or 10
+    seq, npzs, acts, xyz = build_workload(N, prec)
+    # rank r scores its own shard: different decoys per rank, same tables
+    if world > 1:
+        rng = np.random.default_rng(1000 + rank)
+        xyz = (xyz + rng.normal(size=xyz.shape).astype(xyz.dtype) * 0.05).astype(xyz.dtype)
+    stream = torch.cuda.Stream()
+    ctx = capi.Context(local, stream.cuda_stream)
+    tabs = [capi.Tables(ctx, L_TARGET, a) for a in acts]
+    R = [sum(t.info()["counts"]) for t in tabs]
+    half = N // 2
+    parts = [(0, half), (half, N - half)]
+    tdt = torch.float32 if prec == 32 else torch.float64
+    es = prec // 8
+    Lpad = capi.padded_length(L_TARGET)
+
+    dev = []
+    with torch.cuda.stream(stream):
+        for (o, n) in parts:
+            nat = torch.tensor(xyz[o:o + n], device="cuda")
+            G = (n + 31) // 32
+            grp = torch.empty(G * Lpad * 9 * 32, dtype=tdt, device="cuda")
+            capi.to_grouped(ctx, n, L_TARGET, 3, prec, nat.data_ptr(), grp.data_ptr())
+            dev.append(dict(n=n, grp=grp, grad=torch.empty_like(grp), E=torch.empty(3 * G * 32, dtype=torch.float64, device="cuda")))
+        flush = torch.empty(160 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    ctx.sync()
+
+    def step_device():
+        for tb, d in zip(tabs, dev):
+            tb.energy_grad_device(d["n"], d["grp"].data_ptr(), d["E"].data_ptr(), d["grad"].data_ptr(), WEIGHTS, prec)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (value): CUDA events on the launching stream, L2 flushed between steps
+    with torch.cuda.stream(stream):
+        for _ in range(max(args.warmup, 3)):
+            step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ctx.set_timing(True)
+    ctx.reset_timing()
+    launches0 = ctx.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    barrier()
+    with torch.cuda.stream(stream):
+        for a, b in ev:
+            flush.zero_()
+            a.record(stream)
+            step_device()
+            b.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.launch_count - launches0
+    t_dev = sum(a.elapsed_time(b) for a, b in ev) / 1e3
+    k1_ms, k1_n = ctx.timing("restraints")
+    ctx.set_timing(False)
+    if world > 1:
+        t = torch.tensor([t_dev], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_dev = float(t.item())
+
+    # ---- end to end through the C ABI with host buffers (pinned), H2D + D2H inside the timed region
+    host = [torch.tensor(xyz[o:o + n]).pin_memory() for (o, n) in parts]
+    hostE = [torch.empty((n, 3), dtype=torch.float64).pin_memory() for (_, n) in parts]
+    hostG = [torch.empty_like(h).pin_memory() for h in host]
+    import ctypes as C
+    w = np.ascontiguousarray(WEIGHTS, dtype=np.float64)
+
+    def step_e2e():
+        for tb, h, e, g in zip(tabs, host, hostE, hostG):
+            capi.check(capi.lib().trx_energy_grad(ctx._h, tb._h, C.c_int(h.shape[0]), C.c_int(prec), C.c_void_p(h.data_ptr()),
+                                                  w.ctypes.data_as(C.POINTER(C.c_double)), C.c_void_p(e.data_ptr()),
+                                                  C.c_void_p(g.data_ptr())))
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e2e_steps = max(3, steps // 2)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    total = N * world
+    value = total * steps / t_dev
+    peak, peak_src = peaks()
+    # algorithmic bytes of one restraint-kernel launch: 4 knot scalars per restraint-eval
+    # + coordinates read + gradient written, per decoy; launches alternate between the two table sets
+    alg = [(4 * es * r + 2 * 3 * L_TARGET * 3 * es) * n for r, (_, n) in zip(R, parts)]
+    alg_per_launch = float(np.mean(alg))
+    k1_avg_ms = k1_ms / max(k1_n, 1)
+    achieved = alg_per_launch / (k1_avg_ms * 1e-3) / 1e9
+    line = {"metric": "restraint_energy_grad_decoy_evals_per_sec_L300", "value": value, "unit": "decoy-evals/s",
+            "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_dev / steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if prec == 32 else "f64", "data": "synthetic",
+            "config": {"workload": "synthetic L=300 dist+omega+theta+phi, two-model mixing, %d decoys per GPU (configs[2])" % N,
+                       "restraints_per_decoy": R, "l2": "flushed between steps (160 MB write)", "mode": "restraint"},
+            "restraint_evals_per_sec": value * float(np.mean(R)),
+            "clocks": clocks,
+            "e2e": {"value": total * e2e_steps / t_e2e, "unit": "decoy-evals/s",
+                    "h2d_bytes_per_step": int(sum(h.numel() * h.element_size() for h in host)),
+                    "d2h_bytes_per_step": int(sum(g.numel() * g.element_size() for g in hostG) + sum(e.numel() * 8 for e in hostE))},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "restraints_kernel<float>" if prec == 32 else "restraints_kernel<double>",
+                         "kernel_ms": k1_avg_ms, "kernel_share_of_step": k1_ms / (1e3 * t_dev), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_per_launch}}
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        n_sample = max(2 * threads, 64)
+        rate, dt = cpu_restraint_rate(npzs, xyz, n_sample, threads)
+        line["cpu_baseline"] = {"value": rate, "unit": "decoy-evals/s", "cores": threads, "kind": "port",
+                                "sample": "%d decoys of the same workload, oracle/restraints_oracle.c on %d pthreads, %.2f s (PyRosetta absent)" % (n_sample, threads, dt)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

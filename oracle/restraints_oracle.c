@@ -243,3 +243,44 @@ void trxo_energy_grad_flat(int L, const double *xyz,
     trxo_set t = {nt, Kt, at, bt, xt, yt, y2t}, p = {np_, Kp, ap, bp, xp, yp, y2p};
     trxo_energy_grad(L, xyz, nd ? &d : NULL, no ? &o : NULL, nt ? &t : NULL, np_ ? &p : NULL, w, E, grad, NULL, NULL);
 }
+
+/* ---- batch over decoys on several host threads (CPU baseline leg of bench.py) ---- */
+#include <pthread.h>
+
+typedef struct {
+    int L, n0, n1;
+    const double *xyz; const trxo_set *s[4]; const double *w; double *E; double *grad;
+} trxo_job;
+
+static void *trxo_worker(void *arg)
+{
+    trxo_job *j = (trxo_job *)arg;
+    for (int n = j->n0; n < j->n1; ++n)
+        trxo_energy_grad(j->L, j->xyz + (size_t)n * j->L * 9, j->s[0], j->s[1], j->s[2], j->s[3], j->w,
+                         j->E + (size_t)n * 3, j->grad ? j->grad + (size_t)n * j->L * 9 : NULL, NULL, NULL);
+    return NULL;
+}
+
+/* xyz[N][L][3][3], E[N][3], grad[N][L][3][3] (may be NULL); nthreads >= 1. */
+void trxo_energy_grad_batch(int nthreads, int N, int L, const double *xyz,
+                            int nd, const int *ad, const int *bd, int Kd, const double *xd, const double *yd, const double *y2d,
+                            int no, const int *ao, const int *bo, int Ko, const double *xo, const double *yo, const double *y2o,
+                            int nt, const int *at, const int *bt, int Kt, const double *xt, const double *yt, const double *y2t,
+                            int np_, const int *ap, const int *bp, int Kp, const double *xp, const double *yp, const double *y2p,
+                            const double *w, double *E, double *grad)
+{
+    trxo_set d = {nd, Kd, ad, bd, xd, yd, y2d}, o = {no, Ko, ao, bo, xo, yo, y2o};
+    trxo_set t = {nt, Kt, at, bt, xt, yt, y2t}, p = {np_, Kp, ap, bp, xp, yp, y2p};
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 256) nthreads = 256;
+    pthread_t th[256];
+    trxo_job jobs[256];
+    for (int k = 0; k < nthreads; ++k) {
+        jobs[k].L = L; jobs[k].xyz = xyz; jobs[k].w = w; jobs[k].E = E; jobs[k].grad = grad;
+        jobs[k].s[0] = nd ? &d : NULL; jobs[k].s[1] = no ? &o : NULL; jobs[k].s[2] = nt ? &t : NULL; jobs[k].s[3] = np_ ? &p : NULL;
+        jobs[k].n0 = (int)((long long)N * k / nthreads);
+        jobs[k].n1 = (int)((long long)N * (k + 1) / nthreads);
+        pthread_create(&th[k], NULL, trxo_worker, &jobs[k]);
+    }
+    for (int k = 0; k < nthreads; ++k) pthread_join(th[k], NULL);
+}

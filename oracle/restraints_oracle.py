@@ -84,6 +84,32 @@ class RestraintSetOracle:
                                    x=np.ascontiguousarray(x), y=y,
                                    y2=spline_fit(x, y) if len(y) else y.copy())
 
+    def _set_args(self):
+        args = []
+        empty_i = np.zeros(1, dtype=np.int32)
+        empty_d = np.zeros(1, dtype=np.float64)
+        self._keep = (empty_i, empty_d)
+        for name in TYPES:
+            s = self.sets.get(name)
+            if s is None or len(s["a"]) == 0:
+                args += [C.c_int(0), _p(empty_i, C.c_int), _p(empty_i, C.c_int), C.c_int(2),
+                         _p(empty_d), _p(empty_d), _p(empty_d)]
+            else:
+                args += [C.c_int(len(s["a"])), _p(s["a"], C.c_int), _p(s["b"], C.c_int), C.c_int(len(s["x"])),
+                         _p(s["x"]), _p(s["y"]), _p(s["y2"])]
+        return args
+
+    def energy_grad_batch(self, xyz, w=(1.0, 1.0, 1.0), nthreads=1, want_grad=True):
+        """xyz (N,L,3,3) -> (E (N,3), grad (N,L,3,3)); decoys split over host threads."""
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+        N, L = xyz.shape[:2]
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        E = np.zeros((N, 3))
+        grad = np.zeros((N, L, 3, 3)) if want_grad else None
+        lib().trxo_energy_grad_batch(C.c_int(nthreads), C.c_int(N), C.c_int(L), _p(xyz), *self._set_args(),
+                                     _p(w), _p(E), _p(grad) if want_grad else None)
+        return E, grad
+
     def energy_grad(self, xyz, w=(1.0, 1.0, 1.0)):
         """xyz (L,3,3) float64 [res][N,CA,CB][xyz] -> (E[3] unweighted, grad (L,3,3) of w.E)."""
         xyz = np.ascontiguousarray(xyz, dtype=np.float64)
