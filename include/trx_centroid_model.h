@@ -1,0 +1,74 @@
+/* Centroid backbone model: constants shared (as DATA) by the CUDA library and the CPU
+ * oracle.  Plain C, header-only.
+ *
+ * Rosetta's own database tables for the non-restraint centroid terms (atom_vdw, Rama
+ * maps, cen_hb) are not part of the reference tree, so the terms
+ * below are stated approximations with the same functional role; only the three
+ * constraint terms carry a parity claim.
+ *
+ * Ideal backbone geometry [ROSETTA-RECALL, SURVEY 8a row 12]; the virtual-CB formula is
+ * the reference's own (utils_trX2dy/utils.py:132-135), i.e. the CB the network's
+ * orientation labels were computed from.
+ */
+#ifndef TRX_CENTROID_MODEL_H
+#define TRX_CENTROID_MODEL_H
+
+#define TRX_PI 3.14159265358979323846
+#define TRX_DEG (TRX_PI / 180.0)
+
+/* bond lengths (A) and angles (rad) */
+#define TRX_B_N_CA 1.458
+#define TRX_B_CA_C 1.523
+#define TRX_B_C_N 1.329
+#define TRX_B_C_O 1.231
+#define TRX_A_N_CA_C (111.2 * TRX_DEG)
+#define TRX_A_CA_C_N (116.2 * TRX_DEG)
+#define TRX_A_C_N_CA (121.7 * TRX_DEG)
+#define TRX_A_CA_C_O (120.8 * TRX_DEG)
+
+/* virtual CB = CB_A*(b x c) + CB_B*b + CB_C*c + CA,  b = CA-N, c = C-CA */
+#define TRX_CB_A (-0.58273431)
+#define TRX_CB_B (0.56802827)
+#define TRX_CB_C (-0.54067466)
+
+/* atoms per residue in every coordinate / gradient array of the fold path; the order
+ * makes the atoms moved by omega(i-1), phi(i), psi(i) suffixes of the atom sequence */
+enum { TRX_AT_N = 0, TRX_AT_CA = 1, TRX_AT_CB = 2, TRX_AT_C = 3, TRX_AT_O = 4, TRX_NAT = 5 };
+
+/* energy terms of the fold path, order of every terms[] / weights[] array */
+enum { TRX_T_APC = 0, TRX_T_DIH = 1, TRX_T_ANG = 2, TRX_T_VDW = 3, TRX_T_RAMA = 4, TRX_T_OMEGA = 5, TRX_NTERM = 6 };
+
+/* amino-acid index: position in "ARNDCQEGHILKMFPSTWYV" */
+#define TRX_AA_ORDER "ARNDCQEGHILKMFPSTWYV"
+#define TRX_AA_GLY 7
+#define TRX_AA_PRO 14
+#define TRX_AA_ALA 0
+
+/* centroid pseudo-atom: CEN = CA + TRX_CEN_S[aa]*(CB - CA) (on the CA->CB ray) */
+static const double TRX_CEN_S[20] = {
+    /* A     R     N     D     C     Q     E     G     H     I  */
+    0.95, 2.70, 1.65, 1.65, 1.40, 2.05, 2.05, 0.95, 2.05, 1.50,
+    /* L     K     M     F     P     S     T     W     Y     V  */
+    1.70, 2.30, 1.95, 2.25, 1.25, 1.25, 1.25, 2.55, 2.50, 1.30};
+/* soft-sphere radii (A): r_ij = r_i + r_j; backbone atoms then CEN by residue type */
+static const double TRX_R_BB[5] = {1.40, 1.80, 1.80, 1.70, 1.35}; /* N CA CB C O */
+static const double TRX_R_CEN[20] = {
+    1.90, 2.60, 2.20, 2.20, 2.10, 2.40, 2.40, 1.90, 2.40, 2.30,
+    2.40, 2.50, 2.40, 2.60, 2.10, 2.00, 2.10, 2.80, 2.70, 2.20};
+#define TRX_VDW_SCALE 0.8   /* Rosetta's vdw term carries this factor */
+#define TRX_VDW_MINSEP 2    /* residue pairs closer than this in sequence are skipped */
+#define TRX_VDW_CA_CUTOFF 13.0 /* CA-CA distance beyond which no atom pair can touch */
+
+/* Ramachandran term: -ln of a von-Mises mixture, classes: 0 general, 1 proline.
+ * Each basin: phi0, psi0 (deg), kappa_phi, kappa_psi (1/rad^2), weight. */
+#define TRX_RAMA_NB 5
+static const double TRX_RAMA[2][TRX_RAMA_NB][5] = {
+    {{-63.0, -43.0, 9.0, 9.0, 0.45}, {-120.0, 130.0, 4.0, 4.0, 0.30}, {-70.0, 145.0, 8.0, 8.0, 0.17},
+     {57.0, 39.0, 12.0, 12.0, 0.03}, {-90.0, 0.0, 6.0, 6.0, 0.05}},
+    {{-65.0, -35.0, 20.0, 9.0, 0.40}, {-65.0, 145.0, 20.0, 8.0, 0.55}, {-85.0, 70.0, 12.0, 6.0, 0.05},
+     {-65.0, -35.0, 20.0, 9.0, 0.0}, {-65.0, -35.0, 20.0, 9.0, 0.0}}};
+#define TRX_RAMA_FLOOR 1e-4
+/* omega tether: 0.01 * (deviation from 180 in degrees)^2 */
+#define TRX_OMEGA_K 0.01
+
+#endif
