@@ -102,6 +102,48 @@ int trx_padded_length(int L);
 int trx_to_grouped(trx_ctx *ctx, int N, int L, int n_atoms, int precision, const void *d_natural, void *d_grouped);
 int trx_from_grouped(trx_ctx *ctx, int N, int L, int n_atoms, int precision, const void *d_grouped, void *d_natural);
 
+/* ------------------------------------------------------------------ the centroid fold
+ * Energy terms of the fold, order of every w[6] / terms[6]:
+ * atom_pair_constraint, dihedral_constraint, angle_constraint, vdw, rama, omega. */
+enum { TRX_TERM_APC = 0, TRX_TERM_DIH = 1, TRX_TERM_ANG = 2, TRX_TERM_VDW = 3, TRX_TERM_RAMA = 4, TRX_TERM_OMEGA = 5 };
+
+/* One MinMover.apply of the reference's schedule (folding/folding.py:91-104): score
+ * weights (data/ *.wts), max_iter, tolerance.  clash_check = 1 restates remove_clash
+ * (utils_ros.py:699-703): when rama+vdw (weights 1,1) < clash_thr at the start of the run,
+ * execution continues at run skip_to instead. */
+typedef struct {
+    double w[6];
+    int max_iter;
+    double tol;
+    int clash_check;
+    double clash_thr;
+    int skip_to;
+} trx_run;
+
+typedef struct trx_fold_batch trx_fold_batch;
+
+/* A batch of N = sum(ndecoys) decoys of one target; decoy block t is folded against
+ * tabs[t] (two-model mixing: two table sets, half the decoys each).  All blocks but the
+ * last must be multiples of 32 decoys.  aa[L]: residue types (index into
+ * "ARNDCQEGHILKMFPSTWYV"), Gly already mapped to Ala as folding.py:112-115 does.
+ * Replaces: pose_from_sequence + MoveMap/MinMover construction (folding.py:74-115). */
+int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *ndecoys, const int32_t *aa,
+                    const trx_run *runs, int nruns, int lbfgs_m, trx_fold_batch **out);
+int trx_fold_destroy(trx_fold_batch *b);
+/* Minimises every decoy through the schedule, all on device (NeRF, restraint + centroid
+ * terms, torsion gradient, L-BFGS / Armijo); the host only polls a counter every
+ * check_every evaluation rounds.  tors: host [N][L][3] float (phi,psi,omega radians), in/out.
+ * xyz (may be NULL): [N][L][5][3] float, atoms N,CA,CB,C,O.  terms (may be NULL): [N][6].
+ * stats (may be NULL): [N][2] = energy evaluations, accepted L-BFGS iterations.
+ * Replaces: remove_clash + repeat_mover.apply + remove_clash (folding.py:119,164-171). */
+int trx_fold_run(trx_fold_batch *b, float *tors, float *xyz, double *terms, long long *stats, int max_rounds,
+                 int check_every, int *rounds_out);
+/* One evaluation at given torsions under uniform weights (parity entry for the NeRF /
+ * vdw / rama / omega / torsion-gradient kernels): total[N], terms[N][6], gtors[N][L][3],
+ * xyz[N][L][5][3] (any output may be NULL). */
+int trx_fold_eval(trx_fold_batch *b, const float *tors, const double w[6], double *total, double *terms, float *gtors,
+                  float *xyz);
+
 #ifdef __cplusplus
 }
 #endif

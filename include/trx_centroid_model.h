@@ -57,7 +57,7 @@ static const double TRX_R_CEN[20] = {
     2.40, 2.50, 2.40, 2.60, 2.10, 2.00, 2.10, 2.80, 2.70, 2.20};
 #define TRX_VDW_SCALE 0.8   /* Rosetta's vdw term carries this factor */
 #define TRX_VDW_MINSEP 2    /* residue pairs closer than this in sequence are skipped */
-#define TRX_VDW_CA_CUTOFF 13.0 /* CA-CA distance beyond which no atom pair can touch */
+#define TRX_VDW_CA_CUTOFF 14.0 /* CA-CA distance beyond which no atom pair can touch (max reach 6.72 A per residue) */
 
 /* Ramachandran term: -ln of a von-Mises mixture, classes: 0 general, 1 proline.
  * Each basin: phi0, psi0 (deg), kappa_phi, kappa_psi (1/rad^2), weight. */

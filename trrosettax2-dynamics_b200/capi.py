@@ -168,3 +168,64 @@ def to_grouped(ctx, N, L, n_atoms, precision, d_nat, d_grp):
 
 def from_grouped(ctx, N, L, n_atoms, precision, d_grp, d_nat):
     check(lib().trx_from_grouped(ctx._h, C.c_int(N), C.c_int(L), C.c_int(n_atoms), C.c_int(precision), C.c_void_p(d_grp), C.c_void_p(d_nat)))
+
+
+NTERM = 6
+
+
+class Run(C.Structure):
+    """trx_run: one MinMover.apply of the schedule."""
+    _fields_ = [("w", C.c_double * NTERM), ("max_iter", C.c_int), ("tol", C.c_double),
+                ("clash_check", C.c_int), ("clash_thr", C.c_double), ("skip_to", C.c_int)]
+
+
+class FoldBatch:
+    """N decoys of one target folded together on one GPU (trx_fold_*)."""
+
+    def __init__(self, ctx, tabs, ndecoys, aa, runs, lbfgs_m=20):
+        self.ctx, self.tabs = ctx, list(tabs)
+        self.ndecoys = [int(n) for n in ndecoys]
+        self.N, self.L = sum(self.ndecoys), self.tabs[0].L
+        aa = np.ascontiguousarray(aa, dtype=np.int32)
+        arr_t = (C.c_void_p * len(self.tabs))(*[t._h for t in self.tabs])
+        arr_n = (C.c_int * len(self.tabs))(*self.ndecoys)
+        arr_r = (Run * len(runs))(*runs)
+        self._h = C.c_void_p()
+        check(lib().trx_fold_create(ctx._h, C.c_int(len(self.tabs)), arr_t, arr_n, _ptr(aa, C.c_int32), arr_r,
+                                    C.c_int(len(runs)), C.c_int(lbfgs_m), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().trx_fold_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run(self, tors, max_rounds=20000, check_every=16, want_xyz=True):
+        """tors (N,L,3) float32 radians -> dict(tors, xyz (N,L,5,3) [N,CA,CB,C,O], terms (N,6), evals, iters, rounds)."""
+        tors = np.ascontiguousarray(tors, dtype=np.float32).copy()
+        if tors.shape != (self.N, self.L, 3):
+            raise ValueError("tors must be (%d, %d, 3)" % (self.N, self.L))
+        xyz = np.zeros((self.N, self.L, 5, 3), dtype=np.float32) if want_xyz else None
+        terms = np.zeros((self.N, NTERM))
+        stats = np.zeros((self.N, 2), dtype=np.int64)
+        rounds = C.c_int()
+        check(lib().trx_fold_run(self._h, _ptr(tors, C.c_float), _ptr(xyz, C.c_float) if want_xyz else None,
+                                 _ptr(terms, C.c_double), _ptr(stats, C.c_longlong), C.c_int(max_rounds),
+                                 C.c_int(check_every), C.byref(rounds)))
+        return dict(tors=tors, xyz=xyz, terms=terms, evals=stats[:, 0], iters=stats[:, 1], rounds=rounds.value)
+
+    def eval(self, tors, w):
+        """Single evaluation -> (total (N,), terms (N,6), gtors (N,L,3), xyz (N,L,5,3))."""
+        tors = np.ascontiguousarray(tors, dtype=np.float32)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        total, terms = np.zeros(self.N), np.zeros((self.N, NTERM))
+        gt = np.zeros((self.N, self.L, 3), dtype=np.float32)
+        xyz = np.zeros((self.N, self.L, 5, 3), dtype=np.float32)
+        check(lib().trx_fold_eval(self._h, _ptr(tors, C.c_float), _ptr(w, C.c_double), _ptr(total, C.c_double),
+                                  _ptr(terms, C.c_double), _ptr(gt, C.c_float), _ptr(xyz, C.c_float)))
+        return total, terms, gt, xyz

@@ -1,0 +1,857 @@
+// The centroid fold on device: NeRF (K2), soft-sphere vdw (K4), reverse-mode torsion
+// gradient + rama/omega (K3), batched L-BFGS with non-monotone Armijo (K5) and the host
+// loop that walks the reference's staged schedule.
+//
+// Replaces, for N decoys at once, folding/folding.py:109-171 (pose_from_sequence,
+// set_random_dihedral, remove_clash, RepeatMover(min_mover,3), remove_clash) where every
+// step is a PyRosetta MinMover.apply on one decoy in one process.
+//
+// Layout: every per-decoy vector is [group][element][32 lanes] so a warp is 32 decoys
+// and all loads/stores are full lines.  All decoys advance in lock-step evaluation
+// rounds; each decoy carries its own position in the schedule (run, weights, line-search
+// state), so finished or back-tracking decoys never stall the others.  The non-restraint
+// terms (vdw, rama, omega) are approximations of Rosetta's (include/trx_centroid_model.h).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "internal.cuh"
+#include "../../include/trx_centroid_model.h"
+
+namespace trx {
+
+constexpr int NAT3 = TRX_NAT * 3;  // 15 values per residue
+
+struct Run {
+    float w[TRX_NTERM];
+    int max_iter;
+    float tol;
+    int clash_check;
+    float clash_thr;
+    int skip_to;
+};
+
+struct Model {   // centroid model constants in device-friendly (float) form
+    float cen_s[20], r_cen[20], r_bb[5];
+    float rama[2][TRX_RAMA_NB][5];
+};
+__constant__ Model c_model;
+
+// status of a decoy between evaluation rounds
+enum { ST_INIT = 0, ST_LS = 1, ST_DONE = 2 };
+
+struct FoldState {
+    int N, Npad, G, L, Lpad, ndof, m, nruns;
+    // vectors [G][ndof][32]
+    float *x, *g, *d, *xt, *gt;
+    float *S, *Y;            // [G][m][ndof][32]
+    float *rho;              // [G][m][32]
+    // per decoy [Npad]
+    double *f, *fmem;        // accepted energy, last 3 accepted energies [3][Npad]
+    float *alpha, *slope;
+    int force_all;           // evaluate every decoy regardless of status (final consistent pass)
+    int *nmem, *hist, *head, *iter, *run, *bt, *status, *restart;
+    int *evals, *iters;
+    double *terms;           // [TRX_NTERM][Npad] unweighted terms of the last evaluation
+    double *ft;              // [Npad] weighted total of the last evaluation
+    float *wl;               // [TRX_NTERM][Npad] weights in force per decoy
+    // geometry
+    float *X;                // [G][Lpad][15][32]
+    float *xnat, *gnat;      // [Npad][L][15]
+    float *gk1;              // [G][Lpad][9][32]
+    double *E3;              // [3][Npad]
+    double *Evdw;            // [Npad]
+    int *gactive;            // [G]
+    int *nactive;            // [1]
+    const int *aa;           // [L]
+    const Run *runs;
+};
+
+struct f3 { float x, y, z; };
+__device__ __forceinline__ f3 operator-(f3 a, f3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ f3 operator+(f3 a, f3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ f3 operator*(float s, f3 a) { return {s * a.x, s * a.y, s * a.z}; }
+__device__ __forceinline__ float dot(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ f3 cross(f3 a, f3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+__device__ __forceinline__ f3 unit(f3 a) { float r = rsqrtf(dot(a, a)); return r * a; }
+
+// NeRF placement: |cd| = bond, angle(b,c,d) = ang (ca, sa its cos/sin), dihedral(a,b,c,d) = tor (ct, st).
+__device__ __forceinline__ f3 place(f3 a, f3 b, f3 c, float bond, float ca, float sa, float ct, float st)
+{
+    f3 bc = unit(c - b);
+    f3 n = unit(cross(b - a, bc));
+    f3 m = cross(n, bc);
+    return c + (-bond * ca) * bc + (bond * sa * ct) * m + (bond * sa * st) * n;
+}
+
+// K2: one thread per decoy (lane = decoy): torsions xt[g][L*3][32] -> X[g][Lpad][15][32] and
+// the natural-layout copy xnat[n][L][15] the vdw kernel stages into shared memory.
+__global__ void __launch_bounds__(32) nerf_kernel(FoldState s)
+{
+    const int g = blockIdx.x, lane = threadIdx.x, n = g * LANES + lane;
+    if (!s.force_all && !s.gactive[g]) return;
+    const float *__restrict__ t = s.xt + (size_t)g * s.ndof * LANES + lane;
+    float *__restrict__ X = s.X + (size_t)g * s.Lpad * NAT3 * LANES + lane;
+    float *__restrict__ xn = s.xnat + (size_t)n * s.L * NAT3;
+    const float caNCAC = cosf((float)TRX_A_N_CA_C), saNCAC = sinf((float)TRX_A_N_CA_C);
+    const float caCACN = cosf((float)TRX_A_CA_C_N), saCACN = sinf((float)TRX_A_CA_C_N);
+    const float caCNCA = cosf((float)TRX_A_C_N_CA), saCNCA = sinf((float)TRX_A_C_N_CA);
+    const float caCACO = cosf((float)TRX_A_CA_C_O), saCACO = sinf((float)TRX_A_CA_C_O);
+    f3 N = {0.f, 0.f, 0.f}, CA = {(float)TRX_B_N_CA, 0.f, 0.f};
+    f3 C = {(float)TRX_B_N_CA - (float)TRX_B_CA_C * caNCAC, (float)TRX_B_CA_C * saNCAC, 0.f};
+    float psi_prev = 0.f, omg_prev = 0.f;
+    for (int i = 0; i < s.L; ++i) {
+        const float phi = t[(i * 3 + 0) * LANES], psi = t[(i * 3 + 1) * LANES], omg = t[(i * 3 + 2) * LANES];
+        if (i > 0) {
+            float sn, cs;
+            sincosf(psi_prev, &sn, &cs);
+            f3 Nn = place(N, CA, C, (float)TRX_B_C_N, caCACN, saCACN, cs, sn);
+            sincosf(omg_prev, &sn, &cs);
+            f3 CAn = place(CA, C, Nn, (float)TRX_B_N_CA, caCNCA, saCNCA, cs, sn);
+            sincosf(phi, &sn, &cs);
+            f3 Cn = place(C, Nn, CAn, (float)TRX_B_CA_C, caNCAC, saNCAC, cs, sn);
+            N = Nn; CA = CAn; C = Cn;
+        }
+        float sn, cs;
+        sincosf(psi, &sn, &cs);
+        f3 O = place(N, CA, C, (float)TRX_B_C_O, caCACO, saCACO, -cs, -sn);   // torsion psi + pi
+        f3 b = CA - N, c = C - CA, a = cross(b, c);
+        f3 CB = (float)TRX_CB_A * a + (float)TRX_CB_B * b + (float)TRX_CB_C * c + CA;
+        const float v[NAT3] = {N.x, N.y, N.z, CA.x, CA.y, CA.z, CB.x, CB.y, CB.z, C.x, C.y, C.z, O.x, O.y, O.z};
+#pragma unroll
+        for (int k = 0; k < NAT3; ++k) {
+            X[((size_t)i * NAT3 + k) * LANES] = v[k];
+            if (n < s.N) xn[(size_t)i * NAT3 + k] = v[k];
+        }
+        psi_prev = psi;
+        omg_prev = omg;
+    }
+}
+
+// K4: soft-sphere repulsion of one decoy per CTA.  Atoms N,CA,CB,C,O + CEN (on the CA->CB
+// ray) staged in shared memory as float4 (x,y,z,radius); warps scan residue rows for close
+// CA pairs (ballot), then spread the 36 atom pairs of each close residue pair over lanes.
+// Clashes are rare, so gradients go through 64-bit fixed-point shared atomics: integer
+// sums are order-independent => bit-reproducible.
+constexpr int VDW_THREADS = 256;
+constexpr double VDW_FIX = 4294967296.0;  // 2^32
+
+__global__ void __launch_bounds__(VDW_THREADS) vdw_kernel(FoldState s)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = blockIdx.x;
+    if (n >= s.N || (!s.force_all && s.status[n] == ST_DONE)) return;
+    const int L = s.L;
+    float4 *at = reinterpret_cast<float4 *>(smem_raw);                                   // [L][6]
+    long long *acc = reinterpret_cast<long long *>(smem_raw + sizeof(float4) * 6 * L);   // [L][6][3]
+    float *reach = reinterpret_cast<float *>(acc + (size_t)L * 18);                      // [L]
+    __shared__ double ered[VDW_THREADS / 32];
+    const float *__restrict__ xn = s.xnat + (size_t)n * L * NAT3;
+    for (int i = threadIdx.x; i < L; i += VDW_THREADS) {
+        const int aa = s.aa[i];
+        float v[NAT3];
+#pragma unroll
+        for (int k = 0; k < NAT3; ++k) v[k] = xn[(size_t)i * NAT3 + k];
+#pragma unroll
+        for (int a = 0; a < 5; ++a) at[i * 6 + a] = make_float4(v[a * 3], v[a * 3 + 1], v[a * 3 + 2], c_model.r_bb[a]);
+        const float cs = c_model.cen_s[aa];
+        at[i * 6 + 5] = make_float4(v[3] + cs * (v[6] - v[3]), v[4] + cs * (v[7] - v[4]), v[5] + cs * (v[8] - v[5]), c_model.r_cen[aa]);
+        // farthest atom surface from CA: CEN or O (|CA-O| <= 2.45 A)
+        reach[i] = fmaxf(cs * 1.53f + c_model.r_cen[aa], 2.45f + 1.8f);
+    }
+    for (int e = threadIdx.x; e < L * 18; e += VDW_THREADS) acc[e] = 0;
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double e_thread = 0.0;
+    // per-warp queue of close residue pairs
+    __shared__ int queue[VDW_THREADS / 32][64];
+    int qn = 0;
+    auto flush = [&](int count) {
+        for (int item = lane; item < count * 36; item += 32) {
+            const int pr = queue[warp][item / 36], ab = item % 36;
+            const int i = pr >> 16, j = pr & 0xffff, a = ab / 6, b = ab % 6;
+            const float4 pa = at[i * 6 + a], pb = at[j * 6 + b];
+            const float dx = pa.x - pb.x, dy = pa.y - pb.y, dz = pa.z - pb.z;
+            const float r = pa.w + pb.w, r2 = r * r, d2 = dx * dx + dy * dy + dz * dz;
+            if (d2 < r2) {
+                const float c = r2 - d2, ir2 = 1.0f / r2;
+                e_thread += (double)((float)TRX_VDW_SCALE * c * c * ir2);
+                const float f = -4.0f * (float)TRX_VDW_SCALE * c * ir2;
+                const long long gx = (long long)((double)(f * dx) * VDW_FIX), gy = (long long)((double)(f * dy) * VDW_FIX),
+                                gz = (long long)((double)(f * dz) * VDW_FIX);
+                unsigned long long *pi = reinterpret_cast<unsigned long long *>(acc + (i * 6 + a) * 3);
+                unsigned long long *pj = reinterpret_cast<unsigned long long *>(acc + (j * 6 + b) * 3);
+                atomicAdd(pi + 0, (unsigned long long)gx); atomicAdd(pi + 1, (unsigned long long)gy); atomicAdd(pi + 2, (unsigned long long)gz);
+                atomicAdd(pj + 0, (unsigned long long)(-gx)); atomicAdd(pj + 1, (unsigned long long)(-gy)); atomicAdd(pj + 2, (unsigned long long)(-gz));
+            }
+        }
+    };
+    for (int i = warp; i < L - TRX_VDW_MINSEP; i += VDW_THREADS / 32) {
+        const float4 ci = at[i * 6 + TRX_AT_CA];
+        const float ri = reach[i];
+        for (int j0 = i + TRX_VDW_MINSEP; j0 < L; j0 += 32) {
+            const int j = j0 + lane;
+            bool close = false;
+            if (j < L) {
+                const float4 cj = at[j * 6 + TRX_AT_CA];
+                const float dx = ci.x - cj.x, dy = ci.y - cj.y, dz = ci.z - cj.z, cut = ri + reach[j];
+                close = dx * dx + dy * dy + dz * dz < cut * cut;
+            }
+            unsigned m = __ballot_sync(0xffffffffu, close);
+            if (m) {
+                const int pos = qn + __popc(m & ((1u << lane) - 1));
+                if (close) queue[warp][pos] = (i << 16) | j;
+                qn += __popc(m);
+                __syncwarp();
+                if (qn >= 32) {   // 32 pairs = 1152 atom pairs = 36 full warp passes
+                    flush(32);
+                    __syncwarp();
+                    const int rest = qn - 32;
+                    if (lane < rest) {
+                        const int v = queue[warp][32 + lane];
+                        queue[warp][lane] = v;
+                    }
+                    qn = rest;
+                    __syncwarp();
+                }
+            }
+        }
+    }
+    flush(qn);
+    // energy: fixed-shape reduction
+    for (int o = 16; o > 0; o >>= 1) e_thread += __shfl_down_sync(0xffffffffu, e_thread, o);
+    if (lane == 0) ered[warp] = e_thread;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double e = 0.0;
+        for (int k = 0; k < VDW_THREADS / 32; ++k) e += ered[k];
+        s.Evdw[n] = e;
+    }
+    // gradient out (weighted), CEN folded into CA and CB
+    const float w = s.wl[(size_t)TRX_T_VDW * s.Npad + n];
+    float *__restrict__ gn = s.gnat + (size_t)n * L * NAT3;
+    for (int i = threadIdx.x; i < L; i += VDW_THREADS) {
+        const float cs = c_model.cen_s[s.aa[i]];
+        float gv[18];
+#pragma unroll
+        for (int k = 0; k < 18; ++k) gv[k] = w * (float)((double)acc[i * 18 + k] / VDW_FIX);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            gv[TRX_AT_CA * 3 + k] += (1.0f - cs) * gv[15 + k];
+            gv[TRX_AT_CB * 3 + k] += cs * gv[15 + k];
+        }
+#pragma unroll
+        for (int k = 0; k < NAT3; ++k) gn[(size_t)i * NAT3 + k] = gv[k];
+    }
+}
+
+// K3: reverse mode.  One thread per decoy walks the chain backwards accumulating
+// F1 = sum x_a x g_a and F2 = sum g_a over the atoms a torsion moves (a suffix of the atom
+// sequence N,CA,CB,C,O), dE/dtorsion = u.(F1 - p x F2); adds the Ramachandran and omega
+// terms (functions of the torsions alone) and produces the weighted total.
+__global__ void __launch_bounds__(32) torsion_grad_kernel(FoldState s)
+{
+    const int g = blockIdx.x, lane = threadIdx.x, n = g * LANES + lane;
+    if (!s.force_all && !s.gactive[g]) return;
+    const int L = s.L, Npad = s.Npad;
+    const float *__restrict__ X = s.X + (size_t)g * s.Lpad * NAT3 * LANES + lane;
+    const float *__restrict__ G1 = s.gk1 + (size_t)g * s.Lpad * 9 * LANES + lane;
+    const float *__restrict__ gn = s.gnat + (size_t)min(n, s.N - 1) * L * NAT3;
+    const float *__restrict__ t = s.xt + (size_t)g * s.ndof * LANES + lane;
+    float *__restrict__ gt = s.gt + (size_t)g * s.ndof * LANES + lane;
+    const float w_rama = s.wl[(size_t)TRX_T_RAMA * Npad + n], w_omega = s.wl[(size_t)TRX_T_OMEGA * Npad + n];
+    f3 F1 = {0.f, 0.f, 0.f}, F2 = {0.f, 0.f, 0.f};
+    double e_rama = 0.0, e_omega = 0.0;
+    auto load = [&](int i, int a) -> f3 { return {X[((size_t)i * NAT3 + a * 3) * LANES], X[((size_t)i * NAT3 + a * 3 + 1) * LANES], X[((size_t)i * NAT3 + a * 3 + 2) * LANES]}; };
+    auto add = [&](f3 x, f3 gr) { F1 = F1 + cross(x, gr); F2 = F2 + gr; };
+    auto dtor = [&](f3 p, f3 q) -> float { f3 u = unit(q - p); return dot(u, F1 - cross(p, F2)); };
+    for (int i = L - 1; i >= 0; --i) {
+        f3 xa[TRX_NAT], ga[TRX_NAT];
+#pragma unroll
+        for (int a = 0; a < TRX_NAT; ++a) {
+            xa[a] = load(i, a);
+            ga[a] = {gn[(size_t)i * NAT3 + a * 3], gn[(size_t)i * NAT3 + a * 3 + 1], gn[(size_t)i * NAT3 + a * 3 + 2]};
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {   // restraint gradient lives on N, CA, CB
+            ga[a].x += G1[((size_t)i * 9 + a * 3) * LANES];
+            ga[a].y += G1[((size_t)i * 9 + a * 3 + 1) * LANES];
+            ga[a].z += G1[((size_t)i * 9 + a * 3 + 2) * LANES];
+        }
+        const float phi = t[(i * 3 + 0) * LANES], psi = t[(i * 3 + 1) * LANES], omg = t[(i * 3 + 2) * LANES];
+        float gphi = 0.f, gpsi = 0.f;
+        add(xa[TRX_AT_O], ga[TRX_AT_O]);
+        gpsi = dtor(xa[TRX_AT_CA], xa[TRX_AT_C]);
+        add(xa[TRX_AT_C], ga[TRX_AT_C]);
+        add(xa[TRX_AT_CB], ga[TRX_AT_CB]);
+        if (i > 0) gphi = dtor(xa[TRX_AT_N], xa[TRX_AT_CA]);
+        add(xa[TRX_AT_CA], ga[TRX_AT_CA]);
+        if (i > 0) {
+            f3 Cp = load(i - 1, TRX_AT_C);
+            const float go = dtor(Cp, xa[TRX_AT_N]);
+            // omega(i-1): add its tether term here
+            const float om = t[((i - 1) * 3 + 2) * LANES];
+            float dev = om - (float)TRX_PI;
+            dev -= 2.0f * (float)TRX_PI * floorf((dev + (float)TRX_PI) / (2.0f * (float)TRX_PI));
+            const float deg = dev * (float)(1.0 / TRX_DEG);
+            e_omega += (double)((float)TRX_OMEGA_K * deg * deg);
+            float gom = go + w_omega * 2.0f * (float)TRX_OMEGA_K * deg * (float)(1.0 / TRX_DEG);
+            if (i - 1 == L - 1) gom = 0.f;
+            gt[((i - 1) * 3 + 2) * LANES] = gom;
+        }
+        add(xa[TRX_AT_N], ga[TRX_AT_N]);
+        if (i > 0 && i < L - 1) {   // Ramachandran, termini skipped
+            const int cls = s.aa[i] == TRX_AA_PRO ? 1 : 0;
+            float P = (float)TRX_RAMA_FLOOR, dPphi = 0.f, dPpsi = 0.f;
+#pragma unroll
+            for (int k = 0; k < TRX_RAMA_NB; ++k) {
+                const float *b = c_model.rama[cls][k];
+                const float dphi = phi - b[0] * (float)TRX_DEG, dpsi = psi - b[1] * (float)TRX_DEG;
+                float s1, c1, s2, c2;
+                sincosf(dphi, &s1, &c1);
+                sincosf(dpsi, &s2, &c2);
+                const float e = b[4] * expf(b[2] * (c1 - 1.0f) + b[3] * (c2 - 1.0f));
+                P += e;
+                dPphi -= e * b[2] * s1;
+                dPpsi -= e * b[3] * s2;
+            }
+            e_rama += (double)(-logf(P));
+            gphi -= w_rama * dPphi / P;
+            gpsi -= w_rama * dPpsi / P;
+        }
+        (void)omg;
+        gt[(i * 3 + 0) * LANES] = i == 0 ? 0.f : gphi;
+        gt[(i * 3 + 1) * LANES] = gpsi;
+    }
+    gt[((L - 1) * 3 + 2) * LANES] = 0.f;
+    double term[TRX_NTERM];
+    term[TRX_T_APC] = s.E3[0 * (size_t)Npad + n];
+    term[TRX_T_DIH] = s.E3[1 * (size_t)Npad + n];
+    term[TRX_T_ANG] = s.E3[2 * (size_t)Npad + n];
+    term[TRX_T_VDW] = n < s.N ? s.Evdw[n] : 0.0;
+    term[TRX_T_RAMA] = e_rama;
+    term[TRX_T_OMEGA] = e_omega;
+    double tot = 0.0;
+#pragma unroll
+    for (int k = 0; k < TRX_NTERM; ++k) {
+        s.terms[(size_t)k * Npad + n] = term[k];
+        tot += (double)s.wl[(size_t)k * Npad + n] * term[k];
+    }
+    s.ft[n] = tot;
+}
+
+// K5: one CTA per decoy group; 8 warps split the torsion vector, lanes are decoys.
+// Consumes the evaluation of the trial point (ft, gt) and produces the next trial point.
+constexpr int LB_WARPS = 8;
+constexpr int LB_THREADS = LB_WARPS * 32;
+constexpr float LS_SIGMA = 0.1f;
+constexpr int LS_MAXBACK = 20;
+
+__device__ __forceinline__ float cta_sum(float v, float (*red)[LB_WARPS][LANES], int &buf, int warp, int lane)
+{
+    red[buf][warp][lane] = v;
+    __syncthreads();
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < LB_WARPS; ++k) sum += red[buf][k][lane];
+    buf ^= 1;
+    return sum;
+}
+
+__global__ void __launch_bounds__(LB_THREADS) lbfgs_kernel(FoldState s)
+{
+    __shared__ float red[2][LB_WARPS][LANES];
+    __shared__ float alpha_h[64][LANES];   // two-loop alphas (m <= 64)
+    const int g = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = g * LANES + lane;
+    if (!s.gactive[g]) return;
+    const int nd = s.ndof, m = s.m, Npad = s.Npad;
+    int buf = 0;
+    const size_t vb = (size_t)g * nd * LANES + lane;
+    float *x = s.x + vb, *gv = s.g + vb, *d = s.d + vb, *xt = s.xt + vb, *gt = s.gt + vb;
+    float *S = s.S + (size_t)g * m * nd * LANES + lane, *Y = s.Y + (size_t)g * m * nd * LANES + lane;
+    float *rho = s.rho + (size_t)g * m * LANES + lane;
+    const int k0 = warp * ((nd + LB_WARPS - 1) / LB_WARPS), k1 = min(nd, k0 + (nd + LB_WARPS - 1) / LB_WARPS);
+
+    int status = n < s.N ? s.status[n] : ST_DONE;
+    int run = s.run[n], hist = s.hist[n], head = s.head[n], iter = s.iter[n], bt = s.bt[n], restart = s.restart[n], nmem = s.nmem[n];
+    double f = s.f[n];
+    float alpha = s.alpha[n], slope = s.slope[n];
+    const double ft = s.ft[n];
+    const bool fin = isfinite(ft);
+    int evals = s.evals[n] + (status != ST_DONE ? 1 : 0);
+    int iters = s.iters[n];
+    // ---- per-decoy decision (replicated in every warp)
+    // action: 0 none, 1 start run here (g = gt, steepest descent), 2 accepted step, 3 rejected step, 4 re-evaluate (run skipped)
+    int action = 0;
+    if (status == ST_INIT) {
+        bool skip = false;
+        const Run &r = s.runs[run];
+        if (r.clash_check) {
+            const float e = (float)(s.terms[(size_t)TRX_T_VDW * Npad + n] + s.terms[(size_t)TRX_T_RAMA * Npad + n]);
+            skip = e < r.clash_thr;
+        }
+        if (skip) {
+            run = r.skip_to;
+            action = 4;
+        } else {
+            action = 1;
+        }
+    } else if (status == ST_LS) {
+        double fref = s.fmem[n];
+        for (int q = 1; q < min(nmem, 3); ++q) fref = fmax(fref, s.fmem[(size_t)q * Npad + n]);
+        if (fin && ft <= fref + (double)(LS_SIGMA * alpha * slope)) action = 2;
+        else action = 3;
+    }
+    bool run_over = false;
+    if (action == 4) {
+        if (run >= s.nruns) { status = ST_DONE; action = 0; }
+        else {
+#pragma unroll
+            for (int k = 0; k < TRX_NTERM; ++k) if (warp == 0) s.wl[(size_t)k * Npad + n] = s.runs[run].w[k];
+            status = ST_INIT;   // xt stays = x; next round evaluates under the new weights
+        }
+    }
+    // ---- accepted step: history update, convergence
+    float sy = 0.f, ss = 0.f, yy = 0.f;
+    if (action == 2) {
+        for (int k = k0; k < k1; ++k) {
+            const float sk = xt[k * LANES] - x[k * LANES], yk = gt[k * LANES] - gv[k * LANES];
+            S[((size_t)head * nd + k) * LANES] = sk;
+            Y[((size_t)head * nd + k) * LANES] = yk;
+            sy += sk * yk; ss += sk * sk; yy += yk * yk;
+        }
+    }
+    sy = cta_sum(sy, red, buf, warp, lane);
+    ss = cta_sum(ss, red, buf, warp, lane);
+    yy = cta_sum(yy, red, buf, warp, lane);
+    if (action == 2) {
+        if (sy > 1e-10f * sqrtf(ss * yy)) {
+            if (warp == 0) rho[head * LANES] = 1.0f / sy;
+            head = (head + 1) % m;
+            if (hist < m) hist++;
+        }
+        const bool conv = 2.0 * fabs(ft - f) <= (double)s.runs[run].tol * (fabs(ft) + fabs(f) + 1e-10);
+        f = ft;
+        if (warp == 0) s.fmem[(size_t)(nmem % 3) * Npad + n] = f;
+        nmem++;
+        iter++; iters++;
+        restart = 0;
+        bt = 0;
+        if (conv || iter >= s.runs[run].max_iter) run_over = true;
+    }
+    if (action == 1) {
+        f = ft;
+        hist = 0; head = 0; iter = 0; bt = 0; restart = 1; nmem = 1;
+        if (warp == 0) s.fmem[n] = f;
+        if (!fin) run_over = true;   // cannot start from a non-finite energy
+    }
+    if (action == 3) {
+        bt++;
+        if (bt >= LS_MAXBACK) {
+            if (hist > 0) { hist = 0; head = 0; restart = 1; bt = 0; action = 5; }   // retry from steepest descent
+            else run_over = true;
+        } else {
+            float q = fin ? -0.5f * slope * alpha * alpha / (float)(ft - f - (double)(slope * alpha)) : 0.1f * alpha;
+            if (!(q > 0.1f * alpha)) q = 0.1f * alpha;
+            if (q > 0.5f * alpha) q = 0.5f * alpha;
+            alpha = q;
+        }
+    }
+    __syncthreads();   // rho written by warp 0 is read below
+    // x, g take the trial values on accept / run start
+    if (action == 1 || action == 2) {
+        for (int k = k0; k < k1; ++k) {
+            x[k * LANES] = xt[k * LANES];
+            gv[k * LANES] = gt[k * LANES];
+        }
+    }
+    if (run_over) {
+        // the run ends at x (accepted point, or the last accepted point after a failed search)
+        run++;
+        if (run >= s.nruns) status = ST_DONE;
+        else {
+            status = ST_INIT;
+#pragma unroll
+            for (int k = 0; k < TRX_NTERM; ++k) if (warp == 0) s.wl[(size_t)k * Npad + n] = s.runs[run].w[k];
+        }
+        for (int k = k0; k < k1; ++k) xt[k * LANES] = x[k * LANES];
+    }
+    // ---- new direction for decoys that continue: d = -H g (two-loop recursion)
+    const bool need_dir = !run_over && (action == 1 || action == 2 || action == 5);
+    float gnorm2 = 0.f;
+    if (need_dir) for (int k = k0; k < k1; ++k) { const float v = gv[k * LANES]; d[k * LANES] = -v; gnorm2 += v * v; }
+    gnorm2 = cta_sum(gnorm2, red, buf, warp, lane);
+    const int hmax = __reduce_max_sync(0xffffffffu, need_dir ? hist : 0);
+    __shared__ int hmax_s;
+    if (threadIdx.x == 0) hmax_s = 0;
+    __syncthreads();
+    if (lane == 0) atomicMax(&hmax_s, hmax);
+    __syncthreads();
+    const int H = hmax_s;
+    for (int q = 0; q < H; ++q) {
+        const bool on = need_dir && q < hist;
+        const int h = (head - 1 - q + 2 * m) % m;
+        float a = 0.f;
+        if (on) for (int k = k0; k < k1; ++k) a += S[((size_t)h * nd + k) * LANES] * d[k * LANES];
+        a = cta_sum(a, red, buf, warp, lane);
+        if (on) {
+            a *= rho[h * LANES];
+            if (warp == 0) alpha_h[q][lane] = a;
+            for (int k = k0; k < k1; ++k) d[k * LANES] -= a * Y[((size_t)h * nd + k) * LANES];
+        }
+    }
+    {
+        const bool on = need_dir && hist > 0;
+        const int h0 = (head - 1 + m) % m;
+        float y2 = 0.f;
+        if (on) for (int k = k0; k < k1; ++k) { const float v = Y[((size_t)h0 * nd + k) * LANES]; y2 += v * v; }
+        y2 = cta_sum(y2, red, buf, warp, lane);
+        if (on) {
+            const float gamma = 1.0f / (rho[h0 * LANES] * y2);
+            for (int k = k0; k < k1; ++k) d[k * LANES] *= gamma;
+        }
+    }
+    for (int q = H - 1; q >= 0; --q) {
+        const bool on = need_dir && q < hist;
+        const int h = (head - 1 - q + 2 * m) % m;
+        float b = 0.f;
+        if (on) for (int k = k0; k < k1; ++k) b += Y[((size_t)h * nd + k) * LANES] * d[k * LANES];
+        b = cta_sum(b, red, buf, warp, lane);
+        if (on) {
+            const float c = alpha_h[q][lane] - rho[h * LANES] * b;
+            for (int k = k0; k < k1; ++k) d[k * LANES] += c * S[((size_t)h * nd + k) * LANES];
+        }
+    }
+    float sl = 0.f;
+    if (need_dir) for (int k = k0; k < k1; ++k) sl += gv[k * LANES] * d[k * LANES];
+    sl = cta_sum(sl, red, buf, warp, lane);
+    if (need_dir) {
+        const float gnorm = sqrtf(gnorm2);
+        if (!(sl < 0.f)) {   // not a descent direction: steepest descent
+            hist = 0; head = 0; restart = 1;
+            for (int k = k0; k < k1; ++k) d[k * LANES] = -gv[k * LANES];
+            sl = -gnorm2;
+        }
+        slope = sl;
+        alpha = restart ? fminf(1.0f, 1.0f / fmaxf(gnorm, 1e-20f)) : 1.0f;
+        status = ST_LS;
+        if (gnorm2 == 0.f) {   // stationary: the run is over
+            run++;
+            if (run >= s.nruns) status = ST_DONE;
+            else {
+                status = ST_INIT;
+#pragma unroll
+                for (int k = 0; k < TRX_NTERM; ++k) if (warp == 0) s.wl[(size_t)k * Npad + n] = s.runs[run].w[k];
+            }
+        }
+    }
+    // ---- next trial point
+    if (status == ST_LS) for (int k = k0; k < k1; ++k) xt[k * LANES] = x[k * LANES] + alpha * d[k * LANES];
+    if (warp == 0 && n < s.N) {
+        s.status[n] = status; s.run[n] = run; s.hist[n] = hist; s.head[n] = head; s.iter[n] = iter; s.bt[n] = bt;
+        s.restart[n] = restart; s.nmem[n] = nmem; s.f[n] = f; s.alpha[n] = alpha; s.slope[n] = slope;
+        s.evals[n] = evals; s.iters[n] = iters;
+    }
+}
+
+// group activity + number of unfinished decoys
+__global__ void activity_kernel(FoldState s)
+{
+    const int g = blockIdx.x * blockDim.y + threadIdx.y, lane = threadIdx.x;
+    if (g >= s.G) return;
+    const int n = g * LANES + lane;
+    const bool active = n < s.N && s.status[n] != ST_DONE;
+    const unsigned m = __ballot_sync(0xffffffffu, active);
+    if (lane == 0) {
+        s.gactive[g] = m != 0;
+        if (m) atomicAdd(s.nactive, __popc(m));
+    }
+}
+
+__global__ void init_state_kernel(FoldState s, const float *__restrict__ tors_nat)
+{
+    // tors_nat [N][L][3] -> x, xt grouped; scalars reset
+    const int g = blockIdx.x, lane = threadIdx.x, n = g * LANES + lane;
+    float *x = s.x + (size_t)g * s.ndof * LANES + lane, *xt = s.xt + (size_t)g * s.ndof * LANES + lane;
+    for (int k = 0; k < s.ndof; ++k) {
+        const float v = n < s.N ? tors_nat[(size_t)n * s.ndof + k] : (float)TRX_PI;
+        x[k * LANES] = v;
+        xt[k * LANES] = v;
+    }
+    s.status[n] = n < s.N ? ST_INIT : ST_DONE;
+    s.run[n] = 0; s.hist[n] = 0; s.head[n] = 0; s.iter[n] = 0; s.bt[n] = 0; s.restart[n] = 1; s.nmem[n] = 0;
+    s.f[n] = 0.0; s.alpha[n] = 0.f; s.slope[n] = 0.f; s.evals[n] = 0; s.iters[n] = 0;
+    s.ft[n] = 0.0; s.Evdw[n] = 0.0;
+    for (int k = 0; k < TRX_NTERM; ++k) { s.wl[(size_t)k * s.Npad + n] = s.runs[0].w[k]; s.terms[(size_t)k * s.Npad + n] = 0.0; }
+    for (int k = 0; k < 3; ++k) { s.fmem[(size_t)k * s.Npad + n] = 0.0; s.E3[(size_t)k * s.Npad + n] = 0.0; }
+}
+
+__global__ void restore_kernel(FoldState s)
+{
+    // xt = x for every decoy (the accepted point), ahead of the final consistent evaluation
+    const size_t base = (size_t)blockIdx.x * s.ndof * LANES;
+    for (int e = threadIdx.x; e < s.ndof * LANES; e += blockDim.x) s.xt[base + e] = s.x[base + e];
+}
+
+__global__ void export_kernel(FoldState s, float *__restrict__ tors_nat, double *__restrict__ terms_nat, long long *__restrict__ stats)
+{
+    const int g = blockIdx.x, lane = threadIdx.x, n = g * LANES + lane;
+    if (n >= s.N) return;
+    const float *x = s.x + (size_t)g * s.ndof * LANES + lane;
+    for (int k = 0; k < s.ndof; ++k) tors_nat[(size_t)n * s.ndof + k] = x[k * LANES];
+    for (int k = 0; k < TRX_NTERM; ++k) terms_nat[(size_t)n * TRX_NTERM + k] = s.terms[(size_t)k * s.Npad + n];
+    stats[(size_t)n * 2] = s.evals[n];
+    stats[(size_t)n * 2 + 1] = s.iters[n];
+}
+
+static void upload_model()
+{
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (done[dev]) return;
+    Model mdl;
+    for (int k = 0; k < 20; ++k) { mdl.cen_s[k] = (float)TRX_CEN_S[k]; mdl.r_cen[k] = (float)TRX_R_CEN[k]; }
+    for (int k = 0; k < 5; ++k) mdl.r_bb[k] = (float)TRX_R_BB[k];
+    for (int c = 0; c < 2; ++c) for (int k = 0; k < TRX_RAMA_NB; ++k) for (int j = 0; j < 5; ++j) mdl.rama[c][k][j] = (float)TRX_RAMA[c][k][j];
+    cudaMemcpyToSymbol(c_model, &mdl, sizeof(mdl));
+    done[dev] = true;
+}
+
+}  // namespace trx
+
+using namespace trx;
+
+struct trx_fold_batch {
+    trx_ctx *ctx = nullptr;
+    FoldState s{};
+    std::vector<trx_tables *> tabs;
+    std::vector<int> tab_g0, tab_ng;
+    void *arena = nullptr;
+    size_t arena_bytes = 0;
+    int *d_aa = nullptr;
+    Run *d_runs = nullptr;
+    size_t vdw_smem = 0;
+};
+
+extern "C" {
+
+int trx_fold_destroy(trx_fold_batch *b)
+{
+    if (!b) return TRX_OK;
+    cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+    if (b->arena) cudaFree(b->arena);
+    if (b->d_aa) cudaFree(b->d_aa);
+    if (b->d_runs) cudaFree(b->d_runs);
+    delete b;
+    return TRX_OK;
+}
+
+int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *ndecoys, const int32_t *aa,
+                    const trx_run *runs, int nruns, int lbfgs_m, trx_fold_batch **out)
+{
+    TRX_REQUIRE(ctx && tabs && ndecoys && aa && runs && out, "trx_fold_create: NULL argument");
+    TRX_REQUIRE(ntab >= 1 && ntab <= 16, "trx_fold_create: ntab=%d out of range [1,16]", ntab);
+    TRX_REQUIRE(nruns >= 1 && nruns <= 256, "trx_fold_create: nruns=%d out of range [1,256]", nruns);
+    TRX_REQUIRE(lbfgs_m >= 1 && lbfgs_m <= 64, "trx_fold_create: lbfgs_m=%d out of range [1,64]", lbfgs_m);
+    TRX_CUDA(cudaSetDevice(ctx->device));
+    const int L = tabs[0]->L;
+    int G = 0;
+    trx_fold_batch *b = new trx_fold_batch();
+    b->ctx = ctx;
+    for (int t = 0; t < ntab; ++t) {
+        TRX_REQUIRE(tabs[t] && tabs[t]->ctx == ctx && tabs[t]->L == L, "trx_fold_create: tables %d: NULL, other context or other L", t);
+        TRX_REQUIRE(ndecoys[t] > 0, "trx_fold_create: ndecoys[%d] must be positive", t);
+        TRX_REQUIRE(t == ntab - 1 || ndecoys[t] % LANES == 0, "trx_fold_create: all but the last decoy block must be multiples of 32");
+        b->tabs.push_back(tabs[t]);
+        b->tab_g0.push_back(G);
+        b->tab_ng.push_back(num_groups(ndecoys[t]));
+        G += num_groups(ndecoys[t]);
+    }
+    for (int i = 0; i < L; ++i) TRX_REQUIRE(aa[i] >= 0 && aa[i] < 20, "trx_fold_create: aa[%d]=%d out of range", i, aa[i]);
+    for (int r = 0; r < nruns; ++r)
+        TRX_REQUIRE(runs[r].max_iter >= 0 && (!runs[r].clash_check || (runs[r].skip_to > r && runs[r].skip_to <= nruns)),
+                    "trx_fold_create: run %d has a bad skip_to/max_iter", r);
+    int N = 0;
+    for (int t = 0; t < ntab; ++t) N += ndecoys[t];
+    FoldState &s = b->s;
+    s.N = (G - 1) * LANES + ((ndecoys[ntab - 1] - 1) % LANES + 1);
+    TRX_REQUIRE(s.N == N, "trx_fold_create: internal decoy count mismatch");
+    s.G = G; s.Npad = G * LANES; s.L = L; s.Lpad = padded_length(L); s.ndof = 3 * L; s.m = lbfgs_m; s.nruns = nruns;
+    b->vdw_smem = sizeof(float4) * 6 * L + sizeof(long long) * 18 * L + sizeof(float) * L;
+    TRX_REQUIRE(b->vdw_smem <= 220 * 1024, "trx_fold_create: L=%d exceeds the shared-memory budget of the vdw kernel", L);
+    TRX_REQUIRE(L < 65536, "trx_fold_create: L too large");
+    // one arena, carved into aligned pieces
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    const size_t vec = (size_t)G * s.ndof * LANES * sizeof(float), np = (size_t)s.Npad;
+    size_t o_x = carve(vec), o_g = carve(vec), o_d = carve(vec), o_xt = carve(vec), o_gt = carve(vec);
+    size_t o_S = carve(vec * s.m), o_Y = carve(vec * s.m), o_rho = carve((size_t)G * s.m * LANES * sizeof(float));
+    size_t o_f = carve(np * 8), o_al = carve(np * 4), o_sl = carve(np * 4), o_fm = carve(np * 24);
+    size_t o_i[10];
+    for (int k = 0; k < 10; ++k) o_i[k] = carve(np * 4);
+    size_t o_terms = carve(np * 8 * TRX_NTERM), o_ft = carve(np * 8), o_wl = carve(np * 4 * TRX_NTERM);
+    size_t o_X = carve((size_t)G * s.Lpad * NAT3 * LANES * 4), o_xn = carve(np * L * NAT3 * 4), o_gn = carve(np * L * NAT3 * 4);
+    size_t o_gk = carve((size_t)G * s.Lpad * 9 * LANES * 4), o_E3 = carve(np * 8 * 3), o_Ev = carve(np * 8);
+    size_t o_ga = carve((size_t)G * 4), o_na = carve(256);
+    cudaError_t e = cudaMalloc(&b->arena, off);
+    if (e != cudaSuccess) {
+        set_error("trx_fold_create: cudaMalloc(%zu bytes) failed: %s", off, cudaGetErrorString(e));
+        delete b;
+        return TRX_ERR_NOMEM;
+    }
+    b->arena_bytes = off;
+    TRX_CUDA(cudaMemsetAsync(b->arena, 0, off, ctx->stream));
+    char *A = (char *)b->arena;
+    s.x = (float *)(A + o_x); s.g = (float *)(A + o_g); s.d = (float *)(A + o_d); s.xt = (float *)(A + o_xt); s.gt = (float *)(A + o_gt);
+    s.S = (float *)(A + o_S); s.Y = (float *)(A + o_Y); s.rho = (float *)(A + o_rho);
+    s.f = (double *)(A + o_f); s.alpha = (float *)(A + o_al); s.slope = (float *)(A + o_sl); s.fmem = (double *)(A + o_fm);
+    s.nmem = (int *)(A + o_i[0]); s.hist = (int *)(A + o_i[1]); s.head = (int *)(A + o_i[2]); s.iter = (int *)(A + o_i[3]);
+    s.run = (int *)(A + o_i[4]); s.bt = (int *)(A + o_i[5]); s.status = (int *)(A + o_i[6]); s.restart = (int *)(A + o_i[7]);
+    s.evals = (int *)(A + o_i[8]); s.iters = (int *)(A + o_i[9]);
+    s.terms = (double *)(A + o_terms); s.ft = (double *)(A + o_ft); s.wl = (float *)(A + o_wl);
+    s.X = (float *)(A + o_X); s.xnat = (float *)(A + o_xn); s.gnat = (float *)(A + o_gn); s.gk1 = (float *)(A + o_gk);
+    s.E3 = (double *)(A + o_E3); s.Evdw = (double *)(A + o_Ev); s.gactive = (int *)(A + o_ga); s.nactive = (int *)(A + o_na);
+    TRX_CUDA(cudaMalloc(&b->d_aa, L * sizeof(int)));
+    TRX_CUDA(cudaMemcpy(b->d_aa, aa, L * sizeof(int), cudaMemcpyHostToDevice));
+    std::vector<Run> hr(nruns);
+    for (int r = 0; r < nruns; ++r) {
+        for (int k = 0; k < TRX_NTERM; ++k) hr[r].w[k] = (float)runs[r].w[k];
+        hr[r].max_iter = runs[r].max_iter; hr[r].tol = (float)runs[r].tol; hr[r].clash_check = runs[r].clash_check;
+        hr[r].clash_thr = (float)runs[r].clash_thr; hr[r].skip_to = runs[r].skip_to;
+    }
+    TRX_CUDA(cudaMalloc(&b->d_runs, nruns * sizeof(Run)));
+    TRX_CUDA(cudaMemcpy(b->d_runs, hr.data(), nruns * sizeof(Run), cudaMemcpyHostToDevice));
+    s.aa = b->d_aa;
+    s.runs = b->d_runs;
+    upload_model();
+    TRX_CUDA(cudaFuncSetAttribute(vdw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->vdw_smem));
+    *out = b;
+    return TRX_OK;
+}
+
+// One evaluation of the current trial points (xt) of every unfinished decoy:
+// coordinates, restraint terms, vdw, torsion gradient.  Fills ft, gt, terms.
+static int fold_eval(trx_fold_batch *b, bool force_all = false)
+{
+    trx_ctx *ctx = b->ctx;
+    FoldState s = b->s;
+    s.force_all = force_all ? 1 : 0;
+    ctx->time_begin("nerf");
+    nerf_kernel<<<s.G, 32, 0, ctx->stream>>>(s);
+    ctx->time_end("nerf");
+    for (size_t t = 0; t < b->tabs.size(); ++t) {
+        int rc = k1_launch<float>(ctx, b->tabs[t], s.G, b->tab_g0[t], b->tab_ng[t], s.X, NAT3, s.wl, nullptr,
+                                  force_all ? nullptr : s.gactive, s.E3, s.gk1);
+        if (rc) return rc;
+    }
+    ctx->time_begin("centroid");
+    vdw_kernel<<<s.N, VDW_THREADS, b->vdw_smem, ctx->stream>>>(s);
+    ctx->time_end("centroid");
+    ctx->time_begin("torsion_grad");
+    torsion_grad_kernel<<<s.G, 32, 0, ctx->stream>>>(s);
+    ctx->time_end("torsion_grad");
+    TRX_CUDA(cudaGetLastError());
+    return TRX_OK;
+}
+
+/* Runs the schedule to completion (or max_rounds evaluation rounds).  tors: host [N][L][3]
+ * float, in: start torsions, out: final torsions.  xyz (may be NULL): host [N][L][5][3] float,
+ * atoms N,CA,CB,C,O.  terms (may be NULL): [N][6] double.  stats (may be NULL): [N][2]
+ * evaluations, accepted iterations.  *rounds_out (may be NULL): evaluation rounds executed. */
+int trx_fold_run(trx_fold_batch *b, float *tors, float *xyz, double *terms, long long *stats, int max_rounds,
+                 int check_every, int *rounds_out)
+{
+    TRX_REQUIRE(b && tors, "trx_fold_run: NULL argument");
+    trx_ctx *ctx = b->ctx;
+    FoldState &s = b->s;
+    TRX_CUDA(cudaSetDevice(ctx->device));
+    if (check_every < 1) check_every = 16;
+    void *d_tors = nullptr, *d_terms = nullptr, *d_stats = nullptr;
+    int rc;
+    const size_t tb = (size_t)s.N * s.ndof * sizeof(float);
+    if ((rc = ctx->get_scratch("fold_tors", tb, &d_tors))) return rc;
+    if ((rc = ctx->get_scratch("fold_terms", (size_t)s.N * TRX_NTERM * sizeof(double), &d_terms))) return rc;
+    if ((rc = ctx->get_scratch("fold_stats", (size_t)s.N * 2 * sizeof(long long), &d_stats))) return rc;
+    TRX_CUDA(cudaMemcpyAsync(d_tors, tors, tb, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->time_begin("fold_init");
+    init_state_kernel<<<s.G, 32, 0, ctx->stream>>>(s, (const float *)d_tors);
+    ctx->time_end("fold_init");
+    int rounds = 0, active = s.N;
+    int *h_active = nullptr;
+    TRX_CUDA(cudaMallocHost(&h_active, sizeof(int)));
+    dim3 ablk(32, 8), agrd((s.G + 7) / 8);
+    while (active > 0 && rounds < max_rounds) {
+        for (int k = 0; k < check_every && rounds < max_rounds; ++k, ++rounds) {
+            TRX_CUDA(cudaMemsetAsync(s.nactive, 0, sizeof(int), ctx->stream));
+            ctx->time_begin("activity");
+            activity_kernel<<<agrd, ablk, 0, ctx->stream>>>(s);
+            ctx->time_end("activity");
+            if ((rc = fold_eval(b))) { cudaFreeHost(h_active); return rc; }
+            ctx->time_begin("lbfgs");
+            lbfgs_kernel<<<s.G, LB_THREADS, 0, ctx->stream>>>(s);
+            ctx->time_end("lbfgs");
+        }
+        TRX_CUDA(cudaMemcpyAsync(h_active, s.nactive, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        TRX_CUDA(cudaStreamSynchronize(ctx->stream));
+        active = *h_active;   // count at the start of the last round; finished decoys are masked anyway
+    }
+    cudaFreeHost(h_active);
+    // final coordinates / terms at the accepted point x: one more evaluation with xt = x for everyone
+    ctx->time_begin("export");
+    restore_kernel<<<s.G, 256, 0, ctx->stream>>>(s);
+    ctx->time_end("export");
+    if ((rc = fold_eval(b, true))) return rc;
+    ctx->time_begin("export");
+    export_kernel<<<s.G, 32, 0, ctx->stream>>>(s, (float *)d_tors, (double *)d_terms, (long long *)d_stats);
+    ctx->time_end("export");
+    TRX_CUDA(cudaGetLastError());
+    TRX_CUDA(cudaMemcpyAsync(tors, d_tors, tb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (terms) TRX_CUDA(cudaMemcpyAsync(terms, d_terms, (size_t)s.N * TRX_NTERM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (stats) TRX_CUDA(cudaMemcpyAsync(stats, d_stats, (size_t)s.N * 2 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    if (xyz) TRX_CUDA(cudaMemcpyAsync(xyz, s.xnat, (size_t)s.N * s.L * NAT3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    TRX_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (rounds_out) *rounds_out = rounds;
+    return TRX_OK;
+}
+
+/* Single evaluation at given torsions under uniform weights (parity tests of K2-K4):
+ * tors host [N][L][3] float -> total [N], terms [N][6], gtors [N][L][3] float, xyz [N][L][5][3] float. */
+int trx_fold_eval(trx_fold_batch *b, const float *tors, const double w[6], double *total, double *terms, float *gtors, float *xyz)
+{
+    TRX_REQUIRE(b && tors && w, "trx_fold_eval: NULL argument");
+    trx_ctx *ctx = b->ctx;
+    FoldState &s = b->s;
+    TRX_CUDA(cudaSetDevice(ctx->device));
+    void *d_tors = nullptr;
+    int rc;
+    const size_t tb = (size_t)s.N * s.ndof * sizeof(float);
+    if ((rc = ctx->get_scratch("fold_tors", tb, &d_tors))) return rc;
+    TRX_CUDA(cudaMemcpyAsync(d_tors, tors, tb, cudaMemcpyHostToDevice, ctx->stream));
+    init_state_kernel<<<s.G, 32, 0, ctx->stream>>>(s, (const float *)d_tors);
+    std::vector<float> wl((size_t)TRX_NTERM * s.Npad);
+    for (int k = 0; k < TRX_NTERM; ++k) for (int n = 0; n < s.Npad; ++n) wl[(size_t)k * s.Npad + n] = (float)w[k];
+    TRX_CUDA(cudaMemcpyAsync(s.wl, wl.data(), wl.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    TRX_CUDA(cudaMemsetAsync(s.nactive, 0, sizeof(int), ctx->stream));
+    dim3 ablk(32, 8), agrd((s.G + 7) / 8);
+    activity_kernel<<<agrd, ablk, 0, ctx->stream>>>(s);
+    ctx->launches += 2;
+    if ((rc = fold_eval(b, true))) return rc;
+    std::vector<double> ft(s.Npad), tr((size_t)TRX_NTERM * s.Npad);
+    std::vector<float> gt((size_t)s.G * s.ndof * LANES);
+    TRX_CUDA(cudaMemcpyAsync(ft.data(), s.ft, ft.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    TRX_CUDA(cudaMemcpyAsync(tr.data(), s.terms, tr.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    TRX_CUDA(cudaMemcpyAsync(gt.data(), s.gt, gt.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (xyz) TRX_CUDA(cudaMemcpyAsync(xyz, s.xnat, (size_t)s.N * s.L * NAT3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    TRX_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int n = 0; n < s.N; ++n) {
+        if (total) total[n] = ft[n];
+        if (terms) for (int k = 0; k < TRX_NTERM; ++k) terms[(size_t)n * TRX_NTERM + k] = tr[(size_t)k * s.Npad + n];
+        if (gtors) for (int k = 0; k < s.ndof; ++k) gtors[(size_t)n * s.ndof + k] = gt[((size_t)(n / LANES) * s.ndof + k) * LANES + n % LANES];
+    }
+    return TRX_OK;
+}
+
+}  // extern "C"

@@ -107,3 +107,9 @@ struct trx_tables {
     std::map<int, trx::Plan> plans;  // keyed by number of decoy groups
     int get_plan(int groups, trx::Plan **out);
 };
+
+namespace trx {
+template <typename T>
+int k1_launch(trx_ctx *ctx, trx_tables *tb, int Gtot, int g0, int ng, const T *d_xyz, int xstride, const float *wl,
+              const double *w, const int *gactive, double *d_E, T *d_grad);
+}

@@ -51,6 +51,11 @@ struct K1Params {
     T *recs;                                     // [G][nrec][REC_ELEMS]
     double *Epart;                               // [G][nwork][3][32]
     int Lpad, nrec, nwork;
+    int xstride;                                 // values per residue in X (9: N,CA,CB; 15: fold layout)
+    int g0;                                      // first decoy group of this launch
+    const int *gactive;                          // per-group flag or NULL (all active)
+    const float *wl;                             // per-decoy weights [3][Npad] or NULL (use w0..w2)
+    int Npad;
     T w0, w1, w2;
 };
 
@@ -148,7 +153,8 @@ __device__ __forceinline__ void angle_term(const KnotGeom<T> &kn, const typename
 // ri/cj: coordinates N(0..2) CA(3..5) CB(6..8); rg/cg: gradient accumulators.
 template <typename T>
 __device__ __forceinline__ void pair_eval(const K1Params<T> &p, const KnotGeom<T> *geom, const int4 ia, const int4 ib,
-                                          const T *ri, const T *cj, T *rg, T *cg, double &e0, double &e1, double &e2)
+                                          const T *ri, const T *cj, T *rg, T *cg, const T w0, const T w1, const T w2,
+                                          double &e0, double &e1, double &e2)
 {
     using T2 = typename Vec2<T>::type;
     const int mask = ia.x;
@@ -162,24 +168,24 @@ __device__ __forceinline__ void pair_eval(const K1Params<T> &p, const KnotGeom<T
         spline_eval(geom[0], p.tab[0] + (size_t)ia.y * geom[0].K, d2 * rd, f, df);
         e0 += (double)f;
         if (df != (T)0) {
-            const T s = p.w0 * df * rd;
+            const T s = w0 * df * rd;
             cg[6] += s * Dx; cg[7] += s * Dy; cg[8] += s * Dz;
             rg[6] -= s * Dx; rg[7] -= s * Dy; rg[8] -= s * Dz;
         }
     }
     if (mask & 2)    // omega: Dihedral CA_i CB_i CB_j CA_j
-        dihedral_term<T>(geom[1], p.tab[1] + (size_t)ia.z * geom[1].K, Px, Py, Pz, -Dx, -Dy, -Dz, Qx, Qy, Qz, p.w1, e1,
+        dihedral_term<T>(geom[1], p.tab[1] + (size_t)ia.z * geom[1].K, Px, Py, Pz, -Dx, -Dy, -Dz, Qx, Qy, Qz, w1, e1,
                          rg + 3, rg + 6, cg + 6, cg + 3);
     if (mask & 4)    // theta(i,j): Dihedral N_i CA_i CB_i CB_j
         dihedral_term<T>(geom[2], p.tab[2] + (size_t)ia.w * geom[2].K, ri[0] - ri[3], ri[1] - ri[4], ri[2] - ri[5], Px, Py, Pz,
-                         Dx, Dy, Dz, p.w1, e1, rg + 0, rg + 3, rg + 6, cg + 6);
+                         Dx, Dy, Dz, w1, e1, rg + 0, rg + 3, rg + 6, cg + 6);
     if (mask & 8)    // theta(j,i): Dihedral N_j CA_j CB_j CB_i
         dihedral_term<T>(geom[2], p.tab[2] + (size_t)ib.x * geom[2].K, cj[0] - cj[3], cj[1] - cj[4], cj[2] - cj[5], Qx, Qy, Qz,
-                         -Dx, -Dy, -Dz, p.w1, e1, cg + 0, cg + 3, cg + 6, rg + 6);
+                         -Dx, -Dy, -Dz, w1, e1, cg + 0, cg + 3, cg + 6, rg + 6);
     if (mask & 16)   // phi(i,j): Angle CA_i CB_i CB_j
-        angle_term<T>(geom[3], p.tab[3] + (size_t)ib.y * geom[3].K, Px, Py, Pz, Dx, Dy, Dz, p.w2, e2, rg + 3, rg + 6, cg + 6);
+        angle_term<T>(geom[3], p.tab[3] + (size_t)ib.y * geom[3].K, Px, Py, Pz, Dx, Dy, Dz, w2, e2, rg + 3, rg + 6, cg + 6);
     if (mask & 32)   // phi(j,i): Angle CA_j CB_j CB_i
-        angle_term<T>(geom[3], p.tab[3] + (size_t)ib.z * geom[3].K, Qx, Qy, Qz, -Dx, -Dy, -Dz, p.w2, e2, cg + 3, cg + 6, rg + 6);
+        angle_term<T>(geom[3], p.tab[3] + (size_t)ib.z * geom[3].K, Qx, Qy, Qz, -Dx, -Dy, -Dz, w2, e2, cg + 3, cg + 6, rg + 6);
     (void)sizeof(T2);
 }
 
@@ -191,7 +197,8 @@ __global__ void __launch_bounds__(K1_THREADS, (sizeof(T) == 4 ? 2 : 1)) restrain
     double(*ered)[3][LANES] = reinterpret_cast<double(*)[3][LANES]>(colg);  // reused after the last flush
     static_assert(sizeof(double) * K1_WARPS * 3 * LANES <= sizeof(T) * REC_ELEMS, "energy scratch must fit");
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int q = blockIdx.x, g = blockIdx.y;
+    const int q = blockIdx.y, g = p.g0 + blockIdx.x;   // group is the fast grid index: co-resident CTAs share tiles
+    if (p.gactive && !p.gactive[g]) return;
     {
         const int *src = reinterpret_cast<const int *>(p.geom);
         int *dst = reinterpret_cast<int *>(geom);
@@ -199,14 +206,21 @@ __global__ void __launch_bounds__(K1_THREADS, (sizeof(T) == 4 ? 2 : 1)) restrain
         for (int e = threadIdx.x; e < REC_ELEMS; e += K1_THREADS) colg[e] = (T)0;
     }
     const int I = p.work[q * 4 + 0], t0 = p.work[q * 4 + 1], nt = p.work[q * 4 + 2], rowrec = p.work[q * 4 + 3];
-    const T *__restrict__ Xg = p.X + (size_t)g * p.Lpad * 9 * LANES + lane;
+    const int xs = p.xstride;
+    const T *__restrict__ Xg = p.X + (size_t)g * p.Lpad * xs * LANES + lane;
+    T w0 = p.w0, w1 = p.w1, w2 = p.w2;
+    if (p.wl) {
+        w0 = (T)p.wl[0 * (size_t)p.Npad + g * LANES + lane];
+        w1 = (T)p.wl[1 * (size_t)p.Npad + g * LANES + lane];
+        w2 = (T)p.wl[2 * (size_t)p.Npad + g * LANES + lane];
+    }
     T ri[2][9], rg[2][9];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
         const int res = I * TILE + w + K1_WARPS * r;
 #pragma unroll
         for (int c = 0; c < 9; ++c) {
-            ri[r][c] = Xg[((size_t)res * 9 + c) * LANES];
+            ri[r][c] = Xg[((size_t)res * xs + c) * LANES];
             rg[r][c] = (T)0;
         }
     }
@@ -226,11 +240,11 @@ __global__ void __launch_bounds__(K1_THREADS, (sizeof(T) == 4 ? 2 : 1)) restrain
                 const int res = J * TILE + c;
 #pragma unroll
                 for (int k = 0; k < 9; ++k) {
-                    cj[k] = Xg[((size_t)res * 9 + k) * LANES];
+                    cj[k] = Xg[((size_t)res * xs + k) * LANES];
                     cg[k] = (T)0;
                 }
-                if (a0.x) pair_eval<T>(p, geom, a0, __ldg(r0 + 1), ri[0], cj, rg[0], cg, e0, e1, e2);
-                if (a1.x) pair_eval<T>(p, geom, a1, __ldg(r1 + 1), ri[1], cj, rg[1], cg, e0, e1, e2);
+                if (a0.x) pair_eval<T>(p, geom, a0, __ldg(r0 + 1), ri[0], cj, rg[0], cg, w0, w1, w2, e0, e1, e2);
+                if (a1.x) pair_eval<T>(p, geom, a1, __ldg(r1 + 1), ri[1], cj, rg[1], cg, w0, w1, w2, e0, e1, e2);
 #pragma unroll
                 for (int k = 0; k < 9; ++k) colg[(c * 9 + k) * LANES + lane] += cg[k];
             }
@@ -268,9 +282,10 @@ template <typename T>
 __global__ void __launch_bounds__(256) reduce_kernel(const T *__restrict__ recs, int nrec, const int *__restrict__ blk_ptr,
                                                      const int *__restrict__ blk_rec, T *__restrict__ grad, int Lpad, int nb,
                                                      int accumulate, const double *__restrict__ Epart, int nwork,
-                                                     double *__restrict__ E, int Npad)
+                                                     double *__restrict__ E, int Npad, int g0, const int *__restrict__ gactive)
 {
-    const int g = blockIdx.y;
+    const int g = g0 + blockIdx.y;
+    if (gactive && !gactive[g]) return;
     if ((int)blockIdx.x == nb) {
         if (threadIdx.x < 3 * LANES) {
             const int term = threadIdx.x / LANES, lane = threadIdx.x % LANES;
@@ -290,17 +305,19 @@ __global__ void __launch_bounds__(256) reduce_kernel(const T *__restrict__ recs,
     }
 }
 
+// One restraint evaluation of decoy groups [g0, g0+ng) out of Gtot against tables tb.
+// X/grad/E are indexed by the GLOBAL group; the plan (work decomposition) by ng.
 template <typename T>
-static int launch(trx_ctx *ctx, trx_tables *tb, int N, const T *d_xyz, const double *w, double *d_E, T *d_grad)
+int k1_launch(trx_ctx *ctx, trx_tables *tb, int Gtot, int g0, int ng, const T *d_xyz, int xstride, const float *wl,
+              const double *w, const int *gactive, double *d_E, T *d_grad)
 {
-    const int G = num_groups(N);
     Plan *plan = nullptr;
-    int rc = tb->get_plan(G, &plan);
+    int rc = tb->get_plan(ng, &plan);
     if (rc) return rc;
     void *recs = nullptr, *epart = nullptr;
-    rc = ctx->get_scratch(sizeof(T) == 8 ? "k1_recs64" : "k1_recs32", (size_t)G * std::max(1, plan->nrec) * REC_ELEMS * sizeof(T), &recs);
+    rc = ctx->get_scratch(sizeof(T) == 8 ? "k1_recs64" : "k1_recs32", (size_t)Gtot * std::max(1, tb->ntiles + tb->ntiles + tb->nb) * REC_ELEMS * sizeof(T), &recs);
     if (rc) return rc;
-    rc = ctx->get_scratch("k1_epart", (size_t)G * std::max(1, plan->nwork) * 3 * LANES * sizeof(double), &epart);
+    rc = ctx->get_scratch("k1_epart", (size_t)Gtot * std::max(1, tb->ntiles + tb->nb) * 3 * LANES * sizeof(double), &epart);
     if (rc) return rc;
     K1Params<T> p;
     p.X = d_xyz;
@@ -315,24 +332,33 @@ static int launch(trx_ctx *ctx, trx_tables *tb, int N, const T *d_xyz, const dou
     p.Lpad = tb->Lpad;
     p.nrec = plan->nrec;
     p.nwork = plan->nwork;
-    p.w0 = (T)w[0];
-    p.w1 = (T)w[1];
-    p.w2 = (T)w[2];
+    p.xstride = xstride;
+    p.g0 = g0;
+    p.gactive = gactive;
+    p.wl = wl;
+    p.Npad = Gtot * LANES;
+    p.w0 = (T)(w ? w[0] : 0.0);
+    p.w1 = (T)(w ? w[1] : 0.0);
+    p.w2 = (T)(w ? w[2] : 0.0);
     if (plan->nwork > 0) {
         ctx->time_begin("restraints");
-        restraints_kernel<T><<<dim3(plan->nwork, G), K1_THREADS, 0, ctx->stream>>>(p);
+        restraints_kernel<T><<<dim3(ng, plan->nwork), K1_THREADS, 0, ctx->stream>>>(p);
         ctx->time_end("restraints");
         TRX_CUDA(cudaGetLastError());
     }
     ctx->time_begin("reduce");
     const int nbr = d_grad ? tb->nb : 0;
-    reduce_kernel<T><<<dim3(nbr + 1, G), 256, 0, ctx->stream>>>((const T *)recs, plan->nrec, plan->d_blk_ptr, plan->d_blk_rec,
-                                                                  d_grad, tb->Lpad, nbr, 0,
-                                                                  (const double *)epart, plan->nwork, d_E, G * LANES);
+    reduce_kernel<T><<<dim3(nbr + 1, ng), 256, 0, ctx->stream>>>((const T *)recs, plan->nrec, plan->d_blk_ptr, plan->d_blk_rec,
+                                                                   d_grad, tb->Lpad, nbr, 0, (const double *)epart, plan->nwork,
+                                                                   d_E, Gtot * LANES, g0, gactive);
     ctx->time_end("reduce");
     TRX_CUDA(cudaGetLastError());
     return TRX_OK;
 }
+template int k1_launch<float>(trx_ctx *, trx_tables *, int, int, int, const float *, int, const float *, const double *,
+                              const int *, double *, float *);
+template int k1_launch<double>(trx_ctx *, trx_tables *, int, int, int, const double *, int, const float *, const double *,
+                               const int *, double *, double *);
 
 }  // namespace trx
 
@@ -348,8 +374,10 @@ int trx_energy_grad_device(trx_ctx *ctx, trx_tables *tb, int N, int precision, c
     TRX_REQUIRE(N > 0, "trx_energy_grad_device: N must be positive");
     TRX_REQUIRE(precision == TRX_F64 || precision == TRX_F32, "trx_energy_grad_device: precision must be 64 or 32");
     TRX_CUDA(cudaSetDevice(ctx->device));
-    if (precision == TRX_F64) return launch<double>(ctx, tb, N, (const double *)d_xyz, w, d_E, (double *)d_grad);
-    return launch<float>(ctx, tb, N, (const float *)d_xyz, w, d_E, (float *)d_grad);
+    const int G = num_groups(N);
+    if (precision == TRX_F64)
+        return k1_launch<double>(ctx, tb, G, 0, G, (const double *)d_xyz, 9, nullptr, w, nullptr, d_E, (double *)d_grad);
+    return k1_launch<float>(ctx, tb, G, 0, G, (const float *)d_xyz, 9, nullptr, w, nullptr, d_E, (float *)d_grad);
 }
 
 int trx_energy_grad(trx_ctx *ctx, trx_tables *tb, int N, int precision, const void *xyz, const double w[3], double *E,

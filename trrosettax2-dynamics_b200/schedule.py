@@ -1,0 +1,69 @@
+"""The reference's minimisation schedule as data for the device state machine.
+
+folding/folding.py:74-104 builds four ScoreFunctions from data/*.wts and four MinMovers
+('lbfgs_armijo_nonmonotone', tolerance 1e-4, max_iter 1000/1000/500/1000);
+:118-119 and :164-171 (mode 2) apply them:
+    remove_clash(sf_vdw, min_mover_vdw)        <= 5 x { if sf_vdw(pose) < 10: break; minimise }
+    RepeatMover(min_mover, 3)                  3 x minimise under scorefxn.wts
+    min_mover_cart                             Cartesian stage (NOT built in this round)
+    remove_clash(sf_vdw, min_mover1)           <= 5 x { ...; minimise under scorefxn1.wts }
+Terms the library implements: atom_pair_constraint, dihedral_constraint, angle_constraint,
+vdw, rama, omega.  cen_hb / hbond_* / cart_bonded weights are read and ignored (no database)."""
+from __future__ import annotations
+
+import os
+
+from .capi import Run, NTERM
+
+TERMS = ("atom_pair_constraint", "dihedral_constraint", "angle_constraint", "vdw", "rama", "omega")
+_DATA = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "folding", "data")
+
+
+def read_wts(name, data_dir=None):
+    """Weights file -> list of the NTERM weights this library scores (others ignored)."""
+    w = dict.fromkeys(TERMS, 0.0)
+    with open(os.path.join(data_dir or _DATA, name)) as fh:
+        for line in fh:
+            tok = line.split()
+            if len(tok) >= 2 and tok[0] in w:
+                w[tok[0]] = float(tok[1])
+    return [w[t] for t in TERMS]
+
+
+def make_run(w, max_iter, tol=1e-4, clash_check=False, clash_thr=10.0, skip_to=0):
+    r = Run()
+    for k in range(NTERM):
+        r.w[k] = w[k]
+    r.max_iter, r.tol = int(max_iter), float(tol)
+    r.clash_check, r.clash_thr, r.skip_to = int(clash_check), float(clash_thr), int(skip_to)
+    return r
+
+
+def reference_schedule(data_dir=None, stages=1):
+    """Mode-2 schedule (stages=1).  Modes 0 and 1 of folding.py:125-160 repeat the
+    {repeat_mover, cart, remove_clash} block per separation window; the host driver
+    then calls the fold once per window with the window's tables."""
+    sf = read_wts("scorefxn.wts", data_dir)
+    sf1 = read_wts("scorefxn1.wts", data_dir)
+    sf_vdw = read_wts("scorefxn_vdw.wts", data_dir)
+    runs = []
+    first = [make_run(sf_vdw, 500, clash_check=True, skip_to=5) for _ in range(5)]
+    runs += first
+    runs += [make_run(sf, 1000) for _ in range(3)]
+    end = len(runs) + 5
+    runs += [make_run(sf1, 1000, clash_check=True, skip_to=end) for _ in range(5)]
+    return runs
+
+
+def window_schedule(data_dir=None, initial_clash=False):
+    """One separation window of modes 0/1/3: RepeatMover(min_mover,3) + remove_clash(min_mover1)."""
+    sf = read_wts("scorefxn.wts", data_dir)
+    sf1 = read_wts("scorefxn1.wts", data_dir)
+    sf_vdw = read_wts("scorefxn_vdw.wts", data_dir)
+    runs = []
+    if initial_clash:
+        runs += [make_run(sf_vdw, 500, clash_check=True, skip_to=5) for _ in range(5)]
+    runs += [make_run(sf, 1000) for _ in range(3)]
+    end = len(runs) + 5
+    runs += [make_run(sf1, 1000, clash_check=True, skip_to=end) for _ in range(5)]
+    return runs
