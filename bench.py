@@ -38,10 +38,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default=None, choices=["restraint", "fold"])
+    ap.add_argument("--mode", default="fold", choices=["restraint", "fold"])
     ap.add_argument("--decoys", type=int, default=4096, help="decoys per GPU")
     ap.add_argument("--precision", type=int, default=32, choices=[32, 64])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lbfgs-m", type=int, default=20)
     return ap.parse_args()
 
 
@@ -132,9 +133,55 @@ def cpu_restraint_rate(npzs, xyz, n_sample, threads):
     return n_sample / dt, dt
 
 
+def cpu_fold_rate(npzs, seq, n_sample, threads, seed):
+    """Oracle fold (same schedule, fp64, one decoy per host thread) on a bounded sample."""
+    from oracle import fold_oracle as fo
+    sets = oracle_sets(npzs)
+    half = max(1, n_sample // 2)
+    t0 = time.perf_counter()
+    evals = 0
+    for k, rs in enumerate(sets):
+        F = fo.FoldOracle(rs, seq)
+        n = half if k == 0 else n_sample - half
+        if n <= 0:
+            continue
+        out = F.fold(fo.random_torsions(n, len(seq), seed + k), fo.reference_schedule(), m=20, nthreads=threads)
+        evals += int(out["evals"].sum())
+    dt = time.perf_counter() - t0
+    return n_sample / dt, dt, evals
+
+
+def run_reference_fold(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    steps = args.steps or 2
+    n_sample = threads
+    import trx2dyn  # noqa: F401
+    from trx2dyn import synth
+    seq, npzs, _ = synth.target(L_TARGET, SEED, dense=False, two_model=True)
+    t = []
+    for k in range(min(args.warmup, 1) + steps):
+        rate, dt, _ = cpu_fold_rate(npzs, seq, n_sample, threads, SEED + 10 * k)
+        if k >= min(args.warmup, 1):
+            t.append(dt)
+    val = n_sample / float(np.mean(t))
+    sample = "%d decoys (one per host thread) of the L=300 two-model workload per step, oracle/fold_oracle.c, same schedule, fp64 (PyRosetta absent)" % n_sample
+    line = {"impl": "reference", "metric": "decoys_per_sec_L300", "value": val, "unit": "decoys/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * float(np.mean(t)), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "synthetic L=300 dist+omega+theta+phi, two-model mixing (configs[2])", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "decoys/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "decoys/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
 def run_reference(args):
     """Reference arm: the reference's CPU implementation of the path.  PyRosetta is absent
     (un-vendored binary dependency), so this times the oracle port on all host threads."""
+    if args.mode != "restraint":
+        return run_reference_fold(args)
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -160,7 +207,131 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_b200_fold(args):
+    """Metric M1: fully minimised centroid decoys per second (whole schedule, on device)."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import trx2dyn  # noqa: F401
+    from trx2dyn import capi, sampler, schedule, synth, tables
+
+    N = args.decoys
+    steps = args.steps or 3
+    warmup = max(args.warmup, 3)
+    seq, npzs, nat = synth.target(L_TARGET, SEED, dense=False, two_model=True)
+    params = tables.load_params()
+    stream = torch.cuda.Stream()
+    ctx = capi.Context(local, stream.cuda_stream)
+    tabs = [sampler.build_tables(ctx, npz, seq, params) for npz in npzs]
+    R = [sum(t.info()["counts"]) for t in tabs]
+    half = (N // 2 + 31) // 32 * 32
+    nd = [half, N - half]
+    batch = capi.FoldBatch(ctx, tabs, nd, sampler.aa_index(seq), schedule.reference_schedule(), lbfgs_m=args.lbfgs_m)
+    import ctypes as C
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # pinned host buffers: torsions in, coordinates + terms out (the e2e path IS the product call)
+    tors_h = torch.empty((N, L_TARGET, 3), dtype=torch.float32).pin_memory()
+    xyz_h = torch.empty((N, L_TARGET, 5, 3), dtype=torch.float32).pin_memory()
+    terms_h = torch.empty((N, 6), dtype=torch.float64).pin_memory()
+    stats_h = torch.empty((N, 2), dtype=torch.int64).pin_memory()
+    rounds = C.c_int()
+
+    def one_fold(seed):
+        tors_h.copy_(torch.from_numpy(sampler.random_torsions(N, L_TARGET, seed)))
+        t0 = time.perf_counter()
+        capi.check(capi.lib().trx_fold_run(batch._h, C.c_void_p(tors_h.data_ptr()), C.c_void_p(xyz_h.data_ptr()),
+                                           C.c_void_p(terms_h.data_ptr()), C.c_void_p(stats_h.data_ptr()),
+                                           C.c_int(20000), C.c_int(16), C.byref(rounds)))
+        return time.perf_counter() - t0
+
+    for k in range(warmup):
+        one_fold(1000 * rank + k)
+    barrier()
+    sampler_clk = ClockSampler(local)
+    sampler_clk.start()
+    ctx.set_timing(True)
+    ctx.reset_timing()
+    launches0 = ctx.launch_count
+    barrier()
+    t_wall, evals_total, rest_evals = [], 0, 0.0
+    for k in range(steps):
+        t_wall.append(one_fold(1000 * rank + 100 + k))
+        ev = stats_h[:, 0].numpy().astype(np.float64)
+        evals_total += float(ev.sum())
+        rest_evals += float(ev[:nd[0]].sum()) * R[0] + float(ev[nd[0]:].sum()) * R[1]
+    barrier()
+    clocks = sampler_clk.stop()
+    launches = ctx.launch_count - launches0
+    t_dev = ctx.timing("fold_device")[0] / 1e3
+    k1_ms, k1_n = ctx.timing("restraints")
+    shares = {name: ctx.timing(name)[0] / (1e3 * t_dev) for name in ("restraints", "reduce", "nerf", "centroid", "torsion_grad", "lbfgs")}
+    ctx.set_timing(False)
+    t_e2e = float(sum(t_wall))
+    if world > 1:
+        t = torch.tensor([t_dev, t_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e = float(t[0].item()), float(t[1].item())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ca = xyz_h[: min(N, 64), :, 1].numpy().astype(np.float64)
+    from trx2dyn import metrics
+    tm = [metrics.tm_score(c, nat[:, 1]) for c in ca[:32]]
+    total = N * world
+    peak, peak_src = peaks()
+    # algorithmic bytes the restraint kernel processed (SURVEY 8d): 16 B (4 fp32 knot scalars) per
+    # restraint evaluated for a decoy + coordinates in / gradient out per decoy evaluation
+    alg_bytes = 16.0 * rest_evals + 2 * 3 * L_TARGET * 12.0 * evals_total
+    achieved = alg_bytes / (k1_ms * 1e-3) / 1e9
+    line = {"metric": "decoys_per_sec_L300", "value": total * steps / t_dev, "unit": "decoys/s", "n_gpus": world,
+            "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * t_dev / steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "synthetic L=300 dist+omega+theta+phi, two-model mixing, %d decoys per GPU, full mode-2 centroid schedule (configs[2])" % N,
+                       "restraints_per_decoy": R, "l2": "working set per step (%.1f GB of decoy state) exceeds L2" % (batch_bytes(N, L_TARGET, args.lbfgs_m) / 1e9),
+                       "mode": "fold", "lbfgs_m": args.lbfgs_m, "cartesian_stage": "not built (DESIGN.md)"},
+            "restraint_decoy_evals_per_sec": evals_total * world / t_dev,
+            "restraint_evals_per_sec": rest_evals * world / t_dev,
+            "mean_evals_per_decoy": evals_total / (N * steps), "rounds_last_step": rounds.value,
+            "decoy_quality": {"tm_vs_synthetic_native_median": float(np.median(tm)), "tm_gt_0.5_frac": float(np.mean(np.array(tm) > 0.5))},
+            "clocks": clocks,
+            "e2e": {"value": total * steps / t_e2e, "unit": "decoys/s",
+                    "h2d_bytes_per_step": int(tors_h.numel() * 4),
+                    "d2h_bytes_per_step": int(xyz_h.numel() * 4 + tors_h.numel() * 4 + terms_h.numel() * 8 + stats_h.numel() * 8)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "restraints_kernel<float>", "kernel_ms": k1_ms / max(k1_n, 1),
+                         "kernel_share_of_step": shares["restraints"], "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes / max(k1_n, 1), "kernel_shares": shares}}
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        rate, dt, ev = cpu_fold_rate(npzs, seq, threads, threads, SEED)
+        line["cpu_baseline"] = {"value": rate, "unit": "decoys/s", "cores": threads, "kind": "port",
+                                "sample": "%d decoys (one per host thread) of the same workload, oracle/fold_oracle.c same schedule fp64, %.1f s (PyRosetta absent)" % (threads, dt)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def batch_bytes(N, L, m):
+    return N * L * 3 * 4.0 * (5 + 2 * m) + N * L * 15 * 4.0 * 3
+
+
 def run_b200(args):
+    if args.mode != "restraint":
+        return run_b200_fold(args)
     import torch
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))

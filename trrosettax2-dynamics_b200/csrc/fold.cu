@@ -776,6 +776,8 @@ int trx_fold_run(trx_fold_batch *b, float *tors, float *xyz, double *terms, long
     if ((rc = ctx->get_scratch("fold_terms", (size_t)s.N * TRX_NTERM * sizeof(double), &d_terms))) return rc;
     if ((rc = ctx->get_scratch("fold_stats", (size_t)s.N * 2 * sizeof(long long), &d_stats))) return rc;
     TRX_CUDA(cudaMemcpyAsync(d_tors, tors, tb, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->time_begin("fold_device");   // device time of the whole fold, inputs resident (H2D done, D2H not started)
+    --ctx->launches;
     ctx->time_begin("fold_init");
     init_state_kernel<<<s.G, 32, 0, ctx->stream>>>(s, (const float *)d_tors);
     ctx->time_end("fold_init");
@@ -807,6 +809,7 @@ int trx_fold_run(trx_fold_batch *b, float *tors, float *xyz, double *terms, long
     ctx->time_begin("export");
     export_kernel<<<s.G, 32, 0, ctx->stream>>>(s, (float *)d_tors, (double *)d_terms, (long long *)d_stats);
     ctx->time_end("export");
+    ctx->time_end("fold_device");
     TRX_CUDA(cudaGetLastError());
     TRX_CUDA(cudaMemcpyAsync(tors, d_tors, tb, cudaMemcpyDeviceToHost, ctx->stream));
     if (terms) TRX_CUDA(cudaMemcpyAsync(terms, d_terms, (size_t)s.N * TRX_NTERM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

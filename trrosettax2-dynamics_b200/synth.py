@@ -156,10 +156,92 @@ def hinge(xyz, rng, angle_deg=25.0):
     return out
 
 
-def target(L, seed, dense=False, n_domains=1, two_model=False):
+_B = dict(n_ca=1.458, ca_c=1.523, c_n=1.329)
+_A = dict(n_ca_c=np.deg2rad(111.2), ca_c_n=np.deg2rad(116.2), c_n_ca=np.deg2rad(121.7))
+
+
+def _place(a, b, c, bond, ang, tor):
+    """NeRF, vectorised over leading axes: |cd|=bond, angle(b,c,d)=ang, dihedral(a,b,c,d)=tor."""
+    bc = _unit(c - b)
+    n = _unit(np.cross(b - a, bc))
+    m = np.cross(n, bc)
+    tor = np.asarray(tor)[..., None]
+    return c + (-bond * np.cos(ang)) * bc + (bond * np.sin(ang) * np.cos(tor)) * m + (bond * np.sin(ang) * np.sin(tor)) * n
+
+
+def _extend(N, CA, C, tors_prev_psi, tors_prev_omg, phi):
+    """Next residue's N, CA, C from the previous residue's atoms (all (..., 3))."""
+    Nn = _place(N, CA, C, _B["c_n"], _A["ca_c_n"], tors_prev_psi)
+    CAn = _place(CA, C, Nn, _B["n_ca"], _A["c_n_ca"], tors_prev_omg)
+    Cn = _place(C, Nn, CAn, _B["ca_c"], _A["n_ca_c"], phi)
+    return Nn, CAn, Cn
+
+
+def ss_backbone(L, rng, n_cand=96):
+    """Protein-like compact backbone built by NeRF from ideal geometry: helices and strands
+    joined by loops; each loop is chosen among n_cand random candidates so that the next
+    element packs against what is already built (smallest radius of gyration without CA
+    clashes).  Returns (xyz (L,4,3) N,CA,C,CB, torsions (L,3) radians)."""
+    states = np.deg2rad(np.array([[-140, 153], [-72, 145], [-122, 117], [-82, -14], [-61, -41], [57, 39]], dtype=float))
+    tors = np.zeros((L, 3))
+    tors[:, 2] = np.pi
+    N = np.zeros((1, 3)); CA = np.array([[_B["n_ca"], 0, 0]])
+    C = np.array([[_B["n_ca"] - _B["ca_c"] * np.cos(_A["n_ca_c"]), _B["ca_c"] * np.sin(_A["n_ca_c"]), 0]])
+    built = [(N[0], CA[0], C[0])]
+    tors[0, :2] = states[4]
+    i = 1
+    while i < L:
+        for attempt in range(8):
+            helix = rng.random() < 0.6
+            n_ss = int(rng.integers(9, 19) if helix else rng.integers(5, 10))
+            n_loop = int(rng.integers(3, 7)) if i > 1 else 0
+            n_seg = min(n_loop + n_ss, L - i)
+            seg = np.zeros((n_cand, n_seg, 2))
+            k = rng.integers(0, 6, size=(n_cand, n_seg))
+            seg[:] = states[k] + rng.normal(size=(n_cand, n_seg, 2)) * 0.25
+            ss = (states[4] if helix else states[0])
+            seg[:, n_loop:] = ss + rng.normal(size=(n_cand, max(n_seg - n_loop, 0), 2)) * 0.08
+            pN, pCA, pC = (np.repeat(a[None], n_cand, 0) for a in built[-1])
+            prev_psi = np.full(n_cand, tors[i - 1, 1])
+            cas, atoms = [], []
+            for r in range(n_seg):
+                pN, pCA, pC = _extend(pN, pCA, pC, prev_psi, np.pi, seg[:, r, 0])
+                prev_psi = seg[:, r, 1]
+                cas.append(pCA)
+                atoms.append((pN, pCA, pC))
+            cas = np.stack(cas, 1)                                   # (cand, n_seg, 3)
+            old = np.array([b[1] for b in built])                    # (n_old, 3)
+            d = np.linalg.norm(cas[:, :, None, :] - old[None, None, :, :], axis=-1)
+            d[:, 0, -1] = 10.0                                       # bonded neighbour
+            if n_seg > 1:
+                d[:, 1, -1] = np.maximum(d[:, 1, -1], 4.5)
+            clash = (d < 4.2).sum((1, 2))
+            dn = np.linalg.norm(cas[:, :, None, :] - cas[:, None, :, :], axis=-1)   # within the new segment
+            sep = np.abs(np.arange(n_seg)[:, None] - np.arange(n_seg)[None, :])
+            clash = clash + ((dn < 4.2) & (sep > 2)[None]).sum((1, 2))
+            allca = np.concatenate([np.repeat(old[None], n_cand, 0), cas], 1)
+            rg = np.sqrt(((allca - allca.mean(1, keepdims=True)) ** 2).sum(-1).mean(1))
+            score = rg + 100.0 * clash
+            best = int(np.argmin(score))
+            if clash[best] == 0:
+                break
+        for r in range(n_seg):
+            built.append(tuple(a[best] for a in atoms[r]))
+            tors[i + r, :2] = seg[best, r]
+        i += n_seg
+    N = np.array([b[0] for b in built]); CA = np.array([b[1] for b in built]); C = np.array([b[2] for b in built])
+    bb, cc = CA - N, C - CA
+    CB = -0.58273431 * np.cross(bb, cc) + 0.56802827 * bb - 0.54067466 * cc + CA
+    return np.stack([N, CA, C, CB], axis=1), tors
+
+
+def target(L, seed, dense=False, n_domains=1, two_model=False, protein_like=True):
     """Returns (seq, [npz, ...], native_xyz (L,4,3) N,CA,C,CB)."""
     rng = np.random.default_rng(seed)
-    xyz = backbone_from_ca(ca_trace(L, rng, n_domains))
+    if protein_like:
+        xyz, _ = ss_backbone(L, rng)
+    else:
+        xyz = backbone_from_ca(ca_trace(L, rng, n_domains))
     aa = np.array(list("ACDEFGHIKLMNPQRSTVWY"))
     seq = "".join(rng.choice(aa, size=L))
     npzs = [distograms(xyz, rng, dense)]
