@@ -49,7 +49,7 @@ struct FoldState {
     // per decoy [Npad]
     double *f, *fmem;        // accepted energy, last 3 accepted energies [3][Npad]
     float *alpha, *slope;
-    int force_all;           // evaluate every decoy regardless of status (final consistent pass)
+    int lb_smem_d;           // L-BFGS keeps the direction in shared memory (fits)
     int *nmem, *hist, *head, *iter, *run, *bt, *status, *restart;
     int *evals, *iters;
     double *terms;           // [TRX_NTERM][Npad] unweighted terms of the last evaluation
@@ -61,8 +61,16 @@ struct FoldState {
     float *gk1;              // [G][Lpad][9][32]
     double *E3;              // [3][Npad]
     double *Evdw;            // [Npad]
-    int *gactive;            // [G]
+    int *gactive;            // [G] decoy group has an unfinished decoy (L-BFGS kernel)
     int *nactive;            // [1]
+    // slot space: the unfinished decoys of each table block, compacted to the front of the
+    // block every round, so the evaluation kernels only touch live lanes
+    int *perm;               // [Npad] slot -> decoy, -1 for an empty slot
+    int *gslot;              // [G] slot group holds a live slot
+    int *nslot;              // [16] live slots per table block
+    float *wslot;            // [TRX_NTERM][Npad] weights in slot order
+    int ntab;
+    int tab_d0[16], tab_n[16];   // first decoy and decoy count of each table block
     const int *aa;           // [L]
     const Run *runs;
 };
@@ -88,11 +96,16 @@ __device__ __forceinline__ f3 place(f3 a, f3 b, f3 c, float bond, float ca, floa
 // the natural-layout copy xnat[n][L][15] the vdw kernel stages into shared memory.
 __global__ void __launch_bounds__(32) nerf_kernel(FoldState s)
 {
-    const int g = blockIdx.x, lane = threadIdx.x, n = g * LANES + lane;
-    if (!s.force_all && !s.gactive[g]) return;
-    const float *__restrict__ t = s.xt + (size_t)g * s.ndof * LANES + lane;
+    const int g = blockIdx.x, lane = threadIdx.x, n = g * LANES + lane;   // n = slot
+    if (!s.gslot[g]) return;
+    const int dec = s.perm[n];
+    const bool live = dec >= 0;
+    const int dn = live ? dec : 0;      // empty slots replay decoy 0's torsions: finite, ignored
+    const float *__restrict__ t = s.xt + (size_t)(dn / LANES) * s.ndof * LANES + dn % LANES;
     float *__restrict__ X = s.X + (size_t)g * s.Lpad * NAT3 * LANES + lane;
     float *__restrict__ xn = s.xnat + (size_t)n * s.L * NAT3;
+#pragma unroll
+    for (int k = 0; k < TRX_NTERM; ++k) s.wslot[(size_t)k * s.Npad + n] = live ? s.wl[(size_t)k * s.Npad + dec] : 0.f;
     const float caNCAC = cosf((float)TRX_A_N_CA_C), saNCAC = sinf((float)TRX_A_N_CA_C);
     const float caCACN = cosf((float)TRX_A_CA_C_N), saCACN = sinf((float)TRX_A_CA_C_N);
     const float caCNCA = cosf((float)TRX_A_C_N_CA), saCNCA = sinf((float)TRX_A_C_N_CA);
@@ -121,7 +134,7 @@ __global__ void __launch_bounds__(32) nerf_kernel(FoldState s)
 #pragma unroll
         for (int k = 0; k < NAT3; ++k) {
             X[((size_t)i * NAT3 + k) * LANES] = v[k];
-            if (n < s.N) xn[(size_t)i * NAT3 + k] = v[k];
+            if (live) xn[(size_t)i * NAT3 + k] = v[k];
         }
         psi_prev = psi;
         omg_prev = omg;
@@ -139,8 +152,8 @@ constexpr double VDW_FIX = 4294967296.0;  // 2^32
 __global__ void __launch_bounds__(VDW_THREADS) vdw_kernel(FoldState s)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int n = blockIdx.x;
-    if (n >= s.N || (!s.force_all && s.status[n] == ST_DONE)) return;
+    const int n = blockIdx.x;   // slot
+    if (s.perm[n] < 0) return;
     const int L = s.L;
     float4 *at = reinterpret_cast<float4 *>(smem_raw);                                   // [L][6]
     long long *acc = reinterpret_cast<long long *>(smem_raw + sizeof(float4) * 6 * L);   // [L][6][3]
@@ -229,7 +242,7 @@ __global__ void __launch_bounds__(VDW_THREADS) vdw_kernel(FoldState s)
         s.Evdw[n] = e;
     }
     // gradient out (weighted), CEN folded into CA and CB
-    const float w = s.wl[(size_t)TRX_T_VDW * s.Npad + n];
+    const float w = s.wslot[(size_t)TRX_T_VDW * s.Npad + n];
     float *__restrict__ gn = s.gnat + (size_t)n * L * NAT3;
     for (int i = threadIdx.x; i < L; i += VDW_THREADS) {
         const float cs = c_model.cen_s[s.aa[i]];
@@ -252,15 +265,18 @@ __global__ void __launch_bounds__(VDW_THREADS) vdw_kernel(FoldState s)
 // terms (functions of the torsions alone) and produces the weighted total.
 __global__ void __launch_bounds__(32) torsion_grad_kernel(FoldState s)
 {
-    const int g = blockIdx.x, lane = threadIdx.x, n = g * LANES + lane;
-    if (!s.force_all && !s.gactive[g]) return;
+    const int g = blockIdx.x, lane = threadIdx.x, n = g * LANES + lane;   // n = slot
+    if (!s.gslot[g]) return;
+    const int dec = s.perm[n];
+    if (dec < 0) return;
     const int L = s.L, Npad = s.Npad;
     const float *__restrict__ X = s.X + (size_t)g * s.Lpad * NAT3 * LANES + lane;
     const float *__restrict__ G1 = s.gk1 + (size_t)g * s.Lpad * 9 * LANES + lane;
-    const float *__restrict__ gn = s.gnat + (size_t)min(n, s.N - 1) * L * NAT3;
-    const float *__restrict__ t = s.xt + (size_t)g * s.ndof * LANES + lane;
-    float *__restrict__ gt = s.gt + (size_t)g * s.ndof * LANES + lane;
-    const float w_rama = s.wl[(size_t)TRX_T_RAMA * Npad + n], w_omega = s.wl[(size_t)TRX_T_OMEGA * Npad + n];
+    const float *__restrict__ gn = s.gnat + (size_t)n * L * NAT3;
+    const size_t dvb = (size_t)(dec / LANES) * s.ndof * LANES + dec % LANES;
+    const float *__restrict__ t = s.xt + dvb;
+    float *__restrict__ gt = s.gt + dvb;
+    const float w_rama = s.wslot[(size_t)TRX_T_RAMA * Npad + n], w_omega = s.wslot[(size_t)TRX_T_OMEGA * Npad + n];
     f3 F1 = {0.f, 0.f, 0.f}, F2 = {0.f, 0.f, 0.f};
     double e_rama = 0.0, e_omega = 0.0;
     auto load = [&](int i, int a) -> f3 { return {X[((size_t)i * NAT3 + a * 3) * LANES], X[((size_t)i * NAT3 + a * 3 + 1) * LANES], X[((size_t)i * NAT3 + a * 3 + 2) * LANES]}; };
@@ -329,16 +345,16 @@ __global__ void __launch_bounds__(32) torsion_grad_kernel(FoldState s)
     term[TRX_T_APC] = s.E3[0 * (size_t)Npad + n];
     term[TRX_T_DIH] = s.E3[1 * (size_t)Npad + n];
     term[TRX_T_ANG] = s.E3[2 * (size_t)Npad + n];
-    term[TRX_T_VDW] = n < s.N ? s.Evdw[n] : 0.0;
+    term[TRX_T_VDW] = s.Evdw[n];
     term[TRX_T_RAMA] = e_rama;
     term[TRX_T_OMEGA] = e_omega;
     double tot = 0.0;
 #pragma unroll
     for (int k = 0; k < TRX_NTERM; ++k) {
-        s.terms[(size_t)k * Npad + n] = term[k];
-        tot += (double)s.wl[(size_t)k * Npad + n] * term[k];
+        s.terms[(size_t)k * Npad + dec] = term[k];
+        tot += (double)s.wslot[(size_t)k * Npad + n] * term[k];
     }
-    s.ft[n] = tot;
+    s.ft[dec] = tot;
 }
 
 // K5: one CTA per decoy group; 8 warps split the torsion vector, lanes are decoys.
@@ -363,14 +379,19 @@ __global__ void __launch_bounds__(LB_THREADS) lbfgs_kernel(FoldState s)
 {
     __shared__ float red[2][LB_WARPS][LANES];
     __shared__ float alpha_h[64][LANES];   // two-loop alphas (m <= 64)
+    extern __shared__ float dsm[];         // the direction while the two-loop recursion works on it
     const int g = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = g * LANES + lane;
     if (!s.gactive[g]) return;
     const int nd = s.ndof, m = s.m, Npad = s.Npad;
     int buf = 0;
     const size_t vb = (size_t)g * nd * LANES + lane;
-    float *x = s.x + vb, *gv = s.g + vb, *d = s.d + vb, *xt = s.xt + vb, *gt = s.gt + vb;
-    float *S = s.S + (size_t)g * m * nd * LANES + lane, *Y = s.Y + (size_t)g * m * nd * LANES + lane;
-    float *rho = s.rho + (size_t)g * m * LANES + lane;
+    float *__restrict__ x = s.x + vb, *__restrict__ gv = s.g + vb, *__restrict__ dg = s.d + vb;
+    float *__restrict__ xt = s.xt + vb, *__restrict__ gt = s.gt + vb;
+    float *__restrict__ S = s.S + (size_t)g * m * nd * LANES + lane, *__restrict__ Y = s.Y + (size_t)g * m * nd * LANES + lane;
+    float *__restrict__ rho = s.rho + (size_t)g * m * LANES + lane;
+    // shared-memory copy of d (stores to it cannot alias the streaming S/Y loads, so those
+    // pipeline freely); falls back to the global vector when 3L*128 B does not fit
+    float *d = s.lb_smem_d ? dsm + lane : dg;
     const int k0 = warp * ((nd + LB_WARPS - 1) / LB_WARPS), k1 = min(nd, k0 + (nd + LB_WARPS - 1) / LB_WARPS);
 
     int status = n < s.N ? s.status[n] : ST_DONE;
@@ -546,8 +567,12 @@ __global__ void __launch_bounds__(LB_THREADS) lbfgs_kernel(FoldState s)
             }
         }
     }
-    // ---- next trial point
-    if (status == ST_LS) for (int k = k0; k < k1; ++k) xt[k * LANES] = x[k * LANES] + alpha * d[k * LANES];
+    // ---- next trial point (and the direction back to global memory for later rounds)
+    if (need_dir && s.lb_smem_d) for (int k = k0; k < k1; ++k) dg[k * LANES] = d[k * LANES];
+    if (status == ST_LS) {
+        if (need_dir) for (int k = k0; k < k1; ++k) xt[k * LANES] = x[k * LANES] + alpha * d[k * LANES];
+        else for (int k = k0; k < k1; ++k) xt[k * LANES] = x[k * LANES] + alpha * dg[k * LANES];
+    }
     if (warp == 0 && n < s.N) {
         s.status[n] = status; s.run[n] = run; s.hist[n] = hist; s.head[n] = head; s.iter[n] = iter; s.bt[n] = bt;
         s.restart[n] = restart; s.nmem[n] = nmem; s.f[n] = f; s.alpha[n] = alpha; s.slope[n] = slope;
@@ -563,10 +588,38 @@ __global__ void activity_kernel(FoldState s)
     const int n = g * LANES + lane;
     const bool active = n < s.N && s.status[n] != ST_DONE;
     const unsigned m = __ballot_sync(0xffffffffu, active);
-    if (lane == 0) {
-        s.gactive[g] = m != 0;
-        if (m) atomicAdd(s.nactive, __popc(m));
+    if (lane == 0) s.gactive[g] = m != 0;
+}
+
+// Slot assignment: the unfinished decoys of table block t, in decoy order, fill the slots
+// from the start of the block (one CTA per block, chunked block-wide exclusive scan).
+// identity != 0: every decoy gets its own slot (final consistent pass / parity entry).
+__global__ void __launch_bounds__(1024) compact_kernel(FoldState s, int identity)
+{
+    __shared__ int wsum[32];
+    __shared__ int base_s;
+    const int t = blockIdx.x, d0 = s.tab_d0[t], nt = s.tab_n[t];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int span = (nt + LANES - 1) / LANES * LANES;
+    if (threadIdx.x == 0) base_s = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < span; c0 += 1024) {
+        const int i = c0 + threadIdx.x;
+        const bool live = i < nt && (identity || s.status[d0 + i] != ST_DONE);
+        const unsigned m = __ballot_sync(0xffffffffu, live);
+        if (lane == 0) wsum[warp] = __popc(m);
+        __syncthreads();
+        int off = base_s;
+        for (int w = 0; w < warp; ++w) off += wsum[w];
+        if (live) s.perm[d0 + off + __popc(m & ((1u << lane) - 1))] = d0 + i;
+        __syncthreads();
+        if (threadIdx.x == 0) { int tot = 0; for (int w = 0; w < 32; ++w) tot += wsum[w]; base_s += tot; }
+        __syncthreads();
     }
+    const int nlive = base_s;
+    for (int i = nlive + threadIdx.x; i < span; i += 1024) s.perm[d0 + i] = -1;
+    for (int g = threadIdx.x; g < span / LANES; g += 1024) s.gslot[d0 / LANES + g] = g * LANES < nlive;
+    if (threadIdx.x == 0) { s.nslot[t] = nlive; atomicAdd(s.nactive, nlive); }
 }
 
 __global__ void init_state_kernel(FoldState s, const float *__restrict__ tors_nat)
@@ -632,7 +685,7 @@ struct trx_fold_batch {
     size_t arena_bytes = 0;
     int *d_aa = nullptr;
     Run *d_runs = nullptr;
-    size_t vdw_smem = 0;
+    size_t vdw_smem = 0, lb_smem = 0;
 };
 
 extern "C" {
@@ -696,6 +749,7 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     size_t o_X = carve((size_t)G * s.Lpad * NAT3 * LANES * 4), o_xn = carve(np * L * NAT3 * 4), o_gn = carve(np * L * NAT3 * 4);
     size_t o_gk = carve((size_t)G * s.Lpad * 9 * LANES * 4), o_E3 = carve(np * 8 * 3), o_Ev = carve(np * 8);
     size_t o_ga = carve((size_t)G * 4), o_na = carve(256);
+    size_t o_perm = carve(np * 4), o_gs = carve((size_t)G * 4), o_ns = carve(256), o_ws = carve(np * 4 * TRX_NTERM);
     cudaError_t e = cudaMalloc(&b->arena, off);
     if (e != cudaSuccess) {
         set_error("trx_fold_create: cudaMalloc(%zu bytes) failed: %s", off, cudaGetErrorString(e));
@@ -714,6 +768,9 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     s.terms = (double *)(A + o_terms); s.ft = (double *)(A + o_ft); s.wl = (float *)(A + o_wl);
     s.X = (float *)(A + o_X); s.xnat = (float *)(A + o_xn); s.gnat = (float *)(A + o_gn); s.gk1 = (float *)(A + o_gk);
     s.E3 = (double *)(A + o_E3); s.Evdw = (double *)(A + o_Ev); s.gactive = (int *)(A + o_ga); s.nactive = (int *)(A + o_na);
+    s.perm = (int *)(A + o_perm); s.gslot = (int *)(A + o_gs); s.nslot = (int *)(A + o_ns); s.wslot = (float *)(A + o_ws);
+    s.ntab = ntab;
+    for (int t = 0; t < ntab; ++t) { s.tab_d0[t] = b->tab_g0[t] * LANES; s.tab_n[t] = ndecoys[t]; }
     TRX_CUDA(cudaMalloc(&b->d_aa, L * sizeof(int)));
     TRX_CUDA(cudaMemcpy(b->d_aa, aa, L * sizeof(int), cudaMemcpyHostToDevice));
     std::vector<Run> hr(nruns);
@@ -728,23 +785,30 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     s.runs = b->d_runs;
     upload_model();
     TRX_CUDA(cudaFuncSetAttribute(vdw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->vdw_smem));
+    b->lb_smem = (size_t)s.ndof * LANES * sizeof(float);
+    if (b->lb_smem > 200 * 1024) b->lb_smem = 0;
+    s.lb_smem_d = b->lb_smem ? 1 : 0;
+    if (b->lb_smem) TRX_CUDA(cudaFuncSetAttribute(lbfgs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->lb_smem));
     *out = b;
     return TRX_OK;
 }
 
 // One evaluation of the current trial points (xt) of every unfinished decoy:
 // coordinates, restraint terms, vdw, torsion gradient.  Fills ft, gt, terms.
-static int fold_eval(trx_fold_batch *b, bool force_all = false)
+static int fold_eval(trx_fold_batch *b, const int *ng_tab, bool identity)
 {
     trx_ctx *ctx = b->ctx;
-    FoldState s = b->s;
-    s.force_all = force_all ? 1 : 0;
+    FoldState &s = b->s;
+    ctx->time_begin("compact");
+    compact_kernel<<<s.ntab, 1024, 0, ctx->stream>>>(s, identity ? 1 : 0);
+    ctx->time_end("compact");
     ctx->time_begin("nerf");
     nerf_kernel<<<s.G, 32, 0, ctx->stream>>>(s);
     ctx->time_end("nerf");
     for (size_t t = 0; t < b->tabs.size(); ++t) {
-        int rc = k1_launch<float>(ctx, b->tabs[t], s.G, b->tab_g0[t], b->tab_ng[t], s.X, NAT3, s.wl, nullptr,
-                                  force_all ? nullptr : s.gactive, s.E3, s.gk1);
+        const int ng = ng_tab ? std::min(ng_tab[t], b->tab_ng[t]) : b->tab_ng[t];
+        if (ng <= 0) continue;
+        int rc = k1_launch<float>(ctx, b->tabs[t], s.G, b->tab_g0[t], ng, s.X, NAT3, s.wslot, nullptr, s.gslot, s.E3, s.gk1);
         if (rc) return rc;
     }
     ctx->time_begin("centroid");
@@ -782,8 +846,9 @@ int trx_fold_run(trx_fold_batch *b, float *tors, float *xyz, double *terms, long
     init_state_kernel<<<s.G, 32, 0, ctx->stream>>>(s, (const float *)d_tors);
     ctx->time_end("fold_init");
     int rounds = 0, active = s.N;
-    int *h_active = nullptr;
-    TRX_CUDA(cudaMallocHost(&h_active, sizeof(int)));
+    int *h_nslot = nullptr;
+    TRX_CUDA(cudaMallocHost(&h_nslot, 16 * sizeof(int)));
+    std::vector<int> ng(b->tab_ng);   // live slot groups per table block: an upper bound between polls
     dim3 ablk(32, 8), agrd((s.G + 7) / 8);
     while (active > 0 && rounds < max_rounds) {
         for (int k = 0; k < check_every && rounds < max_rounds; ++k, ++rounds) {
@@ -791,21 +856,22 @@ int trx_fold_run(trx_fold_batch *b, float *tors, float *xyz, double *terms, long
             ctx->time_begin("activity");
             activity_kernel<<<agrd, ablk, 0, ctx->stream>>>(s);
             ctx->time_end("activity");
-            if ((rc = fold_eval(b))) { cudaFreeHost(h_active); return rc; }
+            if ((rc = fold_eval(b, ng.data(), false))) { cudaFreeHost(h_nslot); return rc; }
             ctx->time_begin("lbfgs");
-            lbfgs_kernel<<<s.G, LB_THREADS, 0, ctx->stream>>>(s);
+            lbfgs_kernel<<<s.G, LB_THREADS, b->lb_smem, ctx->stream>>>(s);
             ctx->time_end("lbfgs");
         }
-        TRX_CUDA(cudaMemcpyAsync(h_active, s.nactive, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        TRX_CUDA(cudaMemcpyAsync(h_nslot, s.nslot, 16 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         TRX_CUDA(cudaStreamSynchronize(ctx->stream));
-        active = *h_active;   // count at the start of the last round; finished decoys are masked anyway
+        active = 0;   // counts at the start of the last round; they only ever decrease
+        for (int t = 0; t < s.ntab; ++t) { active += h_nslot[t]; ng[t] = num_groups(h_nslot[t]); }
     }
-    cudaFreeHost(h_active);
+    cudaFreeHost(h_nslot);
     // final coordinates / terms at the accepted point x: one more evaluation with xt = x for everyone
     ctx->time_begin("export");
     restore_kernel<<<s.G, 256, 0, ctx->stream>>>(s);
     ctx->time_end("export");
-    if ((rc = fold_eval(b, true))) return rc;
+    if ((rc = fold_eval(b, nullptr, true))) return rc;
     ctx->time_begin("export");
     export_kernel<<<s.G, 32, 0, ctx->stream>>>(s, (float *)d_tors, (double *)d_terms, (long long *)d_stats);
     ctx->time_end("export");
@@ -837,11 +903,8 @@ int trx_fold_eval(trx_fold_batch *b, const float *tors, const double w[6], doubl
     std::vector<float> wl((size_t)TRX_NTERM * s.Npad);
     for (int k = 0; k < TRX_NTERM; ++k) for (int n = 0; n < s.Npad; ++n) wl[(size_t)k * s.Npad + n] = (float)w[k];
     TRX_CUDA(cudaMemcpyAsync(s.wl, wl.data(), wl.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    TRX_CUDA(cudaMemsetAsync(s.nactive, 0, sizeof(int), ctx->stream));
-    dim3 ablk(32, 8), agrd((s.G + 7) / 8);
-    activity_kernel<<<agrd, ablk, 0, ctx->stream>>>(s);
-    ctx->launches += 2;
-    if ((rc = fold_eval(b, true))) return rc;
+    ctx->launches += 1;
+    if ((rc = fold_eval(b, nullptr, true))) return rc;
     std::vector<double> ft(s.Npad), tr((size_t)TRX_NTERM * s.Npad);
     std::vector<float> gt((size_t)s.G * s.ndof * LANES);
     TRX_CUDA(cudaMemcpyAsync(ft.data(), s.ft, ft.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));

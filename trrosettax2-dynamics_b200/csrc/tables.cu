@@ -75,14 +75,15 @@ using namespace trx;
 
 int trx_tables::get_plan(int groups, Plan **out)
 {
-    auto it = plans.find(groups);
-    if (it != plans.end()) { *out = &it->second; return TRX_OK; }
-    Plan p;
-    p.groups = groups;
-    // chunk tiles of one block row so that the grid has a few waves of CTAs
+    // chunk tiles of one block row so that the grid has a few waves of CTAs; plans are
+    // cached by chunk size (the only thing the group count changes)
     const long long want_ctas = 148LL * 3 * 4;
     long long chunk = std::max(1LL, (long long)ntiles * groups / want_ctas);
     chunk = std::min<long long>(chunk, std::max(1, nb));
+    auto it = plans.find((int)chunk);
+    if (it != plans.end()) { *out = &it->second; return TRX_OK; }
+    Plan p;
+    p.groups = groups;
     std::vector<int> work;               // I, first tile, count, row record
     std::vector<std::vector<int>> blk(nb);
     int nrec = 0;
@@ -119,8 +120,8 @@ int trx_tables::get_plan(int groups, Plan **out)
     TRX_CUDA(cudaMemcpy(p.d_work, sorted.data(), sorted.size() * sizeof(int), cudaMemcpyHostToDevice));
     TRX_CUDA(cudaMemcpy(p.d_blk_ptr, ptr.data(), ptr.size() * sizeof(int), cudaMemcpyHostToDevice));
     TRX_CUDA(cudaMemcpy(p.d_blk_rec, recs.data(), recs.size() * sizeof(int), cudaMemcpyHostToDevice));
-    plans[groups] = p;
-    *out = &plans[groups];
+    plans[(int)chunk] = p;
+    *out = &plans[(int)chunk];
     return TRX_OK;
 }
 
