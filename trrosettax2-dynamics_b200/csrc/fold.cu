@@ -92,11 +92,20 @@ __device__ __forceinline__ f3 place(f3 a, f3 b, f3 c, float bond, float ca, floa
     return c + (-bond * ca) * bc + (bond * sa * ct) * m + (bond * sa * st) * n;
 }
 
-// K2: one thread per decoy (lane = decoy): torsions xt[g][L*3][32] -> X[g][Lpad][15][32] and
-// the natural-layout copy xnat[n][L][15] the vdw kernel stages into shared memory.
-__global__ void __launch_bounds__(32) nerf_kernel(FoldState s)
+// K2: NeRF.  One CTA per slot group (lane = decoy), SEG_WARPS warps: warp w builds the chain
+// segment [w*Lseg, (w+1)*Lseg) in its own local frame (first residue in canonical position),
+// plus the first residue of the next segment, whose N/CA/C define the rigid transform from the
+// next segment's frame to this one.  After one barrier every warp composes the transforms of
+// the segments before it and maps its residues to the global frame: a two-level prefix over
+// rigid motions instead of a 3L-long dependent chain.
+// xt[g][L*3][32] -> X[g][Lpad][15][32] and the natural-layout copy xnat[slot][L][15].
+constexpr int SEG_WARPS = 16;
+constexpr int SEG_THREADS = SEG_WARPS * 32;
+
+__global__ void __launch_bounds__(SEG_THREADS) nerf_kernel(FoldState s)
 {
-    const int g = blockIdx.x, lane = threadIdx.x, n = g * LANES + lane;   // n = slot
+    __shared__ float frame[SEG_WARPS][12][LANES];
+    const int g = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = g * LANES + lane;   // n = slot
     if (!s.gslot[g]) return;
     const int dec = s.perm[n];
     const bool live = dec >= 0;
@@ -104,40 +113,87 @@ __global__ void __launch_bounds__(32) nerf_kernel(FoldState s)
     const float *__restrict__ t = s.xt + (size_t)(dn / LANES) * s.ndof * LANES + dn % LANES;
     float *__restrict__ X = s.X + (size_t)g * s.Lpad * NAT3 * LANES + lane;
     float *__restrict__ xn = s.xnat + (size_t)n * s.L * NAT3;
+    if (warp == 0) {
 #pragma unroll
-    for (int k = 0; k < TRX_NTERM; ++k) s.wslot[(size_t)k * s.Npad + n] = live ? s.wl[(size_t)k * s.Npad + dec] : 0.f;
+        for (int k = 0; k < TRX_NTERM; ++k) s.wslot[(size_t)k * s.Npad + n] = live ? s.wl[(size_t)k * s.Npad + dec] : 0.f;
+    }
     const float caNCAC = cosf((float)TRX_A_N_CA_C), saNCAC = sinf((float)TRX_A_N_CA_C);
     const float caCACN = cosf((float)TRX_A_CA_C_N), saCACN = sinf((float)TRX_A_CA_C_N);
     const float caCNCA = cosf((float)TRX_A_C_N_CA), saCNCA = sinf((float)TRX_A_C_N_CA);
     const float caCACO = cosf((float)TRX_A_CA_C_O), saCACO = sinf((float)TRX_A_CA_C_O);
-    f3 N = {0.f, 0.f, 0.f}, CA = {(float)TRX_B_N_CA, 0.f, 0.f};
-    f3 C = {(float)TRX_B_N_CA - (float)TRX_B_CA_C * caNCAC, (float)TRX_B_CA_C * saNCAC, 0.f};
-    float psi_prev = 0.f, omg_prev = 0.f;
-    for (int i = 0; i < s.L; ++i) {
-        const float phi = t[(i * 3 + 0) * LANES], psi = t[(i * 3 + 1) * LANES], omg = t[(i * 3 + 2) * LANES];
-        if (i > 0) {
+    const int L = s.L, Lseg = (L + SEG_WARPS - 1) / SEG_WARPS;
+    const int r0 = warp * Lseg, r1 = min(L, r0 + Lseg);
+    if (r0 < L) {
+        f3 N = {0.f, 0.f, 0.f}, CA = {(float)TRX_B_N_CA, 0.f, 0.f};
+        f3 C = {(float)TRX_B_N_CA - (float)TRX_B_CA_C * caNCAC, (float)TRX_B_CA_C * saNCAC, 0.f};
+        for (int i = r0; i <= r1 && i < L; ++i) {
+            if (i > r0) {
+                const float psi_p = t[((i - 1) * 3 + 1) * LANES], omg_p = t[((i - 1) * 3 + 2) * LANES], phi = t[(i * 3 + 0) * LANES];
+                float sn, cs;
+                sincosf(psi_p, &sn, &cs);
+                f3 Nn = place(N, CA, C, (float)TRX_B_C_N, caCACN, saCACN, cs, sn);
+                sincosf(omg_p, &sn, &cs);
+                f3 CAn = place(CA, C, Nn, (float)TRX_B_N_CA, caCNCA, saCNCA, cs, sn);
+                sincosf(phi, &sn, &cs);
+                f3 Cn = place(C, Nn, CAn, (float)TRX_B_CA_C, caNCAC, saNCAC, cs, sn);
+                N = Nn; CA = CAn; C = Cn;
+            }
+            if (i == r1) {   // first residue of the next segment: its frame in this segment's coordinates
+                const f3 e1 = unit(CA - N), ez = unit(cross(e1, C - N)), e2 = cross(ez, e1);
+                float *fr = &frame[warp + 1][0][lane];
+                fr[0 * LANES] = e1.x; fr[1 * LANES] = e2.x; fr[2 * LANES] = ez.x;
+                fr[3 * LANES] = e1.y; fr[4 * LANES] = e2.y; fr[5 * LANES] = ez.y;
+                fr[6 * LANES] = e1.z; fr[7 * LANES] = e2.z; fr[8 * LANES] = ez.z;
+                fr[9 * LANES] = N.x; fr[10 * LANES] = N.y; fr[11 * LANES] = N.z;
+                break;
+            }
+            const float psi = t[(i * 3 + 1) * LANES];
             float sn, cs;
-            sincosf(psi_prev, &sn, &cs);
-            f3 Nn = place(N, CA, C, (float)TRX_B_C_N, caCACN, saCACN, cs, sn);
-            sincosf(omg_prev, &sn, &cs);
-            f3 CAn = place(CA, C, Nn, (float)TRX_B_N_CA, caCNCA, saCNCA, cs, sn);
-            sincosf(phi, &sn, &cs);
-            f3 Cn = place(C, Nn, CAn, (float)TRX_B_CA_C, caNCAC, saNCAC, cs, sn);
-            N = Nn; CA = CAn; C = Cn;
+            sincosf(psi, &sn, &cs);
+            f3 O = place(N, CA, C, (float)TRX_B_C_O, caCACO, saCACO, -cs, -sn);   // torsion psi + pi
+            f3 b = CA - N, c = C - CA, a = cross(b, c);
+            f3 CB = (float)TRX_CB_A * a + (float)TRX_CB_B * b + (float)TRX_CB_C * c + CA;
+            const float v[NAT3] = {N.x, N.y, N.z, CA.x, CA.y, CA.z, CB.x, CB.y, CB.z, C.x, C.y, C.z, O.x, O.y, O.z};
+#pragma unroll
+            for (int k = 0; k < NAT3; ++k) X[((size_t)i * NAT3 + k) * LANES] = v[k];
         }
-        float sn, cs;
-        sincosf(psi, &sn, &cs);
-        f3 O = place(N, CA, C, (float)TRX_B_C_O, caCACO, saCACO, -cs, -sn);   // torsion psi + pi
-        f3 b = CA - N, c = C - CA, a = cross(b, c);
-        f3 CB = (float)TRX_CB_A * a + (float)TRX_CB_B * b + (float)TRX_CB_C * c + CA;
-        const float v[NAT3] = {N.x, N.y, N.z, CA.x, CA.y, CA.z, CB.x, CB.y, CB.z, C.x, C.y, C.z, O.x, O.y, O.z};
+    }
+    __syncthreads();
+    if (r0 >= L) return;
+    // global frame of this segment: A_1 o A_2 o ... o A_warp
+    float R[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f}, T[3] = {0.f, 0.f, 0.f};
+    for (int j = 1; j <= warp; ++j) {
+        float A[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) A[k] = frame[j][k][lane];
+        float Rn[9], Tn[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) Rn[r * 3 + c] = R[r * 3 + 0] * A[0 * 3 + c] + R[r * 3 + 1] * A[1 * 3 + c] + R[r * 3 + 2] * A[2 * 3 + c];
+            Tn[r] = R[r * 3 + 0] * A[9] + R[r * 3 + 1] * A[10] + R[r * 3 + 2] * A[11] + T[r];
+        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) R[k] = Rn[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) T[k] = Tn[k];
+    }
+    for (int i = r0; i < r1; ++i) {
+        float v[NAT3];
+#pragma unroll
+        for (int k = 0; k < NAT3; ++k) v[k] = X[((size_t)i * NAT3 + k) * LANES];
+#pragma unroll
+        for (int a = 0; a < TRX_NAT; ++a) {
+            const float x = v[a * 3], y = v[a * 3 + 1], z = v[a * 3 + 2];
+            v[a * 3 + 0] = R[0] * x + R[1] * y + R[2] * z + T[0];
+            v[a * 3 + 1] = R[3] * x + R[4] * y + R[5] * z + T[1];
+            v[a * 3 + 2] = R[6] * x + R[7] * y + R[8] * z + T[2];
+        }
 #pragma unroll
         for (int k = 0; k < NAT3; ++k) {
-            X[((size_t)i * NAT3 + k) * LANES] = v[k];
+            if (warp > 0) X[((size_t)i * NAT3 + k) * LANES] = v[k];
             if (live) xn[(size_t)i * NAT3 + k] = v[k];
         }
-        psi_prev = psi;
-        omg_prev = omg;
     }
 }
 
@@ -259,35 +315,42 @@ __global__ void __launch_bounds__(VDW_THREADS) vdw_kernel(FoldState s)
     }
 }
 
-// K3: reverse mode.  One thread per decoy walks the chain backwards accumulating
-// F1 = sum x_a x g_a and F2 = sum g_a over the atoms a torsion moves (a suffix of the atom
-// sequence N,CA,CB,C,O), dE/dtorsion = u.(F1 - p x F2); adds the Ramachandran and omega
-// terms (functions of the torsions alone) and produces the weighted total.
-__global__ void __launch_bounds__(32) torsion_grad_kernel(FoldState s)
+// K3: reverse mode.  dE/dtorsion = u.(F1 - p x F2) with F1 = sum x_a x g_a, F2 = sum g_a over
+// the atoms the torsion moves (a suffix of the atom sequence N,CA,CB,C,O).  One CTA per slot
+// group (lane = decoy), SEG_WARPS warps: each warp walks its chain segment backwards with
+// segment-local sums, the segment totals are exchanged through shared memory, and a second,
+// dependency-free sweep adds the contribution of everything downstream of the segment.
+// Also adds the Ramachandran and omega terms (functions of the torsions alone) and the total.
+__global__ void __launch_bounds__(SEG_THREADS) torsion_grad_kernel(FoldState s)
 {
-    const int g = blockIdx.x, lane = threadIdx.x, n = g * LANES + lane;   // n = slot
+    __shared__ float tot[SEG_WARPS][6][LANES];
+    __shared__ double esum[SEG_WARPS][2][LANES];
+    const int g = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = g * LANES + lane;   // n = slot
     if (!s.gslot[g]) return;
     const int dec = s.perm[n];
-    if (dec < 0) return;
+    const bool live = dec >= 0;
+    const int dn = live ? dec : 0;
     const int L = s.L, Npad = s.Npad;
     const float *__restrict__ X = s.X + (size_t)g * s.Lpad * NAT3 * LANES + lane;
     const float *__restrict__ G1 = s.gk1 + (size_t)g * s.Lpad * 9 * LANES + lane;
     const float *__restrict__ gn = s.gnat + (size_t)n * L * NAT3;
-    const size_t dvb = (size_t)(dec / LANES) * s.ndof * LANES + dec % LANES;
+    const size_t dvb = (size_t)(dn / LANES) * s.ndof * LANES + dn % LANES;
     const float *__restrict__ t = s.xt + dvb;
     float *__restrict__ gt = s.gt + dvb;
     const float w_rama = s.wslot[(size_t)TRX_T_RAMA * Npad + n], w_omega = s.wslot[(size_t)TRX_T_OMEGA * Npad + n];
+    const int Lseg = (L + SEG_WARPS - 1) / SEG_WARPS;
+    const int r0 = warp * Lseg, r1 = min(L, r0 + Lseg);
     f3 F1 = {0.f, 0.f, 0.f}, F2 = {0.f, 0.f, 0.f};
     double e_rama = 0.0, e_omega = 0.0;
     auto load = [&](int i, int a) -> f3 { return {X[((size_t)i * NAT3 + a * 3) * LANES], X[((size_t)i * NAT3 + a * 3 + 1) * LANES], X[((size_t)i * NAT3 + a * 3 + 2) * LANES]}; };
     auto add = [&](f3 x, f3 gr) { F1 = F1 + cross(x, gr); F2 = F2 + gr; };
-    auto dtor = [&](f3 p, f3 q) -> float { f3 u = unit(q - p); return dot(u, F1 - cross(p, F2)); };
-    for (int i = L - 1; i >= 0; --i) {
+    auto dtor = [&](f3 p, f3 q, f3 A1, f3 A2) -> float { f3 u = unit(q - p); return dot(u, A1 - cross(p, A2)); };
+    for (int i = r1 - 1; i >= r0; --i) {
         f3 xa[TRX_NAT], ga[TRX_NAT];
 #pragma unroll
         for (int a = 0; a < TRX_NAT; ++a) {
             xa[a] = load(i, a);
-            ga[a] = {gn[(size_t)i * NAT3 + a * 3], gn[(size_t)i * NAT3 + a * 3 + 1], gn[(size_t)i * NAT3 + a * 3 + 2]};
+            ga[a] = live ? f3{gn[(size_t)i * NAT3 + a * 3], gn[(size_t)i * NAT3 + a * 3 + 1], gn[(size_t)i * NAT3 + a * 3 + 2]} : f3{0.f, 0.f, 0.f};
         }
 #pragma unroll
         for (int a = 0; a < 3; ++a) {   // restraint gradient lives on N, CA, CB
@@ -295,26 +358,23 @@ __global__ void __launch_bounds__(32) torsion_grad_kernel(FoldState s)
             ga[a].y += G1[((size_t)i * 9 + a * 3 + 1) * LANES];
             ga[a].z += G1[((size_t)i * 9 + a * 3 + 2) * LANES];
         }
-        const float phi = t[(i * 3 + 0) * LANES], psi = t[(i * 3 + 1) * LANES], omg = t[(i * 3 + 2) * LANES];
+        const float phi = t[(i * 3 + 0) * LANES], psi = t[(i * 3 + 1) * LANES];
         float gphi = 0.f, gpsi = 0.f;
         add(xa[TRX_AT_O], ga[TRX_AT_O]);
-        gpsi = dtor(xa[TRX_AT_CA], xa[TRX_AT_C]);
+        gpsi = dtor(xa[TRX_AT_CA], xa[TRX_AT_C], F1, F2);
         add(xa[TRX_AT_C], ga[TRX_AT_C]);
         add(xa[TRX_AT_CB], ga[TRX_AT_CB]);
-        if (i > 0) gphi = dtor(xa[TRX_AT_N], xa[TRX_AT_CA]);
+        if (i > 0) gphi = dtor(xa[TRX_AT_N], xa[TRX_AT_CA], F1, F2);
         add(xa[TRX_AT_CA], ga[TRX_AT_CA]);
         if (i > 0) {
             f3 Cp = load(i - 1, TRX_AT_C);
-            const float go = dtor(Cp, xa[TRX_AT_N]);
-            // omega(i-1): add its tether term here
-            const float om = t[((i - 1) * 3 + 2) * LANES];
+            const float go = dtor(Cp, xa[TRX_AT_N], F1, F2);
+            const float om = t[((i - 1) * 3 + 2) * LANES];   // omega(i-1): its tether term lives here
             float dev = om - (float)TRX_PI;
             dev -= 2.0f * (float)TRX_PI * floorf((dev + (float)TRX_PI) / (2.0f * (float)TRX_PI));
             const float deg = dev * (float)(1.0 / TRX_DEG);
             e_omega += (double)((float)TRX_OMEGA_K * deg * deg);
-            float gom = go + w_omega * 2.0f * (float)TRX_OMEGA_K * deg * (float)(1.0 / TRX_DEG);
-            if (i - 1 == L - 1) gom = 0.f;
-            gt[((i - 1) * 3 + 2) * LANES] = gom;
+            if (live) gt[((i - 1) * 3 + 2) * LANES] = go + w_omega * 2.0f * (float)TRX_OMEGA_K * deg * (float)(1.0 / TRX_DEG);
         }
         add(xa[TRX_AT_N], ga[TRX_AT_N]);
         if (i > 0 && i < L - 1) {   // Ramachandran, termini skipped
@@ -336,33 +396,90 @@ __global__ void __launch_bounds__(32) torsion_grad_kernel(FoldState s)
             gphi -= w_rama * dPphi / P;
             gpsi -= w_rama * dPpsi / P;
         }
-        (void)omg;
-        gt[(i * 3 + 0) * LANES] = i == 0 ? 0.f : gphi;
-        gt[(i * 3 + 1) * LANES] = gpsi;
+        if (live) {
+            gt[(i * 3 + 0) * LANES] = i == 0 ? 0.f : gphi;
+            gt[(i * 3 + 1) * LANES] = gpsi;
+        }
     }
-    gt[((L - 1) * 3 + 2) * LANES] = 0.f;
-    double term[TRX_NTERM];
-    term[TRX_T_APC] = s.E3[0 * (size_t)Npad + n];
-    term[TRX_T_DIH] = s.E3[1 * (size_t)Npad + n];
-    term[TRX_T_ANG] = s.E3[2 * (size_t)Npad + n];
-    term[TRX_T_VDW] = s.Evdw[n];
-    term[TRX_T_RAMA] = e_rama;
-    term[TRX_T_OMEGA] = e_omega;
-    double tot = 0.0;
+    tot[warp][0][lane] = F1.x; tot[warp][1][lane] = F1.y; tot[warp][2][lane] = F1.z;
+    tot[warp][3][lane] = F2.x; tot[warp][4][lane] = F2.y; tot[warp][5][lane] = F2.z;
+    esum[warp][0][lane] = e_rama; esum[warp][1][lane] = e_omega;
+    __syncthreads();
+    // everything downstream of this segment
+    f3 D1 = {0.f, 0.f, 0.f}, D2 = {0.f, 0.f, 0.f};
+    for (int w2 = warp + 1; w2 < SEG_WARPS; ++w2) {
+        D1 = D1 + f3{tot[w2][0][lane], tot[w2][1][lane], tot[w2][2][lane]};
+        D2 = D2 + f3{tot[w2][3][lane], tot[w2][4][lane], tot[w2][5][lane]};
+    }
+    if (live && r1 < L) {
+        for (int i = r0; i < r1; ++i) {
+            const f3 N = load(i, TRX_AT_N), CA = load(i, TRX_AT_CA), C = load(i, TRX_AT_C);
+            gt[(i * 3 + 1) * LANES] += dtor(CA, C, D1, D2);
+            if (i > 0) {
+                gt[(i * 3 + 0) * LANES] += dtor(N, CA, D1, D2);
+                gt[((i - 1) * 3 + 2) * LANES] += dtor(load(i - 1, TRX_AT_C), N, D1, D2);
+            }
+        }
+    }
+    if (warp == 0 && live) {
+        gt[((L - 1) * 3 + 2) * LANES] = 0.f;
+        double er = 0.0, eo = 0.0;
+        for (int w2 = 0; w2 < SEG_WARPS; ++w2) { er += esum[w2][0][lane]; eo += esum[w2][1][lane]; }
+        double term[TRX_NTERM];
+        term[TRX_T_APC] = s.E3[0 * (size_t)Npad + n];
+        term[TRX_T_DIH] = s.E3[1 * (size_t)Npad + n];
+        term[TRX_T_ANG] = s.E3[2 * (size_t)Npad + n];
+        term[TRX_T_VDW] = s.Evdw[n];
+        term[TRX_T_RAMA] = er;
+        term[TRX_T_OMEGA] = eo;
+        double total = 0.0;
 #pragma unroll
-    for (int k = 0; k < TRX_NTERM; ++k) {
-        s.terms[(size_t)k * Npad + dec] = term[k];
-        tot += (double)s.wslot[(size_t)k * Npad + n] * term[k];
+        for (int k = 0; k < TRX_NTERM; ++k) {
+            s.terms[(size_t)k * Npad + dec] = term[k];
+            total += (double)s.wslot[(size_t)k * Npad + n] * term[k];
+        }
+        s.ft[dec] = total;
     }
-    s.ft[dec] = tot;
 }
 
 // K5: one CTA per decoy group; 8 warps split the torsion vector, lanes are decoys.
 // Consumes the evaluation of the trial point (ft, gt) and produces the next trial point.
-constexpr int LB_WARPS = 8;
+constexpr int LB_WARPS = 32;
 constexpr int LB_THREADS = LB_WARPS * 32;
 constexpr float LS_SIGMA = 0.1f;
 constexpr int LS_MAXBACK = 20;
+
+constexpr int LB_U = 8;   // loads kept in flight per thread and vector in the streaming loops
+
+// sum_k A[k]*B[k] over [k0,k1), element stride LANES; loads issued LB_U at a time
+__device__ __forceinline__ float lb_dot(const float *__restrict__ A, const float *B, int k0, int k1)
+{
+    float acc = 0.f;
+    for (int k = k0; k < k1; k += LB_U) {
+        float a[LB_U], b[LB_U];
+#pragma unroll
+        for (int u = 0; u < LB_U; ++u) {
+            const int kk = min(k + u, k1 - 1);
+            a[u] = A[(size_t)kk * LANES];
+            b[u] = B[(size_t)kk * LANES];
+        }
+#pragma unroll
+        for (int u = 0; u < LB_U; ++u) if (k + u < k1) acc += a[u] * b[u];
+    }
+    return acc;
+}
+
+// D[k] += c * A[k] over [k0,k1)
+__device__ __forceinline__ void lb_axpy(float *D, float c, const float *__restrict__ A, int k0, int k1)
+{
+    for (int k = k0; k < k1; k += LB_U) {
+        float a[LB_U];
+#pragma unroll
+        for (int u = 0; u < LB_U; ++u) a[u] = A[(size_t)min(k + u, k1 - 1) * LANES];
+#pragma unroll
+        for (int u = 0; u < LB_U; ++u) if (k + u < k1) D[(size_t)(k + u) * LANES] += c * a[u];
+    }
+}
 
 __device__ __forceinline__ float cta_sum(float v, float (*red)[LB_WARPS][LANES], int &buf, int warp, int lane)
 {
@@ -514,19 +631,19 @@ __global__ void __launch_bounds__(LB_THREADS) lbfgs_kernel(FoldState s)
         const bool on = need_dir && q < hist;
         const int h = (head - 1 - q + 2 * m) % m;
         float a = 0.f;
-        if (on) for (int k = k0; k < k1; ++k) a += S[((size_t)h * nd + k) * LANES] * d[k * LANES];
+        if (on) a = lb_dot(S + (size_t)h * nd * LANES, d, k0, k1);
         a = cta_sum(a, red, buf, warp, lane);
         if (on) {
             a *= rho[h * LANES];
             if (warp == 0) alpha_h[q][lane] = a;
-            for (int k = k0; k < k1; ++k) d[k * LANES] -= a * Y[((size_t)h * nd + k) * LANES];
+            lb_axpy(d, -a, Y + (size_t)h * nd * LANES, k0, k1);
         }
     }
     {
         const bool on = need_dir && hist > 0;
         const int h0 = (head - 1 + m) % m;
         float y2 = 0.f;
-        if (on) for (int k = k0; k < k1; ++k) { const float v = Y[((size_t)h0 * nd + k) * LANES]; y2 += v * v; }
+        if (on) y2 = lb_dot(Y + (size_t)h0 * nd * LANES, Y + (size_t)h0 * nd * LANES, k0, k1);
         y2 = cta_sum(y2, red, buf, warp, lane);
         if (on) {
             const float gamma = 1.0f / (rho[h0 * LANES] * y2);
@@ -537,11 +654,11 @@ __global__ void __launch_bounds__(LB_THREADS) lbfgs_kernel(FoldState s)
         const bool on = need_dir && q < hist;
         const int h = (head - 1 - q + 2 * m) % m;
         float b = 0.f;
-        if (on) for (int k = k0; k < k1; ++k) b += Y[((size_t)h * nd + k) * LANES] * d[k * LANES];
+        if (on) b = lb_dot(Y + (size_t)h * nd * LANES, d, k0, k1);
         b = cta_sum(b, red, buf, warp, lane);
         if (on) {
             const float c = alpha_h[q][lane] - rho[h * LANES] * b;
-            for (int k = k0; k < k1; ++k) d[k * LANES] += c * S[((size_t)h * nd + k) * LANES];
+            lb_axpy(d, c, S + (size_t)h * nd * LANES, k0, k1);
         }
     }
     float sl = 0.f;
@@ -803,7 +920,7 @@ static int fold_eval(trx_fold_batch *b, const int *ng_tab, bool identity)
     compact_kernel<<<s.ntab, 1024, 0, ctx->stream>>>(s, identity ? 1 : 0);
     ctx->time_end("compact");
     ctx->time_begin("nerf");
-    nerf_kernel<<<s.G, 32, 0, ctx->stream>>>(s);
+    nerf_kernel<<<s.G, SEG_THREADS, 0, ctx->stream>>>(s);
     ctx->time_end("nerf");
     for (size_t t = 0; t < b->tabs.size(); ++t) {
         const int ng = ng_tab ? std::min(ng_tab[t], b->tab_ng[t]) : b->tab_ng[t];
@@ -815,7 +932,7 @@ static int fold_eval(trx_fold_batch *b, const int *ng_tab, bool identity)
     vdw_kernel<<<s.N, VDW_THREADS, b->vdw_smem, ctx->stream>>>(s);
     ctx->time_end("centroid");
     ctx->time_begin("torsion_grad");
-    torsion_grad_kernel<<<s.G, 32, 0, ctx->stream>>>(s);
+    torsion_grad_kernel<<<s.G, SEG_THREADS, 0, ctx->stream>>>(s);
     ctx->time_end("torsion_grad");
     TRX_CUDA(cudaGetLastError());
     return TRX_OK;
