@@ -112,3 +112,34 @@ def test_fold_example_quality_and_reproducibility(ctx, example):
     np.testing.assert_array_equal(alone["tors"], out["tors"][32:])
     batch.close()
     tb.close()
+
+
+def test_folding_cli_drop_in(tmp_path, golden_dir, example):
+    """The exact command utils_trX2dy/utils.py:491-498 builds (+ seed), and the batched form."""
+    import os, subprocess, sys
+    from trx2dyn import pdbio
+    seq, _, nat = example
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "initial0.pdb"
+    cmd = [sys.executable, "./folding/folding.py", "-NPZ", f"{golden_dir}/example_NMR.npz", "-FASTA",
+           f"{golden_dir}/example_seq.fasta", "-OUT", str(out), "-m", "2", "--orient", "-r", "no-idp", "--seed", "4"]
+    r = subprocess.run(cmd, cwd=root, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "*** time:" in r.stdout
+    s2, at = pdbio.read_backbone(str(out))
+    assert s2 == seq and len(s2) == 90
+    gly = np.array([c == "G" for c in seq])
+    assert np.isnan(at["CB"][gly]).all() and not np.isnan(at["CB"][~gly]).any()
+    pep = np.linalg.norm(at["N"][1:] - at["C"][:-1], axis=1)
+    assert np.allclose(pep, 1.329, atol=0.01)                     # bonded peptide C-N for PPBuilder
+    tm = max(metrics.tm_score(at["CA"], nat["apo"]), metrics.tm_score(at["CA"], nat["holo"]))
+    assert tm > 0.3
+    # batched: 8 decoys in one launch, staged mode 0, distance-only
+    pat = tmp_path / "b" / "initial{i}.pdb"
+    cmd = [sys.executable, "./folding/folding.py", "-NPZ", f"{golden_dir}/example_Xray.npz", "-FASTA",
+           f"{golden_dir}/example_seq.fasta", "-OUT", str(pat), "-m", "0", "--no-orient", "-r", "no-idp",
+           "--ndecoy", "8", "--start-id", "3", "--seed", "1", "--no-fastrelax"]
+    r = subprocess.run(cmd, cwd=root, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    files = sorted(os.listdir(tmp_path / "b"))
+    assert files == ["initial%d.pdb" % i for i in (10, 3, 4, 5, 6, 7, 8, 9)]
