@@ -66,16 +66,23 @@ struct trx_ctx {
 
 namespace trx {
 
+// One spline interval: S(x) = c0 + c1 u + c2 u^2 + c3 u^3 with u = x - x_k (16 B in fp32).
+template <typename T>
+struct alignas(4 * sizeof(T)) Coef {
+    T c0, c1, c2, c3;
+};
+
 // Spline knot geometry of one restraint type, as the kernel keeps it in shared memory.
 template <typename T>
 struct KnotGeom {
     T x[MAXK];      // knot abscissae
-    T rh[MAXK];     // 1/(x[k+1]-x[k])
-    T h2_6[MAXK];   // (x[k+1]-x[k])^2/6
-    T h_6[MAXK];    // (x[k+1]-x[k])/6
+    T rh[MAXK];     // 1/(x[k+1]-x[k])           (kept for reference/debug)
+    T h2_6[MAXK];
+    T h_6[MAXK];
     T gx0, ginv;    // interval guess: k = floor((x-gx0)*ginv)+goff
     int goff;
     int K;
+    int urun0, urun1;   // intervals [urun0, urun1) are (nearly) uniformly spaced
 };
 
 // Work decomposition of the restraint kernel for a given number of decoy groups.
@@ -95,8 +102,9 @@ struct trx_tables {
     int L = 0, Lpad = 0, nb = 0;
     int n[4] = {0, 0, 0, 0};
     int K[4] = {0, 0, 0, 0};
-    double *d_tab64[4] = {nullptr, nullptr, nullptr, nullptr};  // [n][K] (y, y2) double2
-    float *d_tab32[4] = {nullptr, nullptr, nullptr, nullptr};   // [n][K] (y, y2) float2
+    double *d_tab64[4] = {nullptr, nullptr, nullptr, nullptr};  // [n][K] Coef<double>
+    float *d_tab32[4] = {nullptr, nullptr, nullptr, nullptr};   // [n][K] Coef<float>
+    double *d_y2[4] = {nullptr, nullptr, nullptr, nullptr};     // [n][K] fitted second derivatives (parity tests)
     trx::KnotGeom<double> *d_geom64 = nullptr;                  // [4]
     trx::KnotGeom<float> *d_geom32 = nullptr;                   // [4]
     int ntiles = 0;

@@ -20,20 +20,12 @@
 
 namespace trx {
 
-template <typename T> struct Vec2;
-template <> struct Vec2<double> { using type = double2; };
-template <> struct Vec2<float> { using type = float2; };
-
 __device__ __forceinline__ float t_rsqrt(float x) { return rsqrtf(x); }
 __device__ __forceinline__ double t_rsqrt(double x) { return 1.0 / sqrt(x); }
-__device__ __forceinline__ float t_rcp(float x) { return __frcp_rn(x); }
+__device__ __forceinline__ float t_rcp(float x) { return __fdividef(1.0f, x); }
 __device__ __forceinline__ double t_rcp(double x) { return 1.0 / x; }
-__device__ __forceinline__ float t_sqrt(float x) { return sqrtf(x); }
-__device__ __forceinline__ double t_sqrt(double x) { return sqrt(x); }
 __device__ __forceinline__ float t_atan2(float y, float x) { return atan2f(y, x); }
 __device__ __forceinline__ double t_atan2(double y, double x) { return atan2(y, x); }
-__device__ __forceinline__ float t_acos(float x) { return acosf(x); }
-__device__ __forceinline__ double t_acos(double x) { return acos(x); }
 __device__ __forceinline__ float t_floor(float x) { return floorf(x); }
 __device__ __forceinline__ double t_floor(double x) { return floor(x); }
 template <typename T> __device__ __forceinline__ T t_tiny();
@@ -42,8 +34,8 @@ template <> __device__ __forceinline__ double t_tiny<double>() { return 1e-24; }
 
 template <typename T>
 struct K1Params {
-    const T *X;                                  // [G][Lpad][9][32]
-    const typename Vec2<T>::type *tab[4];        // [n][K] (y, y'')
+    const T *X;                                  // [G][Lpad][xstride][32]
+    const Coef<T> *tab[4];                       // [n][K] cubic per interval (+ flat tail entry)
     const KnotGeom<T> *geom;                     // [4]
     const int *pairrec;                          // [ntiles][16][16][8]
     const int *tileJ;                            // [ntiles]
@@ -59,26 +51,30 @@ struct K1Params {
     T w0, w1, w2;
 };
 
-// Rosetta SplineFunc (weight 1): cubic inside [x_0, x_{K-1}], flat outside.
-// NR splint on the interval found from a uniform-grid guess corrected against the
-// true knots (the reference's %.3f rounding makes the angular grids slightly uneven).
+// Rosetta SplineFunc (weight 1): the clamped cubic spline inside [x_0, x_{K-1}], flat outside.
+// Each interval is stored as a cubic in (x - x_k) -- algebraically the NR splint expression --
+// and the flat tail beyond the last knot as one more "interval", so the common case is
+// branch-free: interval index from the uniform part of the grid, one 16 B load, Horner.
+// fp64 (parity mode) always corrects the index against the true knots (the reference's %.3f
+// rounding makes the angular grids uneven at the 5e-4 level); fp32 only below the uniform run.
 template <typename T>
-__device__ __forceinline__ void spline_eval(const KnotGeom<T> &kn, const typename Vec2<T>::type *__restrict__ tab,
-                                            T x, T &f, T &df)
+__device__ __forceinline__ void spline_eval(const KnotGeom<T> &kn, const Coef<T> *__restrict__ tab, T x, T &f, T &df)
 {
     const int K = kn.K;
-    if (x < kn.x[0]) { f = tab[0].x; df = (T)0; return; }
-    if (x > kn.x[K - 1]) { f = tab[K - 1].x; df = (T)0; return; }
     int k = (int)t_floor((x - kn.gx0) * kn.ginv) + kn.goff;
-    k = min(max(k, 0), K - 2);
-    while (k > 0 && x < kn.x[k]) --k;
-    while (k < K - 2 && x >= kn.x[k + 1]) ++k;
-    const typename Vec2<T>::type lo = tab[k], hi = tab[k + 1];
-    const T rh = kn.rh[k];
-    const T a = (kn.x[k + 1] - x) * rh;
-    const T b = (x - kn.x[k]) * rh;
-    f = a * lo.x + b * hi.x + ((a * a * a - a) * lo.y + (b * b * b - b) * hi.y) * kn.h2_6[k];
-    df = (hi.x - lo.x) * rh - (((T)3 * a * a - (T)1) * lo.y - ((T)3 * b * b - (T)1) * hi.y) * kn.h_6[k];
+    if (sizeof(T) == 8 || k < kn.urun0) {
+        if (x < kn.x[0]) { f = tab[0].c0; df = (T)0; return; }
+        k = min(max(k, 0), K - 1);
+        while (k > 0 && x < kn.x[k]) --k;
+        while (k < K - 1 && x >= kn.x[k + 1]) ++k;
+        if (x > kn.x[K - 1]) k = K - 1;
+    } else {
+        k = min(k, K - 1);
+    }
+    const Coef<T> c = tab[k];
+    const T u = x - kn.x[k];
+    f = c.c0 + u * (c.c1 + u * (c.c2 + u * c.c3));
+    df = c.c1 + u * ((T)2 * c.c2 + (T)3 * c.c3 * u);
 }
 
 #define CROSS(o, a, b)                       \
@@ -87,106 +83,131 @@ __device__ __forceinline__ void spline_eval(const KnotGeom<T> &kn, const typenam
     o##z = a##x * b##y - a##y * b##x;
 #define DOT(a, b) (a##x * b##x + a##y * b##y + a##z * b##z)
 
-// Dihedral p1-p2-p3-p4 from F = p1-p2, G = p2-p3, H = p4-p3 (IUPAC sign, equal to the
-// reference's numpy get_dihedrals, utils_trX2dy/utils.py:97-110), spline energy, and
-// gradient (Blondel & Karplus 1996) accumulated into g1..g4 (arrays of 3).
+// Per-column quantities shared by the two rows a warp pairs with the column.
 template <typename T>
-__device__ __forceinline__ void dihedral_term(const KnotGeom<T> &kn, const typename Vec2<T>::type *__restrict__ tab,
-                                              T Fx, T Fy, T Fz, T Gx, T Gy, T Gz, T Hx, T Hy, T Hz, T w,
-                                              double &e, T *g1, T *g2, T *g3, T *g4)
-{
-    T Ax, Ay, Az, Bx, By, Bz;
-    CROSS(A, F, G);
-    CROSS(B, H, G);
-    const T G2 = max(DOT(G, G), t_tiny<T>());
-    const T rG = t_rsqrt(G2);
-    const T Gn = G2 * rG;
-    const T phi = t_atan2(-Gn * DOT(F, B), DOT(A, B));
-    T f, df;
-    spline_eval(kn, tab, phi, f, df);
-    e += (double)f;
-    if (df != (T)0) {
-        const T s = w * df;
-        const T iA2 = t_rcp(max(DOT(A, A), t_tiny<T>()));
-        const T iB2 = t_rcp(max(DOT(B, B), t_tiny<T>()));
-        const T c1 = -s * Gn * iA2, c4 = s * Gn * iB2;
-        const T tA = s * DOT(F, G) * iA2 * rG, tB = s * DOT(H, G) * iB2 * rG;
-        const T u1x = c1 * Ax, u1y = c1 * Ay, u1z = c1 * Az;
-        const T u4x = c4 * Bx, u4y = c4 * By, u4z = c4 * Bz;
-        const T tx = tA * Ax - tB * Bx, ty = tA * Ay - tB * By, tz = tA * Az - tB * Bz;
-        g1[0] += u1x; g1[1] += u1y; g1[2] += u1z;
-        g4[0] += u4x; g4[1] += u4y; g4[2] += u4z;
-        g2[0] += tx - u1x; g2[1] += ty - u1y; g2[2] += tz - u1z;
-        g3[0] -= tx + u4x; g3[1] -= ty + u4y; g3[2] -= tz + u4z;
-    }
-}
-
-// Angle p1-p2-p3 at vertex p2 from U = p1-p2, V = p3-p2 (reference get_angles,
-// utils_trX2dy/utils.py:113-122), spline energy and gradient into g1,g2,g3.
-template <typename T>
-__device__ __forceinline__ void angle_term(const KnotGeom<T> &kn, const typename Vec2<T>::type *__restrict__ tab,
-                                           T Ux, T Uy, T Uz, T Vx, T Vy, T Vz, T w, double &e, T *g1, T *g2, T *g3)
-{
-    const T rU = t_rsqrt(max(DOT(U, U), t_tiny<T>()));
-    const T rV = t_rsqrt(max(DOT(V, V), t_tiny<T>()));
-    T c = DOT(U, V) * rU * rV;
-    c = min(max(c, (T)-1), (T)1);
-    const T ang = t_acos(c);
-    T f, df;
-    spline_eval(kn, tab, ang, f, df);
-    e += (double)f;
-    if (df != (T)0) {
-        const T sn = t_sqrt(max((T)1 - c * c, t_tiny<T>()));
-        const T s = -w * df * t_rcp(sn);
-        const T ux = Ux * rU, uy = Uy * rU, uz = Uz * rU;
-        const T vx = Vx * rV, vy = Vy * rV, vz = Vz * rV;
-        const T a1 = s * rU, a3 = s * rV;
-        const T p1x = a1 * (vx - c * ux), p1y = a1 * (vy - c * uy), p1z = a1 * (vz - c * uz);
-        const T p3x = a3 * (ux - c * vx), p3y = a3 * (uy - c * vy), p3z = a3 * (uz - c * vz);
-        g1[0] += p1x; g1[1] += p1y; g1[2] += p1z;
-        g3[0] += p3x; g3[1] += p3y; g3[2] += p3z;
-        g2[0] -= p1x + p3x; g2[1] -= p1y + p3y; g2[2] -= p1z + p3z;
-    }
-}
+struct ColGeom {
+    T Bx, By, Bz;     // CB_j
+    T Qx, Qy, Qz;     // CA_j - CB_j
+    T Ux, Uy, Uz;     // N_j - CA_j
+    T Wx, Wy, Wz;     // U x Q  (plane normal of N_j, CA_j, CB_j)
+    T qq, ww, uq;
+};
 
 // All restraints of the unordered residue pair (i = row, j = column, i < j).
-// ri/cj: coordinates N(0..2) CA(3..5) CB(6..8); rg/cg: gradient accumulators.
+//   dist  AtomPair CB_i CB_j               omega  Dihedral CA_i CB_i CB_j CA_j
+//   theta Dihedral N_a CA_a CB_a CB_b      phi    Angle CA_a CB_a CB_b     (both directions)
+// With D = CB_j-CB_i, P = CA_i-CB_i, Q = CA_j-CB_j the two cross products X = D x P and
+// Y = D x Q are the plane normals of ALL five angular restraints (Blondel-Karplus A/B
+// vectors up to sign), and |X|, |Y| give the sines of the two phi angles, so the geometry
+// is computed once per pair.  Dihedral sign and range: IUPAC, equal to the reference's numpy
+// get_dihedrals (utils_trX2dy/utils.py:97-110); angle: get_angles (:113-122).
+// row: CB_i(0..2) P(3..5) U=N_i-CA_i(6..8); rg/cg: gradient accumulators N(0..2) CA(3..5) CB(6..8).
 template <typename T>
 __device__ __forceinline__ void pair_eval(const K1Params<T> &p, const KnotGeom<T> *geom, const int4 ia, const int4 ib,
-                                          const T *ri, const T *cj, T *rg, T *cg, const T w0, const T w1, const T w2,
-                                          double &e0, double &e1, double &e2)
+                                          const T *row, const ColGeom<T> &c, T *rg, T *cg, const T w0, const T w1, const T w2,
+                                          T &e0, T &e1, T &e2)
 {
-    using T2 = typename Vec2<T>::type;
     const int mask = ia.x;
-    const T Dx = cj[6] - ri[6], Dy = cj[7] - ri[7], Dz = cj[8] - ri[8];        // CB_j - CB_i
-    const T Px = ri[3] - ri[6], Py = ri[4] - ri[7], Pz = ri[5] - ri[8];        // CA_i - CB_i
-    const T Qx = cj[3] - cj[6], Qy = cj[4] - cj[7], Qz = cj[5] - cj[8];        // CA_j - CB_j
-    if (mask & 1) {  // dist: AtomPair CB_i CB_j
-        const T d2 = max(DOT(D, D), t_tiny<T>());
-        const T rd = t_rsqrt(d2);
-        T f, df;
-        spline_eval(geom[0], p.tab[0] + (size_t)ia.y * geom[0].K, d2 * rd, f, df);
-        e0 += (double)f;
+    const T Dx = c.Bx - row[0], Dy = c.By - row[1], Dz = c.Bz - row[2];
+    const T Px = row[3], Py = row[4], Pz = row[5];
+    const T dd = max(DOT(D, D), t_tiny<T>());
+    const T rd = t_rsqrt(dd);
+    const T d = dd * rd;
+    T f, df;
+    if (mask & 1) {
+        spline_eval(geom[0], p.tab[0] + (size_t)ia.y * geom[0].K, d, f, df);
+        e0 += f;
         if (df != (T)0) {
             const T s = w0 * df * rd;
             cg[6] += s * Dx; cg[7] += s * Dy; cg[8] += s * Dz;
             rg[6] -= s * Dx; rg[7] -= s * Dy; rg[8] -= s * Dz;
         }
     }
-    if (mask & 2)    // omega: Dihedral CA_i CB_i CB_j CA_j
-        dihedral_term<T>(geom[1], p.tab[1] + (size_t)ia.z * geom[1].K, Px, Py, Pz, -Dx, -Dy, -Dz, Qx, Qy, Qz, w1, e1,
-                         rg + 3, rg + 6, cg + 6, cg + 3);
-    if (mask & 4)    // theta(i,j): Dihedral N_i CA_i CB_i CB_j
-        dihedral_term<T>(geom[2], p.tab[2] + (size_t)ia.w * geom[2].K, ri[0] - ri[3], ri[1] - ri[4], ri[2] - ri[5], Px, Py, Pz,
-                         Dx, Dy, Dz, w1, e1, rg + 0, rg + 3, rg + 6, cg + 6);
-    if (mask & 8)    // theta(j,i): Dihedral N_j CA_j CB_j CB_i
-        dihedral_term<T>(geom[2], p.tab[2] + (size_t)ib.x * geom[2].K, cj[0] - cj[3], cj[1] - cj[4], cj[2] - cj[5], Qx, Qy, Qz,
-                         -Dx, -Dy, -Dz, w1, e1, cg + 0, cg + 3, cg + 6, rg + 6);
-    if (mask & 16)   // phi(i,j): Angle CA_i CB_i CB_j
-        angle_term<T>(geom[3], p.tab[3] + (size_t)ib.y * geom[3].K, Px, Py, Pz, Dx, Dy, Dz, w2, e2, rg + 3, rg + 6, cg + 6);
-    if (mask & 32)   // phi(j,i): Angle CA_j CB_j CB_i
-        angle_term<T>(geom[3], p.tab[3] + (size_t)ib.z * geom[3].K, Qx, Qy, Qz, -Dx, -Dy, -Dz, w2, e2, cg + 3, cg + 6, rg + 6);
-    (void)sizeof(T2);
+    if (!(mask & 0x3e)) return;
+    T Xx, Xy, Xz, Yx, Yy, Yz;
+    CROSS(X, D, P);
+    const T Qx = c.Qx, Qy = c.Qy, Qz = c.Qz;
+    CROSS(Y, D, Q);
+    const T xx = max(DOT(X, X), t_tiny<T>()), yy = max(DOT(Y, Y), t_tiny<T>());
+    const T pd = DOT(P, D), qd = DOT(Q, D);
+    const T pp = max(DOT(P, P), t_tiny<T>());
+    const T ixx = t_rcp(xx), iyy = t_rcp(yy);
+    if (mask & 2) {   // omega: F = P, G = -D, H = Q  =>  A = X, B = Y
+        const T val = t_atan2(-d * DOT(P, Y), DOT(X, Y));
+        spline_eval(geom[1], p.tab[1] + (size_t)ia.z * geom[1].K, val, f, df);
+        e1 += f;
+        if (df != (T)0) {
+            const T s = w1 * df;
+            const T c1 = -s * d * ixx, c4 = s * d * iyy, tA = -s * pd * ixx * rd, tB = -s * qd * iyy * rd;
+            const T tx = tA * Xx - tB * Yx, ty = tA * Xy - tB * Yy, tz = tA * Xz - tB * Yz;
+            rg[3] += c1 * Xx; rg[4] += c1 * Xy; rg[5] += c1 * Xz;                  // CA_i
+            cg[3] += c4 * Yx; cg[4] += c4 * Yy; cg[5] += c4 * Yz;                  // CA_j
+            rg[6] += tx - c1 * Xx; rg[7] += ty - c1 * Xy; rg[8] += tz - c1 * Xz;   // CB_i
+            cg[6] -= tx + c4 * Yx; cg[7] -= ty + c4 * Yy; cg[8] -= tz + c4 * Yz;   // CB_j
+        }
+    }
+    if (mask & 4) {   // theta(i,j): F = U_i, G = P, H = D  =>  A = U_i x P, B = X
+        const T Ux = row[6], Uy = row[7], Uz = row[8];
+        T Wx, Wy, Wz;
+        CROSS(W, U, P);
+        const T ww = max(DOT(W, W), t_tiny<T>()), up = DOT(U, P);
+        const T rp = t_rsqrt(pp), np_ = pp * rp;
+        const T val = t_atan2(-np_ * DOT(U, X), DOT(W, X));
+        spline_eval(geom[2], p.tab[2] + (size_t)ia.w * geom[2].K, val, f, df);
+        e1 += f;
+        if (df != (T)0) {
+            const T s = w1 * df, iww = t_rcp(ww);
+            const T c1 = -s * np_ * iww, c4 = s * np_ * ixx, tA = s * up * iww * rp, tB = s * pd * ixx * rp;
+            const T tx = tA * Wx - tB * Xx, ty = tA * Wy - tB * Xy, tz = tA * Wz - tB * Xz;
+            rg[0] += c1 * Wx; rg[1] += c1 * Wy; rg[2] += c1 * Wz;                  // N_i
+            cg[6] += c4 * Xx; cg[7] += c4 * Xy; cg[8] += c4 * Xz;                  // CB_j
+            rg[3] += tx - c1 * Wx; rg[4] += ty - c1 * Wy; rg[5] += tz - c1 * Wz;   // CA_i
+            rg[6] -= tx + c4 * Xx; rg[7] -= ty + c4 * Xy; rg[8] -= tz + c4 * Xz;   // CB_i
+        }
+    }
+    if (mask & 8) {   // theta(j,i): F = U_j, G = Q, H = -D  =>  A = W_j, B = -Y
+        const T rq = t_rsqrt(c.qq), nq = c.qq * rq;
+        const T val = t_atan2(nq * (c.Ux * Yx + c.Uy * Yy + c.Uz * Yz), -(c.Wx * Yx + c.Wy * Yy + c.Wz * Yz));
+        spline_eval(geom[2], p.tab[2] + (size_t)ib.x * geom[2].K, val, f, df);
+        e1 += f;
+        if (df != (T)0) {
+            const T s = w1 * df, iww = t_rcp(c.ww);
+            const T c1 = -s * nq * iww, c4 = s * nq * iyy, tA = s * c.uq * iww * rq, tB = s * qd * iyy * rq;
+            const T tx = tA * c.Wx - tB * Yx, ty = tA * c.Wy - tB * Yy, tz = tA * c.Wz - tB * Yz;
+            cg[0] += c1 * c.Wx; cg[1] += c1 * c.Wy; cg[2] += c1 * c.Wz;                    // N_j
+            rg[6] -= c4 * Yx; rg[7] -= c4 * Yy; rg[8] -= c4 * Yz;                          // CB_i  (c4 * B, B = -Y)
+            cg[3] += tx - c1 * c.Wx; cg[4] += ty - c1 * c.Wy; cg[5] += tz - c1 * c.Wz;     // CA_j
+            cg[6] -= tx - c4 * Yx; cg[7] -= ty - c4 * Yy; cg[8] -= tz - c4 * Yz;           // CB_j
+        }
+    }
+    if (mask & 16) {  // phi(i,j): angle between P and D at CB_i; sin = |X| / (|P||D|)
+        const T rX = t_rsqrt(xx);
+        const T val = t_atan2(xx * rX, pd);
+        spline_eval(geom[3], p.tab[3] + (size_t)ib.y * geom[3].K, val, f, df);
+        e2 += f;
+        if (df != (T)0) {
+            const T s = w2 * df * rX, a = pd * t_rcp(pp), b = pd * rd * rd;
+            const T ux = -s * (Dx - a * Px), uy = -s * (Dy - a * Py), uz = -s * (Dz - a * Pz);   // d/dCA_i
+            const T vx = -s * (Px - b * Dx), vy = -s * (Py - b * Dy), vz = -s * (Pz - b * Dz);   // d/dCB_j
+            rg[3] += ux; rg[4] += uy; rg[5] += uz;
+            cg[6] += vx; cg[7] += vy; cg[8] += vz;
+            rg[6] -= ux + vx; rg[7] -= uy + vy; rg[8] -= uz + vz;
+        }
+    }
+    if (mask & 32) {  // phi(j,i): angle between Q and -D at CB_j; sin = |Y| / (|Q||D|)
+        const T rY = t_rsqrt(yy);
+        const T val = t_atan2(yy * rY, -qd);
+        spline_eval(geom[3], p.tab[3] + (size_t)ib.z * geom[3].K, val, f, df);
+        e2 += f;
+        if (df != (T)0) {
+            const T s = w2 * df * rY, a = qd * t_rcp(c.qq), b = qd * rd * rd;
+            const T ux = s * (Dx - a * Qx), uy = s * (Dy - a * Qy), uz = s * (Dz - a * Qz);      // d/dCA_j
+            const T vx = -s * (Qx - b * Dx), vy = -s * (Qy - b * Dy), vz = -s * (Qz - b * Dz);   // d/dCB_i
+            cg[3] += ux; cg[4] += uy; cg[5] += uz;
+            rg[6] += vx; rg[7] += vy; rg[8] += vz;
+            cg[6] -= ux + vx; cg[7] -= uy + vy; cg[8] -= uz + vz;
+        }
+    }
 }
 
 template <typename T>
@@ -214,14 +235,22 @@ __global__ void __launch_bounds__(K1_THREADS, (sizeof(T) == 4 ? 2 : 1)) restrain
         w1 = (T)p.wl[1 * (size_t)p.Npad + g * LANES + lane];
         w2 = (T)p.wl[2 * (size_t)p.Npad + g * LANES + lane];
     }
-    T ri[2][9], rg[2][9];
+    // rows w and w+8: CB, P = CA-CB, U = N-CA; gradient accumulators N, CA, CB
+    T row[2][9], rg[2][9];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
         const int res = I * TILE + w + K1_WARPS * r;
+        T v[9];
 #pragma unroll
         for (int c = 0; c < 9; ++c) {
-            ri[r][c] = Xg[((size_t)res * xs + c) * LANES];
+            v[c] = Xg[((size_t)res * xs + c) * LANES];
             rg[r][c] = (T)0;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            row[r][k] = v[6 + k];
+            row[r][3 + k] = v[3 + k] - v[6 + k];
+            row[r][6 + k] = v[k] - v[3 + k];
         }
     }
     double e0 = 0.0, e1 = 0.0, e2 = 0.0;
@@ -230,26 +259,43 @@ __global__ void __launch_bounds__(K1_THREADS, (sizeof(T) == 4 ? 2 : 1)) restrain
     for (int t = t0; t < t0 + nt; ++t) {
         const int J = p.tileJ[t];
         const int *__restrict__ rec_t = p.pairrec + (size_t)t * TILE * TILE * 8;
-        for (int s = 0; s < TILE; ++s) {
-            const int c = (2 * w + s) & (TILE - 1);
-            const int4 *r0 = reinterpret_cast<const int4 *>(rec_t + (w * TILE + c) * 8);
-            const int4 *r1 = reinterpret_cast<const int4 *>(rec_t + ((w + K1_WARPS) * TILE + c) * 8);
-            const int4 a0 = __ldg(r0), a1 = __ldg(r1);
-            if (a0.x | a1.x) {
-                T cj[9], cg[9];
-                const int res = J * TILE + c;
+        T f0 = (T)0, f1 = (T)0, f2 = (T)0;   // per-tile partial energies (<= 64 restraints per term)
+        // staggered schedule: in step s warp w owns columns 2(w+s) and 2(w+s)+1 (mod 16),
+        // so no two warps touch the same column between barriers
+        for (int s = 0; s < TILE / 2; ++s) {
 #pragma unroll
-                for (int k = 0; k < 9; ++k) {
-                    cj[k] = Xg[((size_t)res * xs + k) * LANES];
-                    cg[k] = (T)0;
+            for (int h = 0; h < 2; ++h) {
+                const int c = (2 * (w + s) + h) & (TILE - 1);
+                const int4 *r0 = reinterpret_cast<const int4 *>(rec_t + (w * TILE + c) * 8);
+                const int4 *r1 = reinterpret_cast<const int4 *>(rec_t + ((w + K1_WARPS) * TILE + c) * 8);
+                const int4 a0 = __ldg(r0), a1 = __ldg(r1);
+                if (a0.x | a1.x) {
+                    T cj[9], cg[9];
+                    const int res = J * TILE + c;
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) {
+                        cj[k] = Xg[((size_t)res * xs + k) * LANES];
+                        cg[k] = (T)0;
+                    }
+                    ColGeom<T> cgm;
+                    cgm.Bx = cj[6]; cgm.By = cj[7]; cgm.Bz = cj[8];
+                    cgm.Qx = cj[3] - cj[6]; cgm.Qy = cj[4] - cj[7]; cgm.Qz = cj[5] - cj[8];
+                    cgm.Ux = cj[0] - cj[3]; cgm.Uy = cj[1] - cj[4]; cgm.Uz = cj[2] - cj[5];
+                    cgm.Wx = cgm.Uy * cgm.Qz - cgm.Uz * cgm.Qy;
+                    cgm.Wy = cgm.Uz * cgm.Qx - cgm.Ux * cgm.Qz;
+                    cgm.Wz = cgm.Ux * cgm.Qy - cgm.Uy * cgm.Qx;
+                    cgm.qq = max(cgm.Qx * cgm.Qx + cgm.Qy * cgm.Qy + cgm.Qz * cgm.Qz, t_tiny<T>());
+                    cgm.ww = max(cgm.Wx * cgm.Wx + cgm.Wy * cgm.Wy + cgm.Wz * cgm.Wz, t_tiny<T>());
+                    cgm.uq = cgm.Ux * cgm.Qx + cgm.Uy * cgm.Qy + cgm.Uz * cgm.Qz;
+                    if (a0.x) pair_eval<T>(p, geom, a0, __ldg(r0 + 1), row[0], cgm, rg[0], cg, w0, w1, w2, f0, f1, f2);
+                    if (a1.x) pair_eval<T>(p, geom, a1, __ldg(r1 + 1), row[1], cgm, rg[1], cg, w0, w1, w2, f0, f1, f2);
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) colg[(c * 9 + k) * LANES + lane] += cg[k];
                 }
-                if (a0.x) pair_eval<T>(p, geom, a0, __ldg(r0 + 1), ri[0], cj, rg[0], cg, w0, w1, w2, e0, e1, e2);
-                if (a1.x) pair_eval<T>(p, geom, a1, __ldg(r1 + 1), ri[1], cj, rg[1], cg, w0, w1, w2, e0, e1, e2);
-#pragma unroll
-                for (int k = 0; k < 9; ++k) colg[(c * 9 + k) * LANES + lane] += cg[k];
             }
             __syncthreads();
         }
+        e0 += (double)f0; e1 += (double)f1; e2 += (double)f2;
         T *__restrict__ dst = p.recs + ((size_t)g * p.nrec + t) * REC_ELEMS;
         for (int e = threadIdx.x; e < REC_ELEMS; e += K1_THREADS) {
             dst[e] = colg[e];
@@ -322,7 +368,7 @@ int k1_launch(trx_ctx *ctx, trx_tables *tb, int Gtot, int g0, int ng, const T *d
     K1Params<T> p;
     p.X = d_xyz;
     for (int t = 0; t < 4; ++t)
-        p.tab[t] = reinterpret_cast<const typename Vec2<T>::type *>(sizeof(T) == 8 ? (const void *)tb->d_tab64[t] : (const void *)tb->d_tab32[t]);
+        p.tab[t] = reinterpret_cast<const Coef<T> *>(sizeof(T) == 8 ? (const void *)tb->d_tab64[t] : (const void *)tb->d_tab32[t]);
     p.geom = reinterpret_cast<const KnotGeom<T> *>(sizeof(T) == 8 ? (const void *)tb->d_geom64 : (const void *)tb->d_geom32);
     p.pairrec = tb->d_pairrec;
     p.tileJ = tb->d_tileJ;

@@ -16,7 +16,7 @@ namespace trx {
 // SplineGenerator(lbx,lby,0, ubx,uby,0) -> SimpleInterpolator computes).  One thread
 // per restraint; the scratch vector u lives in registers/local memory (K <= MAXK).
 __global__ void spline_fit_kernel(int n, int K, const double *__restrict__ x, const double *__restrict__ y,
-                                  double2 *__restrict__ tab64, float2 *__restrict__ tab32)
+                                  double *__restrict__ y2out, Coef<double> *__restrict__ tab64, Coef<float> *__restrict__ tab32)
 {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
@@ -34,9 +34,24 @@ __global__ void spline_fit_kernel(int n, int K, const double *__restrict__ x, co
     double un = (3.0 / (x[K - 1] - x[K - 2])) * (0.0 - (yr[K - 1] - yr[K - 2]) / (x[K - 1] - x[K - 2]));
     y2[K - 1] = (un - 0.5 * u[K - 2]) / (0.5 * y2[K - 2] + 1.0);
     for (int k = K - 2; k >= 0; --k) y2[k] = y2[k] * y2[k + 1] + u[k];
+    for (int k = 0; k < K; ++k) y2out[(size_t)r * K + k] = y2[k];
+    // the same cubic per interval in powers of (x - x_k): 4 scalars = one 16 B (fp32) load.
+    // Entry K-1 carries the flat value beyond the last knot.
     for (int k = 0; k < K; ++k) {
-        tab64[(size_t)r * K + k] = make_double2(yr[k], y2[k]);
-        tab32[(size_t)r * K + k] = make_float2((float)yr[k], (float)y2[k]);
+        Coef<double> c;
+        if (k < K - 1) {
+            const double h = x[k + 1] - x[k];
+            c.c0 = yr[k];
+            c.c1 = (yr[k + 1] - yr[k]) / h - h * (2.0 * y2[k] + y2[k + 1]) / 6.0;
+            c.c2 = 0.5 * y2[k];
+            c.c3 = (y2[k + 1] - y2[k]) / (6.0 * h);
+        } else {
+            c.c0 = yr[K - 1]; c.c1 = 0.0; c.c2 = 0.0; c.c3 = 0.0;
+        }
+        tab64[(size_t)r * K + k] = c;
+        Coef<float> f;
+        f.c0 = (float)c.c0; f.c1 = (float)c.c1; f.c2 = (float)c.c2; f.c3 = (float)c.c3;
+        tab32[(size_t)r * K + k] = f;
     }
 }
 
@@ -67,6 +82,8 @@ static void fill_geom(KnotGeom<T> &g, int K, const double *x)
     g.gx0 = (T)x[best];
     g.ginv = (T)(1.0 / h);
     g.goff = best;
+    g.urun0 = best;
+    g.urun1 = best + bestlen;
 }
 
 }  // namespace trx
@@ -166,13 +183,14 @@ int trx_tables_create(trx_ctx *ctx, int L, const trx_rst_set sets[4], trx_tables
         size_t ny = (size_t)s.n * s.K;
         TRX_CUDA(cudaMalloc(&d_x, s.K * sizeof(double)));
         TRX_CUDA(cudaMalloc(&d_y, ny * sizeof(double)));
-        TRX_CUDA(cudaMalloc(&T->d_tab64[t], ny * sizeof(double2)));
-        TRX_CUDA(cudaMalloc(&T->d_tab32[t], ny * sizeof(float2)));
+        TRX_CUDA(cudaMalloc(&T->d_tab64[t], ny * sizeof(Coef<double>)));
+        TRX_CUDA(cudaMalloc(&T->d_tab32[t], ny * sizeof(Coef<float>)));
+        TRX_CUDA(cudaMalloc(&T->d_y2[t], ny * sizeof(double)));
         TRX_CUDA(cudaMemcpyAsync(d_x, s.x, s.K * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         TRX_CUDA(cudaMemcpyAsync(d_y, s.y, ny * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         ctx->time_begin("spline_fit");
-        spline_fit_kernel<<<(s.n + 127) / 128, 128, 0, ctx->stream>>>(s.n, s.K, d_x, d_y, (double2 *)T->d_tab64[t],
-                                                                     (float2 *)T->d_tab32[t]);
+        spline_fit_kernel<<<(s.n + 127) / 128, 128, 0, ctx->stream>>>(s.n, s.K, d_x, d_y, T->d_y2[t], (Coef<double> *)T->d_tab64[t],
+                                                                     (Coef<float> *)T->d_tab32[t]);
         ctx->time_end("spline_fit");
         TRX_CUDA(cudaGetLastError());
         TRX_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -245,6 +263,7 @@ int trx_tables_destroy(trx_tables *T)
     for (int t = 0; t < 4; ++t) {
         if (T->d_tab64[t]) cudaFree(T->d_tab64[t]);
         if (T->d_tab32[t]) cudaFree(T->d_tab32[t]);
+        if (T->d_y2[t]) cudaFree(T->d_y2[t]);
     }
     if (T->d_geom64) cudaFree(T->d_geom64);
     if (T->d_geom32) cudaFree(T->d_geom32);
@@ -273,9 +292,7 @@ int trx_tables_get_y2(trx_tables *T, int type, double *y2)
     TRX_REQUIRE(T && y2 && type >= 0 && type < 4, "trx_tables_get_y2: bad argument");
     size_t n = (size_t)T->n[type] * T->K[type];
     if (n == 0) return TRX_OK;
-    std::vector<double> tmp(n * 2);
-    TRX_CUDA(cudaMemcpy(tmp.data(), T->d_tab64[type], n * 2 * sizeof(double), cudaMemcpyDeviceToHost));
-    for (size_t i = 0; i < n; ++i) y2[i] = tmp[2 * i + 1];
+    TRX_CUDA(cudaMemcpy(y2, T->d_y2[type], n * sizeof(double), cudaMemcpyDeviceToHost));
     return TRX_OK;
 }
 
