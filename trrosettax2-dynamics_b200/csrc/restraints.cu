@@ -24,7 +24,31 @@ __device__ __forceinline__ float t_rsqrt(float x) { return rsqrtf(x); }
 __device__ __forceinline__ double t_rsqrt(double x) { return 1.0 / sqrt(x); }
 __device__ __forceinline__ float t_rcp(float x) { return __fdividef(1.0f, x); }
 __device__ __forceinline__ double t_rcp(double x) { return 1.0 / x; }
-__device__ __forceinline__ float t_atan2(float y, float x) { return atan2f(y, x); }
+#define ATAN_C0 9.999993354e-01f
+#define ATAN_C1 -3.332986002e-01f
+#define ATAN_C2 1.994655755e-01f
+#define ATAN_C3 -1.390859233e-01f
+#define ATAN_C4 9.642109384e-02f
+#define ATAN_C5 -5.591120728e-02f
+#define ATAN_C6 2.186222795e-02f
+#define ATAN_C7 -4.054375906e-03f
+// Branch-free atan2 for the throughput (fp32) mode: octant reduction to a = min/max in [0,1],
+// degree-7 polynomial in a^2 for atan(a)/a (max error 4e-8 rad before rounding, ~1e-7 in fp32),
+// selects instead of the special-case branches of atan2f (which break the instruction stream
+// into reconvergence regions and stop the six restraints of a pair from overlapping).
+__device__ __forceinline__ float t_atan2(float y, float x)
+{
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(fmaxf(ax, ay), 1e-30f), mn = fminf(ax, ay);
+    const float a = __fdividef(mn, mx), s = a * a;
+    float r = ATAN_C7;
+    r = r * s + ATAN_C6; r = r * s + ATAN_C5; r = r * s + ATAN_C4; r = r * s + ATAN_C3;
+    r = r * s + ATAN_C2; r = r * s + ATAN_C1; r = r * s + ATAN_C0;
+    r *= a;
+    r = ay > ax ? 1.57079632679f - r : r;
+    r = x < 0.f ? 3.14159265359f - r : r;
+    return copysignf(r, y);
+}
 __device__ __forceinline__ double t_atan2(double y, double x) { return atan2(y, x); }
 __device__ __forceinline__ float t_floor(float x) { return floorf(x); }
 __device__ __forceinline__ double t_floor(double x) { return floor(x); }
@@ -57,25 +81,47 @@ struct K1Params {
 // branch-free: interval index from the uniform part of the grid, one 16 B load, Horner.
 // fp64 (parity mode) always corrects the index against the true knots (the reference's %.3f
 // rounding makes the angular grids uneven at the 5e-4 level); fp32 only below the uniform run.
+// Split in two so that a pair can issue the table loads of all its restraints together.
 template <typename T>
-__device__ __forceinline__ void spline_eval(const KnotGeom<T> &kn, const Coef<T> *__restrict__ tab, T x, T &f, T &df)
+__device__ __forceinline__ int spline_locate_exact(const KnotGeom<T> &kn, T x, T &u)
 {
     const int K = kn.K;
     int k = (int)t_floor((x - kn.gx0) * kn.ginv) + kn.goff;
-    if (sizeof(T) == 8 || k < kn.urun0) {
-        if (x < kn.x[0]) { f = tab[0].c0; df = (T)0; return; }
-        k = min(max(k, 0), K - 1);
-        while (k > 0 && x < kn.x[k]) --k;
-        while (k < K - 1 && x >= kn.x[k + 1]) ++k;
-        if (x > kn.x[K - 1]) k = K - 1;
-    } else {
-        k = min(k, K - 1);
-    }
-    const Coef<T> c = tab[k];
-    const T u = x - kn.x[k];
-    f = c.c0 + u * (c.c1 + u * (c.c2 + u * c.c3));
-    df = c.c1 + u * ((T)2 * c.c2 + (T)3 * c.c3 * u);
+    k = min(max(k, 0), K - 1);
+    while (k > 0 && x < kn.x[k]) --k;
+    while (k < K - 1 && x >= kn.x[k + 1]) ++k;
+    u = x - kn.x[k];
+    if (k == 0) u = max(u, (T)0);   // below the first knot: clamped spline => value y_0, slope 0
+    return k;
 }
+
+// fp32: no loops, no divergent branches.  Inside the uniform run the guess is the interval
+// (a guess that is one off next to a knot evaluates the neighbouring cubic <= 5e-4 outside
+// its interval: error ~1e-8, the spline being C2); the few uneven intervals below the run
+// (the 0 / 2 / 3.5 A knots of the distance grid; at most 6, checked at table creation) are
+// counted with compares.
+__device__ __forceinline__ int spline_locate(const KnotGeom<float> &kn, float x, float &u)
+{
+    const int K = kn.K, r0 = kn.urun0;
+    int k = (int)floorf((x - kn.gx0) * kn.ginv) + kn.goff;
+    if (r0 > 0) {
+        int kh = 0;
+#pragma unroll
+        for (int m = 1; m <= 6; ++m) kh += (m <= r0 && x >= kn.x[m]) ? 1 : 0;
+        k = k >= r0 ? k : kh;
+    }
+    k = min(max(k, 0), K - 1);
+    u = x - kn.x[k];
+    u = k == 0 ? fmaxf(u, 0.f) : u;
+    return k;
+}
+__device__ __forceinline__ int spline_locate(const KnotGeom<double> &kn, double x, double &u) { return spline_locate_exact(kn, x, u); }
+
+template <typename T>
+__device__ __forceinline__ Coef<T> spline_load(const Coef<T> *__restrict__ tab, int k) { return tab[k]; }
+
+#define SPLINE_F(c, u) ((c).c0 + (u) * ((c).c1 + (u) * ((c).c2 + (u) * (c).c3)))
+#define SPLINE_DF(c, u) ((c).c1 + (u) * ((T)2 * (c).c2 + (T)3 * (c).c3 * (u)))
 
 #define CROSS(o, a, b)                       \
     o##x = a##y * b##z - a##z * b##y;        \
@@ -99,7 +145,9 @@ struct ColGeom {
 // With D = CB_j-CB_i, P = CA_i-CB_i, Q = CA_j-CB_j the two cross products X = D x P and
 // Y = D x Q are the plane normals of ALL five angular restraints (Blondel-Karplus A/B
 // vectors up to sign), and |X|, |Y| give the sines of the two phi angles, so the geometry
-// is computed once per pair.  Dihedral sign and range: IUPAC, equal to the reference's numpy
+// is computed once per pair.  Phase 1 computes the six geometric values and issues the six
+// table loads (independent gathers in flight together); phase 2 evaluates the cubics and
+// accumulates the gradients.  Dihedral sign and range: IUPAC, equal to the reference's numpy
 // get_dihedrals (utils_trX2dy/utils.py:97-110); angle: get_angles (:113-122).
 // row: CB_i(0..2) P(3..5) U=N_i-CA_i(6..8); rg/cg: gradient accumulators N(0..2) CA(3..5) CB(6..8).
 template <typename T>
@@ -110,103 +158,93 @@ __device__ __forceinline__ void pair_eval(const K1Params<T> &p, const KnotGeom<T
     const int mask = ia.x;
     const T Dx = c.Bx - row[0], Dy = c.By - row[1], Dz = c.Bz - row[2];
     const T Px = row[3], Py = row[4], Pz = row[5];
+    const T Qx = c.Qx, Qy = c.Qy, Qz = c.Qz;
     const T dd = max(DOT(D, D), t_tiny<T>());
     const T rd = t_rsqrt(dd);
     const T d = dd * rd;
-    T f, df;
-    if (mask & 1) {
-        spline_eval(geom[0], p.tab[0] + (size_t)ia.y * geom[0].K, d, f, df);
-        e0 += f;
-        if (df != (T)0) {
-            const T s = w0 * df * rd;
-            cg[6] += s * Dx; cg[7] += s * Dy; cg[8] += s * Dz;
-            rg[6] -= s * Dx; rg[7] -= s * Dy; rg[8] -= s * Dz;
-        }
-    }
-    if (!(mask & 0x3e)) return;
     T Xx, Xy, Xz, Yx, Yy, Yz;
     CROSS(X, D, P);
-    const T Qx = c.Qx, Qy = c.Qy, Qz = c.Qz;
     CROSS(Y, D, Q);
     const T xx = max(DOT(X, X), t_tiny<T>()), yy = max(DOT(Y, Y), t_tiny<T>());
     const T pd = DOT(P, D), qd = DOT(Q, D);
     const T pp = max(DOT(P, P), t_tiny<T>());
-    const T ixx = t_rcp(xx), iyy = t_rcp(yy);
-    if (mask & 2) {   // omega: F = P, G = -D, H = Q  =>  A = X, B = Y
-        const T val = t_atan2(-d * DOT(P, Y), DOT(X, Y));
-        spline_eval(geom[1], p.tab[1] + (size_t)ia.z * geom[1].K, val, f, df);
-        e1 += f;
-        if (df != (T)0) {
-            const T s = w1 * df;
-            const T c1 = -s * d * ixx, c4 = s * d * iyy, tA = -s * pd * ixx * rd, tB = -s * qd * iyy * rd;
-            const T tx = tA * Xx - tB * Yx, ty = tA * Xy - tB * Yy, tz = tA * Xz - tB * Yz;
-            rg[3] += c1 * Xx; rg[4] += c1 * Xy; rg[5] += c1 * Xz;                  // CA_i
-            cg[3] += c4 * Yx; cg[4] += c4 * Yy; cg[5] += c4 * Yz;                  // CA_j
-            rg[6] += tx - c1 * Xx; rg[7] += ty - c1 * Xy; rg[8] += tz - c1 * Xz;   // CB_i
-            cg[6] -= tx + c4 * Yx; cg[7] -= ty + c4 * Yy; cg[8] -= tz + c4 * Yz;   // CB_j
-        }
+    const T rX = t_rsqrt(xx), rY = t_rsqrt(yy);
+    // theta(i,j) plane normal of N_i, CA_i, CB_i
+    const T Ux = row[6], Uy = row[7], Uz = row[8];
+    T Wx, Wy, Wz;
+    CROSS(W, U, P);
+    const T ww = max(DOT(W, W), t_tiny<T>());
+    const T rp = t_rsqrt(pp), np_ = pp * rp;
+    const T rq = t_rsqrt(c.qq), nq = c.qq * rq;
+
+    // ---- phase 1: values, intervals, loads
+    T u0 = (T)0, u1 = (T)0, u2 = (T)0, u3 = (T)0, u4 = (T)0, u5 = (T)0;
+    Coef<T> c0 = {(T)0, (T)0, (T)0, (T)0}, c1 = c0, c2 = c0, c3 = c0, c4 = c0, c5 = c0;
+    if (mask & 1) c0 = spline_load(p.tab[0] + (size_t)ia.y * geom[0].K, spline_locate(geom[0], d, u0));
+    if (mask & 2)    // omega: F = P, G = -D, H = Q  =>  A = X, B = Y
+        c1 = spline_load(p.tab[1] + (size_t)ia.z * geom[1].K, spline_locate(geom[1], t_atan2(-d * DOT(P, Y), DOT(X, Y)), u1));
+    if (mask & 4)    // theta(i,j): F = U_i, G = P, H = D  =>  A = U_i x P, B = X
+        c2 = spline_load(p.tab[2] + (size_t)ia.w * geom[2].K, spline_locate(geom[2], t_atan2(-np_ * DOT(U, X), DOT(W, X)), u2));
+    if (mask & 8)    // theta(j,i): F = U_j, G = Q, H = -D  =>  A = W_j, B = -Y
+        c3 = spline_load(p.tab[2] + (size_t)ib.x * geom[2].K,
+                         spline_locate(geom[2], t_atan2(nq * (c.Ux * Yx + c.Uy * Yy + c.Uz * Yz), -(c.Wx * Yx + c.Wy * Yy + c.Wz * Yz)), u3));
+    if (mask & 16)   // phi(i,j): angle between P and D at CB_i; sin = |X| / (|P||D|)
+        c4 = spline_load(p.tab[3] + (size_t)ib.y * geom[3].K, spline_locate(geom[3], t_atan2(xx * rX, pd), u4));
+    if (mask & 32)   // phi(j,i): angle between Q and -D at CB_j; sin = |Y| / (|Q||D|)
+        c5 = spline_load(p.tab[3] + (size_t)ib.z * geom[3].K, spline_locate(geom[3], t_atan2(yy * rY, -qd), u5));
+
+    // ---- phase 2: energies and gradients
+    const T ixx = rX * rX, iyy = rY * rY;
+    e0 += SPLINE_F(c0, u0);
+    e1 += SPLINE_F(c1, u1) + SPLINE_F(c2, u2) + SPLINE_F(c3, u3);
+    e2 += SPLINE_F(c4, u4) + SPLINE_F(c5, u5);
+    {
+        const T s = w0 * SPLINE_DF(c0, u0) * rd;
+        cg[6] += s * Dx; cg[7] += s * Dy; cg[8] += s * Dz;
+        rg[6] -= s * Dx; rg[7] -= s * Dy; rg[8] -= s * Dz;
     }
-    if (mask & 4) {   // theta(i,j): F = U_i, G = P, H = D  =>  A = U_i x P, B = X
-        const T Ux = row[6], Uy = row[7], Uz = row[8];
-        T Wx, Wy, Wz;
-        CROSS(W, U, P);
-        const T ww = max(DOT(W, W), t_tiny<T>()), up = DOT(U, P);
-        const T rp = t_rsqrt(pp), np_ = pp * rp;
-        const T val = t_atan2(-np_ * DOT(U, X), DOT(W, X));
-        spline_eval(geom[2], p.tab[2] + (size_t)ia.w * geom[2].K, val, f, df);
-        e1 += f;
-        if (df != (T)0) {
-            const T s = w1 * df, iww = t_rcp(ww);
-            const T c1 = -s * np_ * iww, c4 = s * np_ * ixx, tA = s * up * iww * rp, tB = s * pd * ixx * rp;
-            const T tx = tA * Wx - tB * Xx, ty = tA * Wy - tB * Xy, tz = tA * Wz - tB * Xz;
-            rg[0] += c1 * Wx; rg[1] += c1 * Wy; rg[2] += c1 * Wz;                  // N_i
-            cg[6] += c4 * Xx; cg[7] += c4 * Xy; cg[8] += c4 * Xz;                  // CB_j
-            rg[3] += tx - c1 * Wx; rg[4] += ty - c1 * Wy; rg[5] += tz - c1 * Wz;   // CA_i
-            rg[6] -= tx + c4 * Xx; rg[7] -= ty + c4 * Xy; rg[8] -= tz + c4 * Xz;   // CB_i
-        }
+    if (mask & 2) {
+        const T s = w1 * SPLINE_DF(c1, u1);
+        const T a1 = -s * d * ixx, a4 = s * d * iyy, tA = -s * pd * ixx * rd, tB = -s * qd * iyy * rd;
+        const T tx = tA * Xx - tB * Yx, ty = tA * Xy - tB * Yy, tz = tA * Xz - tB * Yz;
+        rg[3] += a1 * Xx; rg[4] += a1 * Xy; rg[5] += a1 * Xz;                  // CA_i
+        cg[3] += a4 * Yx; cg[4] += a4 * Yy; cg[5] += a4 * Yz;                  // CA_j
+        rg[6] += tx - a1 * Xx; rg[7] += ty - a1 * Xy; rg[8] += tz - a1 * Xz;   // CB_i
+        cg[6] -= tx + a4 * Yx; cg[7] -= ty + a4 * Yy; cg[8] -= tz + a4 * Yz;   // CB_j
     }
-    if (mask & 8) {   // theta(j,i): F = U_j, G = Q, H = -D  =>  A = W_j, B = -Y
-        const T rq = t_rsqrt(c.qq), nq = c.qq * rq;
-        const T val = t_atan2(nq * (c.Ux * Yx + c.Uy * Yy + c.Uz * Yz), -(c.Wx * Yx + c.Wy * Yy + c.Wz * Yz));
-        spline_eval(geom[2], p.tab[2] + (size_t)ib.x * geom[2].K, val, f, df);
-        e1 += f;
-        if (df != (T)0) {
-            const T s = w1 * df, iww = t_rcp(c.ww);
-            const T c1 = -s * nq * iww, c4 = s * nq * iyy, tA = s * c.uq * iww * rq, tB = s * qd * iyy * rq;
-            const T tx = tA * c.Wx - tB * Yx, ty = tA * c.Wy - tB * Yy, tz = tA * c.Wz - tB * Yz;
-            cg[0] += c1 * c.Wx; cg[1] += c1 * c.Wy; cg[2] += c1 * c.Wz;                    // N_j
-            rg[6] -= c4 * Yx; rg[7] -= c4 * Yy; rg[8] -= c4 * Yz;                          // CB_i  (c4 * B, B = -Y)
-            cg[3] += tx - c1 * c.Wx; cg[4] += ty - c1 * c.Wy; cg[5] += tz - c1 * c.Wz;     // CA_j
-            cg[6] -= tx - c4 * Yx; cg[7] -= ty - c4 * Yy; cg[8] -= tz - c4 * Yz;           // CB_j
-        }
+    if (mask & 4) {
+        const T s = w1 * SPLINE_DF(c2, u2), iww = t_rcp(ww), up = DOT(U, P);
+        const T a1 = -s * np_ * iww, a4 = s * np_ * ixx, tA = s * up * iww * rp, tB = s * pd * ixx * rp;
+        const T tx = tA * Wx - tB * Xx, ty = tA * Wy - tB * Xy, tz = tA * Wz - tB * Xz;
+        rg[0] += a1 * Wx; rg[1] += a1 * Wy; rg[2] += a1 * Wz;                  // N_i
+        cg[6] += a4 * Xx; cg[7] += a4 * Xy; cg[8] += a4 * Xz;                  // CB_j
+        rg[3] += tx - a1 * Wx; rg[4] += ty - a1 * Wy; rg[5] += tz - a1 * Wz;   // CA_i
+        rg[6] -= tx + a4 * Xx; rg[7] -= ty + a4 * Xy; rg[8] -= tz + a4 * Xz;   // CB_i
     }
-    if (mask & 16) {  // phi(i,j): angle between P and D at CB_i; sin = |X| / (|P||D|)
-        const T rX = t_rsqrt(xx);
-        const T val = t_atan2(xx * rX, pd);
-        spline_eval(geom[3], p.tab[3] + (size_t)ib.y * geom[3].K, val, f, df);
-        e2 += f;
-        if (df != (T)0) {
-            const T s = w2 * df * rX, a = pd * t_rcp(pp), b = pd * rd * rd;
-            const T ux = -s * (Dx - a * Px), uy = -s * (Dy - a * Py), uz = -s * (Dz - a * Pz);   // d/dCA_i
-            const T vx = -s * (Px - b * Dx), vy = -s * (Py - b * Dy), vz = -s * (Pz - b * Dz);   // d/dCB_j
-            rg[3] += ux; rg[4] += uy; rg[5] += uz;
-            cg[6] += vx; cg[7] += vy; cg[8] += vz;
-            rg[6] -= ux + vx; rg[7] -= uy + vy; rg[8] -= uz + vz;
-        }
+    if (mask & 8) {
+        const T s = w1 * SPLINE_DF(c3, u3), iww = t_rcp(c.ww);
+        const T a1 = -s * nq * iww, a4 = s * nq * iyy, tA = s * c.uq * iww * rq, tB = s * qd * iyy * rq;
+        const T tx = tA * c.Wx - tB * Yx, ty = tA * c.Wy - tB * Yy, tz = tA * c.Wz - tB * Yz;
+        cg[0] += a1 * c.Wx; cg[1] += a1 * c.Wy; cg[2] += a1 * c.Wz;                    // N_j
+        rg[6] -= a4 * Yx; rg[7] -= a4 * Yy; rg[8] -= a4 * Yz;                          // CB_i  (a4 * B, B = -Y)
+        cg[3] += tx - a1 * c.Wx; cg[4] += ty - a1 * c.Wy; cg[5] += tz - a1 * c.Wz;     // CA_j
+        cg[6] -= tx - a4 * Yx; cg[7] -= ty - a4 * Yy; cg[8] -= tz - a4 * Yz;           // CB_j
     }
-    if (mask & 32) {  // phi(j,i): angle between Q and -D at CB_j; sin = |Y| / (|Q||D|)
-        const T rY = t_rsqrt(yy);
-        const T val = t_atan2(yy * rY, -qd);
-        spline_eval(geom[3], p.tab[3] + (size_t)ib.z * geom[3].K, val, f, df);
-        e2 += f;
-        if (df != (T)0) {
-            const T s = w2 * df * rY, a = qd * t_rcp(c.qq), b = qd * rd * rd;
-            const T ux = s * (Dx - a * Qx), uy = s * (Dy - a * Qy), uz = s * (Dz - a * Qz);      // d/dCA_j
-            const T vx = -s * (Qx - b * Dx), vy = -s * (Qy - b * Dy), vz = -s * (Qz - b * Dz);   // d/dCB_i
-            cg[3] += ux; cg[4] += uy; cg[5] += uz;
-            rg[6] += vx; rg[7] += vy; rg[8] += vz;
-            cg[6] -= ux + vx; cg[7] -= uy + vy; cg[8] -= uz + vz;
-        }
+    if (mask & 16) {
+        const T s = w2 * SPLINE_DF(c4, u4) * rX, a = pd * rp * rp, b = pd * rd * rd;
+        const T ux = -s * (Dx - a * Px), uy = -s * (Dy - a * Py), uz = -s * (Dz - a * Pz);   // d/dCA_i
+        const T vx = -s * (Px - b * Dx), vy = -s * (Py - b * Dy), vz = -s * (Pz - b * Dz);   // d/dCB_j
+        rg[3] += ux; rg[4] += uy; rg[5] += uz;
+        cg[6] += vx; cg[7] += vy; cg[8] += vz;
+        rg[6] -= ux + vx; rg[7] -= uy + vy; rg[8] -= uz + vz;
+    }
+    if (mask & 32) {
+        const T s = w2 * SPLINE_DF(c5, u5) * rY, a = qd * rq * rq, b = qd * rd * rd;
+        const T ux = s * (Dx - a * Qx), uy = s * (Dy - a * Qy), uz = s * (Dz - a * Qz);      // d/dCA_j
+        const T vx = -s * (Qx - b * Dx), vy = -s * (Qy - b * Dy), vz = -s * (Qz - b * Dz);   // d/dCB_i
+        cg[3] += ux; cg[4] += uy; cg[5] += uz;
+        rg[6] += vx; rg[7] += vy; rg[8] += vz;
+        cg[6] -= ux + vx; cg[7] -= uy + vy; cg[8] -= uz + vz;
     }
 }
 

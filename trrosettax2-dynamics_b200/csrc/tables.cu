@@ -178,6 +178,12 @@ int trx_tables_create(trx_ctx *ctx, int L, const trx_rst_set sets[4], trx_tables
         static const double dummy[2] = {0.0, 1.0};
         fill_geom(g64[t], s.n ? s.K : 2, s.n ? s.x : dummy);
         fill_geom(g32[t], s.n ? s.K : 2, s.n ? s.x : dummy);
+        if (s.n && (g32[t].urun0 > 6 || g32[t].urun1 < s.K - 1)) {
+            set_error("trx_tables_create: sets[%d].x must be uniformly spaced after at most 6 leading uneven intervals "
+                      "(uniform run found: intervals [%d,%d) of %d)", t, g32[t].urun0, g32[t].urun1, s.K - 1);
+            trx_tables_destroy(T);
+            return TRX_ERR_INVALID;
+        }
         if (s.n == 0) continue;
         double *d_x = nullptr, *d_y = nullptr;
         size_t ny = (size_t)s.n * s.K;
