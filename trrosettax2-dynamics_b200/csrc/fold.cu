@@ -45,11 +45,11 @@ struct FoldState {
     // vectors [G][ndof][32]
     float *x, *g, *d, *xt, *gt;
     float *S, *Y;            // [G][m][ndof][32]
-    float *rho;              // [G][m][32]
+    float *gram;             // [G][2][M*M][32]: s_i.y_j and y_i.y_j of the stored pairs (M = padded history)
     // per decoy [Npad]
     double *f, *fmem;        // accepted energy, last 3 accepted energies [3][Npad]
     float *alpha, *slope;
-    int lb_smem_d;           // L-BFGS keeps the direction in shared memory (fits)
+    int lb_M;                // compile-time history bound of the L-BFGS kernel in use (8, 16 or 24)
     int *nmem, *hist, *head, *iter, *run, *bt, *status, *restart;
     int *evals, *iters;
     double *terms;           // [TRX_NTERM][Npad] unweighted terms of the last evaluation
@@ -442,258 +442,304 @@ __global__ void __launch_bounds__(SEG_THREADS) torsion_grad_kernel(FoldState s)
     }
 }
 
-// K5: one CTA per decoy group; 8 warps split the torsion vector, lanes are decoys.
-// Consumes the evaluation of the trial point (ft, gt) and produces the next trial point.
-constexpr int LB_WARPS = 32;
+// K5: batched L-BFGS with non-monotone Armijo back-tracking, one CTA per decoy group
+// (lane = decoy, 8 warps split the torsion vector).  Consumes the evaluation of the trial
+// point (ft, gt) and produces the next trial point.
+//
+// The two-loop recursion is done on Gram matrices: per decoy we keep SY[i][j] = s_i.y_j and
+// YY[i][j] = y_i.y_j of the stored pairs.  One streaming pass over the history computes every
+// dot product the step needs (s_j.g, y_j.g and the new pair's products with all stored pairs:
+// 5 accumulators per slot, all loads independent), the m-dimensional recursion then runs on
+// scalars, and a second streaming pass forms d = c_g g + sum a_j s_j + sum b_j y_j and the
+// trial point.  2 bandwidth-bound sweeps instead of 4m latency-bound dependent ones.
+constexpr int LB_WARPS = 8;
 constexpr int LB_THREADS = LB_WARPS * 32;
 constexpr float LS_SIGMA = 0.1f;
 constexpr int LS_MAXBACK = 20;
+constexpr int LB_NSCAL = 8;   // ss, sy, yy, gg, s.g, y.g (+2 spare)
 
-constexpr int LB_U = 8;   // loads kept in flight per thread and vector in the streaming loops
+template <int M>
+struct LbSmem {
+    static constexpr int NRED = 5 * M + LB_NSCAL;
+    // phase A: per-warp partial sums; afterwards the same storage holds the Gram matrices
+    union {
+        float red[LB_WARPS][NRED][LANES];
+        float gram[2][M * M][LANES];
+    } u;
+    float sum[NRED][LANES];      // reduced sums: YG, YYn, YSn, SG, SYn (M each) then the scalars
+    float coefS[M][LANES], coefY[M][LANES];
+    float cg[LANES], alpha[LANES];
+    int mode[LANES];             // what pass B does for the lane: 0 nothing, 1 new direction, 2 x + alpha d, 3 xt = x
+    int slot[LANES];             // slot the new pair was written to (accepted steps)
+};
 
-// sum_k A[k]*B[k] over [k0,k1), element stride LANES; loads issued LB_U at a time
-__device__ __forceinline__ float lb_dot(const float *__restrict__ A, const float *B, int k0, int k1)
+template <int M>
+__global__ void __launch_bounds__(LB_THREADS, 1) lbfgs_kernel(FoldState s)
 {
-    float acc = 0.f;
-    for (int k = k0; k < k1; k += LB_U) {
-        float a[LB_U], b[LB_U];
-#pragma unroll
-        for (int u = 0; u < LB_U; ++u) {
-            const int kk = min(k + u, k1 - 1);
-            a[u] = A[(size_t)kk * LANES];
-            b[u] = B[(size_t)kk * LANES];
-        }
-#pragma unroll
-        for (int u = 0; u < LB_U; ++u) if (k + u < k1) acc += a[u] * b[u];
-    }
-    return acc;
-}
-
-// D[k] += c * A[k] over [k0,k1)
-__device__ __forceinline__ void lb_axpy(float *D, float c, const float *__restrict__ A, int k0, int k1)
-{
-    for (int k = k0; k < k1; k += LB_U) {
-        float a[LB_U];
-#pragma unroll
-        for (int u = 0; u < LB_U; ++u) a[u] = A[(size_t)min(k + u, k1 - 1) * LANES];
-#pragma unroll
-        for (int u = 0; u < LB_U; ++u) if (k + u < k1) D[(size_t)(k + u) * LANES] += c * a[u];
-    }
-}
-
-__device__ __forceinline__ float cta_sum(float v, float (*red)[LB_WARPS][LANES], int &buf, int warp, int lane)
-{
-    red[buf][warp][lane] = v;
-    __syncthreads();
-    float sum = 0.f;
-#pragma unroll
-    for (int k = 0; k < LB_WARPS; ++k) sum += red[buf][k][lane];
-    buf ^= 1;
-    return sum;
-}
-
-__global__ void __launch_bounds__(LB_THREADS) lbfgs_kernel(FoldState s)
-{
-    __shared__ float red[2][LB_WARPS][LANES];
-    __shared__ float alpha_h[64][LANES];   // two-loop alphas (m <= 64)
-    extern __shared__ float dsm[];         // the direction while the two-loop recursion works on it
+    extern __shared__ __align__(16) unsigned char lb_raw[];
+    LbSmem<M> &sm = *reinterpret_cast<LbSmem<M> *>(lb_raw);
+    constexpr int NRED = LbSmem<M>::NRED;
     const int g = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = g * LANES + lane;
     if (!s.gactive[g]) return;
     const int nd = s.ndof, m = s.m, Npad = s.Npad;
-    int buf = 0;
     const size_t vb = (size_t)g * nd * LANES + lane;
-    float *__restrict__ x = s.x + vb, *__restrict__ gv = s.g + vb, *__restrict__ dg = s.d + vb;
-    float *__restrict__ xt = s.xt + vb, *__restrict__ gt = s.gt + vb;
+    float *__restrict__ x = s.x + vb, *__restrict__ gv = s.g + vb, *__restrict__ d = s.d + vb;
+    float *__restrict__ xt = s.xt + vb;
+    const float *__restrict__ gt = s.gt + vb;
     float *__restrict__ S = s.S + (size_t)g * m * nd * LANES + lane, *__restrict__ Y = s.Y + (size_t)g * m * nd * LANES + lane;
-    float *__restrict__ rho = s.rho + (size_t)g * m * LANES + lane;
-    // shared-memory copy of d (stores to it cannot alias the streaming S/Y loads, so those
-    // pipeline freely); falls back to the global vector when 3L*128 B does not fit
-    float *d = s.lb_smem_d ? dsm + lane : dg;
-    const int k0 = warp * ((nd + LB_WARPS - 1) / LB_WARPS), k1 = min(nd, k0 + (nd + LB_WARPS - 1) / LB_WARPS);
+    float *__restrict__ gram = s.gram + (size_t)g * 2 * M * M * LANES;
 
+    // ---- per-decoy decision (replicated in every warp)
     int status = n < s.N ? s.status[n] : ST_DONE;
     int run = s.run[n], hist = s.hist[n], head = s.head[n], iter = s.iter[n], bt = s.bt[n], restart = s.restart[n], nmem = s.nmem[n];
     double f = s.f[n];
     float alpha = s.alpha[n], slope = s.slope[n];
     const double ft = s.ft[n];
     const bool fin = isfinite(ft);
-    int evals = s.evals[n] + (status != ST_DONE ? 1 : 0);
-    int iters = s.iters[n];
-    // ---- per-decoy decision (replicated in every warp)
-    // action: 0 none, 1 start run here (g = gt, steepest descent), 2 accepted step, 3 rejected step, 4 re-evaluate (run skipped)
+    // action: 0 none, 1 start run here (steepest descent), 2 accepted step, 3 rejected step, 4 run skipped (clash check)
     int action = 0;
     if (status == ST_INIT) {
-        bool skip = false;
         const Run &r = s.runs[run];
-        if (r.clash_check) {
-            const float e = (float)(s.terms[(size_t)TRX_T_VDW * Npad + n] + s.terms[(size_t)TRX_T_RAMA * Npad + n]);
-            skip = e < r.clash_thr;
-        }
-        if (skip) {
-            run = r.skip_to;
-            action = 4;
-        } else {
-            action = 1;
-        }
+        bool skip = false;
+        if (r.clash_check) skip = (float)(s.terms[(size_t)TRX_T_VDW * Npad + n] + s.terms[(size_t)TRX_T_RAMA * Npad + n]) < r.clash_thr;
+        action = skip ? 4 : 1;
     } else if (status == ST_LS) {
         double fref = s.fmem[n];
         for (int q = 1; q < min(nmem, 3); ++q) fref = fmax(fref, s.fmem[(size_t)q * Npad + n]);
-        if (fin && ft <= fref + (double)(LS_SIGMA * alpha * slope)) action = 2;
-        else action = 3;
+        action = (fin && ft <= fref + (double)(LS_SIGMA * alpha * slope)) ? 2 : 3;
     }
-    bool run_over = false;
-    if (action == 4) {
-        if (run >= s.nruns) { status = ST_DONE; action = 0; }
-        else {
+    const bool is_acc = action == 2, is_new = action == 1 || action == 2;
+
+    // ---- pass A: every dot product of the step in one sweep over the history
+    float aYG[M], aYY[M], aYS[M], aSG[M], aSY[M], sc[LB_NSCAL];
 #pragma unroll
-            for (int k = 0; k < TRX_NTERM; ++k) if (warp == 0) s.wl[(size_t)k * Npad + n] = s.runs[run].w[k];
-            status = ST_INIT;   // xt stays = x; next round evaluates under the new weights
-        }
-    }
-    // ---- accepted step: history update, convergence
-    float sy = 0.f, ss = 0.f, yy = 0.f;
-    if (action == 2) {
-        for (int k = k0; k < k1; ++k) {
-            const float sk = xt[k * LANES] - x[k * LANES], yk = gt[k * LANES] - gv[k * LANES];
-            S[((size_t)head * nd + k) * LANES] = sk;
-            Y[((size_t)head * nd + k) * LANES] = yk;
-            sy += sk * yk; ss += sk * sk; yy += yk * yk;
-        }
-    }
-    sy = cta_sum(sy, red, buf, warp, lane);
-    ss = cta_sum(ss, red, buf, warp, lane);
-    yy = cta_sum(yy, red, buf, warp, lane);
-    if (action == 2) {
-        if (sy > 1e-10f * sqrtf(ss * yy)) {
-            if (warp == 0) rho[head * LANES] = 1.0f / sy;
-            head = (head + 1) % m;
-            if (hist < m) hist++;
-        }
-        const bool conv = 2.0 * fabs(ft - f) <= (double)s.runs[run].tol * (fabs(ft) + fabs(f) + 1e-10);
-        f = ft;
-        if (warp == 0) s.fmem[(size_t)(nmem % 3) * Npad + n] = f;
-        nmem++;
-        iter++; iters++;
-        restart = 0;
-        bt = 0;
-        if (conv || iter >= s.runs[run].max_iter) run_over = true;
-    }
-    if (action == 1) {
-        f = ft;
-        hist = 0; head = 0; iter = 0; bt = 0; restart = 1; nmem = 1;
-        if (warp == 0) s.fmem[n] = f;
-        if (!fin) run_over = true;   // cannot start from a non-finite energy
-    }
-    if (action == 3) {
-        bt++;
-        if (bt >= LS_MAXBACK) {
-            if (hist > 0) { hist = 0; head = 0; restart = 1; bt = 0; action = 5; }   // retry from steepest descent
-            else run_over = true;
-        } else {
-            float q = fin ? -0.5f * slope * alpha * alpha / (float)(ft - f - (double)(slope * alpha)) : 0.1f * alpha;
-            if (!(q > 0.1f * alpha)) q = 0.1f * alpha;
-            if (q > 0.5f * alpha) q = 0.5f * alpha;
-            alpha = q;
-        }
-    }
-    __syncthreads();   // rho written by warp 0 is read below
-    // x, g take the trial values on accept / run start
-    if (action == 1 || action == 2) {
-        for (int k = k0; k < k1; ++k) {
-            x[k * LANES] = xt[k * LANES];
-            gv[k * LANES] = gt[k * LANES];
-        }
-    }
-    if (run_over) {
-        // the run ends at x (accepted point, or the last accepted point after a failed search)
-        run++;
-        if (run >= s.nruns) status = ST_DONE;
-        else {
-            status = ST_INIT;
+    for (int j = 0; j < M; ++j) { aYG[j] = 0.f; aYY[j] = 0.f; aYS[j] = 0.f; aSG[j] = 0.f; aSY[j] = 0.f; }
 #pragma unroll
-            for (int k = 0; k < TRX_NTERM; ++k) if (warp == 0) s.wl[(size_t)k * Npad + n] = s.runs[run].w[k];
+    for (int j = 0; j < LB_NSCAL; ++j) sc[j] = 0.f;
+    for (int k = warp; k < nd; k += LB_WARPS) {
+        const float xk = x[(size_t)k * LANES], xtk = xt[(size_t)k * LANES], gk = gv[(size_t)k * LANES], gtk = gt[(size_t)k * LANES];
+        const float sn = xtk - xk, yn = gtk - gk, gn = is_new ? gtk : gk;
+        float yj[M], sj[M];
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+            yj[j] = j < m ? Y[((size_t)j * nd + k) * LANES] : 0.f;
+            sj[j] = j < m ? S[((size_t)j * nd + k) * LANES] : 0.f;
         }
-        for (int k = k0; k < k1; ++k) xt[k * LANES] = x[k * LANES];
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+            aYG[j] += yj[j] * gn; aYY[j] += yj[j] * yn; aYS[j] += yj[j] * sn;
+            aSG[j] += sj[j] * gn; aSY[j] += sj[j] * yn;
+        }
+        sc[0] += sn * sn; sc[1] += sn * yn; sc[2] += yn * yn; sc[3] += gn * gn; sc[4] += sn * gn; sc[5] += yn * gn;
+        if (is_acc) {
+            S[((size_t)head * nd + k) * LANES] = sn;
+            Y[((size_t)head * nd + k) * LANES] = yn;
+        }
+        if (is_new) {
+            x[(size_t)k * LANES] = xtk;
+            gv[(size_t)k * LANES] = gtk;
+        }
     }
-    // ---- new direction for decoys that continue: d = -H g (two-loop recursion)
-    const bool need_dir = !run_over && (action == 1 || action == 2 || action == 5);
-    float gnorm2 = 0.f;
-    if (need_dir) for (int k = k0; k < k1; ++k) { const float v = gv[k * LANES]; d[k * LANES] = -v; gnorm2 += v * v; }
-    gnorm2 = cta_sum(gnorm2, red, buf, warp, lane);
-    const int hmax = __reduce_max_sync(0xffffffffu, need_dir ? hist : 0);
-    __shared__ int hmax_s;
-    if (threadIdx.x == 0) hmax_s = 0;
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+        sm.u.red[warp][j][lane] = aYG[j]; sm.u.red[warp][M + j][lane] = aYY[j]; sm.u.red[warp][2 * M + j][lane] = aYS[j];
+        sm.u.red[warp][3 * M + j][lane] = aSG[j]; sm.u.red[warp][4 * M + j][lane] = aSY[j];
+    }
+#pragma unroll
+    for (int j = 0; j < LB_NSCAL; ++j) sm.u.red[warp][5 * M + j][lane] = sc[j];
     __syncthreads();
-    if (lane == 0) atomicMax(&hmax_s, hmax);
+    for (int e = threadIdx.x; e < NRED * LANES; e += LB_THREADS) {
+        const int idx = e / LANES, l = e % LANES;
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < LB_WARPS; ++w) t += sm.u.red[w][idx][l];
+        sm.sum[idx][l] = t;
+    }
     __syncthreads();
-    const int H = hmax_s;
-    for (int q = 0; q < H; ++q) {
-        const bool on = need_dir && q < hist;
-        const int h = (head - 1 - q + 2 * m) % m;
-        float a = 0.f;
-        if (on) a = lb_dot(S + (size_t)h * nd * LANES, d, k0, k1);
-        a = cta_sum(a, red, buf, warp, lane);
-        if (on) {
-            a *= rho[h * LANES];
-            if (warp == 0) alpha_h[q][lane] = a;
-            lb_axpy(d, -a, Y + (size_t)h * nd * LANES, k0, k1);
+    // Gram matrices into shared memory (the partial sums are no longer needed)
+    for (int e = threadIdx.x; e < 2 * M * M * LANES; e += LB_THREADS) (&sm.u.gram[0][0][0])[e] = gram[e];
+    __syncthreads();
+
+    // ---- per-decoy step logic on scalars (warp 0, one lane per decoy)
+    if (warp == 0) {
+        float(*SYm)[LANES] = sm.u.gram[0];
+        float(*YYm)[LANES] = sm.u.gram[1];
+        const float ss = sm.sum[5 * M + 0][lane], sy = sm.sum[5 * M + 1][lane], yy = sm.sum[5 * M + 2][lane];
+        const float gg = sm.sum[5 * M + 3][lane], sgn = sm.sum[5 * M + 4][lane], ygn = sm.sum[5 * M + 5][lane];
+        int evals = s.evals[n] + (status != ST_DONE ? 1 : 0), iters = s.iters[n];
+        bool run_over = false, need_dir = false;
+        int mode = 0;
+        if (action == 4) {
+            run = s.runs[run].skip_to;
+            if (run >= s.nruns) status = ST_DONE;
+            else {
+                for (int k = 0; k < TRX_NTERM; ++k) s.wl[(size_t)k * Npad + n] = s.runs[run].w[k];
+                status = ST_INIT;   // xt stays = x; the next round evaluates it under the new weights
+            }
         }
-    }
-    {
-        const bool on = need_dir && hist > 0;
-        const int h0 = (head - 1 + m) % m;
-        float y2 = 0.f;
-        if (on) y2 = lb_dot(Y + (size_t)h0 * nd * LANES, Y + (size_t)h0 * nd * LANES, k0, k1);
-        y2 = cta_sum(y2, red, buf, warp, lane);
-        if (on) {
-            const float gamma = 1.0f / (rho[h0 * LANES] * y2);
-            for (int k = k0; k < k1; ++k) d[k * LANES] *= gamma;
+        if (action == 2) {
+            const int h = head;
+            if (sy > 1e-10f * sqrtf(ss * yy)) {
+                // the new pair enters slot h: its row and column of the Gram matrices
+                for (int q = 0; q < hist; ++q) {
+                    const int j = (head - 1 - q + 2 * m) % m;
+                    if (j == h) continue;   // the slot being overwritten (history full)
+                    SYm[h * M + j][lane] = sm.sum[2 * M + j][lane];   // s_new . y_j
+                    SYm[j * M + h][lane] = sm.sum[4 * M + j][lane];   // s_j . y_new
+                    YYm[h * M + j][lane] = sm.sum[M + j][lane];       // y_new . y_j
+                    YYm[j * M + h][lane] = sm.sum[M + j][lane];
+                }
+                SYm[h * M + h][lane] = sy;
+                YYm[h * M + h][lane] = yy;
+                sm.sum[3 * M + h][lane] = sgn;   // s_new . g_new
+                sm.sum[0 * M + h][lane] = ygn;   // y_new . g_new
+                head = (head + 1) % m;
+                if (hist < m) hist++;
+            } else if (hist == m) {
+                hist = m - 1;   // the write in pass A clobbered the oldest pair: drop it
+            }
+            const bool conv = 2.0 * fabs(ft - f) <= (double)s.runs[run].tol * (fabs(ft) + fabs(f) + 1e-10);
+            f = ft;
+            s.fmem[(size_t)(nmem % 3) * Npad + n] = f;
+            nmem++; iter++; iters++;
+            restart = 0; bt = 0;
+            if (conv || iter >= s.runs[run].max_iter) run_over = true;
+            else need_dir = true;
+        } else if (action == 1) {
+            f = ft;
+            hist = 0; head = 0; iter = 0; bt = 0; restart = 1; nmem = 1;
+            s.fmem[n] = f;
+            if (!fin) run_over = true;   // cannot start from a non-finite energy
+            else need_dir = true;
+        } else if (action == 3) {
+            bt++;
+            if (bt >= LS_MAXBACK) {
+                if (hist > 0) { hist = 0; head = 0; restart = 1; bt = 0; need_dir = true; }   // retry from steepest descent
+                else run_over = true;
+            } else {
+                float q = fin ? -0.5f * slope * alpha * alpha / (float)(ft - f - (double)(slope * alpha)) : 0.1f * alpha;
+                if (!(q > 0.1f * alpha)) q = 0.1f * alpha;
+                if (q > 0.5f * alpha) q = 0.5f * alpha;
+                alpha = q;
+                mode = 2;
+            }
         }
-    }
-    for (int q = H - 1; q >= 0; --q) {
-        const bool on = need_dir && q < hist;
-        const int h = (head - 1 - q + 2 * m) % m;
-        float b = 0.f;
-        if (on) b = lb_dot(Y + (size_t)h * nd * LANES, d, k0, k1);
-        b = cta_sum(b, red, buf, warp, lane);
-        if (on) {
-            const float c = alpha_h[q][lane] - rho[h * LANES] * b;
-            lb_axpy(d, c, S + (size_t)h * nd * LANES, k0, k1);
-        }
-    }
-    float sl = 0.f;
-    if (need_dir) for (int k = k0; k < k1; ++k) sl += gv[k * LANES] * d[k * LANES];
-    sl = cta_sum(sl, red, buf, warp, lane);
-    if (need_dir) {
-        const float gnorm = sqrtf(gnorm2);
-        if (!(sl < 0.f)) {   // not a descent direction: steepest descent
-            hist = 0; head = 0; restart = 1;
-            for (int k = k0; k < k1; ++k) d[k * LANES] = -gv[k * LANES];
-            sl = -gnorm2;
-        }
-        slope = sl;
-        alpha = restart ? fminf(1.0f, 1.0f / fmaxf(gnorm, 1e-20f)) : 1.0f;
-        status = ST_LS;
-        if (gnorm2 == 0.f) {   // stationary: the run is over
+        if (run_over) {
             run++;
             if (run >= s.nruns) status = ST_DONE;
             else {
                 status = ST_INIT;
+                for (int k = 0; k < TRX_NTERM; ++k) s.wl[(size_t)k * Npad + n] = s.runs[run].w[k];
+            }
+            mode = 3;   // the run ends at x (last accepted point)
+        }
+        float cgv = -1.f;
 #pragma unroll
-                for (int k = 0; k < TRX_NTERM; ++k) if (warp == 0) s.wl[(size_t)k * Npad + n] = s.runs[run].w[k];
+        for (int j = 0; j < M; ++j) { sm.coefS[j][lane] = 0.f; sm.coefY[j][lane] = 0.f; }
+        if (need_dir) {
+            // two-loop recursion on scalars; q-th newest pair lives in slot (head-1-q) mod m
+            // d = -r,  r = gamma (g - sum a_j y_j) + sum c_j s_j
+            float sl = -gg;
+            if (hist > 0) {
+                const float *SGv = &sm.sum[3 * M][0], *YGv = &sm.sum[0][0];
+                float al[M];
+                for (int q = 0; q < hist; ++q) {
+                    const int i = (head - 1 - q + 2 * m) % m;
+                    float t = SGv[i * LANES + lane];
+                    for (int q2 = 0; q2 < q; ++q2) {
+                        const int j = (head - 1 - q2 + 2 * m) % m;
+                        t -= al[q2] * SYm[i * M + j][lane];
+                    }
+                    al[q] = t / SYm[i * M + i][lane];
+                }
+                const int h0 = (head - 1 + m) % m;
+                const float gamma = SYm[h0 * M + h0][lane] / YYm[h0 * M + h0][lane];
+                float cc[M];
+                for (int q = hist - 1; q >= 0; --q) {
+                    const int i = (head - 1 - q + 2 * m) % m;
+                    float t = YGv[i * LANES + lane];
+                    for (int q2 = 0; q2 < hist; ++q2) {
+                        const int j = (head - 1 - q2 + 2 * m) % m;
+                        t -= al[q2] * YYm[i * M + j][lane];
+                    }
+                    t *= gamma;
+                    for (int q2 = hist - 1; q2 > q; --q2) {
+                        const int j = (head - 1 - q2 + 2 * m) % m;
+                        t += cc[q2] * SYm[j * M + i][lane];
+                    }
+                    const float beta = t / SYm[i * M + i][lane];
+                    cc[q] = al[q] - beta;
+                }
+                cgv = -gamma;
+                sl = -gamma * gg;
+                for (int q = 0; q < hist; ++q) {
+                    const int i = (head - 1 - q + 2 * m) % m;
+                    sm.coefY[i][lane] = gamma * al[q];
+                    sm.coefS[i][lane] = -cc[q];
+                    sl += gamma * al[q] * YGv[i * LANES + lane] - cc[q] * SGv[i * LANES + lane];
+                }
+            }
+            if (!(sl < 0.f) || !isfinite(sl)) {   // not a descent direction: steepest descent
+                hist = 0; head = 0; restart = 1;
+                cgv = -1.f;
+#pragma unroll
+                for (int j = 0; j < M; ++j) { sm.coefS[j][lane] = 0.f; sm.coefY[j][lane] = 0.f; }
+                sl = -gg;
+            }
+            slope = sl;
+            const float gnorm = sqrtf(gg);
+            alpha = restart ? fminf(1.0f, 1.0f / fmaxf(gnorm, 1e-20f)) : 1.0f;
+            status = ST_LS;
+            mode = 1;
+            if (gg == 0.f) {   // stationary: the run is over
+                run++;
+                if (run >= s.nruns) status = ST_DONE;
+                else {
+                    status = ST_INIT;
+                    for (int k = 0; k < TRX_NTERM; ++k) s.wl[(size_t)k * Npad + n] = s.runs[run].w[k];
+                }
+                mode = 3;
             }
         }
+        sm.cg[lane] = cgv;
+        sm.alpha[lane] = alpha;
+        sm.mode[lane] = mode;
+        if (n < s.N) {
+            s.status[n] = status; s.run[n] = run; s.hist[n] = hist; s.head[n] = head; s.iter[n] = iter; s.bt[n] = bt;
+            s.restart[n] = restart; s.nmem[n] = nmem; s.f[n] = f; s.alpha[n] = alpha; s.slope[n] = slope;
+            s.evals[n] = evals; s.iters[n] = iters;
+        }
     }
-    // ---- next trial point (and the direction back to global memory for later rounds)
-    if (need_dir && s.lb_smem_d) for (int k = k0; k < k1; ++k) dg[k * LANES] = d[k * LANES];
-    if (status == ST_LS) {
-        if (need_dir) for (int k = k0; k < k1; ++k) xt[k * LANES] = x[k * LANES] + alpha * d[k * LANES];
-        else for (int k = k0; k < k1; ++k) xt[k * LANES] = x[k * LANES] + alpha * dg[k * LANES];
-    }
-    if (warp == 0 && n < s.N) {
-        s.status[n] = status; s.run[n] = run; s.hist[n] = hist; s.head[n] = head; s.iter[n] = iter; s.bt[n] = bt;
-        s.restart[n] = restart; s.nmem[n] = nmem; s.f[n] = f; s.alpha[n] = alpha; s.slope[n] = slope;
-        s.evals[n] = evals; s.iters[n] = iters;
+    __syncthreads();
+    // Gram matrices back to global memory
+    for (int e = threadIdx.x; e < 2 * M * M * LANES; e += LB_THREADS) gram[e] = (&sm.u.gram[0][0][0])[e];
+
+    // ---- pass B: new direction and next trial point
+    const int mode = sm.mode[lane];
+    const float cgv = sm.cg[lane], al = sm.alpha[lane];
+    float cS[M], cY[M];
+#pragma unroll
+    for (int j = 0; j < M; ++j) { cS[j] = sm.coefS[j][lane]; cY[j] = sm.coefY[j][lane]; }
+    const int anydir = __syncthreads_or(mode == 1);
+    for (int k = warp; k < nd; k += LB_WARPS) {
+        const float xk = x[(size_t)k * LANES];
+        if (anydir) {
+            float dk = cgv * gv[(size_t)k * LANES];
+            float yj[M], sj[M];
+#pragma unroll
+            for (int j = 0; j < M; ++j) {
+                yj[j] = j < m ? Y[((size_t)j * nd + k) * LANES] : 0.f;
+                sj[j] = j < m ? S[((size_t)j * nd + k) * LANES] : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < M; ++j) dk += cS[j] * sj[j] + cY[j] * yj[j];
+            if (mode == 1) {
+                d[(size_t)k * LANES] = dk;
+                xt[(size_t)k * LANES] = xk + al * dk;
+            }
+        }
+        if (mode == 2) xt[(size_t)k * LANES] = xk + al * d[(size_t)k * LANES];
+        else if (mode == 3) xt[(size_t)k * LANES] = xk;
     }
 }
 
@@ -825,7 +871,7 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     TRX_REQUIRE(ctx && tabs && ndecoys && aa && runs && out, "trx_fold_create: NULL argument");
     TRX_REQUIRE(ntab >= 1 && ntab <= 16, "trx_fold_create: ntab=%d out of range [1,16]", ntab);
     TRX_REQUIRE(nruns >= 1 && nruns <= 256, "trx_fold_create: nruns=%d out of range [1,256]", nruns);
-    TRX_REQUIRE(lbfgs_m >= 1 && lbfgs_m <= 64, "trx_fold_create: lbfgs_m=%d out of range [1,64]", lbfgs_m);
+    TRX_REQUIRE(lbfgs_m >= 1 && lbfgs_m <= 24, "trx_fold_create: lbfgs_m=%d out of range [1,24]", lbfgs_m);
     TRX_CUDA(cudaSetDevice(ctx->device));
     const int L = tabs[0]->L;
     int G = 0;
@@ -858,7 +904,8 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
     const size_t vec = (size_t)G * s.ndof * LANES * sizeof(float), np = (size_t)s.Npad;
     size_t o_x = carve(vec), o_g = carve(vec), o_d = carve(vec), o_xt = carve(vec), o_gt = carve(vec);
-    size_t o_S = carve(vec * s.m), o_Y = carve(vec * s.m), o_rho = carve((size_t)G * s.m * LANES * sizeof(float));
+    const int lbM = lbfgs_m <= 8 ? 8 : (lbfgs_m <= 16 ? 16 : 24);
+    size_t o_S = carve(vec * s.m), o_Y = carve(vec * s.m), o_rho = carve((size_t)G * 2 * lbM * lbM * LANES * sizeof(float));
     size_t o_f = carve(np * 8), o_al = carve(np * 4), o_sl = carve(np * 4), o_fm = carve(np * 24);
     size_t o_i[10];
     for (int k = 0; k < 10; ++k) o_i[k] = carve(np * 4);
@@ -877,7 +924,7 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     TRX_CUDA(cudaMemsetAsync(b->arena, 0, off, ctx->stream));
     char *A = (char *)b->arena;
     s.x = (float *)(A + o_x); s.g = (float *)(A + o_g); s.d = (float *)(A + o_d); s.xt = (float *)(A + o_xt); s.gt = (float *)(A + o_gt);
-    s.S = (float *)(A + o_S); s.Y = (float *)(A + o_Y); s.rho = (float *)(A + o_rho);
+    s.S = (float *)(A + o_S); s.Y = (float *)(A + o_Y); s.gram = (float *)(A + o_rho); s.lb_M = lbM;
     s.f = (double *)(A + o_f); s.alpha = (float *)(A + o_al); s.slope = (float *)(A + o_sl); s.fmem = (double *)(A + o_fm);
     s.nmem = (int *)(A + o_i[0]); s.hist = (int *)(A + o_i[1]); s.head = (int *)(A + o_i[2]); s.iter = (int *)(A + o_i[3]);
     s.run = (int *)(A + o_i[4]); s.bt = (int *)(A + o_i[5]); s.status = (int *)(A + o_i[6]); s.restart = (int *)(A + o_i[7]);
@@ -902,10 +949,9 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     s.runs = b->d_runs;
     upload_model();
     TRX_CUDA(cudaFuncSetAttribute(vdw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->vdw_smem));
-    b->lb_smem = (size_t)s.ndof * LANES * sizeof(float);
-    if (b->lb_smem > 200 * 1024) b->lb_smem = 0;
-    s.lb_smem_d = b->lb_smem ? 1 : 0;
-    if (b->lb_smem) TRX_CUDA(cudaFuncSetAttribute(lbfgs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->lb_smem));
+    if (lbM == 8) { b->lb_smem = sizeof(LbSmem<8>); TRX_CUDA(cudaFuncSetAttribute(lbfgs_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->lb_smem)); }
+    else if (lbM == 16) { b->lb_smem = sizeof(LbSmem<16>); TRX_CUDA(cudaFuncSetAttribute(lbfgs_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->lb_smem)); }
+    else { b->lb_smem = sizeof(LbSmem<24>); TRX_CUDA(cudaFuncSetAttribute(lbfgs_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->lb_smem)); }
     *out = b;
     return TRX_OK;
 }
@@ -975,7 +1021,9 @@ int trx_fold_run(trx_fold_batch *b, float *tors, float *xyz, double *terms, long
             ctx->time_end("activity");
             if ((rc = fold_eval(b, ng.data(), false))) { cudaFreeHost(h_nslot); return rc; }
             ctx->time_begin("lbfgs");
-            lbfgs_kernel<<<s.G, LB_THREADS, b->lb_smem, ctx->stream>>>(s);
+            if (s.lb_M == 8) lbfgs_kernel<8><<<s.G, LB_THREADS, b->lb_smem, ctx->stream>>>(s);
+            else if (s.lb_M == 16) lbfgs_kernel<16><<<s.G, LB_THREADS, b->lb_smem, ctx->stream>>>(s);
+            else lbfgs_kernel<24><<<s.G, LB_THREADS, b->lb_smem, ctx->stream>>>(s);
             ctx->time_end("lbfgs");
         }
         TRX_CUDA(cudaMemcpyAsync(h_nslot, s.nslot, 16 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
