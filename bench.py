@@ -265,9 +265,19 @@ def run_b200_fold(args):
     ctx.reset_timing()
     launches0 = ctx.launch_count
     barrier()
+    from trx2dyn import parallel
     t_wall, evals_total, rest_evals = [], 0, 0.0
+    pool = None
     for k in range(steps):
-        t_wall.append(one_fold(1000 * rank + 100 + k))
+        t0 = time.perf_counter()
+        dt = one_fold(1000 * rank + 100 + k)
+        if world > 1:
+            # the path's only exchange: all-gather of per-decoy energies (NCCL) for pool selection
+            score = (terms_h.numpy() * np.array([5.0, 4.0, 4.0, 1.0, 1.0, 0.5])).sum(1)
+            full = parallel.gather_scalars(score, N * world, rank, world, device="cuda")
+            pool = parallel.select_pool(full[:, 0], 10)
+            dt = time.perf_counter() - t0
+        t_wall.append(dt)
         ev = stats_h[:, 0].numpy().astype(np.float64)
         evals_total += float(ev.sum())
         rest_evals += float(ev[:nd[0]].sum()) * R[0] + float(ev[nd[0]:].sum()) * R[1]
@@ -301,7 +311,8 @@ def run_b200_fold(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "synthetic L=300 dist+omega+theta+phi, two-model mixing, %d decoys per GPU, full mode-2 centroid schedule (configs[2])" % N,
                        "restraints_per_decoy": R, "l2": "working set per step (%.1f GB of decoy state) exceeds L2" % (batch_bytes(N, L_TARGET, args.lbfgs_m) / 1e9),
-                       "mode": "fold", "lbfgs_m": args.lbfgs_m, "cartesian_stage": "not built (DESIGN.md)"},
+                       "mode": "fold", "lbfgs_m": args.lbfgs_m, "cartesian_stage": "not built (DESIGN.md)",
+                       "collective": "all-gather of per-decoy energies for pool selection (N>1 only)"},
             "restraint_decoy_evals_per_sec": evals_total * world / t_dev,
             "restraint_evals_per_sec": rest_evals * world / t_dev,
             "mean_evals_per_decoy": evals_total / (N * steps), "rounds_last_step": rounds.value,

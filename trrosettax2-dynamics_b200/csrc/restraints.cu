@@ -63,6 +63,8 @@ struct K1Params {
     const KnotGeom<T> *geom;                     // [4]
     const int *pairrec;                          // [ntiles][16][16][8]
     const int *tileJ;                            // [ntiles]
+    const unsigned char *sched;                  // [ntiles][16][8] step schedule (column per warp, 0xff idle)
+    const int *nsteps;                           // [ntiles]
     const int *work;                             // [nwork][4]
     T *recs;                                     // [G][nrec][REC_ELEMS]
     double *Epart;                               // [G][nwork][3][32]
@@ -273,11 +275,12 @@ __global__ void __launch_bounds__(K1_THREADS, (sizeof(T) == 4 ? 2 : 1)) restrain
         w1 = (T)p.wl[1 * (size_t)p.Npad + g * LANES + lane];
         w2 = (T)p.wl[2 * (size_t)p.Npad + g * LANES + lane];
     }
-    // rows w and w+8: CB, P = CA-CB, U = N-CA; gradient accumulators N, CA, CB
+    // rows 2w and 2w+1 (adjacent residues have near-identical contact patterns, which keeps the
+    // two pairs of a step balanced): CB, P = CA-CB, U = N-CA; gradient accumulators N, CA, CB
     T row[2][9], rg[2][9];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-        const int res = I * TILE + w + K1_WARPS * r;
+        const int res = I * TILE + 2 * w + r;
         T v[9];
 #pragma unroll
         for (int c = 0; c < 9; ++c) {
@@ -298,38 +301,37 @@ __global__ void __launch_bounds__(K1_THREADS, (sizeof(T) == 4 ? 2 : 1)) restrain
         const int J = p.tileJ[t];
         const int *__restrict__ rec_t = p.pairrec + (size_t)t * TILE * TILE * 8;
         T f0 = (T)0, f1 = (T)0, f2 = (T)0;   // per-tile partial energies (<= 64 restraints per term)
-        // staggered schedule: in step s warp w owns columns 2(w+s) and 2(w+s)+1 (mod 16),
-        // so no two warps touch the same column between barriers
-        for (int s = 0; s < TILE / 2; ++s) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int c = (2 * (w + s) + h) & (TILE - 1);
-                const int4 *r0 = reinterpret_cast<const int4 *>(rec_t + (w * TILE + c) * 8);
-                const int4 *r1 = reinterpret_cast<const int4 *>(rec_t + ((w + K1_WARPS) * TILE + c) * 8);
+        // host-built schedule (edge colouring of warps x columns): in a step every warp has at most
+        // one column and no column is shared, so column gradients need no atomics
+        const int ns = p.nsteps[t];
+        const unsigned char *__restrict__ sc_t = p.sched + (size_t)t * TILE * K1_WARPS;
+        for (int s = 0; s < ns; ++s) {
+            const int c = sc_t[s * K1_WARPS + w];
+            if (c != 0xff) {
+                const int4 *r0 = reinterpret_cast<const int4 *>(rec_t + ((2 * w) * TILE + c) * 8);
+                const int4 *r1 = reinterpret_cast<const int4 *>(rec_t + ((2 * w + 1) * TILE + c) * 8);
                 const int4 a0 = __ldg(r0), a1 = __ldg(r1);
-                if (a0.x | a1.x) {
-                    T cj[9], cg[9];
-                    const int res = J * TILE + c;
+                T cj[9], cg[9];
+                const int res = J * TILE + c;
 #pragma unroll
-                    for (int k = 0; k < 9; ++k) {
-                        cj[k] = Xg[((size_t)res * xs + k) * LANES];
-                        cg[k] = (T)0;
-                    }
-                    ColGeom<T> cgm;
-                    cgm.Bx = cj[6]; cgm.By = cj[7]; cgm.Bz = cj[8];
-                    cgm.Qx = cj[3] - cj[6]; cgm.Qy = cj[4] - cj[7]; cgm.Qz = cj[5] - cj[8];
-                    cgm.Ux = cj[0] - cj[3]; cgm.Uy = cj[1] - cj[4]; cgm.Uz = cj[2] - cj[5];
-                    cgm.Wx = cgm.Uy * cgm.Qz - cgm.Uz * cgm.Qy;
-                    cgm.Wy = cgm.Uz * cgm.Qx - cgm.Ux * cgm.Qz;
-                    cgm.Wz = cgm.Ux * cgm.Qy - cgm.Uy * cgm.Qx;
-                    cgm.qq = max(cgm.Qx * cgm.Qx + cgm.Qy * cgm.Qy + cgm.Qz * cgm.Qz, t_tiny<T>());
-                    cgm.ww = max(cgm.Wx * cgm.Wx + cgm.Wy * cgm.Wy + cgm.Wz * cgm.Wz, t_tiny<T>());
-                    cgm.uq = cgm.Ux * cgm.Qx + cgm.Uy * cgm.Qy + cgm.Uz * cgm.Qz;
-                    if (a0.x) pair_eval<T>(p, geom, a0, __ldg(r0 + 1), row[0], cgm, rg[0], cg, w0, w1, w2, f0, f1, f2);
-                    if (a1.x) pair_eval<T>(p, geom, a1, __ldg(r1 + 1), row[1], cgm, rg[1], cg, w0, w1, w2, f0, f1, f2);
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) colg[(c * 9 + k) * LANES + lane] += cg[k];
+                for (int k = 0; k < 9; ++k) {
+                    cj[k] = Xg[((size_t)res * xs + k) * LANES];
+                    cg[k] = (T)0;
                 }
+                ColGeom<T> cgm;
+                cgm.Bx = cj[6]; cgm.By = cj[7]; cgm.Bz = cj[8];
+                cgm.Qx = cj[3] - cj[6]; cgm.Qy = cj[4] - cj[7]; cgm.Qz = cj[5] - cj[8];
+                cgm.Ux = cj[0] - cj[3]; cgm.Uy = cj[1] - cj[4]; cgm.Uz = cj[2] - cj[5];
+                cgm.Wx = cgm.Uy * cgm.Qz - cgm.Uz * cgm.Qy;
+                cgm.Wy = cgm.Uz * cgm.Qx - cgm.Ux * cgm.Qz;
+                cgm.Wz = cgm.Ux * cgm.Qy - cgm.Uy * cgm.Qx;
+                cgm.qq = max(cgm.Qx * cgm.Qx + cgm.Qy * cgm.Qy + cgm.Qz * cgm.Qz, t_tiny<T>());
+                cgm.ww = max(cgm.Wx * cgm.Wx + cgm.Wy * cgm.Wy + cgm.Wz * cgm.Wz, t_tiny<T>());
+                cgm.uq = cgm.Ux * cgm.Qx + cgm.Uy * cgm.Qy + cgm.Uz * cgm.Qz;
+                if (a0.x) pair_eval<T>(p, geom, a0, __ldg(r0 + 1), row[0], cgm, rg[0], cg, w0, w1, w2, f0, f1, f2);
+                if (a1.x) pair_eval<T>(p, geom, a1, __ldg(r1 + 1), row[1], cgm, rg[1], cg, w0, w1, w2, f0, f1, f2);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) colg[(c * 9 + k) * LANES + lane] += cg[k];
             }
             __syncthreads();
         }
@@ -346,7 +348,7 @@ __global__ void __launch_bounds__(K1_THREADS, (sizeof(T) == 4 ? 2 : 1)) restrain
 #pragma unroll
         for (int r = 0; r < 2; ++r)
 #pragma unroll
-            for (int k = 0; k < 9; ++k) dst[((w + K1_WARPS * r) * 9 + k) * LANES + lane] = rg[r][k];
+            for (int k = 0; k < 9; ++k) dst[((2 * w + r) * 9 + k) * LANES + lane] = rg[r][k];
     }
     ered[w][0][lane] = e0;
     ered[w][1][lane] = e1;
@@ -410,6 +412,8 @@ int k1_launch(trx_ctx *ctx, trx_tables *tb, int Gtot, int g0, int ng, const T *d
     p.geom = reinterpret_cast<const KnotGeom<T> *>(sizeof(T) == 8 ? (const void *)tb->d_geom64 : (const void *)tb->d_geom32);
     p.pairrec = tb->d_pairrec;
     p.tileJ = tb->d_tileJ;
+    p.sched = tb->d_sched;
+    p.nsteps = tb->d_nsteps;
     p.work = plan->d_work;
     p.recs = (T *)recs;
     p.Epart = (double *)epart;

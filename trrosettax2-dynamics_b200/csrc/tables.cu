@@ -251,6 +251,56 @@ int trx_tables_create(trx_ctx *ctx, int L, const trx_rst_set sets[4], trx_tables
             rec[p] |= 1 << slot;
             rec[p + 1 + slot] = r;
         }
+    // ---- per-tile step schedule.  Warp w of the restraint kernel owns rows 2w, 2w+1; a unit of
+    // work is (warp, column) = the two pairs of those rows with one column.  Units sharing a
+    // warp or a column must run in different steps (column gradients are accumulated without
+    // atomics), so a schedule is an edge colouring of the bipartite graph warps x columns; the
+    // alternating-path construction (Koenig) uses exactly max-degree colours, i.e. sparse tiles
+    // take as few barrier-separated steps as their busiest row pair / column allows.
+    std::vector<unsigned char> sched((size_t)std::max(1, T->ntiles) * TILE * K1_WARPS, 0xff);
+    std::vector<int> nsteps(std::max(1, T->ntiles), 0);
+    for (int t = 0; t < T->ntiles; ++t) {
+        int colU[K1_WARPS][TILE], colV[TILE][TILE];
+        for (int u = 0; u < K1_WARPS; ++u) for (int c = 0; c < TILE; ++c) colU[u][c] = -1;
+        for (int v = 0; v < TILE; ++v) for (int c = 0; c < TILE; ++c) colV[v][c] = -1;
+        int maxc = 0;
+        for (int u = 0; u < K1_WARPS; ++u)
+            for (int v = 0; v < TILE; ++v) {
+                const size_t p0 = (((size_t)t * TILE + 2 * u) * TILE + v) * 8, p1 = (((size_t)t * TILE + 2 * u + 1) * TILE + v) * 8;
+                if (!(rec[p0] | rec[p1])) continue;
+                int a = 0, b = 0;
+                while (colU[u][a] >= 0) ++a;
+                while (colV[v][b] >= 0) ++b;
+                if (a != b) {   // free colour a at v by swapping a and b along the alternating path from v
+                    struct E { int u, v, c; };
+                    std::vector<E> path;
+                    int cur = v;
+                    bool atV = true;
+                    for (;;) {
+                        if (atV) { int uu = colV[cur][a]; if (uu < 0) break; path.push_back({uu, cur, a}); cur = uu; atV = false; }
+                        else { int vv = colU[cur][b]; if (vv < 0) break; path.push_back({cur, vv, b}); cur = vv; atV = true; }
+                    }
+                    for (auto &e : path) { colU[e.u][e.c] = -1; colV[e.v][e.c] = -1; }
+                    for (auto &e : path) { const int nc = e.c == a ? b : a; colU[e.u][nc] = e.v; colV[e.v][nc] = e.u; }
+                }
+                colU[u][a] = v;
+                colV[v][a] = u;
+                maxc = std::max(maxc, std::max(a, b) + 1);
+            }
+        int ns = 0;
+        for (int c = 0; c < TILE; ++c) {
+            bool any = false;
+            for (int u = 0; u < K1_WARPS; ++u) any |= colU[u][c] >= 0;
+            if (!any) continue;
+            for (int u = 0; u < K1_WARPS; ++u) sched[((size_t)t * TILE + ns) * K1_WARPS + u] = colU[u][c] >= 0 ? (unsigned char)colU[u][c] : 0xff;
+            ++ns;
+        }
+        nsteps[t] = ns;
+    }
+    TRX_CUDA(cudaMalloc(&T->d_sched, sched.size()));
+    TRX_CUDA(cudaMalloc(&T->d_nsteps, nsteps.size() * sizeof(int)));
+    TRX_CUDA(cudaMemcpy(T->d_sched, sched.data(), sched.size(), cudaMemcpyHostToDevice));
+    TRX_CUDA(cudaMemcpy(T->d_nsteps, nsteps.data(), nsteps.size() * sizeof(int), cudaMemcpyHostToDevice));
     std::vector<int> tj = T->tileJ;
     if (tj.empty()) tj.push_back(0);
     TRX_CUDA(cudaMalloc(&T->d_tileJ, tj.size() * sizeof(int)));
@@ -275,6 +325,8 @@ int trx_tables_destroy(trx_tables *T)
     if (T->d_geom32) cudaFree(T->d_geom32);
     if (T->d_tileJ) cudaFree(T->d_tileJ);
     if (T->d_pairrec) cudaFree(T->d_pairrec);
+    if (T->d_sched) cudaFree(T->d_sched);
+    if (T->d_nsteps) cudaFree(T->d_nsteps);
     for (auto &kv : T->plans) {
         cudaFree(kv.second.d_work);
         cudaFree(kv.second.d_blk_ptr);
