@@ -111,8 +111,9 @@ struct trx_tables {
     std::vector<int> tileI, tileJ;   // host copies, tiles sorted by (I, J)
     int *d_tileJ = nullptr;          // [ntiles]
     int *d_pairrec = nullptr;        // [ntiles][16][16][8]: mask, 6 restraint indices, pad
-    unsigned char *d_sched = nullptr; // [ntiles][16 steps][8 warps]: column of the step, 0xff = idle
-    int *d_nsteps = nullptr;         // [ntiles]
+    unsigned short *d_sched = nullptr; // [steps][8 warps]: row | column<<4 of the pair, 0xffff = idle
+    int *d_nsteps = nullptr;         // [ntiles+1] first step of each tile (CSR)
+    int total_steps = 0;
     long long active_pairs = 0;
     std::map<int, trx::Plan> plans;  // keyed by number of decoy groups
     int get_plan(int groups, trx::Plan **out);

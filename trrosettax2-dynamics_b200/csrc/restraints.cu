@@ -63,8 +63,8 @@ struct K1Params {
     const KnotGeom<T> *geom;                     // [4]
     const int *pairrec;                          // [ntiles][16][16][8]
     const int *tileJ;                            // [ntiles]
-    const unsigned char *sched;                  // [ntiles][16][8] step schedule (column per warp, 0xff idle)
-    const int *nsteps;                           // [ntiles]
+    const unsigned short *sched;                 // [steps][8] pair of each warp: row | col<<4, 0xffff idle
+    const int *nsteps;                           // [ntiles+1] CSR of steps per tile
     const int *work;                             // [nwork][4]
     T *recs;                                     // [G][nrec][REC_ELEMS]
     double *Epart;                               // [G][nwork][3][32]
@@ -251,10 +251,12 @@ __device__ __forceinline__ void pair_eval(const K1Params<T> &p, const KnotGeom<T
 }
 
 template <typename T>
-__global__ void __launch_bounds__(K1_THREADS, (sizeof(T) == 4 ? 2 : 1)) restraints_kernel(const K1Params<T> p)
+__global__ void __launch_bounds__(K1_THREADS, (sizeof(T) == 4 ? 3 : 1)) restraints_kernel(const K1Params<T> p)
 {
     __shared__ KnotGeom<T> geom[4];
-    __shared__ __align__(16) T colg[REC_ELEMS];
+    extern __shared__ __align__(16) unsigned char k1_dyn[];
+    T *colg = reinterpret_cast<T *>(k1_dyn);      // column-block gradient of the current tile
+    T *rowg = colg + REC_ELEMS;                    // row-block gradient of the whole work item
     double(*ered)[3][LANES] = reinterpret_cast<double(*)[3][LANES]>(colg);  // reused after the last flush
     static_assert(sizeof(double) * K1_WARPS * 3 * LANES <= sizeof(T) * REC_ELEMS, "energy scratch must fit");
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -264,7 +266,7 @@ __global__ void __launch_bounds__(K1_THREADS, (sizeof(T) == 4 ? 2 : 1)) restrain
         const int *src = reinterpret_cast<const int *>(p.geom);
         int *dst = reinterpret_cast<int *>(geom);
         for (int e = threadIdx.x; e < (int)(sizeof(geom) / sizeof(int)); e += K1_THREADS) dst[e] = src[e];
-        for (int e = threadIdx.x; e < REC_ELEMS; e += K1_THREADS) colg[e] = (T)0;
+        for (int e = threadIdx.x; e < REC_ELEMS; e += K1_THREADS) { colg[e] = (T)0; rowg[e] = (T)0; }
     }
     const int I = p.work[q * 4 + 0], t0 = p.work[q * 4 + 1], nt = p.work[q * 4 + 2], rowrec = p.work[q * 4 + 3];
     const int xs = p.xstride;
@@ -275,48 +277,37 @@ __global__ void __launch_bounds__(K1_THREADS, (sizeof(T) == 4 ? 2 : 1)) restrain
         w1 = (T)p.wl[1 * (size_t)p.Npad + g * LANES + lane];
         w2 = (T)p.wl[2 * (size_t)p.Npad + g * LANES + lane];
     }
-    // rows 2w and 2w+1 (adjacent residues have near-identical contact patterns, which keeps the
-    // two pairs of a step balanced): CB, P = CA-CB, U = N-CA; gradient accumulators N, CA, CB
-    T row[2][9], rg[2][9];
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        const int res = I * TILE + 2 * w + r;
-        T v[9];
-#pragma unroll
-        for (int c = 0; c < 9; ++c) {
-            v[c] = Xg[((size_t)res * xs + c) * LANES];
-            rg[r][c] = (T)0;
-        }
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            row[r][k] = v[6 + k];
-            row[r][3 + k] = v[3 + k] - v[6 + k];
-            row[r][6 + k] = v[k] - v[3 + k];
-        }
-    }
     double e0 = 0.0, e1 = 0.0, e2 = 0.0;
     __syncthreads();
 
     for (int t = t0; t < t0 + nt; ++t) {
         const int J = p.tileJ[t];
         const int *__restrict__ rec_t = p.pairrec + (size_t)t * TILE * TILE * 8;
-        T f0 = (T)0, f1 = (T)0, f2 = (T)0;   // per-tile partial energies (<= 64 restraints per term)
-        // host-built schedule (edge colouring of warps x columns): in a step every warp has at most
-        // one column and no column is shared, so column gradients need no atomics
-        const int ns = p.nsteps[t];
-        const unsigned char *__restrict__ sc_t = p.sched + (size_t)t * TILE * K1_WARPS;
-        for (int s = 0; s < ns; ++s) {
-            const int c = sc_t[s * K1_WARPS + w];
-            if (c != 0xff) {
-                const int4 *r0 = reinterpret_cast<const int4 *>(rec_t + ((2 * w) * TILE + c) * 8);
-                const int4 *r1 = reinterpret_cast<const int4 *>(rec_t + ((2 * w + 1) * TILE + c) * 8);
-                const int4 a0 = __ldg(r0), a1 = __ldg(r1);
-                T cj[9], cg[9];
-                const int res = J * TILE + c;
+        T f0 = (T)0, f1 = (T)0, f2 = (T)0;   // per-tile partial energies
+        // host-built schedule: the (<= 8) pairs of a step have distinct rows and distinct columns,
+        // so one warp per pair can add its row and column gradients to shared memory without atomics
+        const int s0 = p.nsteps[t], s1 = p.nsteps[t + 1];
+        for (int s = s0; s < s1; ++s) {
+            const int e = p.sched[(size_t)s * K1_WARPS + w];
+            if (e != 0xffff) {
+                const int r = e & 15, c = (e >> 4) & 15;
+                const int4 *rp = reinterpret_cast<const int4 *>(rec_t + (r * TILE + c) * 8);
+                const int4 ia = __ldg(rp), ib = __ldg(rp + 1);
+                T ri[9], cj[9], rg[9], cg[9];
+                const int ires = I * TILE + r, jres = J * TILE + c;
 #pragma unroll
                 for (int k = 0; k < 9; ++k) {
-                    cj[k] = Xg[((size_t)res * xs + k) * LANES];
+                    ri[k] = Xg[((size_t)ires * xs + k) * LANES];
+                    cj[k] = Xg[((size_t)jres * xs + k) * LANES];
+                    rg[k] = (T)0;
                     cg[k] = (T)0;
+                }
+                T row[9];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    row[k] = ri[6 + k];
+                    row[3 + k] = ri[3 + k] - ri[6 + k];
+                    row[6 + k] = ri[k] - ri[3 + k];
                 }
                 ColGeom<T> cgm;
                 cgm.Bx = cj[6]; cgm.By = cj[7]; cgm.Bz = cj[8];
@@ -328,10 +319,12 @@ __global__ void __launch_bounds__(K1_THREADS, (sizeof(T) == 4 ? 2 : 1)) restrain
                 cgm.qq = max(cgm.Qx * cgm.Qx + cgm.Qy * cgm.Qy + cgm.Qz * cgm.Qz, t_tiny<T>());
                 cgm.ww = max(cgm.Wx * cgm.Wx + cgm.Wy * cgm.Wy + cgm.Wz * cgm.Wz, t_tiny<T>());
                 cgm.uq = cgm.Ux * cgm.Qx + cgm.Uy * cgm.Qy + cgm.Uz * cgm.Qz;
-                if (a0.x) pair_eval<T>(p, geom, a0, __ldg(r0 + 1), row[0], cgm, rg[0], cg, w0, w1, w2, f0, f1, f2);
-                if (a1.x) pair_eval<T>(p, geom, a1, __ldg(r1 + 1), row[1], cgm, rg[1], cg, w0, w1, w2, f0, f1, f2);
+                pair_eval<T>(p, geom, ia, ib, row, cgm, rg, cg, w0, w1, w2, f0, f1, f2);
 #pragma unroll
-                for (int k = 0; k < 9; ++k) colg[(c * 9 + k) * LANES + lane] += cg[k];
+                for (int k = 0; k < 9; ++k) {
+                    rowg[(r * 9 + k) * LANES + lane] += rg[k];
+                    colg[(c * 9 + k) * LANES + lane] += cg[k];
+                }
             }
             __syncthreads();
         }
@@ -345,10 +338,7 @@ __global__ void __launch_bounds__(K1_THREADS, (sizeof(T) == 4 ? 2 : 1)) restrain
     }
     {
         T *__restrict__ dst = p.recs + ((size_t)g * p.nrec + rowrec) * REC_ELEMS;
-#pragma unroll
-        for (int r = 0; r < 2; ++r)
-#pragma unroll
-            for (int k = 0; k < 9; ++k) dst[((2 * w + r) * 9 + k) * LANES + lane] = rg[r][k];
+        for (int e = threadIdx.x; e < REC_ELEMS; e += K1_THREADS) dst[e] = rowg[e];
     }
     ered[w][0][lane] = e0;
     ered[w][1][lane] = e1;
@@ -430,7 +420,13 @@ int k1_launch(trx_ctx *ctx, trx_tables *tb, int Gtot, int g0, int ng, const T *d
     p.w2 = (T)(w ? w[2] : 0.0);
     if (plan->nwork > 0) {
         ctx->time_begin("restraints");
-        restraints_kernel<T><<<dim3(ng, plan->nwork), K1_THREADS, 0, ctx->stream>>>(p);
+        const size_t dyn = 2 * REC_ELEMS * sizeof(T);
+        static bool attr_set[2] = {false, false};
+        if (!attr_set[sizeof(T) == 8]) {
+            TRX_CUDA(cudaFuncSetAttribute(restraints_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            attr_set[sizeof(T) == 8] = true;
+        }
+        restraints_kernel<T><<<dim3(ng, plan->nwork), K1_THREADS, dyn, ctx->stream>>>(p);
         ctx->time_end("restraints");
         TRX_CUDA(cudaGetLastError());
     }

@@ -251,56 +251,46 @@ int trx_tables_create(trx_ctx *ctx, int L, const trx_rst_set sets[4], trx_tables
             rec[p] |= 1 << slot;
             rec[p + 1 + slot] = r;
         }
-    // ---- per-tile step schedule.  Warp w of the restraint kernel owns rows 2w, 2w+1; a unit of
-    // work is (warp, column) = the two pairs of those rows with one column.  Units sharing a
-    // warp or a column must run in different steps (column gradients are accumulated without
-    // atomics), so a schedule is an edge colouring of the bipartite graph warps x columns; the
-    // alternating-path construction (Koenig) uses exactly max-degree colours, i.e. sparse tiles
-    // take as few barrier-separated steps as their busiest row pair / column allows.
-    std::vector<unsigned char> sched((size_t)std::max(1, T->ntiles) * TILE * K1_WARPS, 0xff);
-    std::vector<int> nsteps(std::max(1, T->ntiles), 0);
+    // ---- per-tile step schedule.  In one step each of the 8 warps of the restraint kernel
+    // evaluates one residue pair; row and column gradients are accumulated in shared memory
+    // without atomics, so the pairs of a step must have distinct rows and distinct columns
+    // (a matching of the tile's rows x columns graph).  Greedy list scheduling, busiest
+    // rows/columns first: sparse tiles take about max(pairs/8, max degree) steps.
+    std::vector<unsigned short> sched;
+    std::vector<int> step_ptr(std::max(1, T->ntiles) + 1, 0);
     for (int t = 0; t < T->ntiles; ++t) {
-        int colU[K1_WARPS][TILE], colV[TILE][TILE];
-        for (int u = 0; u < K1_WARPS; ++u) for (int c = 0; c < TILE; ++c) colU[u][c] = -1;
-        for (int v = 0; v < TILE; ++v) for (int c = 0; c < TILE; ++c) colV[v][c] = -1;
-        int maxc = 0;
-        for (int u = 0; u < K1_WARPS; ++u)
-            for (int v = 0; v < TILE; ++v) {
-                const size_t p0 = (((size_t)t * TILE + 2 * u) * TILE + v) * 8, p1 = (((size_t)t * TILE + 2 * u + 1) * TILE + v) * 8;
-                if (!(rec[p0] | rec[p1])) continue;
-                int a = 0, b = 0;
-                while (colU[u][a] >= 0) ++a;
-                while (colV[v][b] >= 0) ++b;
-                if (a != b) {   // free colour a at v by swapping a and b along the alternating path from v
-                    struct E { int u, v, c; };
-                    std::vector<E> path;
-                    int cur = v;
-                    bool atV = true;
-                    for (;;) {
-                        if (atV) { int uu = colV[cur][a]; if (uu < 0) break; path.push_back({uu, cur, a}); cur = uu; atV = false; }
-                        else { int vv = colU[cur][b]; if (vv < 0) break; path.push_back({cur, vv, b}); cur = vv; atV = true; }
-                    }
-                    for (auto &e : path) { colU[e.u][e.c] = -1; colV[e.v][e.c] = -1; }
-                    for (auto &e : path) { const int nc = e.c == a ? b : a; colU[e.u][nc] = e.v; colV[e.v][nc] = e.u; }
-                }
-                colU[u][a] = v;
-                colV[v][a] = u;
-                maxc = std::max(maxc, std::max(a, b) + 1);
-            }
-        int ns = 0;
-        for (int c = 0; c < TILE; ++c) {
-            bool any = false;
-            for (int u = 0; u < K1_WARPS; ++u) any |= colU[u][c] >= 0;
-            if (!any) continue;
-            for (int u = 0; u < K1_WARPS; ++u) sched[((size_t)t * TILE + ns) * K1_WARPS + u] = colU[u][c] >= 0 ? (unsigned char)colU[u][c] : 0xff;
-            ++ns;
+        struct P { int r, c, key; };
+        std::vector<P> pairs;
+        int degr[TILE] = {0}, degc[TILE] = {0};
+        for (int r = 0; r < TILE; ++r)
+            for (int c = 0; c < TILE; ++c)
+                if (rec[(((size_t)t * TILE + r) * TILE + c) * 8]) { degr[r]++; degc[c]++; pairs.push_back({r, c, 0}); }
+        for (auto &q : pairs) q.key = std::max(degr[q.r], degc[q.c]);
+        std::stable_sort(pairs.begin(), pairs.end(), [](const P &a, const P &b) { return a.key > b.key; });
+        std::vector<unsigned> rowmask, colmask;   // per step: rows / columns in use
+        std::vector<int> fill;
+        std::vector<std::vector<unsigned short>> steps;
+        for (auto &q : pairs) {
+            size_t sidx = 0;
+            for (; sidx < steps.size(); ++sidx)
+                if (fill[sidx] < K1_WARPS && !(rowmask[sidx] >> q.r & 1u) && !(colmask[sidx] >> q.c & 1u)) break;
+            if (sidx == steps.size()) { steps.emplace_back(); rowmask.push_back(0); colmask.push_back(0); fill.push_back(0); }
+            steps[sidx].push_back((unsigned short)(q.r | (q.c << 4)));
+            rowmask[sidx] |= 1u << q.r;
+            colmask[sidx] |= 1u << q.c;
+            fill[sidx]++;
         }
-        nsteps[t] = ns;
+        for (auto &st : steps) {
+            for (int w = 0; w < K1_WARPS; ++w) sched.push_back(w < (int)st.size() ? st[w] : (unsigned short)0xffff);
+        }
+        step_ptr[t + 1] = step_ptr[t] + (int)steps.size();
     }
-    TRX_CUDA(cudaMalloc(&T->d_sched, sched.size()));
-    TRX_CUDA(cudaMalloc(&T->d_nsteps, nsteps.size() * sizeof(int)));
-    TRX_CUDA(cudaMemcpy(T->d_sched, sched.data(), sched.size(), cudaMemcpyHostToDevice));
-    TRX_CUDA(cudaMemcpy(T->d_nsteps, nsteps.data(), nsteps.size() * sizeof(int), cudaMemcpyHostToDevice));
+    if (sched.empty()) sched.assign(K1_WARPS, 0xffff);
+    T->total_steps = step_ptr[std::max(1, T->ntiles)];
+    TRX_CUDA(cudaMalloc(&T->d_sched, sched.size() * sizeof(unsigned short)));
+    TRX_CUDA(cudaMalloc(&T->d_nsteps, step_ptr.size() * sizeof(int)));
+    TRX_CUDA(cudaMemcpy(T->d_sched, sched.data(), sched.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+    TRX_CUDA(cudaMemcpy(T->d_nsteps, step_ptr.data(), step_ptr.size() * sizeof(int), cudaMemcpyHostToDevice));
     std::vector<int> tj = T->tileJ;
     if (tj.empty()) tj.push_back(0);
     TRX_CUDA(cudaMalloc(&T->d_tileJ, tj.size() * sizeof(int)));
