@@ -138,6 +138,17 @@ int trx_fold_destroy(trx_fold_batch *b);
  * Replaces: remove_clash + repeat_mover.apply + remove_clash (folding.py:119,164-171). */
 int trx_fold_run(trx_fold_batch *b, float *tors, float *xyz, double *terms, long long *stats, int max_rounds,
                  int check_every, int *rounds_out);
+/* Monte-Carlo sampling on top of the fold -- an EXTENSION with no reference behaviour
+ * (BASELINE config 4; the reference's folding/ has no Metropolis step).
+ * Minimises through the whole schedule, whose LAST run (index mc_run) defines the MC score;
+ * then `cycles` times: perturb phi/psi of a random block of block_min..block_max residues by
+ * N(0, sigma_deg), re-minimise with run mc_run, Metropolis accept at temperature kT.
+ * Perturbation, minimisation and acceptance run on device; the generator is counter-based
+ * and keyed by (seed, id_offset + decoy index), so results do not depend on the sharding.
+ * stats (may be NULL): [N][3] = evaluations, accepted L-BFGS iterations, accepted MC moves. */
+int trx_fold_mc(trx_fold_batch *b, float *tors, float *xyz, double *terms, long long *stats, int mc_run, int cycles,
+                double kT, int block_min, int block_max, double sigma_deg, unsigned long long seed,
+                unsigned long long id_offset, int max_rounds, int check_every, int *rounds_out);
 /* One evaluation at given torsions under uniform weights (parity entry for the NeRF /
  * vdw / rama / omega / torsion-gradient kernels): total[N], terms[N][6], gtors[N][L][3],
  * xyz[N][L][5][3] (any output may be NULL). */

@@ -143,3 +143,32 @@ def test_folding_cli_drop_in(tmp_path, golden_dir, example):
     assert r.returncode == 0, r.stderr[-2000:]
     files = sorted(os.listdir(tmp_path / "b"))
     assert files == ["initial%d.pdb" % i for i in (10, 3, 4, 5, 6, 7, 8, 9)]
+
+
+def test_monte_carlo_extension(ctx):
+    """Extension with no reference behaviour: checks the invariants it can have --
+    Metropolis never loses the best state at kT -> 0, counters are sane, trajectories are
+    reproducible and independent of how decoys are batched (id_offset)."""
+    seq, npzs, nat = synth.target(64, seed=7)
+    params = tables.load_params()
+    tb = sampler.build_tables(ctx, npzs[0], seq, params)
+    runs = schedule.mc_schedule(mc_max_iter=100)
+    w = np.array(list(runs[-1].w))
+    t0 = sampler.random_torsions(64, 64, seed=2)
+    batch = capi.FoldBatch(ctx, [tb], [64], sampler.aa_index(seq), runs)
+    base = batch.run_mc(t0, cycles=0)
+    mc = batch.run_mc(t0, cycles=6, kT=1e-6, sigma_deg=25.0, seed=9)
+    e0, e1 = base["terms"] @ w, mc["terms"] @ w
+    assert np.all(mc["accepted"] >= 0) and np.all(mc["accepted"] <= 6) and mc["accepted"].sum() > 0
+    assert np.all(e1 <= e0 + 1e-3 * np.abs(e0))          # greedy MC (kT ~ 0) cannot end above its start
+    assert e1.mean() < e0.mean()
+    assert np.all(mc["evals"] > base["evals"])
+    hot = batch.run_mc(t0, cycles=6, kT=50.0, sigma_deg=25.0, seed=9)
+    assert hot["accepted"].sum() >= mc["accepted"].sum()   # a hotter chain accepts at least as often
+    again = batch.run_mc(t0, cycles=6, kT=1e-6, sigma_deg=25.0, seed=9)
+    np.testing.assert_array_equal(again["tors"], mc["tors"])
+    half = capi.FoldBatch(ctx, [tb], [32], sampler.aa_index(seq), runs)
+    sub = half.run_mc(t0[32:], cycles=6, kT=1e-6, sigma_deg=25.0, seed=9, id_offset=32)
+    np.testing.assert_array_equal(sub["tors"], mc["tors"][32:])
+    np.testing.assert_array_equal(sub["accepted"], mc["accepted"][32:])
+    batch.close(); half.close(); tb.close()

@@ -186,6 +186,7 @@ class FoldBatch:
         self.ctx, self.tabs = ctx, list(tabs)
         self.ndecoys = [int(n) for n in ndecoys]
         self.N, self.L = sum(self.ndecoys), self.tabs[0].L
+        self.nruns = len(runs)
         aa = np.ascontiguousarray(aa, dtype=np.int32)
         arr_t = (C.c_void_p * len(self.tabs))(*[t._h for t in self.tabs])
         arr_n = (C.c_int * len(self.tabs))(*self.ndecoys)
@@ -218,6 +219,22 @@ class FoldBatch:
                                  _ptr(terms, C.c_double), _ptr(stats, C.c_longlong), C.c_int(max_rounds),
                                  C.c_int(check_every), C.byref(rounds)))
         return dict(tors=tors, xyz=xyz, terms=terms, evals=stats[:, 0], iters=stats[:, 1], rounds=rounds.value)
+
+    def run_mc(self, tors, cycles, kT=2.0, block=(3, 9), sigma_deg=20.0, seed=0, id_offset=0, max_rounds=20000,
+               check_every=16):
+        """Fold, then `cycles` Monte-Carlo cycles (perturb / re-minimise with the schedule's LAST run /
+        Metropolis) on device.  Returns the dict of run() plus 'accepted' (N,)."""
+        tors = np.ascontiguousarray(tors, dtype=np.float32).copy()
+        xyz = np.zeros((self.N, self.L, 5, 3), dtype=np.float32)
+        terms = np.zeros((self.N, NTERM))
+        stats = np.zeros((self.N, 3), dtype=np.int64)
+        rounds = C.c_int()
+        check(lib().trx_fold_mc(self._h, _ptr(tors, C.c_float), _ptr(xyz, C.c_float), _ptr(terms, C.c_double),
+                                _ptr(stats, C.c_longlong), C.c_int(self.nruns - 1), C.c_int(cycles), C.c_double(kT),
+                                C.c_int(block[0]), C.c_int(block[1]), C.c_double(sigma_deg), C.c_ulonglong(seed),
+                                C.c_ulonglong(id_offset), C.c_int(max_rounds), C.c_int(check_every), C.byref(rounds)))
+        return dict(tors=tors, xyz=xyz, terms=terms, evals=stats[:, 0], iters=stats[:, 1], accepted=stats[:, 2],
+                    rounds=rounds.value)
 
     def eval(self, tors, w):
         """Single evaluation -> (total (N,), terms (N,6), gtors (N,L,3), xyz (N,L,5,3))."""

@@ -71,6 +71,10 @@ struct FoldState {
     float *wslot;            // [TRX_NTERM][Npad] weights in slot order
     int ntab;
     int tab_d0[16], tab_n[16];   // first decoy and decoy count of each table block
+    // Monte-Carlo extension: state saved before a perturbation
+    float *xsave;            // [G][ndof][32]
+    double *fsave;           // [Npad]
+    int *naccept;            // [Npad]
     const int *aa;           // [L]
     const Run *runs;
 };
@@ -213,7 +217,7 @@ __global__ void __launch_bounds__(VDW_THREADS) vdw_kernel(FoldState s)
     const int L = s.L;
     float4 *at = reinterpret_cast<float4 *>(smem_raw);                                   // [L][6]
     long long *acc = reinterpret_cast<long long *>(smem_raw + sizeof(float4) * 6 * L);   // [L][6][3]
-    float *reach = reinterpret_cast<float *>(acc + (size_t)L * 18);                      // [L]
+    float4 *bsph = reinterpret_cast<float4 *>(acc + (size_t)L * 18);                     // [L] bounding spheres
     __shared__ double ered[VDW_THREADS / 32];
     const float *__restrict__ xn = s.xnat + (size_t)n * L * NAT3;
     for (int i = threadIdx.x; i < L; i += VDW_THREADS) {
@@ -225,8 +229,19 @@ __global__ void __launch_bounds__(VDW_THREADS) vdw_kernel(FoldState s)
         for (int a = 0; a < 5; ++a) at[i * 6 + a] = make_float4(v[a * 3], v[a * 3 + 1], v[a * 3 + 2], c_model.r_bb[a]);
         const float cs = c_model.cen_s[aa];
         at[i * 6 + 5] = make_float4(v[3] + cs * (v[6] - v[3]), v[4] + cs * (v[7] - v[4]), v[5] + cs * (v[8] - v[5]), c_model.r_cen[aa]);
-        // farthest atom surface from CA: CEN or O (|CA-O| <= 2.45 A)
-        reach[i] = fmaxf(cs * 1.53f + c_model.r_cen[aa], 2.45f + 1.8f);
+        // bounding sphere of the residue's six soft spheres: centre = mean position, radius =
+        // farthest sphere surface.  Two residues can only touch when their bounding spheres do.
+        float cx = 0.f, cy = 0.f, cz = 0.f;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) { cx += at[i * 6 + a].x; cy += at[i * 6 + a].y; cz += at[i * 6 + a].z; }
+        cx *= (1.0f / 6.0f); cy *= (1.0f / 6.0f); cz *= (1.0f / 6.0f);
+        float rb = 0.f;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            const float4 q = at[i * 6 + a];
+            rb = fmaxf(rb, sqrtf((q.x - cx) * (q.x - cx) + (q.y - cy) * (q.y - cy) + (q.z - cz) * (q.z - cz)) + q.w);
+        }
+        bsph[i] = make_float4(cx, cy, cz, rb + 1e-3f);
     }
     for (int e = threadIdx.x; e < L * 18; e += VDW_THREADS) acc[e] = 0;
     __syncthreads();
@@ -257,14 +272,13 @@ __global__ void __launch_bounds__(VDW_THREADS) vdw_kernel(FoldState s)
         }
     };
     for (int i = warp; i < L - TRX_VDW_MINSEP; i += VDW_THREADS / 32) {
-        const float4 ci = at[i * 6 + TRX_AT_CA];
-        const float ri = reach[i];
+        const float4 ci = bsph[i];
         for (int j0 = i + TRX_VDW_MINSEP; j0 < L; j0 += 32) {
             const int j = j0 + lane;
             bool close = false;
             if (j < L) {
-                const float4 cj = at[j * 6 + TRX_AT_CA];
-                const float dx = ci.x - cj.x, dy = ci.y - cj.y, dz = ci.z - cj.z, cut = ri + reach[j];
+                const float4 cj = bsph[j];
+                const float dx = ci.x - cj.x, dy = ci.y - cj.y, dz = ci.z - cj.z, cut = ci.w + cj.w;
                 close = dx * dx + dy * dy + dz * dz < cut * cut;
             }
             unsigned m = __ballot_sync(0xffffffffu, close);
@@ -821,6 +835,84 @@ __global__ void export_kernel(FoldState s, float *__restrict__ tors_nat, double 
     stats[(size_t)n * 2 + 1] = s.iters[n];
 }
 
+
+// ---- Monte-Carlo extension (no reference behaviour: BASELINE config 4 / SURVEY 8a row 16).
+// A cycle = perturb a block of consecutive residues' phi/psi, re-minimise through one run of
+// the schedule, Metropolis accept/reject on the run's weighted score.  Everything below is on
+// device; the counter-based generator is keyed by (seed, global decoy id, cycle, draw), so a
+// decoy's trajectory does not depend on the batch or GPU it sits in.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z)
+{
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ float u01(unsigned long long seed, unsigned long long id, unsigned cycle, unsigned draw)
+{
+    const unsigned long long h = mix64(mix64(seed ^ mix64(id)) ^ ((unsigned long long)cycle << 32 | draw));
+    return ((h >> 40) + 0.5f) * (1.0f / 16777216.0f);
+}
+
+struct McOpts {
+    unsigned long long seed, id_offset;
+    int cycle, block_min, block_max, mc_run;
+    float sigma, kT;
+};
+
+// save (x, f), perturb, and restart the decoy at run mc_run
+__global__ void mc_begin_kernel(FoldState s, McOpts o)
+{
+    const int g = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, n = g * LANES + lane;
+    if (n >= s.N) return;
+    const size_t vb = (size_t)g * s.ndof * LANES + lane;
+    float *x = s.x + vb, *xt = s.xt + vb, *xs = s.xsave + vb;
+    const unsigned long long id = o.id_offset + n;
+    const int L = s.L;
+    const int blk = o.block_min + (int)(u01(o.seed, id, o.cycle, 0) * (o.block_max - o.block_min + 1));
+    const int len = min(max(blk, 1), L - 2);
+    const int start = 1 + (int)(u01(o.seed, id, o.cycle, 1) * (L - 1 - len));
+    for (int k = warp; k < s.ndof; k += nw) {
+        const float v = x[(size_t)k * LANES];
+        xs[(size_t)k * LANES] = v;
+        const int res = k / 3, t = k % 3;
+        float nv = v;
+        if (t < 2 && res >= start && res < start + len) {
+            // Box-Muller from two counter-based uniforms
+            const float a = u01(o.seed, id, o.cycle, 2 + 2 * k), b = u01(o.seed, id, o.cycle, 3 + 2 * k);
+            nv = v + o.sigma * sqrtf(-2.0f * logf(a)) * cospif(2.0f * b);
+        }
+        x[(size_t)k * LANES] = nv;
+        xt[(size_t)k * LANES] = nv;
+    }
+    if (warp == 0) {
+        if (o.cycle == 0) s.naccept[n] = 0;
+        s.fsave[n] = s.f[n];
+        s.status[n] = ST_INIT; s.run[n] = o.mc_run; s.hist[n] = 0; s.head[n] = 0; s.iter[n] = 0; s.bt[n] = 0;
+        s.restart[n] = 1; s.nmem[n] = 0;
+        for (int k = 0; k < TRX_NTERM; ++k) s.wl[(size_t)k * s.Npad + n] = s.runs[o.mc_run].w[k];
+    }
+}
+
+// Metropolis on the minimised score; a rejected decoy returns to its saved state.
+// first != 0: no perturbation preceded (scoring pass under the MC weights), always keep.
+__global__ void mc_accept_kernel(FoldState s, McOpts o, int first)
+{
+    const int g = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, n = g * LANES + lane;
+    if (n >= s.N) return;
+    const double fnew = s.f[n], fold = s.fsave[n];
+    bool keep = true;
+    if (!first) {
+        keep = isfinite(fnew) && (fnew <= fold || u01(o.seed, o.id_offset + n, o.cycle, 0x7fffffffu) < expf((float)((fold - fnew) / (double)o.kT)));
+        if (warp == 0 && keep) s.naccept[n] += 1;
+    }
+    if (!keep) {
+        const size_t vb = (size_t)g * s.ndof * LANES + lane;
+        for (int k = warp; k < s.ndof; k += nw) s.x[vb + (size_t)k * LANES] = s.xsave[vb + (size_t)k * LANES];
+        if (warp == 0) s.f[n] = fold;
+    }
+}
+
 static void upload_model()
 {
     static bool done[64] = {false};
@@ -896,7 +988,7 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     s.N = (G - 1) * LANES + ((ndecoys[ntab - 1] - 1) % LANES + 1);
     TRX_REQUIRE(s.N == N, "trx_fold_create: internal decoy count mismatch");
     s.G = G; s.Npad = G * LANES; s.L = L; s.Lpad = padded_length(L); s.ndof = 3 * L; s.m = lbfgs_m; s.nruns = nruns;
-    b->vdw_smem = sizeof(float4) * 6 * L + sizeof(long long) * 18 * L + sizeof(float) * L;
+    b->vdw_smem = sizeof(float4) * 6 * L + sizeof(long long) * 18 * L + sizeof(float4) * L;
     TRX_REQUIRE(b->vdw_smem <= 220 * 1024, "trx_fold_create: L=%d exceeds the shared-memory budget of the vdw kernel", L);
     TRX_REQUIRE(L < 65536, "trx_fold_create: L too large");
     // one arena, carved into aligned pieces
@@ -913,6 +1005,7 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     size_t o_X = carve((size_t)G * s.Lpad * NAT3 * LANES * 4), o_xn = carve(np * L * NAT3 * 4), o_gn = carve(np * L * NAT3 * 4);
     size_t o_gk = carve((size_t)G * s.Lpad * 9 * LANES * 4), o_E3 = carve(np * 8 * 3), o_Ev = carve(np * 8);
     size_t o_ga = carve((size_t)G * 4), o_na = carve(256);
+    size_t o_xs = carve(vec), o_fs = carve(np * 8), o_nacc = carve(np * 4);
     size_t o_perm = carve(np * 4), o_gs = carve((size_t)G * 4), o_ns = carve(256), o_ws = carve(np * 4 * TRX_NTERM);
     cudaError_t e = cudaMalloc(&b->arena, off);
     if (e != cudaSuccess) {
@@ -932,6 +1025,7 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     s.terms = (double *)(A + o_terms); s.ft = (double *)(A + o_ft); s.wl = (float *)(A + o_wl);
     s.X = (float *)(A + o_X); s.xnat = (float *)(A + o_xn); s.gnat = (float *)(A + o_gn); s.gk1 = (float *)(A + o_gk);
     s.E3 = (double *)(A + o_E3); s.Evdw = (double *)(A + o_Ev); s.gactive = (int *)(A + o_ga); s.nactive = (int *)(A + o_na);
+    s.xsave = (float *)(A + o_xs); s.fsave = (double *)(A + o_fs); s.naccept = (int *)(A + o_nacc);
     s.perm = (int *)(A + o_perm); s.gslot = (int *)(A + o_gs); s.nslot = (int *)(A + o_ns); s.wslot = (float *)(A + o_ws);
     s.ntab = ntab;
     for (int t = 0; t < ntab; ++t) { s.tab_d0[t] = b->tab_g0[t] * LANES; s.tab_n[t] = ndecoys[t]; }
@@ -984,6 +1078,39 @@ static int fold_eval(trx_fold_batch *b, const int *ng_tab, bool identity)
     return TRX_OK;
 }
 
+// Evaluation rounds until every decoy has finished its schedule (or max_rounds).
+static int run_rounds(trx_fold_batch *b, int max_rounds, int check_every, int *rounds_io)
+{
+    trx_ctx *ctx = b->ctx;
+    FoldState &s = b->s;
+    int rc, rounds = 0, active = s.N;
+    int *h_nslot = nullptr;
+    TRX_CUDA(cudaMallocHost(&h_nslot, 16 * sizeof(int)));
+    std::vector<int> ng(b->tab_ng);   // live slot groups per table block: an upper bound between polls
+    dim3 ablk(32, 8), agrd((s.G + 7) / 8);
+    while (active > 0 && rounds < max_rounds) {
+        for (int k = 0; k < check_every && rounds < max_rounds; ++k, ++rounds) {
+            TRX_CUDA(cudaMemsetAsync(s.nactive, 0, sizeof(int), ctx->stream));
+            ctx->time_begin("activity");
+            activity_kernel<<<agrd, ablk, 0, ctx->stream>>>(s);
+            ctx->time_end("activity");
+            if ((rc = fold_eval(b, ng.data(), false))) { cudaFreeHost(h_nslot); return rc; }
+            ctx->time_begin("lbfgs");
+            if (s.lb_M == 8) lbfgs_kernel<8><<<s.G, LB_THREADS, b->lb_smem, ctx->stream>>>(s);
+            else if (s.lb_M == 16) lbfgs_kernel<16><<<s.G, LB_THREADS, b->lb_smem, ctx->stream>>>(s);
+            else lbfgs_kernel<24><<<s.G, LB_THREADS, b->lb_smem, ctx->stream>>>(s);
+            ctx->time_end("lbfgs");
+        }
+        TRX_CUDA(cudaMemcpyAsync(h_nslot, s.nslot, 16 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        TRX_CUDA(cudaStreamSynchronize(ctx->stream));
+        active = 0;   // counts at the start of the last round; they only ever decrease
+        for (int t = 0; t < s.ntab; ++t) { active += h_nslot[t]; ng[t] = num_groups(h_nslot[t]); }
+    }
+    cudaFreeHost(h_nslot);
+    *rounds_io += rounds;
+    return TRX_OK;
+}
+
 /* Runs the schedule to completion (or max_rounds evaluation rounds).  tors: host [N][L][3]
  * float, in: start torsions, out: final torsions.  xyz (may be NULL): host [N][L][5][3] float,
  * atoms N,CA,CB,C,O.  terms (may be NULL): [N][6] double.  stats (may be NULL): [N][2]
@@ -1008,30 +1135,8 @@ int trx_fold_run(trx_fold_batch *b, float *tors, float *xyz, double *terms, long
     ctx->time_begin("fold_init");
     init_state_kernel<<<s.G, 32, 0, ctx->stream>>>(s, (const float *)d_tors);
     ctx->time_end("fold_init");
-    int rounds = 0, active = s.N;
-    int *h_nslot = nullptr;
-    TRX_CUDA(cudaMallocHost(&h_nslot, 16 * sizeof(int)));
-    std::vector<int> ng(b->tab_ng);   // live slot groups per table block: an upper bound between polls
-    dim3 ablk(32, 8), agrd((s.G + 7) / 8);
-    while (active > 0 && rounds < max_rounds) {
-        for (int k = 0; k < check_every && rounds < max_rounds; ++k, ++rounds) {
-            TRX_CUDA(cudaMemsetAsync(s.nactive, 0, sizeof(int), ctx->stream));
-            ctx->time_begin("activity");
-            activity_kernel<<<agrd, ablk, 0, ctx->stream>>>(s);
-            ctx->time_end("activity");
-            if ((rc = fold_eval(b, ng.data(), false))) { cudaFreeHost(h_nslot); return rc; }
-            ctx->time_begin("lbfgs");
-            if (s.lb_M == 8) lbfgs_kernel<8><<<s.G, LB_THREADS, b->lb_smem, ctx->stream>>>(s);
-            else if (s.lb_M == 16) lbfgs_kernel<16><<<s.G, LB_THREADS, b->lb_smem, ctx->stream>>>(s);
-            else lbfgs_kernel<24><<<s.G, LB_THREADS, b->lb_smem, ctx->stream>>>(s);
-            ctx->time_end("lbfgs");
-        }
-        TRX_CUDA(cudaMemcpyAsync(h_nslot, s.nslot, 16 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        TRX_CUDA(cudaStreamSynchronize(ctx->stream));
-        active = 0;   // counts at the start of the last round; they only ever decrease
-        for (int t = 0; t < s.ntab; ++t) { active += h_nslot[t]; ng[t] = num_groups(h_nslot[t]); }
-    }
-    cudaFreeHost(h_nslot);
+    int rounds = 0;
+    if ((rc = run_rounds(b, max_rounds, check_every, &rounds))) return rc;
     // final coordinates / terms at the accepted point x: one more evaluation with xt = x for everyone
     ctx->time_begin("export");
     restore_kernel<<<s.G, 256, 0, ctx->stream>>>(s);
@@ -1047,6 +1152,75 @@ int trx_fold_run(trx_fold_batch *b, float *tors, float *xyz, double *terms, long
     if (stats) TRX_CUDA(cudaMemcpyAsync(stats, d_stats, (size_t)s.N * 2 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
     if (xyz) TRX_CUDA(cudaMemcpyAsync(xyz, s.xnat, (size_t)s.N * s.L * NAT3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     TRX_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (rounds_out) *rounds_out = rounds;
+    return TRX_OK;
+}
+
+/* Monte-Carlo sampling on top of the fold (extension, BASELINE config 4): minimise through
+ * runs [0, mc_run) exactly as trx_fold_run, then `cycles` times { perturb phi/psi of a random
+ * block of block_min..block_max residues by N(0, sigma_deg); re-minimise with run mc_run;
+ * Metropolis at temperature kT on that run's weighted score }.  stats: [N][3] = evaluations,
+ * accepted L-BFGS iterations, accepted MC moves.  id_offset: global index of decoy 0 (keeps
+ * random streams independent of the sharding). */
+int trx_fold_mc(trx_fold_batch *b, float *tors, float *xyz, double *terms, long long *stats, int mc_run, int cycles,
+                double kT, int block_min, int block_max, double sigma_deg, unsigned long long seed,
+                unsigned long long id_offset, int max_rounds, int check_every, int *rounds_out)
+{
+    TRX_REQUIRE(b && tors, "trx_fold_mc: NULL argument");
+    trx_ctx *ctx = b->ctx;
+    FoldState &s = b->s;
+    TRX_REQUIRE(mc_run >= 1 && mc_run == s.nruns - 1, "trx_fold_mc: mc_run must be the last run of the schedule (got %d of %d)", mc_run, s.nruns);
+    TRX_REQUIRE(cycles >= 0 && kT > 0 && block_min >= 1 && block_max >= block_min && sigma_deg >= 0, "trx_fold_mc: bad options");
+    TRX_CUDA(cudaSetDevice(ctx->device));
+    if (check_every < 1) check_every = 16;
+    void *d_tors = nullptr, *d_terms = nullptr, *d_stats = nullptr;
+    int rc;
+    const size_t tb = (size_t)s.N * s.ndof * sizeof(float);
+    if ((rc = ctx->get_scratch("fold_tors", tb, &d_tors))) return rc;
+    if ((rc = ctx->get_scratch("fold_terms", (size_t)s.N * TRX_NTERM * sizeof(double), &d_terms))) return rc;
+    if ((rc = ctx->get_scratch("fold_stats", (size_t)s.N * 2 * sizeof(long long), &d_stats))) return rc;
+    TRX_CUDA(cudaMemcpyAsync(d_tors, tors, tb, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->time_begin("fold_device");
+    --ctx->launches;
+    init_state_kernel<<<s.G, 32, 0, ctx->stream>>>(s, (const float *)d_tors);
+    ++ctx->launches;
+    int rounds = 0;
+    // runs [0, mc_run] once: the last one scores the minimised decoy under the MC weights
+    if ((rc = run_rounds(b, max_rounds, check_every, &rounds))) return rc;
+    McOpts o;
+    o.seed = seed; o.id_offset = id_offset; o.block_min = block_min; o.block_max = block_max; o.mc_run = mc_run;
+    o.sigma = (float)(sigma_deg * TRX_DEG); o.kT = (float)kT; o.cycle = 0;
+    for (int c = 0; c < cycles; ++c) {
+        o.cycle = c;
+        ctx->time_begin("mc");
+        mc_begin_kernel<<<s.G, 256, 0, ctx->stream>>>(s, o);
+        ctx->time_end("mc");
+        if ((rc = run_rounds(b, max_rounds, check_every, &rounds))) return rc;
+        ctx->time_begin("mc");
+        mc_accept_kernel<<<s.G, 256, 0, ctx->stream>>>(s, o, 0);
+        ctx->time_end("mc");
+    }
+    restore_kernel<<<s.G, 256, 0, ctx->stream>>>(s);
+    ++ctx->launches;
+    if ((rc = fold_eval(b, nullptr, true))) return rc;
+    export_kernel<<<s.G, 32, 0, ctx->stream>>>(s, (float *)d_tors, (double *)d_terms, (long long *)d_stats);
+    ++ctx->launches;
+    ctx->time_end("fold_device");
+    TRX_CUDA(cudaGetLastError());
+    std::vector<long long> st2((size_t)s.N * 2);
+    std::vector<int> acc(s.Npad);
+    TRX_CUDA(cudaMemcpyAsync(tors, d_tors, tb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (terms) TRX_CUDA(cudaMemcpyAsync(terms, d_terms, (size_t)s.N * TRX_NTERM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    TRX_CUDA(cudaMemcpyAsync(st2.data(), d_stats, st2.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    TRX_CUDA(cudaMemcpyAsync(acc.data(), s.naccept, acc.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (xyz) TRX_CUDA(cudaMemcpyAsync(xyz, s.xnat, (size_t)s.N * s.L * NAT3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    TRX_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (stats)
+        for (int n = 0; n < s.N; ++n) {
+            stats[(size_t)n * 3] = st2[(size_t)n * 2];
+            stats[(size_t)n * 3 + 1] = st2[(size_t)n * 2 + 1];
+            stats[(size_t)n * 3 + 2] = cycles > 0 ? acc[n] : 0;
+        }
     if (rounds_out) *rounds_out = rounds;
     return TRX_OK;
 }

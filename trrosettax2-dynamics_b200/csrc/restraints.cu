@@ -106,7 +106,7 @@ __device__ __forceinline__ int spline_locate(const KnotGeom<float> &kn, float x,
 {
     const int K = kn.K, r0 = kn.urun0;
     int k = (int)floorf((x - kn.gx0) * kn.ginv) + kn.goff;
-    if (r0 > 0) {
+    if (r0 > 0 && __any_sync(0xffffffffu, k < r0)) {   // rare: some decoy below the uniform run (d < 4.25 A)
         int kh = 0;
 #pragma unroll
         for (int m = 1; m <= 6; ++m) kh += (m <= r0 && x >= kn.x[m]) ? 1 : 0;
@@ -182,18 +182,18 @@ __device__ __forceinline__ void pair_eval(const K1Params<T> &p, const KnotGeom<T
     // ---- phase 1: values, intervals, loads
     T u0 = (T)0, u1 = (T)0, u2 = (T)0, u3 = (T)0, u4 = (T)0, u5 = (T)0;
     Coef<T> c0 = {(T)0, (T)0, (T)0, (T)0}, c1 = c0, c2 = c0, c3 = c0, c4 = c0, c5 = c0;
-    if (mask & 1) c0 = spline_load(p.tab[0] + (size_t)ia.y * geom[0].K, spline_locate(geom[0], d, u0));
+    if (mask & 1) c0 = spline_load(p.tab[0] + ia.y, spline_locate(geom[0], d, u0));
     if (mask & 2)    // omega: F = P, G = -D, H = Q  =>  A = X, B = Y
-        c1 = spline_load(p.tab[1] + (size_t)ia.z * geom[1].K, spline_locate(geom[1], t_atan2(-d * DOT(P, Y), DOT(X, Y)), u1));
+        c1 = spline_load(p.tab[1] + ia.z, spline_locate(geom[1], t_atan2(-d * DOT(P, Y), DOT(X, Y)), u1));
     if (mask & 4)    // theta(i,j): F = U_i, G = P, H = D  =>  A = U_i x P, B = X
-        c2 = spline_load(p.tab[2] + (size_t)ia.w * geom[2].K, spline_locate(geom[2], t_atan2(-np_ * DOT(U, X), DOT(W, X)), u2));
+        c2 = spline_load(p.tab[2] + ia.w, spline_locate(geom[2], t_atan2(-np_ * DOT(U, X), DOT(W, X)), u2));
     if (mask & 8)    // theta(j,i): F = U_j, G = Q, H = -D  =>  A = W_j, B = -Y
-        c3 = spline_load(p.tab[2] + (size_t)ib.x * geom[2].K,
+        c3 = spline_load(p.tab[2] + ib.x,
                          spline_locate(geom[2], t_atan2(nq * (c.Ux * Yx + c.Uy * Yy + c.Uz * Yz), -(c.Wx * Yx + c.Wy * Yy + c.Wz * Yz)), u3));
     if (mask & 16)   // phi(i,j): angle between P and D at CB_i; sin = |X| / (|P||D|)
-        c4 = spline_load(p.tab[3] + (size_t)ib.y * geom[3].K, spline_locate(geom[3], t_atan2(xx * rX, pd), u4));
+        c4 = spline_load(p.tab[3] + ib.y, spline_locate(geom[3], t_atan2(xx * rX, pd), u4));
     if (mask & 32)   // phi(j,i): angle between Q and -D at CB_j; sin = |Y| / (|Q||D|)
-        c5 = spline_load(p.tab[3] + (size_t)ib.z * geom[3].K, spline_locate(geom[3], t_atan2(yy * rY, -qd), u5));
+        c5 = spline_load(p.tab[3] + ib.z, spline_locate(geom[3], t_atan2(yy * rY, -qd), u5));
 
     // ---- phase 2: energies and gradients
     const T ixx = rX * rX, iyy = rY * rY;

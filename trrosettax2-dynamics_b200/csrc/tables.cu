@@ -249,7 +249,7 @@ int trx_tables_create(trx_ctx *ctx, int L, const trx_rst_set sets[4], trx_tables
             }
             if (rec[p] == 0) T->active_pairs++;
             rec[p] |= 1 << slot;
-            rec[p + 1 + slot] = r;
+            rec[p + 1 + slot] = r * sets[t].K;   // element offset of the restraint's first interval
         }
     // ---- per-tile step schedule.  In one step each of the 8 warps of the restraint kernel
     // evaluates one residue pair; row and column gradients are accumulated in shared memory

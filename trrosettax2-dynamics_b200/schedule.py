@@ -67,3 +67,11 @@ def window_schedule(data_dir=None, initial_clash=False):
     end = len(runs) + 5
     runs += [make_run(sf1, 1000, clash_check=True, skip_to=end) for _ in range(5)]
     return runs
+
+
+def mc_schedule(data_dir=None, mc_max_iter=200):
+    """reference_schedule() followed by the run Monte-Carlo cycles re-minimise with and score
+    on (scorefxn.wts, shorter cap).  An extension: the reference has no MC step in folding/."""
+    runs = reference_schedule(data_dir)
+    runs.append(make_run(read_wts("scorefxn.wts", data_dir), mc_max_iter))
+    return runs
