@@ -35,9 +35,13 @@ def random_torsions(N, L, seed):
     return np.deg2rad(t).astype(np.float32)
 
 
-def build_tables(ctx, npz, seq, params, sep=(1, None), rule="H1", nogly=False):
+def build_tables(ctx, npz, seq, params, sep=(1, None), rule="H1", nogly=False, use_orient=None):
+    """use_orient: None = what params['USE_ORIENT'] says, else True/False (--orient / --no-orient);
+    an npz without orientation maps is folded on distances alone."""
     L = len(seq)
-    rst = tables.gen_rst(npz, params)
+    if use_orient is None:
+        use_orient = params.get("USE_ORIENT", True) in (True, "True") and all(k in npz for k in ("omega", "theta", "phi"))
+    rst = tables.gen_rst(npz, params, use_orient=use_orient)
     masks = tables.select(rst, sep[0], sep[1] or L, params, seq, nogly)
     return capi.Tables(ctx, L, tables.active_restraints(rst, masks, rule))
 
