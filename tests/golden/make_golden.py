@@ -128,5 +128,39 @@ def main():
     print("golden fixtures written to", HERE)
 
 
+
+
+def make_dynamics_golden():
+    """Reference outer-loop arithmetic (get_neighbors, pros, process_distribution...) on the first
+    48 residues of the example (a reference decoy + the NMR distograms)."""
+    ug = load_reference_geometry()
+    seq = "".join(l.strip() for l in open(f"{REF}/example/seq.fasta") if not l.startswith(">"))[:48]
+    at = {k: [] for k in ("N", "CA", "C", "CB")}
+    res = {}
+    for ln in open(f"{REF}/example/output/seq/pred_pdb/conf_1_1.pdb"):
+        if ln.startswith("ATOM") and ln[12:16].strip() in at:
+            res.setdefault(int(ln[22:26]), {})[ln[12:16].strip()] = [float(ln[30:38]), float(ln[38:46]), float(ln[46:54])]
+    ids = sorted(res)[:48]
+    xyzs = {"N": np.array([res[i]["N"] for i in ids]), "CA": np.array([res[i]["CA"] for i in ids]),
+            "C": np.array([res[i]["C"] for i in ids]), "CB": {k: res[i]["CB"] for k, i in enumerate(ids) if "CB" in res[i]}}
+    cb = np.array([res[i].get("CB", [np.nan] * 3) for i in ids])
+    key, d6, o6, t6, p6 = ug.get_neighbors(xyzs, seq, 20)
+    assert key is False
+    fact = ug.pros(d6[None], o6[None], t6[None], p6[None], angle=True)
+    fd, ft, fo, fp = (fact[k][0, 0] for k in range(4))           # order: dist, theta, omega, phi
+    npz = np.load(f"{HERE}/example_NMR.npz")
+    crop = {k: np.ascontiguousarray(npz[k][:48, :48]) for k in ("dist", "omega", "theta", "phi")}
+    out = dict(seq=np.array(seq), n=xyzs["N"], ca=xyzs["CA"], c=xyzs["C"], cb=cb, d6=d6, o6=o6, t6=t6, p6=p6,
+               jd=fd.argmax(-1), jo=fo.argmax(-1), jt=ft.argmax(-1), jp=fp.argmax(-1))
+    for k, f in (("dist", fd), ("omega", fo), ("theta", ft), ("phi", fp)):
+        out[f"in_{k}"] = crop[k]
+        out[f"proc_{k}"] = ug.process_distribution_with_pred_distribution(crop[k], f, norm=True, smooth=True, sigma=1.0)
+    out["tmp"] = ug.process_distribution_with_pred_distribution(crop["dist"], fd, norm=False)
+    np.savez_compressed(f"{HERE}/dynamics_example48.npz", **out)
+    print("dynamics golden written")
+
+
 if __name__ == "__main__":
-    main()
+    if "--dynamics-only" not in sys.argv:
+        main()
+    make_dynamics_golden()

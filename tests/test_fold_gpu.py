@@ -172,3 +172,25 @@ def test_monte_carlo_extension(ctx):
     np.testing.assert_array_equal(sub["tors"], mc["tors"][32:])
     np.testing.assert_array_equal(sub["accepted"], mc["accepted"][32:])
     batch.close(); half.close(); tb.close()
+
+
+def test_dynamics_pipeline_on_example(tmp_path, golden_dir, example, ctx):
+    """run_inference's fold -> decay -> fold loop in process (N1/N2): two models, 4 initial decoys
+    each, up to 3 iterations; both natives' basins should be visited by some decoy."""
+    from trx2dyn import pipeline, pdbio
+    seq, _, nat = example
+    files = pipeline.run_single_from_npz("seq", f"{golden_dir}/example_seq.fasta",
+                                         [f"{golden_dir}/example_NMR.npz", f"{golden_dir}/example_Xray.npz"],
+                                         str(tmp_path), init_num=4, n_max=3, seed=5, ctx=ctx)
+    names = sorted(os.path.basename(f) for f in files) if False else [f.split("/")[-1] for f in files]
+    assert names[:4] == ["conf_1_%d.pdb" % k for k in range(1, 5)]
+    n1 = sum(n.startswith("conf_1_") for n in names)
+    n2 = sum(n.startswith("conf_2_") for n in names)
+    assert 5 <= n1 <= 7 and 5 <= n2 <= 7
+    tms = []
+    for f in files:
+        s2, at = pdbio.read_backbone(f)
+        assert s2 == seq
+        tms.append((metrics.tm_score(at["CA"], nat["apo"]), metrics.tm_score(at["CA"], nat["holo"])))
+    tms = np.array(tms)
+    assert tms.max(axis=0).min() > 0.5, tms
