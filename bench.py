@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--precision", type=int, default=32, choices=[32, 64])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lbfgs-m", type=int, default=20)
+    ap.add_argument("--streams", type=int, default=1, help="independent fold batches per GPU (own stream each)")
     return ap.parse_args()
 
 
@@ -227,14 +228,25 @@ def run_b200_fold(args):
     warmup = max(args.warmup, 3)
     seq, npzs, nat = synth.target(L_TARGET, SEED, dense=False, two_model=True)
     params = tables.load_params()
-    stream = torch.cuda.Stream()
-    ctx = capi.Context(local, stream.cuda_stream)
-    tabs = [sampler.build_tables(ctx, npz, seq, params) for npz in npzs]
-    R = [sum(t.info()["counts"]) for t in tabs]
-    half = (N // 2 + 31) // 32 * 32
-    nd = [half, N - half]
-    batch = capi.FoldBatch(ctx, tabs, nd, sampler.aa_index(seq), schedule.reference_schedule(), lbfgs_m=args.lbfgs_m)
+    # The batch is split over `streams` independent fold batches (own context + CUDA stream each,
+    # driven by one host thread each): while one batch is in its latency-bound tail (few decoys
+    # left) the others keep the SMs busy.  Same work, same results per decoy.
+    S = max(1, args.streams)
     import ctypes as C
+    from concurrent.futures import ThreadPoolExecutor
+    per = [(N // S + (1 if k < N % S else 0)) for k in range(S)]
+    offs = np.concatenate([[0], np.cumsum(per)]).astype(int)
+    lanes = []
+    for k in range(S):
+        stream = torch.cuda.Stream()
+        ctx_k = capi.Context(local, stream.cuda_stream)
+        tabs_k = [sampler.build_tables(ctx_k, npz, seq, params) for npz in npzs]
+        half = (per[k] // 2 + 31) // 32 * 32
+        nd_k = [half, per[k] - half]
+        batch_k = capi.FoldBatch(ctx_k, tabs_k, nd_k, sampler.aa_index(seq), schedule.reference_schedule(), lbfgs_m=args.lbfgs_m)
+        lanes.append(dict(stream=stream, ctx=ctx_k, tabs=tabs_k, nd=nd_k, batch=batch_k, rounds=C.c_int()))
+    R = [sum(t.info()["counts"]) for t in lanes[0]["tabs"]]
+    pool_exec = ThreadPoolExecutor(max_workers=S)
 
     def barrier():
         if world > 1:
@@ -246,24 +258,32 @@ def run_b200_fold(args):
     xyz_h = torch.empty((N, L_TARGET, 5, 3), dtype=torch.float32).pin_memory()
     terms_h = torch.empty((N, 6), dtype=torch.float64).pin_memory()
     stats_h = torch.empty((N, 2), dtype=torch.int64).pin_memory()
-    rounds = C.c_int()
+
+    def fold_lane(k):
+        ln, o, n = lanes[k], int(offs[k]), per[k]
+        capi.check(capi.lib().trx_fold_run(ln["batch"]._h, C.c_void_p(tors_h[o:o + n].data_ptr()), C.c_void_p(xyz_h[o:o + n].data_ptr()),
+                                           C.c_void_p(terms_h[o:o + n].data_ptr()), C.c_void_p(stats_h[o:o + n].data_ptr()),
+                                           C.c_int(20000), C.c_int(16), C.byref(ln["rounds"])))
 
     def one_fold(seed):
         tors_h.copy_(torch.from_numpy(sampler.random_torsions(N, L_TARGET, seed)))
         t0 = time.perf_counter()
-        capi.check(capi.lib().trx_fold_run(batch._h, C.c_void_p(tors_h.data_ptr()), C.c_void_p(xyz_h.data_ptr()),
-                                           C.c_void_p(terms_h.data_ptr()), C.c_void_p(stats_h.data_ptr()),
-                                           C.c_int(20000), C.c_int(16), C.byref(rounds)))
+        list(pool_exec.map(fold_lane, range(S)))
         return time.perf_counter() - t0
+
+    ctx = lanes[0]["ctx"]
+    rounds = lanes[0]["rounds"]
+    nd = None
 
     for k in range(warmup):
         one_fold(1000 * rank + k)
     barrier()
     sampler_clk = ClockSampler(local)
     sampler_clk.start()
-    ctx.set_timing(True)
-    ctx.reset_timing()
-    launches0 = ctx.launch_count
+    for ln in lanes:
+        ln["ctx"].set_timing(True)
+        ln["ctx"].reset_timing()
+    launches0 = sum(ln["ctx"].launch_count for ln in lanes)
     barrier()
     from trx2dyn import parallel
     t_wall, evals_total, rest_evals = [], 0, 0.0
@@ -280,14 +300,23 @@ def run_b200_fold(args):
         t_wall.append(dt)
         ev = stats_h[:, 0].numpy().astype(np.float64)
         evals_total += float(ev.sum())
-        rest_evals += float(ev[:nd[0]].sum()) * R[0] + float(ev[nd[0]:].sum()) * R[1]
+        for q in range(S):
+            o, n0 = int(offs[q]), lanes[q]["nd"][0]
+            rest_evals += float(ev[o:o + n0].sum()) * R[0] + float(ev[o + n0:int(offs[q + 1])].sum()) * R[1]
     barrier()
     clocks = sampler_clk.stop()
-    launches = ctx.launch_count - launches0
-    t_dev = ctx.timing("fold_device")[0] / 1e3
-    k1_ms, k1_n = ctx.timing("restraints")
-    shares = {name: ctx.timing(name)[0] / (1e3 * t_dev) for name in ("restraints", "reduce", "nerf", "centroid", "torsion_grad", "lbfgs")}
-    ctx.set_timing(False)
+    launches = sum(ln["ctx"].launch_count for ln in lanes) - launches0
+    # device time of a step: the slowest lane's fold (CUDA events on its stream, inputs resident);
+    # lanes run concurrently, so steps cost max over lanes, not the sum
+    lane_dev = [ln["ctx"].timing("fold_device")[0] / 1e3 for ln in lanes]
+    t_dev = max(lane_dev)
+    k1_ms = sum(ln["ctx"].timing("restraints")[0] for ln in lanes)
+    k1_n = sum(ln["ctx"].timing("restraints")[1] for ln in lanes)
+    busy = {name: sum(ln["ctx"].timing(name)[0] for ln in lanes) for name in ("restraints", "reduce", "nerf", "centroid", "torsion_grad", "lbfgs")}
+    tot_busy = sum(busy.values())
+    shares = {name: v / tot_busy for name, v in busy.items()}
+    for ln in lanes:
+        ln["ctx"].set_timing(False)
     t_e2e = float(sum(t_wall))
     if world > 1:
         t = torch.tensor([t_dev, t_e2e], device="cuda", dtype=torch.float64)
@@ -311,6 +340,7 @@ def run_b200_fold(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "synthetic L=300 dist+omega+theta+phi, two-model mixing, %d decoys per GPU, full mode-2 centroid schedule (configs[2])" % N,
                        "restraints_per_decoy": R, "l2": "working set per step (%.1f GB of decoy state) exceeds L2" % (batch_bytes(N, L_TARGET, args.lbfgs_m) / 1e9),
+                       "streams": S,
                        "mode": "fold", "lbfgs_m": args.lbfgs_m, "cartesian_stage": "not built (DESIGN.md)",
                        "collective": "all-gather of per-decoy energies for pool selection (N>1 only)"},
             "restraint_decoy_evals_per_sec": evals_total * world / t_dev,
