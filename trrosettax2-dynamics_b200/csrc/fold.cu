@@ -204,10 +204,10 @@ __global__ void __launch_bounds__(SEG_THREADS) nerf_kernel(FoldState s)
 // K4: soft-sphere repulsion of one decoy per CTA.  Atoms N,CA,CB,C,O + CEN (on the CA->CB
 // ray) staged in shared memory as float4 (x,y,z,radius); warps scan residue rows for close
 // CA pairs (ballot), then spread the 36 atom pairs of each close residue pair over lanes.
-// Clashes are rare, so gradients go through 64-bit fixed-point shared atomics: integer
-// sums are order-independent => bit-reproducible.
+// Gradients of clashing atom pairs go through 32-bit fixed-point shared atomics (native
+// ATOMS.ADD, no CAS loop): integer sums are order-independent => bit-reproducible.
 constexpr int VDW_THREADS = 256;
-constexpr double VDW_FIX = 4294967296.0;  // 2^32
+constexpr float VDW_FIX = 65536.0f;   // 2^16: gradients as 32-bit fixed point (range +-32768, step 1.5e-5)
 
 __global__ void __launch_bounds__(VDW_THREADS) vdw_kernel(FoldState s)
 {
@@ -216,8 +216,8 @@ __global__ void __launch_bounds__(VDW_THREADS) vdw_kernel(FoldState s)
     if (s.perm[n] < 0) return;
     const int L = s.L;
     float4 *at = reinterpret_cast<float4 *>(smem_raw);                                   // [L][6]
-    long long *acc = reinterpret_cast<long long *>(smem_raw + sizeof(float4) * 6 * L);   // [L][6][3]
-    float4 *bsph = reinterpret_cast<float4 *>(acc + (size_t)L * 18);                     // [L] bounding spheres
+    int *acc = reinterpret_cast<int *>(smem_raw + sizeof(float4) * 6 * L);               // [L][6][3]
+    float4 *bsph = reinterpret_cast<float4 *>(smem_raw + sizeof(float4) * 6 * L + ((sizeof(int) * 18 * L + 15) / 16) * 16);   // [L] bounding spheres
     __shared__ double ered[VDW_THREADS / 32];
     const float *__restrict__ xn = s.xnat + (size_t)n * L * NAT3;
     for (int i = threadIdx.x; i < L; i += VDW_THREADS) {
@@ -262,12 +262,10 @@ __global__ void __launch_bounds__(VDW_THREADS) vdw_kernel(FoldState s)
                 const float c = r2 - d2, ir2 = 1.0f / r2;
                 e_thread += (double)((float)TRX_VDW_SCALE * c * c * ir2);
                 const float f = -4.0f * (float)TRX_VDW_SCALE * c * ir2;
-                const long long gx = (long long)((double)(f * dx) * VDW_FIX), gy = (long long)((double)(f * dy) * VDW_FIX),
-                                gz = (long long)((double)(f * dz) * VDW_FIX);
-                unsigned long long *pi = reinterpret_cast<unsigned long long *>(acc + (i * 6 + a) * 3);
-                unsigned long long *pj = reinterpret_cast<unsigned long long *>(acc + (j * 6 + b) * 3);
-                atomicAdd(pi + 0, (unsigned long long)gx); atomicAdd(pi + 1, (unsigned long long)gy); atomicAdd(pi + 2, (unsigned long long)gz);
-                atomicAdd(pj + 0, (unsigned long long)(-gx)); atomicAdd(pj + 1, (unsigned long long)(-gy)); atomicAdd(pj + 2, (unsigned long long)(-gz));
+                const int gx = __float2int_rn(f * dx * VDW_FIX), gy = __float2int_rn(f * dy * VDW_FIX), gz = __float2int_rn(f * dz * VDW_FIX);
+                int *pi = acc + (i * 6 + a) * 3, *pj = acc + (j * 6 + b) * 3;
+                atomicAdd(pi + 0, gx); atomicAdd(pi + 1, gy); atomicAdd(pi + 2, gz);
+                atomicAdd(pj + 0, -gx); atomicAdd(pj + 1, -gy); atomicAdd(pj + 2, -gz);
             }
         }
     };
@@ -318,7 +316,7 @@ __global__ void __launch_bounds__(VDW_THREADS) vdw_kernel(FoldState s)
         const float cs = c_model.cen_s[s.aa[i]];
         float gv[18];
 #pragma unroll
-        for (int k = 0; k < 18; ++k) gv[k] = w * (float)((double)acc[i * 18 + k] / VDW_FIX);
+        for (int k = 0; k < 18; ++k) gv[k] = w * ((float)acc[i * 18 + k] * (1.0f / VDW_FIX));
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             gv[TRX_AT_CA * 3 + k] += (1.0f - cs) * gv[15 + k];
@@ -988,7 +986,7 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     s.N = (G - 1) * LANES + ((ndecoys[ntab - 1] - 1) % LANES + 1);
     TRX_REQUIRE(s.N == N, "trx_fold_create: internal decoy count mismatch");
     s.G = G; s.Npad = G * LANES; s.L = L; s.Lpad = padded_length(L); s.ndof = 3 * L; s.m = lbfgs_m; s.nruns = nruns;
-    b->vdw_smem = sizeof(float4) * 6 * L + sizeof(long long) * 18 * L + sizeof(float4) * L;
+    b->vdw_smem = sizeof(float4) * 6 * L + ((sizeof(int) * 18 * L + 15) / 16) * 16 + sizeof(float4) * L;
     TRX_REQUIRE(b->vdw_smem <= 220 * 1024, "trx_fold_create: L=%d exceeds the shared-memory budget of the vdw kernel", L);
     TRX_REQUIRE(L < 65536, "trx_fold_create: L too large");
     // one arena, carved into aligned pieces
