@@ -27,8 +27,8 @@ def lib():
     """Loads (building if sources are newer) the in-tree CUDA library."""
     global _lib
     if _lib is None:
-        path = _build.LIB
-        if _build.needs_build():
+        path = os.environ.get("TRX2DYN_LIB") or _build.LIB      # TRX2DYN_LIB: load a specific build (A/B tests)
+        if path == _build.LIB and _build.needs_build():
             if not os.path.exists(_build.NVCC):
                 if not os.path.exists(path):
                     raise TrxError("libtrx2dyn.so is missing and nvcc is not available; there is no CPU fallback")

@@ -18,6 +18,10 @@
 // reduce kernel sums in a fixed order.
 #include "internal.cuh"
 
+#ifndef TRX_K1_MINBLOCKS
+#define TRX_K1_MINBLOCKS 3
+#endif
+
 namespace trx {
 
 __device__ __forceinline__ float t_rsqrt(float x) { return rsqrtf(x); }
@@ -152,7 +156,7 @@ struct ColGeom {
 // accumulates the gradients.  Dihedral sign and range: IUPAC, equal to the reference's numpy
 // get_dihedrals (utils_trX2dy/utils.py:97-110); angle: get_angles (:113-122).
 // row: CB_i(0..2) P(3..5) U=N_i-CA_i(6..8); rg/cg: gradient accumulators N(0..2) CA(3..5) CB(6..8).
-template <typename T>
+template <typename T, bool ALL>
 __device__ __forceinline__ void pair_eval(const K1Params<T> &p, const KnotGeom<T> *geom, const int4 ia, const int4 ib,
                                           const T *row, const ColGeom<T> &c, T *rg, T *cg, const T w0, const T w1, const T w2,
                                           T &e0, T &e1, T &e2)
@@ -182,17 +186,17 @@ __device__ __forceinline__ void pair_eval(const K1Params<T> &p, const KnotGeom<T
     // ---- phase 1: values, intervals, loads
     T u0 = (T)0, u1 = (T)0, u2 = (T)0, u3 = (T)0, u4 = (T)0, u5 = (T)0;
     Coef<T> c0 = {(T)0, (T)0, (T)0, (T)0}, c1 = c0, c2 = c0, c3 = c0, c4 = c0, c5 = c0;
-    if (mask & 1) c0 = spline_load(p.tab[0] + ia.y, spline_locate(geom[0], d, u0));
-    if (mask & 2)    // omega: F = P, G = -D, H = Q  =>  A = X, B = Y
+    if (ALL || (mask & 1)) c0 = spline_load(p.tab[0] + ia.y, spline_locate(geom[0], d, u0));
+    if (ALL || (mask & 2))    // omega: F = P, G = -D, H = Q  =>  A = X, B = Y
         c1 = spline_load(p.tab[1] + ia.z, spline_locate(geom[1], t_atan2(-d * DOT(P, Y), DOT(X, Y)), u1));
-    if (mask & 4)    // theta(i,j): F = U_i, G = P, H = D  =>  A = U_i x P, B = X
+    if (ALL || (mask & 4))    // theta(i,j): F = U_i, G = P, H = D  =>  A = U_i x P, B = X
         c2 = spline_load(p.tab[2] + ia.w, spline_locate(geom[2], t_atan2(-np_ * DOT(U, X), DOT(W, X)), u2));
-    if (mask & 8)    // theta(j,i): F = U_j, G = Q, H = -D  =>  A = W_j, B = -Y
+    if (ALL || (mask & 8))    // theta(j,i): F = U_j, G = Q, H = -D  =>  A = W_j, B = -Y
         c3 = spline_load(p.tab[2] + ib.x,
                          spline_locate(geom[2], t_atan2(nq * (c.Ux * Yx + c.Uy * Yy + c.Uz * Yz), -(c.Wx * Yx + c.Wy * Yy + c.Wz * Yz)), u3));
-    if (mask & 16)   // phi(i,j): angle between P and D at CB_i; sin = |X| / (|P||D|)
+    if (ALL || (mask & 16))   // phi(i,j): angle between P and D at CB_i; sin = |X| / (|P||D|)
         c4 = spline_load(p.tab[3] + ib.y, spline_locate(geom[3], t_atan2(xx * rX, pd), u4));
-    if (mask & 32)   // phi(j,i): angle between Q and -D at CB_j; sin = |Y| / (|Q||D|)
+    if (ALL || (mask & 32))   // phi(j,i): angle between Q and -D at CB_j; sin = |Y| / (|Q||D|)
         c5 = spline_load(p.tab[3] + ib.z, spline_locate(geom[3], t_atan2(yy * rY, -qd), u5));
 
     // ---- phase 2: energies and gradients
@@ -205,7 +209,7 @@ __device__ __forceinline__ void pair_eval(const K1Params<T> &p, const KnotGeom<T
         cg[6] += s * Dx; cg[7] += s * Dy; cg[8] += s * Dz;
         rg[6] -= s * Dx; rg[7] -= s * Dy; rg[8] -= s * Dz;
     }
-    if (mask & 2) {
+    if (ALL || (mask & 2)) {
         const T s = w1 * SPLINE_DF(c1, u1);
         const T a1 = -s * d * ixx, a4 = s * d * iyy, tA = -s * pd * ixx * rd, tB = -s * qd * iyy * rd;
         const T tx = tA * Xx - tB * Yx, ty = tA * Xy - tB * Yy, tz = tA * Xz - tB * Yz;
@@ -214,7 +218,7 @@ __device__ __forceinline__ void pair_eval(const K1Params<T> &p, const KnotGeom<T
         rg[6] += tx - a1 * Xx; rg[7] += ty - a1 * Xy; rg[8] += tz - a1 * Xz;   // CB_i
         cg[6] -= tx + a4 * Yx; cg[7] -= ty + a4 * Yy; cg[8] -= tz + a4 * Yz;   // CB_j
     }
-    if (mask & 4) {
+    if (ALL || (mask & 4)) {
         const T s = w1 * SPLINE_DF(c2, u2), iww = t_rcp(ww), up = DOT(U, P);
         const T a1 = -s * np_ * iww, a4 = s * np_ * ixx, tA = s * up * iww * rp, tB = s * pd * ixx * rp;
         const T tx = tA * Wx - tB * Xx, ty = tA * Wy - tB * Xy, tz = tA * Wz - tB * Xz;
@@ -223,7 +227,7 @@ __device__ __forceinline__ void pair_eval(const K1Params<T> &p, const KnotGeom<T
         rg[3] += tx - a1 * Wx; rg[4] += ty - a1 * Wy; rg[5] += tz - a1 * Wz;   // CA_i
         rg[6] -= tx + a4 * Xx; rg[7] -= ty + a4 * Xy; rg[8] -= tz + a4 * Xz;   // CB_i
     }
-    if (mask & 8) {
+    if (ALL || (mask & 8)) {
         const T s = w1 * SPLINE_DF(c3, u3), iww = t_rcp(c.ww);
         const T a1 = -s * nq * iww, a4 = s * nq * iyy, tA = s * c.uq * iww * rq, tB = s * qd * iyy * rq;
         const T tx = tA * c.Wx - tB * Yx, ty = tA * c.Wy - tB * Yy, tz = tA * c.Wz - tB * Yz;
@@ -232,7 +236,7 @@ __device__ __forceinline__ void pair_eval(const K1Params<T> &p, const KnotGeom<T
         cg[3] += tx - a1 * c.Wx; cg[4] += ty - a1 * c.Wy; cg[5] += tz - a1 * c.Wz;     // CA_j
         cg[6] -= tx - a4 * Yx; cg[7] -= ty - a4 * Yy; cg[8] -= tz - a4 * Yz;           // CB_j
     }
-    if (mask & 16) {
+    if (ALL || (mask & 16)) {
         const T s = w2 * SPLINE_DF(c4, u4) * rX, a = pd * rp * rp, b = pd * rd * rd;
         const T ux = -s * (Dx - a * Px), uy = -s * (Dy - a * Py), uz = -s * (Dz - a * Pz);   // d/dCA_i
         const T vx = -s * (Px - b * Dx), vy = -s * (Py - b * Dy), vz = -s * (Pz - b * Dz);   // d/dCB_j
@@ -240,7 +244,7 @@ __device__ __forceinline__ void pair_eval(const K1Params<T> &p, const KnotGeom<T
         cg[6] += vx; cg[7] += vy; cg[8] += vz;
         rg[6] -= ux + vx; rg[7] -= uy + vy; rg[8] -= uz + vz;
     }
-    if (mask & 32) {
+    if (ALL || (mask & 32)) {
         const T s = w2 * SPLINE_DF(c5, u5) * rY, a = qd * rq * rq, b = qd * rd * rd;
         const T ux = s * (Dx - a * Qx), uy = s * (Dy - a * Qy), uz = s * (Dz - a * Qz);      // d/dCA_j
         const T vx = -s * (Qx - b * Dx), vy = -s * (Qy - b * Dy), vz = -s * (Qz - b * Dz);   // d/dCB_i
@@ -251,7 +255,7 @@ __device__ __forceinline__ void pair_eval(const K1Params<T> &p, const KnotGeom<T
 }
 
 template <typename T>
-__global__ void __launch_bounds__(K1_THREADS, (sizeof(T) == 4 ? 3 : 1)) restraints_kernel(const K1Params<T> p)
+__global__ void __launch_bounds__(K1_THREADS, (sizeof(T) == 4 ? TRX_K1_MINBLOCKS : 1)) restraints_kernel(const K1Params<T> p)
 {
     __shared__ KnotGeom<T> geom[4];
     extern __shared__ __align__(16) unsigned char k1_dyn[];
@@ -319,7 +323,9 @@ __global__ void __launch_bounds__(K1_THREADS, (sizeof(T) == 4 ? 3 : 1)) restrain
                 cgm.qq = max(cgm.Qx * cgm.Qx + cgm.Qy * cgm.Qy + cgm.Qz * cgm.Qz, t_tiny<T>());
                 cgm.ww = max(cgm.Wx * cgm.Wx + cgm.Wy * cgm.Wy + cgm.Wz * cgm.Wz, t_tiny<T>());
                 cgm.uq = cgm.Ux * cgm.Qx + cgm.Uy * cgm.Qy + cgm.Uz * cgm.Qz;
-                pair_eval<T>(p, geom, ia, ib, row, cgm, rg, cg, w0, w1, w2, f0, f1, f2);
+                // pairs carrying all six restraints take a straight-line path (no per-restraint branches)
+                if (ia.x == 63) pair_eval<T, true>(p, geom, ia, ib, row, cgm, rg, cg, w0, w1, w2, f0, f1, f2);
+                else pair_eval<T, false>(p, geom, ia, ib, row, cgm, rg, cg, w0, w1, w2, f0, f1, f2);
 #pragma unroll
                 for (int k = 0; k < 9; ++k) {
                     rowg[(r * 9 + k) * LANES + lane] += rg[k];
