@@ -256,7 +256,7 @@ def run_b200_fold(args):
     # pinned host buffers: torsions in, coordinates + terms out (the e2e path IS the product call)
     tors_h = torch.empty((N, L_TARGET, 3), dtype=torch.float32).pin_memory()
     xyz_h = torch.empty((N, L_TARGET, 5, 3), dtype=torch.float32).pin_memory()
-    terms_h = torch.empty((N, 6), dtype=torch.float64).pin_memory()
+    terms_h = torch.empty((N, 7), dtype=torch.float64).pin_memory()
     stats_h = torch.empty((N, 2), dtype=torch.int64).pin_memory()
 
     def fold_lane(k):
@@ -293,7 +293,7 @@ def run_b200_fold(args):
         dt = one_fold(1000 * rank + 100 + k)
         if world > 1:
             # the path's only exchange: all-gather of per-decoy energies (NCCL) for pool selection
-            score = (terms_h.numpy() * np.array([5.0, 4.0, 4.0, 1.0, 1.0, 0.5])).sum(1)
+            score = (terms_h.numpy() * np.array([5.0, 4.0, 4.0, 1.0, 1.0, 0.5, 0.0])).sum(1)
             full = parallel.gather_scalars(score, N * world, rank, world, device="cuda")
             pool = parallel.select_pool(full[:, 0], 10)
             dt = time.perf_counter() - t0

@@ -103,21 +103,25 @@ int trx_to_grouped(trx_ctx *ctx, int N, int L, int n_atoms, int precision, const
 int trx_from_grouped(trx_ctx *ctx, int N, int L, int n_atoms, int precision, const void *d_grouped, void *d_natural);
 
 /* ------------------------------------------------------------------ the centroid fold
- * Energy terms of the fold, order of every w[6] / terms[6]:
- * atom_pair_constraint, dihedral_constraint, angle_constraint, vdw, rama, omega. */
-enum { TRX_TERM_APC = 0, TRX_TERM_DIH = 1, TRX_TERM_ANG = 2, TRX_TERM_VDW = 3, TRX_TERM_RAMA = 4, TRX_TERM_OMEGA = 5 };
+ * Energy terms of the fold, order of every w[7] / terms[7]:
+ * atom_pair_constraint, dihedral_constraint, angle_constraint, vdw, rama, omega, cart_bonded. */
+enum { TRX_TERM_APC = 0, TRX_TERM_DIH = 1, TRX_TERM_ANG = 2, TRX_TERM_VDW = 3, TRX_TERM_RAMA = 4, TRX_TERM_OMEGA = 5, TRX_TERM_CART = 6, TRX_NTERMS = 7 };
 
 /* One MinMover.apply of the reference's schedule (folding/folding.py:91-104): score
  * weights (data/ *.wts), max_iter, tolerance.  clash_check = 1 restates remove_clash
  * (utils_ros.py:699-703): when rama+vdw (weights 1,1) < clash_thr at the start of the run,
  * execution continues at run skip_to instead. */
 typedef struct {
-    double w[6];
+    double w[7];
     int max_iter;
     double tol;
     int clash_check;
     double clash_thr;
     int skip_to;
+    int cartesian; /* 1: MinMover.cartesian(True) (min_mover_cart, folding.py:100-102): the coordinates of
+                    * N,CA,CB,C,O are the degrees of freedom.  Afterwards the decoy HOLDS those coordinates:
+                    * a following clash check scores them, and the next torsion-space run that actually
+                    * starts rebuilds the chain from the read-back torsions with ideal bond geometry. */
 } trx_run;
 
 typedef struct trx_fold_batch trx_fold_batch;
@@ -133,7 +137,7 @@ int trx_fold_destroy(trx_fold_batch *b);
 /* Minimises every decoy through the schedule, all on device (NeRF, restraint + centroid
  * terms, torsion gradient, L-BFGS / Armijo); the host only polls a counter every
  * check_every evaluation rounds.  tors: host [N][L][3] float (phi,psi,omega radians), in/out.
- * xyz (may be NULL): [N][L][5][3] float, atoms N,CA,CB,C,O.  terms (may be NULL): [N][6].
+ * xyz (may be NULL): [N][L][5][3] float, atoms N,CA,CB,C,O.  terms (may be NULL): [N][7].
  * stats (may be NULL): [N][2] = energy evaluations, accepted L-BFGS iterations.
  * Replaces: remove_clash + repeat_mover.apply + remove_clash (folding.py:119,164-171). */
 int trx_fold_run(trx_fold_batch *b, float *tors, float *xyz, double *terms, long long *stats, int max_rounds,
@@ -150,10 +154,18 @@ int trx_fold_mc(trx_fold_batch *b, float *tors, float *xyz, double *terms, long 
                 double kT, int block_min, int block_max, double sigma_deg, unsigned long long seed,
                 unsigned long long id_offset, int max_rounds, int check_every, int *rounds_out);
 /* One evaluation at given torsions under uniform weights (parity entry for the NeRF /
- * vdw / rama / omega / torsion-gradient kernels): total[N], terms[N][6], gtors[N][L][3],
+ * vdw / rama / omega / torsion-gradient kernels): total[N], terms[N][7], gtors[N][L][3],
  * xyz[N][L][5][3] (any output may be NULL). */
-int trx_fold_eval(trx_fold_batch *b, const float *tors, const double w[6], double *total, double *terms, float *gtors,
+int trx_fold_eval(trx_fold_batch *b, const float *tors, const double w[7], double *total, double *terms, float *gtors,
                   float *xyz);
+
+/* One Cartesian-mode evaluation under uniform weights (parity entry for the Cartesian stage:
+ * cart_bonded springs, rama / omega from coordinates, restraint + vdw gradients on xyz):
+ * xyz[N][L][5][3] in; total[N], terms[N][7], grad[N][L][5][3], tors[N][L][3] (torsions read
+ * back from the coordinates) out, any of which may be NULL.  The batch's schedule must
+ * contain a Cartesian run. */
+int trx_fold_eval_cart(trx_fold_batch *b, const float *xyz, const double w[7], double *total, double *terms, float *grad,
+                       float *tors);
 
 #ifdef __cplusplus
 }

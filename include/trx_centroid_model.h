@@ -36,7 +36,7 @@
 enum { TRX_AT_N = 0, TRX_AT_CA = 1, TRX_AT_CB = 2, TRX_AT_C = 3, TRX_AT_O = 4, TRX_NAT = 5 };
 
 /* energy terms of the fold path, order of every terms[] / weights[] array */
-enum { TRX_T_APC = 0, TRX_T_DIH = 1, TRX_T_ANG = 2, TRX_T_VDW = 3, TRX_T_RAMA = 4, TRX_T_OMEGA = 5, TRX_NTERM = 6 };
+enum { TRX_T_APC = 0, TRX_T_DIH = 1, TRX_T_ANG = 2, TRX_T_VDW = 3, TRX_T_RAMA = 4, TRX_T_OMEGA = 5, TRX_T_CART = 6, TRX_NTERM = 7 };
 
 /* amino-acid index: position in "ARNDCQEGHILKMFPSTWYV" */
 #define TRX_AA_ORDER "ARNDCQEGHILKMFPSTWYV"
@@ -70,5 +70,19 @@ static const double TRX_RAMA[2][TRX_RAMA_NB][5] = {
 #define TRX_RAMA_FLOOR 1e-4
 /* omega tether: 0.01 * (deviation from 180 in degrees)^2 */
 #define TRX_OMEGA_K 0.01
+
+
+/* Cartesian stage (min_mover_cart, folding.py:100-102,170): a cart_bonded-like term keeps the
+ * backbone near ideal geometry while xyz are the degrees of freedom.  Rosetta's cart_bonded
+ * parameter database is not in the reference tree: harmonic springs with round constants.
+ *   bonds   E = KB (d - d0)^2      N-CA, CA-C, C-O, C-N(+1)
+ *   angles  E = KA (t - t0)^2      N-CA-C, CA-C-O, CA-C-N(+1), O-C-N(+1), C-N(+1)-CA(+1)
+ *   CB      E = KCB |CB - vCB|^2   tether to the virtual-CB position of (N, CA, C)
+ *   planar  E = KPL t^2, t = ((CA-C) x (N(+1)-C)) . (O-C)   carbonyl O in the peptide plane */
+#define TRX_CART_KB 300.0
+#define TRX_CART_KA 80.0
+#define TRX_CART_KCB 300.0
+#define TRX_CART_KPL 40.0
+#define TRX_A_O_C_N (123.0 * TRX_DEG)
 
 #endif

@@ -5,7 +5,9 @@
  * (soft-sphere vdw, Ramachandran, omega tether -- stated APPROXIMATIONS of Rosetta's
  * vdw / rama / omega, whose database tables are not in the reference tree), the
  * reverse-mode torsion gradient (Abe-Go / Rosetta F1,F2 suffix sums), an L-BFGS with
- * non-monotone Armijo back-tracking, and the reference's staged schedule
+ * non-monotone Armijo back-tracking, the Cartesian stage (min_mover_cart,
+ * folding/folding.py:100-102,170: xyz as degrees of freedom, a cart_bonded-like spring
+ * term, rama/omega evaluated from coordinates) and the reference's staged schedule
  * (folding/folding.py:86-104,118-119,164-171; utils_ros.py:699-703).
  * PARITY UNPINNED against PyRosetta (absent); the three constraint terms it calls are
  * the ones of restraints_oracle.c.  Only tests/, smoke() and bench.py's CPU-baseline /
@@ -210,6 +212,7 @@ double trxo_eval(const trxo_target *T, const double *w, const double *tors, doub
     trxo_energy_grad(L, x9, T->sets[0], T->sets[1], T->sets[2], T->sets[3], w, terms, g9, NULL, NULL);
     for (int i = 0; i < L; ++i) memcpy(g + (size_t)i * TRX_NAT * 3, g9 + (size_t)i * 9, 9 * sizeof(double));
     terms[TRX_T_VDW] = trxo_vdw(L, T->aa, xyz, w[TRX_T_VDW], g);
+    terms[TRX_T_CART] = 0.0;   /* ideal internal geometry in torsion space */
     memset(gt, 0, sizeof(double) * (size_t)L * 3);
     trxo_rama_omega(L, T->aa, tors, w[TRX_T_RAMA], w[TRX_T_OMEGA], &terms[TRX_T_RAMA], &terms[TRX_T_OMEGA], gt);
     trxo_torsion_grad(L, xyz, g, gt);
@@ -221,6 +224,171 @@ double trxo_eval(const trxo_target *T, const double *w, const double *tors, doub
     return tot;
 }
 
+/* ------------------------------------------------------------------ Cartesian stage */
+/* from restraints_oracle.c */
+double trxo_dihedral(const double *p1, const double *p2, const double *p3, const double *p4);
+void trxo_dihedral_grad(const double *p1, const double *p2, const double *p3, const double *p4, double *g1, double *g2,
+                        double *g3, double *g4);
+double trxo_angle(const double *p1, const double *p2, const double *p3);
+void trxo_angle_grad(const double *p1, const double *p2, const double *p3, double *g1, double *g2, double *g3);
+
+#define GRD(r, at) (grad + ((size_t)(r) * TRX_NAT + (at)) * 3)
+
+static double spring_bond(const double *a, const double *b, double d0, double k, double w, double *ga, double *gb)
+{
+    double d[3];
+    v_sub(a, b, d);
+    double len = sqrt(v_dot(d, d)), dev = len - d0;
+    if (ga) for (int c = 0; c < 3; ++c) { double f = w * 2.0 * k * dev * d[c] / len; ga[c] += f; gb[c] -= f; }
+    return k * dev * dev;
+}
+
+static double spring_angle(const double *a, const double *b, const double *c, double t0, double k, double w, double *ga,
+                           double *gb, double *gc)
+{
+    double dev = trxo_angle(a, b, c) - t0;
+    if (ga) {
+        double g1[3], g2[3], g3[3];
+        trxo_angle_grad(a, b, c, g1, g2, g3);
+        for (int q = 0; q < 3; ++q) { double f = w * 2.0 * k * dev; ga[q] += f * g1[q]; gb[q] += f * g2[q]; gc[q] += f * g3[q]; }
+    }
+    return k * dev * dev;
+}
+
+static void add_dihedral_grad(const double *p1, const double *p2, const double *p3, const double *p4, double f, double *g1,
+                              double *g2, double *g3, double *g4)
+{
+    double d1[3], d2[3], d3[3], d4[3];
+    trxo_dihedral_grad(p1, p2, p3, p4, d1, d2, d3, d4);
+    for (int q = 0; q < 3; ++q) { g1[q] += f * d1[q]; g2[q] += f * d2[q]; g3[q] += f * d3[q]; g4[q] += f * d4[q]; }
+}
+
+/* phi(i) = dihedral(C_i-1, N_i, CA_i, C_i), psi(i) = dihedral(N_i, CA_i, C_i, N_i+1), omega(i) =
+ * dihedral(CA_i, C_i, N_i+1, CA_i+1) read back from coordinates; the torsions that move nothing
+ * (phi(0), omega(L-1)) are set to pi and psi(L-1) is taken from the carbonyl O (NeRF places
+ * O at psi + pi). */
+void trxo_torsions_from_xyz(int L, const double *xyz, double *tors)
+{
+    for (int i = 0; i < L; ++i) {
+        double *t = tors + (size_t)i * 3;
+        t[0] = i > 0 ? trxo_dihedral(XYZ(i - 1, TRX_AT_C), XYZ(i, TRX_AT_N), XYZ(i, TRX_AT_CA), XYZ(i, TRX_AT_C)) : TRX_PI;
+        if (i < L - 1) {
+            t[1] = trxo_dihedral(XYZ(i, TRX_AT_N), XYZ(i, TRX_AT_CA), XYZ(i, TRX_AT_C), XYZ(i + 1, TRX_AT_N));
+            t[2] = trxo_dihedral(XYZ(i, TRX_AT_CA), XYZ(i, TRX_AT_C), XYZ(i + 1, TRX_AT_N), XYZ(i + 1, TRX_AT_CA));
+        } else {
+            double p = trxo_dihedral(XYZ(i, TRX_AT_N), XYZ(i, TRX_AT_CA), XYZ(i, TRX_AT_C), XYZ(i, TRX_AT_O)) - TRX_PI;
+            t[1] = p <= -TRX_PI ? p + 2.0 * TRX_PI : p;
+            t[2] = TRX_PI;
+        }
+    }
+}
+
+/* cart_bonded-like springs (include/trx_centroid_model.h) + Ramachandran + omega tether as
+ * functions of the coordinates.  E[3] = unweighted (cart, rama, omega); grad[L][5][3] is
+ * ACCUMULATED with the weighted derivatives (may be NULL). */
+void trxo_cart_terms(int L, const int *aa, const double *xyz, double w_cart, double w_rama, double w_omega, double *E,
+                     double *grad)
+{
+    double ec = 0.0, er = 0.0, eo = 0.0;
+    for (int i = 0; i < L; ++i) {
+        const double *N = XYZ(i, TRX_AT_N), *CA = XYZ(i, TRX_AT_CA), *CB = XYZ(i, TRX_AT_CB), *Cc = XYZ(i, TRX_AT_C), *O = XYZ(i, TRX_AT_O);
+        double *gN = grad ? GRD(i, TRX_AT_N) : NULL, *gCA = grad ? GRD(i, TRX_AT_CA) : NULL, *gCB = grad ? GRD(i, TRX_AT_CB) : NULL;
+        double *gC = grad ? GRD(i, TRX_AT_C) : NULL, *gO = grad ? GRD(i, TRX_AT_O) : NULL;
+        ec += spring_bond(CA, N, TRX_B_N_CA, TRX_CART_KB, w_cart, gCA, gN);
+        ec += spring_bond(Cc, CA, TRX_B_CA_C, TRX_CART_KB, w_cart, gC, gCA);
+        ec += spring_bond(O, Cc, TRX_B_C_O, TRX_CART_KB, w_cart, gO, gC);
+        ec += spring_angle(N, CA, Cc, TRX_A_N_CA_C, TRX_CART_KA, w_cart, gN, gCA, gC);
+        ec += spring_angle(CA, Cc, O, TRX_A_CA_C_O, TRX_CART_KA, w_cart, gCA, gC, gO);
+        {   /* CB tether to the virtual-CB position */
+            double b[3], c[3], a[3], r[3];
+            v_sub(CA, N, b); v_sub(Cc, CA, c); v_cross(b, c, a);
+            for (int k = 0; k < 3; ++k) r[k] = CB[k] - (TRX_CB_A * a[k] + TRX_CB_B * b[k] + TRX_CB_C * c[k] + CA[k]);
+            ec += TRX_CART_KCB * v_dot(r, r);
+            if (grad) {
+                double q[3], cq[3], qb[3];
+                for (int k = 0; k < 3; ++k) q[k] = -w_cart * 2.0 * TRX_CART_KCB * r[k];   /* dE/d vCB */
+                v_cross(c, q, cq); v_cross(q, b, qb);
+                for (int k = 0; k < 3; ++k) {
+                    double gb = TRX_CB_A * cq[k] + TRX_CB_B * q[k], gc = TRX_CB_A * qb[k] + TRX_CB_C * q[k];
+                    gCB[k] -= q[k];
+                    gN[k] -= gb;
+                    gCA[k] += gb - gc + q[k];
+                    gC[k] += gc;
+                }
+            }
+        }
+        if (i < L - 1) {
+            const double *N1 = XYZ(i + 1, TRX_AT_N), *CA1 = XYZ(i + 1, TRX_AT_CA);
+            double *gN1 = grad ? GRD(i + 1, TRX_AT_N) : NULL, *gCA1 = grad ? GRD(i + 1, TRX_AT_CA) : NULL;
+            ec += spring_bond(N1, Cc, TRX_B_C_N, TRX_CART_KB, w_cart, gN1, gC);
+            ec += spring_angle(CA, Cc, N1, TRX_A_CA_C_N, TRX_CART_KA, w_cart, gCA, gC, gN1);
+            ec += spring_angle(O, Cc, N1, TRX_A_O_C_N, TRX_CART_KA, w_cart, gO, gC, gN1);
+            ec += spring_angle(Cc, N1, CA1, TRX_A_C_N_CA, TRX_CART_KA, w_cart, gC, gN1, gCA1);
+            {   /* carbonyl O in the peptide plane */
+                double u[3], v[3], o[3], uv[3], vo[3], ou[3];
+                v_sub(CA, Cc, u); v_sub(N1, Cc, v); v_sub(O, Cc, o);
+                v_cross(u, v, uv); v_cross(v, o, vo); v_cross(o, u, ou);
+                double t = v_dot(uv, o);
+                ec += TRX_CART_KPL * t * t;
+                if (grad) {
+                    double f = w_cart * 2.0 * TRX_CART_KPL * t;
+                    for (int k = 0; k < 3; ++k) {
+                        gCA[k] += f * vo[k]; gN1[k] += f * ou[k]; gO[k] += f * uv[k];
+                        gC[k] -= f * (vo[k] + ou[k] + uv[k]);
+                    }
+                }
+            }
+            {   /* omega tether */
+                double om = trxo_dihedral(CA, Cc, N1, CA1), dev = om - TRX_PI;
+                dev -= 2.0 * TRX_PI * floor((dev + TRX_PI) / (2.0 * TRX_PI));
+                double deg = dev / TRX_DEG;
+                eo += TRX_OMEGA_K * deg * deg;
+                if (grad) add_dihedral_grad(CA, Cc, N1, CA1, w_omega * 2.0 * TRX_OMEGA_K * deg / TRX_DEG, gCA, gC, gN1, gCA1);
+            }
+        }
+        if (i > 0 && i < L - 1) {   /* Ramachandran */
+            const double *Cp = XYZ(i - 1, TRX_AT_C), *N1 = XYZ(i + 1, TRX_AT_N);
+            double phi = trxo_dihedral(Cp, N, CA, Cc), psi = trxo_dihedral(N, CA, Cc, N1);
+            int cls = aa[i] == TRX_AA_PRO ? 1 : 0;
+            double P = TRX_RAMA_FLOOR, dP_dphi = 0.0, dP_dpsi = 0.0;
+            for (int k = 0; k < TRX_RAMA_NB; ++k) {
+                const double *b = TRX_RAMA[cls][k];
+                double dphi = phi - b[0] * TRX_DEG, dpsi = psi - b[1] * TRX_DEG;
+                double e = b[4] * exp(b[2] * (cos(dphi) - 1.0) + b[3] * (cos(dpsi) - 1.0));
+                P += e;
+                dP_dphi += -e * b[2] * sin(dphi);
+                dP_dpsi += -e * b[3] * sin(dpsi);
+            }
+            er += -log(P);
+            if (grad) {
+                add_dihedral_grad(Cp, N, CA, Cc, -w_rama * dP_dphi / P, GRD(i - 1, TRX_AT_C), gN, gCA, gC);
+                add_dihedral_grad(N, CA, Cc, N1, -w_rama * dP_dpsi / P, gN, gCA, gC, GRD(i + 1, TRX_AT_N));
+            }
+        }
+    }
+    E[0] = ec; E[1] = er; E[2] = eo;
+}
+
+/* Cartesian-mode evaluation: xyz[L][5][3] are the degrees of freedom.  terms[TRX_NTERM]
+ * unweighted; g[L][5][3] = d total / d xyz; returns the weighted total. */
+double trxo_eval_cart(const trxo_target *T, const double *w, const double *xyz, double *terms, double *g)
+{
+    const int L = T->L;
+    double *x9 = (double *)malloc(sizeof(double) * (size_t)L * 9), *g9 = (double *)malloc(sizeof(double) * (size_t)L * 9);
+    memset(g, 0, sizeof(double) * (size_t)L * TRX_NAT * 3);
+    for (int i = 0; i < L; ++i) memcpy(x9 + (size_t)i * 9, XYZ(i, 0), 9 * sizeof(double));
+    trxo_energy_grad(L, x9, T->sets[0], T->sets[1], T->sets[2], T->sets[3], w, terms, g9, NULL, NULL);
+    for (int i = 0; i < L; ++i) memcpy(g + (size_t)i * TRX_NAT * 3, g9 + (size_t)i * 9, 9 * sizeof(double));
+    terms[TRX_T_VDW] = trxo_vdw(L, T->aa, xyz, w[TRX_T_VDW], g);
+    double E[3];
+    trxo_cart_terms(L, T->aa, xyz, w[TRX_T_CART], w[TRX_T_RAMA], w[TRX_T_OMEGA], E, g);
+    terms[TRX_T_CART] = E[0]; terms[TRX_T_RAMA] = E[1]; terms[TRX_T_OMEGA] = E[2];
+    double tot = 0.0;
+    for (int k = 0; k < TRX_NTERM; ++k) tot += w[k] * terms[k];
+    free(x9); free(g9);
+    return tot;
+}
+
 /* ------------------------------------------------------------------ L-BFGS */
 typedef struct {
     double w[TRX_NTERM];
@@ -229,6 +397,7 @@ typedef struct {
     int clash_check;     /* 1: skip to run `skip_to` when rama+vdw (weights 1,1) < clash_thr at run start */
     double clash_thr;
     int skip_to;
+    int cartesian;       /* 1: MinMover.cartesian(True): the coordinates are the degrees of freedom */
 } trx_run;
 
 typedef struct { long long evals, iters; } trxo_stats;
@@ -237,17 +406,29 @@ typedef struct { long long evals, iters; } trxo_stats;
 #define LS_MAXBACK 20
 #define NM_MEMORY 3
 
-/* One MinMover.apply: L-BFGS (history m) with non-monotone Armijo back-tracking.
- * tors in/out.  Returns the final weighted energy. */
-double trxo_lbfgs(const trxo_target *T, const trx_run *run, int m, double *tors, double *terms, double *xyz, trxo_stats *st)
+/* the function a run minimises: torsion space (x = tors, xyz rebuilt by NeRF) or Cartesian */
+typedef struct {
+    const trxo_target *T;
+    const double *w;
+    int cartesian;
+    double *xyz;   /* torsion mode: coordinates of the last evaluation */
+} objective;
+
+static double obj_eval(const objective *o, const double *x, double *terms, double *g)
 {
-    const int n = T->L * 3;
+    return o->cartesian ? trxo_eval_cart(o->T, o->w, x, terms, g) : trxo_eval(o->T, o->w, x, terms, g, o->xyz);
+}
+
+/* One MinMover.apply: L-BFGS (history m) with non-monotone Armijo back-tracking over the n
+ * degrees of freedom x (in/out).  Returns the final weighted energy. */
+static double lbfgs_core(const objective *o, int n, const trx_run *run, int m, double *x, double *terms, trxo_stats *st)
+{
     double *g = malloc(sizeof(double) * n), *gn = malloc(sizeof(double) * n), *d = malloc(sizeof(double) * n);
     double *xn = malloc(sizeof(double) * n), *S = malloc(sizeof(double) * (size_t)n * m), *Y = malloc(sizeof(double) * (size_t)n * m);
     double *rho = malloc(sizeof(double) * m), *al = malloc(sizeof(double) * m);
     double fmem[NM_MEMORY];
     int hist = 0, head = 0, nmem = 0;
-    double f = trxo_eval(T, run->w, tors, terms, g, xyz);
+    double f = obj_eval(o, x, terms, g);
     st->evals++;
     fmem[nmem++ % NM_MEMORY] = f;
     int restart = 1;
@@ -292,8 +473,8 @@ double trxo_lbfgs(const trxo_target *T, const trx_run *run, int m, double *tors,
         double fn = 0.0;
         int ok = 0;
         for (int bt = 0; bt < LS_MAXBACK; ++bt) {
-            for (int k = 0; k < n; ++k) xn[k] = tors[k] + alpha * d[k];
-            fn = trxo_eval(T, run->w, xn, terms, gn, xyz);
+            for (int k = 0; k < n; ++k) xn[k] = x[k] + alpha * d[k];
+            fn = obj_eval(o, xn, terms, gn);
             st->evals++;
             if (isfinite(fn) && fn <= fref + LS_SIGMA * alpha * slope) { ok = 1; break; }
             double q = isfinite(fn) ? -0.5 * slope * alpha * alpha / (fn - f - slope * alpha) : 0.1 * alpha;
@@ -309,38 +490,66 @@ double trxo_lbfgs(const trxo_target *T, const trx_run *run, int m, double *tors,
         double sy = 0.0, ss = 0.0, yy = 0.0;
         double *s = S + (size_t)head * n, *y = Y + (size_t)head * n;
         for (int k = 0; k < n; ++k) {
-            s[k] = xn[k] - tors[k]; y[k] = gn[k] - g[k];
+            s[k] = xn[k] - x[k]; y[k] = gn[k] - g[k];
             sy += s[k] * y[k]; ss += s[k] * s[k]; yy += y[k] * y[k];
         }
         if (sy > 1e-10 * sqrt(ss * yy)) { rho[head] = 1.0 / sy; head = (head + 1) % m; if (hist < m) hist++; }
         int converged = 2.0 * fabs(fn - f) <= run->tol * (fabs(fn) + fabs(f) + 1e-10);
-        memcpy(tors, xn, sizeof(double) * n);
+        memcpy(x, xn, sizeof(double) * n);
         memcpy(g, gn, sizeof(double) * n);
         f = fn;
         fmem[nmem++ % NM_MEMORY] = f;
         restart = 0;
         if (converged) break;
     }
-    f = trxo_eval(T, run->w, tors, terms, g, xyz);   /* leave terms/xyz consistent with tors */
+    f = obj_eval(o, x, terms, g);   /* leave terms (and xyz) consistent with x */
     st->evals++;
     free(g); free(gn); free(d); free(xn); free(S); free(Y); free(rho); free(al);
     return f;
 }
 
-/* The staged schedule: runs[] in order; a run with clash_check evaluates rama+vdw first. */
+double trxo_lbfgs(const trxo_target *T, const trx_run *run, int m, double *tors, double *terms, double *xyz, trxo_stats *st)
+{
+    objective o = {T, run->w, 0, xyz};
+    return lbfgs_core(&o, T->L * 3, run, m, tors, terms, st);
+}
+
+/* The staged schedule: runs[] in order; a run with clash_check evaluates rama+vdw first.
+ * A Cartesian run minimises the coordinates the decoy currently has; afterwards the decoy
+ * HOLDS those coordinates (xyz, terms) and its torsions are read back from them.  A clash
+ * check on a holding decoy scores the held coordinates; the next torsion-space run that
+ * actually starts rebuilds the chain from the torsions with ideal bond geometry. */
 double trxo_fold(const trxo_target *T, const trx_run *runs, int nruns, int m, double *tors, double *terms, double *xyz,
                  trxo_stats *st)
 {
     double f = 0.0;
-    double *gt = malloc(sizeof(double) * (size_t)T->L * 3);
+    const int L = T->L;
+    double *gt = malloc(sizeof(double) * (size_t)L * TRX_NAT * 3);
+    int held = 0;
+    {   /* coordinates of the start point (a schedule may open with a Cartesian run) */
+        double w0[TRX_NTERM] = {0};
+        trxo_eval(T, w0, tors, terms, gt, xyz);
+    }
     for (int r = 0; r < nruns;) {
         if (runs[r].clash_check) {
-            double wv[TRX_NTERM] = {0, 0, 0, 1.0, 1.0, 0};
-            double e = trxo_eval(T, wv, tors, terms, gt, xyz);
-            st->evals++;
+            double e;
+            if (held) e = terms[TRX_T_VDW] + terms[TRX_T_RAMA];
+            else {
+                double wv[TRX_NTERM] = {0, 0, 0, 1.0, 1.0, 0, 0};
+                e = trxo_eval(T, wv, tors, terms, gt, xyz);
+                st->evals++;
+            }
             if (e < runs[r].clash_thr) { r = runs[r].skip_to; continue; }
         }
-        f = trxo_lbfgs(T, &runs[r], m, tors, terms, xyz, st);
+        if (runs[r].cartesian) {
+            objective o = {T, runs[r].w, 1, NULL};
+            f = lbfgs_core(&o, L * TRX_NAT * 3, &runs[r], m, xyz, terms, st);
+            trxo_torsions_from_xyz(L, xyz, tors);
+            held = 1;
+        } else {
+            f = trxo_lbfgs(T, &runs[r], m, tors, terms, xyz, st);
+            held = 0;
+        }
         ++r;
     }
     free(gt);
@@ -364,6 +573,15 @@ double trxo_eval_flat(int L, const int *aa, const int *n, const int *const *a, c
     trxo_set s[4]; trxo_target T; T.L = L; T.aa = aa;
     mk_sets(s, T.sets, n, a, b, K, x, y, y2);
     return trxo_eval(&T, w, tors, terms, gt, xyz);
+}
+
+double trxo_eval_cart_flat(int L, const int *aa, const int *n, const int *const *a, const int *const *b, const int *K,
+                           const double *const *x, const double *const *y, const double *const *y2, const double *w,
+                           const double *xyz, double *terms, double *g)
+{
+    trxo_set s[4]; trxo_target T; T.L = L; T.aa = aa;
+    mk_sets(s, T.sets, n, a, b, K, x, y, y2);
+    return trxo_eval_cart(&T, w, xyz, terms, g);
 }
 
 /* Folds N decoys (tors[N][L][3] in/out) on nthreads host threads. */
@@ -405,4 +623,4 @@ void trxo_fold_batch(int nthreads, int N, int L, const int *aa, const int *n, co
     for (int k = 0; k < nthreads; ++k) pthread_join(th[k], NULL);
 }
 
-int trxo_fold_abi_version(void) { return 1; }
+int trxo_fold_abi_version(void) { return 2; }

@@ -8,13 +8,13 @@ import numpy as np
 
 from .restraints_oracle import lib, TYPES
 
-NTERM = 6
+NTERM = 7
 AA_ORDER = "ARNDCQEGHILKMFPSTWYV"
 
 
 class Run(C.Structure):
     _fields_ = [("w", C.c_double * NTERM), ("max_iter", C.c_int), ("tol", C.c_double),
-                ("clash_check", C.c_int), ("clash_thr", C.c_double), ("skip_to", C.c_int)]
+                ("clash_check", C.c_int), ("clash_thr", C.c_double), ("skip_to", C.c_int), ("cartesian", C.c_int)]
 
 
 def aa_index(seq, gly_to_ala=True):
@@ -25,21 +25,25 @@ def aa_index(seq, gly_to_ala=True):
     return idx
 
 
-def reference_schedule(orient=True):
-    """folding.py:74-104,118-119,164-171 (mode 2) with data/*.wts; torsion-space runs only.
-    Term order: apc, dih, ang, vdw, rama, omega."""
-    def run(w, it, clash=False, skip_to=0):
+def reference_schedule(cartesian=True):
+    """folding.py:74-104,118-119,164-171 (mode 2) with data/*.wts (hbond_* / cen_hb have no
+    restatement and are dropped).  Term order: apc, dih, ang, vdw, rama, omega, cart_bonded."""
+    def run(w, it, clash=False, skip_to=0, cart=False):
         r = Run()
         r.w[:] = w
         r.max_iter, r.tol = it, 1e-4
-        r.clash_check, r.clash_thr, r.skip_to = int(clash), 10.0, skip_to
+        r.clash_check, r.clash_thr, r.skip_to, r.cartesian = int(clash), 10.0, skip_to, int(cart)
         return r
-    sf = [5, 4, 4, 1, 1, 0.5]
-    sf1 = [3, 1, 1, 3, 1, 0.5]
-    sf_vdw = [0, 0, 0, 1, 1, 0]
+    sf = [5, 4, 4, 1, 1, 0.5, 0]
+    sf1 = [3, 1, 1, 3, 1, 0.5, 0]
+    sf_vdw = [0, 0, 0, 1, 1, 0, 0]
+    sf_cart = [5, 4, 4, 0.5, 1, 0.5, 0.1]
     runs = [run(sf_vdw, 500, True, 5) for _ in range(5)]          # remove_clash(sf_vdw, min_mover_vdw)
     runs += [run(sf, 1000) for _ in range(3)]                     # RepeatMover(min_mover, 3)
-    runs += [run(sf1, 1000, True, 13) for _ in range(5)]          # remove_clash(sf_vdw, min_mover1)
+    if cartesian:
+        runs += [run(sf_cart, 1000, cart=True)]                   # min_mover_cart
+    end = len(runs) + 5
+    runs += [run(sf1, 1000, True, end) for _ in range(5)]         # remove_clash(sf_vdw, min_mover1)
     return runs
 
 
@@ -74,7 +78,7 @@ class FoldOracle:
         return xyz
 
     def eval(self, tors, w):
-        """-> (total, terms[6], gtors (L,3), xyz (L,5,3))"""
+        """-> (total, terms[7], gtors (L,3), xyz (L,5,3))"""
         tors = np.ascontiguousarray(tors, dtype=np.float64)
         w = np.ascontiguousarray(w, dtype=np.float64)
         terms, gt, xyz = np.zeros(NTERM), np.zeros((self.L, 3)), np.zeros((self.L, 5, 3))
@@ -83,8 +87,26 @@ class FoldOracle:
                                    P(terms), P(gt), P(xyz))
         return tot, terms, gt, xyz
 
+    def eval_cart(self, xyz, w):
+        """Cartesian-mode evaluation -> (total, terms[7], grad (L,5,3))."""
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        terms, g = np.zeros(NTERM), np.zeros((self.L, 5, 3))
+        P = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        lib().trxo_eval_cart_flat.restype = C.c_double
+        tot = lib().trxo_eval_cart_flat(C.c_int(self.L), self.aa.ctypes.data_as(C.POINTER(C.c_int)), *self._args, P(w), P(xyz),
+                                        P(terms), P(g))
+        return tot, terms, g
+
+    def torsions(self, xyz):
+        """(phi, psi, omega) read back from coordinates (L,5,3) -> (L,3)."""
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+        t = np.zeros((self.L, 3))
+        lib().trxo_torsions_from_xyz(C.c_int(self.L), xyz.ctypes.data_as(C.POINTER(C.c_double)), t.ctypes.data_as(C.POINTER(C.c_double)))
+        return t
+
     def fold(self, tors0, runs, m=20, nthreads=1):
-        """tors0 (N,L,3) -> dict(tors, terms (N,6), xyz (N,L,5,3), f, evals, iters)."""
+        """tors0 (N,L,3) -> dict(tors, terms (N,7), xyz (N,L,5,3), f, evals, iters)."""
         tors = np.ascontiguousarray(tors0, dtype=np.float64).copy()
         N = tors.shape[0]
         arr = (Run * len(runs))(*runs)

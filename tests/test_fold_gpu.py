@@ -47,7 +47,7 @@ def test_single_evaluation_matches_oracle(ctx, example):
     tors[N // 2:] += np.random.default_rng(0).normal(size=(N - N // 2, L, 3)).astype(np.float32) * 0.3
     runs = schedule.reference_schedule()
     batch = capi.FoldBatch(ctx, [tb], [N], sampler.aa_index(seq), runs)
-    w = np.array([5.0, 4.0, 4.0, 1.0, 1.0, 0.5])
+    w = np.array([5.0, 4.0, 4.0, 1.0, 1.0, 0.5, 0.0])
     total, terms, gt, xyz = batch.eval(tors, w)
     for n in (0, 7, 20, 33, 39):
         to, termo, gto, xyzo = F.eval(tors[n].astype(np.float64), w)
@@ -71,7 +71,7 @@ def test_vdw_only_on_clashing_start(ctx):
     N = 33
     tors = np.random.default_rng(2).uniform(-np.pi, np.pi, size=(N, 64, 3)).astype(np.float32)
     batch = capi.FoldBatch(ctx, [tb], [N], sampler.aa_index(seq), schedule.reference_schedule())
-    w = np.array([0.0, 0.0, 0.0, 1.0, 1.0, 0.5])
+    w = np.array([0.0, 0.0, 0.0, 1.0, 1.0, 0.5, 0.0])
     total, terms, gt, xyz = batch.eval(tors, w)
     assert terms[:, 3].max() > 10.0
     for n in (0, 16, 32):
@@ -112,6 +112,85 @@ def test_fold_example_quality_and_reproducibility(ctx, example):
     np.testing.assert_array_equal(alone["tors"], out["tors"][32:])
     batch.close()
     tb.close()
+
+
+def test_cartesian_evaluation_matches_oracle(ctx, example):
+    """min_mover_cart's objective (folding.py:100-102, scorefxn_cart.wts): restraint + vdw gradients on
+    the coordinates, cart_bonded springs, rama / omega from coordinates; fp32 device vs fp64 oracle."""
+    seq, npzs, _ = example
+    L = len(seq)
+    tb = sampler.build_tables(ctx, npzs[0], seq, tables.load_params())
+    F = _oracle(npzs[0], seq)
+    N = 40
+    tors = sampler.random_torsions(N, L, seed=3).astype(np.float64)
+    tors += np.random.default_rng(0).normal(size=(N, L, 3)) * 0.3
+    rng = np.random.default_rng(1)
+    xyz = np.stack([F.nerf(t) for t in tors])
+    xyz[N // 2:] += rng.normal(size=(N - N // 2, L, 5, 3)) * 0.04      # half ideal, half strained
+    xyz = xyz.astype(np.float32)
+    batch = capi.FoldBatch(ctx, [tb], [N], sampler.aa_index(seq), schedule.reference_schedule())
+    for w in (np.array([5.0, 4.0, 4.0, 0.5, 1.0, 0.5, 0.1]), np.array([0.0, 0.0, 0.0, 0.0, 1.0, 0.5, 1.0])):
+        total, terms, grad, back = batch.eval_cart(xyz, w)
+        for n in (0, 7, 19, 20, 33, 39):
+            to, termo, go = F.eval_cart(xyz[n].astype(np.float64), w)
+            assert abs(total[n] - to) < 1e-5 * max(abs(to), 1e4)
+            # springs: (d - d0)^2 with d ~ 1.5 A in fp32 -> 1e-4 relative + 1e-3 absolute
+            assert np.all(np.abs(terms[n] - termo) < 1e-4 * np.maximum(np.abs(termo), 1e2) + 2e-2), (terms[n], termo)
+            assert np.abs(grad[n] - go).max() < 1e-3 * np.abs(go).max()
+            d = (back[n] - F.torsions(xyz[n].astype(np.float64)) + np.pi) % (2 * np.pi) - np.pi
+            assert np.abs(d).max() < 2e-4
+    # the schedule without a Cartesian run has no Cartesian buffers: the entry refuses loudly
+    plain = capi.FoldBatch(ctx, [tb], [N], sampler.aa_index(seq), schedule.reference_schedule(cartesian=False))
+    with pytest.raises(RuntimeError, match="Cartesian"):
+        plain.eval_cart(xyz, np.ones(7))
+    plain.close(); batch.close(); tb.close()
+
+
+def test_cartesian_stage_in_the_schedule(ctx):
+    """Segmented schedule: torsion runs -> Cartesian run -> remove_clash.  (a) reference thresholds: the
+    final min_mover1 rebuilds ideal bonds; (b) remove_clash skipped: the decoy keeps (holds) the Cartesian
+    coordinates, and what is reported is exactly their score."""
+    seq, npzs, nat = synth.target(64, seed=7)
+    L = len(seq)
+    tb = sampler.build_tables(ctx, npzs[0], seq, tables.load_params())
+    rst = gen_rst_oracle(npzs[0])
+    F = fo.FoldOracle(ro.RestraintSetOracle(rst, select_oracle(rst, 1, L, 0.05), "H1"), seq)
+    aa = sampler.aa_index(seq)
+    t0 = sampler.random_torsions(64, L, seed=2)
+    runs = schedule.reference_schedule()
+    batch = capi.FoldBatch(ctx, [tb], [64], aa, runs)
+    out = batch.run(t0)
+    bond = np.linalg.norm(out["xyz"][:, :, 1] - out["xyz"][:, :, 0], axis=-1)
+    assert np.abs(bond - 1.458).max() < 1e-4 and np.all(out["terms"][:, 6] == 0.0)
+    np.testing.assert_array_equal(batch.run(t0)["tors"], out["tors"])             # bit-reproducible
+    batch.close()
+    torsion_only = capi.FoldBatch(ctx, [tb], [64], aa, schedule.reference_schedule(cartesian=False)[:8])
+    base = torsion_only.run(t0)
+    torsion_only.close()
+    for r in runs[9:]:
+        r.clash_thr = 1e9
+    batch = capi.FoldBatch(ctx, [tb], [64], aa, runs)
+    held = batch.run(t0)
+    bond = np.linalg.norm(held["xyz"][:, :, 1] - held["xyz"][:, :, 0], axis=-1)
+    assert np.abs(bond - 1.458).max() > 1e-3 and np.abs(bond - 1.458).mean() < 0.1
+    assert np.all(held["terms"][:, 6] > 0.0)
+    assert np.all(held["evals"] > base["evals"]) and np.all(held["iters"] > base["iters"])
+    w = np.array(list(runs[8].w))
+    e_start = np.array([F.eval_cart(base["xyz"][n].astype(np.float64), w)[0] for n in range(0, 64, 7)])
+    for k, n in enumerate(range(0, 64, 7)):
+        to, termo, _ = F.eval_cart(held["xyz"][n].astype(np.float64), w)
+        assert np.all(np.abs(held["terms"][n] - termo) < 1e-4 * np.maximum(np.abs(termo), 1e2) + 2e-2)
+        d = (held["tors"][n] - F.torsions(held["xyz"][n].astype(np.float64)) + np.pi) % (2 * np.pi) - np.pi
+        assert np.abs(d).max() < 2e-4
+        assert to < e_start[k]                       # the Cartesian run lowered its own objective
+    tm = np.array([metrics.tm_score(c, nat[:, 1]) for c in held["xyz"][:, :, 1]])
+    assert np.median(tm) > 0.5
+    # independent of batch composition
+    half = capi.FoldBatch(ctx, [tb], [32], aa, runs)
+    sub = half.run(t0[32:])
+    np.testing.assert_array_equal(sub["tors"], held["tors"][32:])
+    np.testing.assert_array_equal(sub["xyz"], held["xyz"][32:])
+    half.close(); batch.close(); tb.close()
 
 
 def test_folding_cli_drop_in(tmp_path, golden_dir, example):

@@ -14,16 +14,23 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_schedule_matches_reference_weights_and_caps():
     runs = schedule.reference_schedule()
-    # remove_clash (<=5 x, max_iter 500, rama+vdw) ; 3 x min_mover (1000) ; remove_clash with sf1 (<=5 x, 1000)
-    assert len(runs) == 13
-    assert [r.max_iter for r in runs] == [500] * 5 + [1000] * 8
-    assert list(runs[0].w) == [0, 0, 0, 1, 1, 0]                 # scorefxn_vdw.wts
-    assert list(runs[5].w) == [5, 4, 4, 1, 1, 0.5]               # scorefxn.wts
-    assert list(runs[8].w) == [3, 1, 1, 3, 1, 0.5]               # scorefxn1.wts
+    # remove_clash (<=5 x, max_iter 500, rama+vdw) ; 3 x min_mover (1000) ; min_mover_cart (1000, Cartesian) ;
+    # remove_clash with sf1 (<=5 x, 1000)            folding.py:86-104,118-119,164-171
+    assert len(runs) == 14
+    assert [r.max_iter for r in runs] == [500] * 5 + [1000] * 9
+    assert list(runs[0].w) == [0, 0, 0, 1, 1, 0, 0]                 # scorefxn_vdw.wts
+    assert list(runs[5].w) == [5, 4, 4, 1, 1, 0.5, 0]               # scorefxn.wts
+    assert list(runs[8].w) == [5, 4, 4, 0.5, 1, 0.5, 0.1]           # scorefxn_cart.wts (hbond_* dropped)
+    assert list(runs[9].w) == [3, 1, 1, 3, 1, 0.5, 0]               # scorefxn1.wts
     assert all(r.tol == 1e-4 for r in runs)
-    assert [r.clash_check for r in runs] == [1] * 5 + [0] * 3 + [1] * 5
-    assert all(r.skip_to == 5 for r in runs[:5]) and all(r.skip_to == 13 for r in runs[8:])
+    assert [r.cartesian for r in runs] == [0] * 8 + [1] + [0] * 5
+    assert [r.clash_check for r in runs] == [1] * 5 + [0] * 4 + [1] * 5
+    assert all(r.skip_to == 5 for r in runs[:5]) and all(r.skip_to == 14 for r in runs[9:])
     assert all(r.clash_thr == 10.0 for r in runs)
+    # the torsion-only variant and the per-window block of modes 0/1
+    assert [r.cartesian for r in schedule.reference_schedule(cartesian=False)] == [0] * 13
+    win = schedule.window_schedule(initial_clash=False)
+    assert [r.cartesian for r in win] == [0, 0, 0, 1] + [0] * 5 and all(r.skip_to == 9 for r in win[4:])
 
 
 def test_random_torsions_follow_the_six_state_table():

@@ -1,5 +1,6 @@
 """Pins oracle/fold_oracle.c on the CPU: NeRF geometry, analytic torsion gradient of the full
-score vs central differences, and that the L-BFGS schedule actually folds a small target."""
+score vs central differences, the Cartesian-stage terms vs torch autograd, and that the L-BFGS
+schedule (torsion runs + Cartesian run) actually folds a small target."""
 import ctypes as C
 import numpy as np
 import pytest
@@ -40,7 +41,7 @@ def test_nerf_ideal_geometry_and_torsions(small):
     np.testing.assert_allclose(CB, -0.58273431 * np.cross(b, c) + 0.56802827 * b - 0.54067466 * c + CA, atol=1e-12)
 
 
-@pytest.mark.parametrize("w", [(5, 4, 4, 1, 1, 0.5), (0, 0, 0, 1, 1, 0), (3, 1, 1, 3, 1, 0.5)])
+@pytest.mark.parametrize("w", [(5, 4, 4, 1, 1, 0.5, 0), (0, 0, 0, 1, 1, 0, 0), (3, 1, 1, 3, 1, 0.5, 0)])
 def test_torsion_gradient_matches_central_differences(small, w):
     seq, nat, F = small
     L = len(seq)
@@ -64,7 +65,7 @@ def test_schedule_folds_a_small_target(small):
     L = len(seq)
     t0 = fo.random_torsions(6, L, 5)
     out = F.fold(t0, fo.reference_schedule(), m=20, nthreads=6)
-    w = np.array([5, 4, 4, 1, 1, 0.5.__float__()])
+    w = np.array([5, 4, 4, 1, 1, 0.5, 0.0])
     e_start = np.array([F.eval(t, w)[0] for t in t0])
     assert np.all(out["terms"] @ w < e_start)
     assert np.all(out["evals"] > out["iters"]) and np.all(out["iters"] > 20)
@@ -72,3 +73,71 @@ def test_schedule_folds_a_small_target(small):
     assert tm.max() > 0.5
     again = F.fold(t0, fo.reference_schedule(), m=20, nthreads=2)
     np.testing.assert_array_equal(again["tors"], out["tors"])      # deterministic, thread-count independent
+
+
+def test_cartesian_terms_match_autograd_and_vanish_on_ideal_geometry(small):
+    from oracle import cart_oracle as co
+    seq, nat, F = small
+    L = len(seq)
+    tors = fo.random_torsions(1, L, 0)[0] + np.random.default_rng(0).normal(size=(L, 3)) * 0.2
+    w = np.array([5, 4, 4, 0.5, 1, 0.5, 0.1])
+    xyz = F.nerf(tors)
+    tot, terms, g = F.eval_cart(xyz, w)
+    tot_t, terms_t, _, _ = F.eval(tors, w)
+    assert terms[6] < 1e-20                                          # NeRF builds exactly the springs' rest geometry
+    np.testing.assert_allclose(terms[:6], terms_t[:6], rtol=1e-10)   # rama / omega from coordinates == from torsions
+    xyz2 = xyz + np.random.default_rng(1).normal(size=xyz.shape) * 0.05
+    w0 = np.array([0, 0, 0, 0, 1, 0.5, 0.1])
+    tot, terms, g = F.eval_cart(xyz2, w0)
+    ref, gref = co.cart_energy_grad(xyz2, F.aa, 0.1, 1.0, 0.5)
+    np.testing.assert_allclose([terms[6], terms[4], terms[5]], [ref["cart"], ref["rama"], ref["omega"]], rtol=1e-12)
+    assert np.abs(g - gref).max() < 1e-10 * np.abs(gref).max()
+    # full Cartesian objective (restraints + vdw + springs) vs central differences
+    tot, terms, g = F.eval_cart(xyz2, w)
+    rng = np.random.default_rng(2)
+    for _ in range(12):
+        i, a, k = rng.integers(L), rng.integers(5), rng.integers(3)
+        h = 1e-6
+        xp, xm = xyz2.copy(), xyz2.copy()
+        xp[i, a, k] += h; xm[i, a, k] -= h
+        fd = (F.eval_cart(xp, w)[0] - F.eval_cart(xm, w)[0]) / (2 * h)
+        assert abs(fd - g[i, a, k]) < 1e-5 * max(1.0, abs(g[i, a, k]))
+
+
+def test_torsions_read_back_from_coordinates(small):
+    seq, nat, F = small
+    L = len(seq)
+    tors = fo.random_torsions(1, L, 4)[0] + np.random.default_rng(4).normal(size=(L, 3)) * 0.3
+    back = F.torsions(F.nerf(tors))
+    d = (back - tors + np.pi) % (2 * np.pi) - np.pi
+    d[0, 0] = 0.0; d[L - 1, 2] = 0.0                                  # phi(0), omega(L-1) move nothing: reported as pi
+    assert np.abs(d).max() < 1e-9
+    np.testing.assert_allclose(F.nerf(back), F.nerf(tors), atol=1e-8)
+
+
+def test_cartesian_run_is_held_until_a_torsion_run_starts(small):
+    seq, nat, F = small
+    L = len(seq)
+    t0 = fo.random_torsions(3, L, 9)
+    runs = fo.reference_schedule(cartesian=True)
+    # (a) reference thresholds: rama+vdw >= 10 after the Cartesian run -> min_mover1 rebuilds with ideal bonds
+    out = F.fold(t0, runs, m=20, nthreads=3)
+    bond = np.linalg.norm(out["xyz"][:, :, 1] - out["xyz"][:, :, 0], axis=-1)
+    assert np.abs(bond - 1.458).max() < 1e-9 and np.all(out["terms"][:, 6] == 0.0)
+    # (b) clash threshold so high that the final remove_clash is skipped: the decoy keeps its Cartesian coordinates
+    for r in runs[9:]:
+        r.clash_thr = 1e9
+    held = F.fold(t0, runs, m=20, nthreads=3)
+    bond = np.linalg.norm(held["xyz"][:, :, 1] - held["xyz"][:, :, 0], axis=-1)
+    # (cart_bonded carries weight 0.1 against restraint weights 5/4/4: bonds give visibly, as in the reference's stage)
+    assert np.abs(bond - 1.458).max() > 1e-4 and np.abs(bond - 1.458).mean() < 0.1
+    assert np.all(held["terms"][:, 6] > 0.0)
+    w = np.array(list(runs[8].w))
+    for n in range(3):
+        tot, terms, g = F.eval_cart(held["xyz"][n], w)
+        np.testing.assert_allclose(terms, held["terms"][n], rtol=1e-12)           # reported terms are those of the held coordinates
+        np.testing.assert_allclose(F.torsions(held["xyz"][n]), held["tors"][n], atol=1e-12)
+        # the Cartesian run lowered its own objective relative to the torsion-space minimum it started from
+    no_cart = F.fold(t0, fo.reference_schedule(cartesian=False)[:8], m=20, nthreads=3)
+    e0 = np.array([F.eval_cart(no_cart["xyz"][n], w)[0] for n in range(3)])
+    assert np.all(held["terms"] @ w < e0)

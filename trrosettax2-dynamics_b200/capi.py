@@ -170,13 +170,13 @@ def from_grouped(ctx, N, L, n_atoms, precision, d_grp, d_nat):
     check(lib().trx_from_grouped(ctx._h, C.c_int(N), C.c_int(L), C.c_int(n_atoms), C.c_int(precision), C.c_void_p(d_grp), C.c_void_p(d_nat)))
 
 
-NTERM = 6
+NTERM = 7
 
 
 class Run(C.Structure):
     """trx_run: one MinMover.apply of the schedule."""
     _fields_ = [("w", C.c_double * NTERM), ("max_iter", C.c_int), ("tol", C.c_double),
-                ("clash_check", C.c_int), ("clash_thr", C.c_double), ("skip_to", C.c_int)]
+                ("clash_check", C.c_int), ("clash_thr", C.c_double), ("skip_to", C.c_int), ("cartesian", C.c_int)]
 
 
 class FoldBatch:
@@ -207,7 +207,7 @@ class FoldBatch:
             pass
 
     def run(self, tors, max_rounds=20000, check_every=16, want_xyz=True):
-        """tors (N,L,3) float32 radians -> dict(tors, xyz (N,L,5,3) [N,CA,CB,C,O], terms (N,6), evals, iters, rounds)."""
+        """tors (N,L,3) float32 radians -> dict(tors, xyz (N,L,5,3) [N,CA,CB,C,O], terms (N,7), evals, iters, rounds)."""
         tors = np.ascontiguousarray(tors, dtype=np.float32).copy()
         if tors.shape != (self.N, self.L, 3):
             raise ValueError("tors must be (%d, %d, 3)" % (self.N, self.L))
@@ -237,7 +237,7 @@ class FoldBatch:
                     rounds=rounds.value)
 
     def eval(self, tors, w):
-        """Single evaluation -> (total (N,), terms (N,6), gtors (N,L,3), xyz (N,L,5,3))."""
+        """Single evaluation -> (total (N,), terms (N,7), gtors (N,L,3), xyz (N,L,5,3))."""
         tors = np.ascontiguousarray(tors, dtype=np.float32)
         w = np.ascontiguousarray(w, dtype=np.float64)
         total, terms = np.zeros(self.N), np.zeros((self.N, NTERM))
@@ -246,3 +246,16 @@ class FoldBatch:
         check(lib().trx_fold_eval(self._h, _ptr(tors, C.c_float), _ptr(w, C.c_double), _ptr(total, C.c_double),
                                   _ptr(terms, C.c_double), _ptr(gt, C.c_float), _ptr(xyz, C.c_float)))
         return total, terms, gt, xyz
+
+    def eval_cart(self, xyz, w):
+        """Single Cartesian-mode evaluation: xyz (N,L,5,3) -> (total (N,), terms (N,7), grad (N,L,5,3), tors (N,L,3))."""
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        if xyz.shape != (self.N, self.L, 5, 3):
+            raise ValueError("xyz must be (%d, %d, 5, 3)" % (self.N, self.L))
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        total, terms = np.zeros(self.N), np.zeros((self.N, NTERM))
+        grad = np.zeros((self.N, self.L, 5, 3), dtype=np.float32)
+        tors = np.zeros((self.N, self.L, 3), dtype=np.float32)
+        check(lib().trx_fold_eval_cart(self._h, _ptr(xyz, C.c_float), _ptr(w, C.c_double), _ptr(total, C.c_double),
+                                       _ptr(terms, C.c_double), _ptr(grad, C.c_float), _ptr(tors, C.c_float)))
+        return total, terms, grad, tors

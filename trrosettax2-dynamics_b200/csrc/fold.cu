@@ -10,7 +10,14 @@
 // and all loads/stores are full lines.  All decoys advance in lock-step evaluation
 // rounds; each decoy carries its own position in the schedule (run, weights, line-search
 // state), so finished or back-tracking decoys never stall the others.  The non-restraint
-// terms (vdw, rama, omega) are approximations of Rosetta's (include/trx_centroid_model.h).
+// terms (vdw, rama, omega, cart_bonded) are approximations of Rosetta's
+// (include/trx_centroid_model.h).
+//
+// The schedule is cut into segments of torsion-space runs and Cartesian runs
+// (min_mover_cart, folding.py:100-102,170).  Within a segment the decoys run free; a
+// segment boundary is a batch-wide barrier at which the degrees of freedom change
+// (torsions -> coordinates by NeRF, coordinates -> torsions by reading the dihedrals back).
+// The same L-BFGS kernel serves both: it only sees a vector of ndof floats per decoy.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -29,6 +36,7 @@ struct Run {
     int clash_check;
     float clash_thr;
     int skip_to;
+    int cartesian;
 };
 
 struct Model {   // centroid model constants in device-friendly (float) form
@@ -42,6 +50,9 @@ enum { ST_INIT = 0, ST_LS = 1, ST_DONE = 2 };
 
 struct FoldState {
     int N, Npad, G, L, Lpad, ndof, m, nruns;
+    int ndof_t, ndof_c;      // torsion space: 3 L; Cartesian: 15 Lpad (the layout of X)
+    int cart;                // the segment in progress is Cartesian
+    int seg_hi;              // first run after the segment in progress
     // vectors [G][ndof][32]
     float *x, *g, *d, *xt, *gt;
     float *S, *Y;            // [G][m][ndof][32]
@@ -75,6 +86,11 @@ struct FoldState {
     float *xsave;            // [G][ndof][32]
     double *fsave;           // [Npad]
     int *naccept;            // [Npad]
+    // a decoy that went through a Cartesian run HOLDS those coordinates (and their terms)
+    // until a torsion-space run starts and rebuilds it with ideal bond geometry
+    int *held;               // [Npad]
+    float *xheld;            // [Npad][L][15]
+    double *theld;           // [TRX_NTERM][Npad]
     const int *aa;           // [L]
     const Run *runs;
 };
@@ -444,6 +460,7 @@ __global__ void __launch_bounds__(SEG_THREADS) torsion_grad_kernel(FoldState s)
         term[TRX_T_VDW] = s.Evdw[n];
         term[TRX_T_RAMA] = er;
         term[TRX_T_OMEGA] = eo;
+        term[TRX_T_CART] = 0.0;   // ideal internal geometry in torsion space
         double total = 0.0;
 #pragma unroll
         for (int k = 0; k < TRX_NTERM; ++k) {
@@ -452,6 +469,301 @@ __global__ void __launch_bounds__(SEG_THREADS) torsion_grad_kernel(FoldState s)
         }
         s.ft[dec] = total;
     }
+}
+
+
+// ---- Cartesian stage (min_mover_cart, folding.py:100-102,170) ------------------------------
+// The degrees of freedom are the coordinates themselves, x = [Lpad][15] per decoy in the
+// layout of X.  Evaluation = gather (below) -> K1 -> vdw -> cart_grad_kernel.
+__device__ __forceinline__ void axpy(f3 &a, float s, f3 b) { a.x += s * b.x; a.y += s * b.y; a.z += s * b.z; }
+
+// Trial coordinates of the decoy in each live slot -> X (slot-grouped, for K1) and xnat.
+__global__ void __launch_bounds__(256) cart_gather_kernel(FoldState s)
+{
+    const int g = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, n = g * LANES + lane;
+    if (!s.gslot[g]) return;
+    const int dec = s.perm[n];
+    const bool live = dec >= 0;
+    const int dn = live ? dec : 0;
+    const float *__restrict__ xt = s.xt + (size_t)(dn / LANES) * s.ndof * LANES + dn % LANES;
+    float *__restrict__ X = s.X + (size_t)g * s.Lpad * NAT3 * LANES + lane;
+    float *__restrict__ xn = s.xnat + (size_t)n * s.L * NAT3;
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < TRX_NTERM; ++k) s.wslot[(size_t)k * s.Npad + n] = live ? s.wl[(size_t)k * s.Npad + dec] : 0.f;
+    }
+    for (int k = warp; k < s.L * NAT3; k += nw) {
+        const float v = xt[(size_t)k * LANES];
+        X[(size_t)k * LANES] = v;
+        if (live) xn[k] = v;
+    }
+}
+
+// |a-b| spring: returns (d-d0)^2, adds f * d(d)/dx with f = wk2 (d-d0)
+__device__ __forceinline__ float cart_bond(f3 a, f3 b, float d0, float wk2, f3 &ga, f3 &gb)
+{
+    const f3 d = a - b;
+    const float len = sqrtf(dot(d, d)), dev = len - d0, f = wk2 * dev / len;
+    axpy(ga, f, d);
+    axpy(gb, -f, d);
+    return dev * dev;
+}
+
+// angle a-b-c spring (vertex b)
+__device__ __forceinline__ float cart_angle(f3 a, f3 b, f3 c, float t0, float wk2, f3 &ga, f3 &gb, f3 &gc)
+{
+    const f3 v = a - b, w = c - b;
+    const float inv = 1.0f / sqrtf(dot(v, v)), inw = 1.0f / sqrtf(dot(w, w));
+    const f3 vu = inv * v, wu = inw * w;
+    const float cs = dot(vu, wu);
+    const f3 cr = cross(vu, wu);
+    const float sn = sqrtf(dot(cr, cr));
+    const float dev = atan2f(sn, cs) - t0, f = wk2 * dev;
+    const f3 g1 = (-inv / sn) * (wu - cs * vu), g3 = (-inw / sn) * (vu - cs * wu);
+    axpy(ga, f, g1);
+    axpy(gc, f, g3);
+    axpy(gb, -f, g1 + g3);
+    return dev * dev;
+}
+
+// dihedral p1-p2-p3-p4 (IUPAC sign, as oracle trxo_dihedral) and its gradient (Blondel & Karplus)
+__device__ __forceinline__ float cart_dihedral(f3 p1, f3 p2, f3 p3, f3 p4, f3 &d1, f3 &d2, f3 &d3, f3 &d4)
+{
+    const f3 F = p1 - p2, G = p2 - p3, H = p4 - p3;
+    const f3 A = cross(F, G), B = cross(H, G);
+    const float A2 = dot(A, A), B2 = dot(B, B), Gn = sqrtf(dot(G, G)), FG = dot(F, G), HG = dot(H, G);
+    const float iA = 1.0f / A2, iB = 1.0f / B2, iG = 1.0f / Gn;
+    d1 = (-Gn * iA) * A;
+    d4 = (Gn * iB) * B;
+    const f3 t = (FG * iA * iG) * A - (HG * iB * iG) * B;
+    d2 = (Gn * iA) * A + t;
+    d3 = (-Gn * iB) * B - t;
+    return atan2f(Gn * dot(A, H), dot(A, B));
+}
+
+// Cartesian-mode gradient assembly.  One CTA per slot group (lane = decoy), SEG_WARPS warps:
+// warp w owns residues [r0, r1).  Step i evaluates every term ANCHORED at residue i -- its
+// own springs, the peptide link (i, i+1) and Ramachandran(i) -- which touch residues i-1
+// (C only), i and i+1 (N, CA only).  A warp also replays the steps r0-1 and r1 of its
+// neighbours (without counting their energy), so every residue it owns is completed in
+// registers: no atomics, no halo exchange, fixed summation order.
+// gt = restraint gradient (K1) + vdw gradient + these terms; also the terms and the total.
+__global__ void __launch_bounds__(SEG_THREADS) cart_grad_kernel(FoldState s)
+{
+    __shared__ double esum[SEG_WARPS][3][LANES];
+    const int g = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = g * LANES + lane;   // n = slot
+    if (!s.gslot[g]) return;
+    const int dec = s.perm[n];
+    const bool live = dec >= 0;
+    const int dn = live ? dec : 0;
+    const int L = s.L, Npad = s.Npad;
+    const float *__restrict__ X = s.X + (size_t)g * s.Lpad * NAT3 * LANES + lane;
+    const float *__restrict__ G1 = s.gk1 + (size_t)g * s.Lpad * 9 * LANES + lane;
+    const float *__restrict__ gn = s.gnat + (size_t)n * L * NAT3;
+    float *__restrict__ gt = s.gt + (size_t)(dn / LANES) * s.ndof * LANES + dn % LANES;
+    const float w_cart = s.wslot[(size_t)TRX_T_CART * Npad + n], w_rama = s.wslot[(size_t)TRX_T_RAMA * Npad + n];
+    const float w_omega = s.wslot[(size_t)TRX_T_OMEGA * Npad + n];
+    const float kb2 = w_cart * 2.0f * (float)TRX_CART_KB, ka2 = w_cart * 2.0f * (float)TRX_CART_KA;
+    const int Lseg = (L + SEG_WARPS - 1) / SEG_WARPS;
+    const int r0 = warp * Lseg, r1 = min(L, r0 + Lseg);
+    auto load = [&](int i, int a) -> f3 { return {X[((size_t)i * NAT3 + a * 3) * LANES], X[((size_t)i * NAT3 + a * 3 + 1) * LANES], X[((size_t)i * NAT3 + a * 3 + 2) * LANES]}; };
+    const f3 zero = {0.f, 0.f, 0.f};
+    double e_cart = 0.0, e_rama = 0.0, e_omega = 0.0;
+    if (r0 < L) {
+        f3 gp[TRX_NAT], gc[TRX_NAT], gx[2];   // gradient of residue i-1, i, and of N/CA of i+1
+#pragma unroll
+        for (int a = 0; a < TRX_NAT; ++a) { gp[a] = zero; gc[a] = zero; }
+        gx[0] = zero; gx[1] = zero;
+        auto store = [&](int i, const f3 *gr) {
+            if (!live) return;
+            float v[NAT3];
+#pragma unroll
+            for (int a = 0; a < TRX_NAT; ++a) { v[a * 3] = gr[a].x; v[a * 3 + 1] = gr[a].y; v[a * 3 + 2] = gr[a].z; }
+#pragma unroll
+            for (int k = 0; k < NAT3; ++k) v[k] += gn[(size_t)i * NAT3 + k];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) v[k] += G1[((size_t)i * 9 + k) * LANES];
+#pragma unroll
+            for (int k = 0; k < NAT3; ++k) gt[((size_t)i * NAT3 + k) * LANES] = v[k];
+        };
+        const int i0 = max(r0 - 1, 0), i1 = min(r1, L - 1);
+        f3 Cp = i0 > 0 ? load(i0 - 1, TRX_AT_C) : zero;
+        f3 N = load(i0, TRX_AT_N), CA = load(i0, TRX_AT_CA);
+        for (int i = i0; i <= i1; ++i) {
+            const bool own = i >= r0 && i < r1;
+            const f3 CB = load(i, TRX_AT_CB), C = load(i, TRX_AT_C), O = load(i, TRX_AT_O);
+            float ec = 0.f;
+            ec += (float)TRX_CART_KB * cart_bond(CA, N, (float)TRX_B_N_CA, kb2, gc[TRX_AT_CA], gc[TRX_AT_N]);
+            ec += (float)TRX_CART_KB * cart_bond(C, CA, (float)TRX_B_CA_C, kb2, gc[TRX_AT_C], gc[TRX_AT_CA]);
+            ec += (float)TRX_CART_KB * cart_bond(O, C, (float)TRX_B_C_O, kb2, gc[TRX_AT_O], gc[TRX_AT_C]);
+            ec += (float)TRX_CART_KA * cart_angle(N, CA, C, (float)TRX_A_N_CA_C, ka2, gc[TRX_AT_N], gc[TRX_AT_CA], gc[TRX_AT_C]);
+            ec += (float)TRX_CART_KA * cart_angle(CA, C, O, (float)TRX_A_CA_C_O, ka2, gc[TRX_AT_CA], gc[TRX_AT_C], gc[TRX_AT_O]);
+            {   // CB tether to the virtual-CB position
+                const f3 b = CA - N, c = C - CA, a = cross(b, c);
+                const f3 r = CB - ((float)TRX_CB_A * a + (float)TRX_CB_B * b + (float)TRX_CB_C * c + CA);
+                ec += (float)TRX_CART_KCB * dot(r, r);
+                const f3 q = (-w_cart * 2.0f * (float)TRX_CART_KCB) * r;   // dE/d vCB
+                const f3 gb = (float)TRX_CB_A * cross(c, q) + (float)TRX_CB_B * q;
+                const f3 gcv = (float)TRX_CB_A * cross(q, b) + (float)TRX_CB_C * q;
+                axpy(gc[TRX_AT_CB], -1.0f, q);
+                axpy(gc[TRX_AT_N], -1.0f, gb);
+                axpy(gc[TRX_AT_CA], 1.0f, gb - gcv + q);
+                axpy(gc[TRX_AT_C], 1.0f, gcv);
+            }
+            f3 N1 = zero, CA1 = zero;
+            float eo = 0.f, er = 0.f;
+            if (i < L - 1) {
+                N1 = load(i + 1, TRX_AT_N); CA1 = load(i + 1, TRX_AT_CA);
+                ec += (float)TRX_CART_KB * cart_bond(N1, C, (float)TRX_B_C_N, kb2, gx[0], gc[TRX_AT_C]);
+                ec += (float)TRX_CART_KA * cart_angle(CA, C, N1, (float)TRX_A_CA_C_N, ka2, gc[TRX_AT_CA], gc[TRX_AT_C], gx[0]);
+                ec += (float)TRX_CART_KA * cart_angle(O, C, N1, (float)TRX_A_O_C_N, ka2, gc[TRX_AT_O], gc[TRX_AT_C], gx[0]);
+                ec += (float)TRX_CART_KA * cart_angle(C, N1, CA1, (float)TRX_A_C_N_CA, ka2, gc[TRX_AT_C], gx[0], gx[1]);
+                {   // carbonyl O in the peptide plane
+                    const f3 u = CA - C, v = N1 - C, o = O - C;
+                    const f3 uv = cross(u, v), vo = cross(v, o), ou = cross(o, u);
+                    const float t = dot(uv, o), f = w_cart * 2.0f * (float)TRX_CART_KPL * t;
+                    ec += (float)TRX_CART_KPL * t * t;
+                    axpy(gc[TRX_AT_CA], f, vo);
+                    axpy(gx[0], f, ou);
+                    axpy(gc[TRX_AT_O], f, uv);
+                    axpy(gc[TRX_AT_C], -f, vo + ou + uv);
+                }
+                {   // omega tether
+                    f3 d1, d2, d3, d4;
+                    const float om = cart_dihedral(CA, C, N1, CA1, d1, d2, d3, d4);
+                    float dev = om - (float)TRX_PI;
+                    dev -= 2.0f * (float)TRX_PI * floorf((dev + (float)TRX_PI) / (2.0f * (float)TRX_PI));
+                    const float deg = dev * (float)(1.0 / TRX_DEG);
+                    eo = (float)TRX_OMEGA_K * deg * deg;
+                    const float f = w_omega * 2.0f * (float)TRX_OMEGA_K * deg * (float)(1.0 / TRX_DEG);
+                    axpy(gc[TRX_AT_CA], f, d1); axpy(gc[TRX_AT_C], f, d2); axpy(gx[0], f, d3); axpy(gx[1], f, d4);
+                }
+                if (i > 0) {   // Ramachandran, termini skipped
+                    f3 a1, a2, a3, a4, b1, b2, b3, b4;
+                    const float phi = cart_dihedral(Cp, N, CA, C, a1, a2, a3, a4);
+                    const float psi = cart_dihedral(N, CA, C, N1, b1, b2, b3, b4);
+                    const int cls = s.aa[i] == TRX_AA_PRO ? 1 : 0;
+                    float P = (float)TRX_RAMA_FLOOR, dPphi = 0.f, dPpsi = 0.f;
+#pragma unroll
+                    for (int k = 0; k < TRX_RAMA_NB; ++k) {
+                        const float *b = c_model.rama[cls][k];
+                        const float dphi = phi - b[0] * (float)TRX_DEG, dpsi = psi - b[1] * (float)TRX_DEG;
+                        float s1, c1, s2, c2;
+                        sincosf(dphi, &s1, &c1);
+                        sincosf(dpsi, &s2, &c2);
+                        const float e = b[4] * expf(b[2] * (c1 - 1.0f) + b[3] * (c2 - 1.0f));
+                        P += e;
+                        dPphi -= e * b[2] * s1;
+                        dPpsi -= e * b[3] * s2;
+                    }
+                    er = -logf(P);
+                    const float fphi = -w_rama * dPphi / P, fpsi = -w_rama * dPpsi / P;
+                    axpy(gp[TRX_AT_C], fphi, a1); axpy(gc[TRX_AT_N], fphi, a2); axpy(gc[TRX_AT_CA], fphi, a3); axpy(gc[TRX_AT_C], fphi, a4);
+                    axpy(gc[TRX_AT_N], fpsi, b1); axpy(gc[TRX_AT_CA], fpsi, b2); axpy(gc[TRX_AT_C], fpsi, b3); axpy(gx[0], fpsi, b4);
+                }
+            }
+            if (own) { e_cart += (double)ec; e_rama += (double)er; e_omega += (double)eo; }
+            if (i - 1 >= r0) store(i - 1, gp);   // residue i-1 is complete (i-1 < r1 holds inside the loop)
+#pragma unroll
+            for (int a = 0; a < TRX_NAT; ++a) { gp[a] = gc[a]; gc[a] = zero; }
+            gc[TRX_AT_N] = gx[0]; gc[TRX_AT_CA] = gx[1];
+            gx[0] = zero; gx[1] = zero;
+            Cp = C; N = N1; CA = CA1;
+        }
+        if (i1 >= r0 && i1 < r1) store(i1, gp);   // the chain's last residue
+    }
+    // padded residues never move
+    if (live) for (int k = L * NAT3 + warp; k < s.Lpad * NAT3; k += SEG_WARPS) gt[(size_t)k * LANES] = 0.f;
+    esum[warp][0][lane] = e_cart; esum[warp][1][lane] = e_rama; esum[warp][2][lane] = e_omega;
+    __syncthreads();
+    if (warp == 0 && live) {
+        double ec = 0.0, er = 0.0, eo = 0.0;
+        for (int w2 = 0; w2 < SEG_WARPS; ++w2) { ec += esum[w2][0][lane]; er += esum[w2][1][lane]; eo += esum[w2][2][lane]; }
+        double term[TRX_NTERM];
+        term[TRX_T_APC] = s.E3[0 * (size_t)Npad + n];
+        term[TRX_T_DIH] = s.E3[1 * (size_t)Npad + n];
+        term[TRX_T_ANG] = s.E3[2 * (size_t)Npad + n];
+        term[TRX_T_VDW] = s.Evdw[n];
+        term[TRX_T_RAMA] = er;
+        term[TRX_T_OMEGA] = eo;
+        term[TRX_T_CART] = ec;
+        double total = 0.0;
+#pragma unroll
+        for (int k = 0; k < TRX_NTERM; ++k) {
+            s.terms[(size_t)k * Npad + dec] = term[k];
+            total += (double)s.wslot[(size_t)k * Npad + n] * term[k];
+        }
+        s.ft[dec] = total;
+    }
+}
+
+// Start of a Cartesian segment: x = xt = current coordinates of every decoy (X of the
+// identity-slot evaluation just made, or the coordinates the decoy still holds).
+__global__ void __launch_bounds__(256) cart_begin_kernel(FoldState s)
+{
+    const int g = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, n = g * LANES + lane;
+    const bool hd = n < s.N && s.held[n];
+    const float *__restrict__ X = s.X + (size_t)g * s.Lpad * NAT3 * LANES + lane;
+    const float *__restrict__ xh = s.xheld + (size_t)n * s.L * NAT3;
+    float *__restrict__ x = s.x + (size_t)g * s.ndof_c * LANES + lane, *__restrict__ xt = s.xt + (size_t)g * s.ndof_c * LANES + lane;
+    for (int k = warp; k < s.ndof_c; k += nw) {
+        float v = 0.f;
+        if (k < s.L * NAT3) v = hd ? xh[k] : X[(size_t)k * LANES];
+        x[(size_t)k * LANES] = v;
+        xt[(size_t)k * LANES] = v;
+    }
+}
+
+// End of a Cartesian segment (after the identity-slot evaluation of the accepted points):
+// every decoy now holds its coordinates and terms; its torsions are read back from them.
+__global__ void __launch_bounds__(256) cart_end_kernel(FoldState s)
+{
+    const int g = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, n = g * LANES + lane;
+    if (n >= s.N) return;
+    const int L = s.L;
+    const float *__restrict__ X = s.X + (size_t)g * s.Lpad * NAT3 * LANES + lane;
+    float *__restrict__ xh = s.xheld + (size_t)n * L * NAT3;
+    float *__restrict__ x = s.x + (size_t)g * s.ndof_t * LANES + lane, *__restrict__ xt = s.xt + (size_t)g * s.ndof_t * LANES + lane;
+    auto load = [&](int i, int a) -> f3 { return {X[((size_t)i * NAT3 + a * 3) * LANES], X[((size_t)i * NAT3 + a * 3 + 1) * LANES], X[((size_t)i * NAT3 + a * 3 + 2) * LANES]}; };
+    if (warp == 0) {
+        s.held[n] = 1;
+        for (int k = 0; k < TRX_NTERM; ++k) s.theld[(size_t)k * s.Npad + n] = s.terms[(size_t)k * s.Npad + n];
+    }
+    for (int k = warp; k < L * NAT3; k += nw) xh[k] = X[(size_t)k * LANES];
+    for (int i = warp; i < L; i += nw) {
+        const f3 N = load(i, TRX_AT_N), CA = load(i, TRX_AT_CA), C = load(i, TRX_AT_C);
+        f3 d1, d2, d3, d4;
+        float phi = (float)TRX_PI, psi, omg = (float)TRX_PI;
+        if (i > 0) phi = cart_dihedral(load(i - 1, TRX_AT_C), N, CA, C, d1, d2, d3, d4);
+        if (i < L - 1) {
+            const f3 N1 = load(i + 1, TRX_AT_N), CA1 = load(i + 1, TRX_AT_CA);
+            psi = cart_dihedral(N, CA, C, N1, d1, d2, d3, d4);
+            omg = cart_dihedral(CA, C, N1, CA1, d1, d2, d3, d4);
+        } else {
+            psi = cart_dihedral(N, CA, C, load(i, TRX_AT_O), d1, d2, d3, d4) - (float)TRX_PI;   // NeRF places O at psi + pi
+            if (psi <= -(float)TRX_PI) psi += 2.0f * (float)TRX_PI;
+        }
+        x[(size_t)(i * 3 + 0) * LANES] = phi; xt[(size_t)(i * 3 + 0) * LANES] = phi;
+        x[(size_t)(i * 3 + 1) * LANES] = psi; xt[(size_t)(i * 3 + 1) * LANES] = psi;
+        x[(size_t)(i * 3 + 2) * LANES] = omg; xt[(size_t)(i * 3 + 2) * LANES] = omg;
+    }
+}
+
+// Start of a segment [lo, hi) of the schedule: the decoys whose next run lies in it wake up.
+__global__ void seg_begin_kernel(FoldState s, int lo, int hi)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= s.Npad) return;
+    s.status[n] = (n < s.N && s.run[n] >= lo && s.run[n] < hi) ? ST_INIT : ST_DONE;
+}
+
+// Held coordinates replace the (ideal-geometry) rebuild in the natural-layout output.
+__global__ void held_xyz_kernel(FoldState s)
+{
+    const int n = blockIdx.x;
+    if (!s.held[n]) return;
+    const size_t base = (size_t)n * s.L * NAT3;
+    for (int k = threadIdx.x; k < s.L * NAT3; k += blockDim.x) s.xnat[base + k] = s.xheld[base + k];
 }
 
 // K5: batched L-BFGS with non-monotone Armijo back-tracking, one CTA per decoy group
@@ -513,7 +825,10 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lbfgs_kernel(FoldState s)
     if (status == ST_INIT) {
         const Run &r = s.runs[run];
         bool skip = false;
-        if (r.clash_check) skip = (float)(s.terms[(size_t)TRX_T_VDW * Npad + n] + s.terms[(size_t)TRX_T_RAMA * Npad + n]) < r.clash_thr;
+        if (r.clash_check) {   // a decoy holding Cartesian coordinates is judged on those
+            const double *tv = s.held[n] ? s.theld : s.terms;
+            skip = (float)(tv[(size_t)TRX_T_VDW * Npad + n] + tv[(size_t)TRX_T_RAMA * Npad + n]) < r.clash_thr;
+        }
         action = skip ? 4 : 1;
     } else if (status == ST_LS) {
         double fref = s.fmem[n];
@@ -581,13 +896,16 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lbfgs_kernel(FoldState s)
         int evals = s.evals[n] + (status != ST_DONE ? 1 : 0), iters = s.iters[n];
         bool run_over = false, need_dir = false;
         int mode = 0;
+        // the decoy moves on to run r: its weights come into force; beyond the segment in
+        // progress it waits for the batch (DONE until the next segment begins)
+        auto enter = [&](int r) {
+            if (r < s.nruns)
+                for (int k = 0; k < TRX_NTERM; ++k) s.wl[(size_t)k * Npad + n] = s.runs[r].w[k];
+            status = r < s.seg_hi ? ST_INIT : ST_DONE;
+        };
         if (action == 4) {
             run = s.runs[run].skip_to;
-            if (run >= s.nruns) status = ST_DONE;
-            else {
-                for (int k = 0; k < TRX_NTERM; ++k) s.wl[(size_t)k * Npad + n] = s.runs[run].w[k];
-                status = ST_INIT;   // xt stays = x; the next round evaluates it under the new weights
-            }
+            enter(run);   // xt stays = x; the next round evaluates it under the new weights
         }
         if (action == 2) {
             const int h = head;
@@ -621,6 +939,7 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lbfgs_kernel(FoldState s)
             f = ft;
             hist = 0; head = 0; iter = 0; bt = 0; restart = 1; nmem = 1;
             s.fmem[n] = f;
+            if (!s.cart && n < s.N) s.held[n] = 0;   // a torsion-space run rebuilds the chain with ideal geometry
             if (!fin) run_over = true;   // cannot start from a non-finite energy
             else need_dir = true;
         } else if (action == 3) {
@@ -638,11 +957,7 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lbfgs_kernel(FoldState s)
         }
         if (run_over) {
             run++;
-            if (run >= s.nruns) status = ST_DONE;
-            else {
-                status = ST_INIT;
-                for (int k = 0; k < TRX_NTERM; ++k) s.wl[(size_t)k * Npad + n] = s.runs[run].w[k];
-            }
+            enter(run);
             mode = 3;   // the run ends at x (last accepted point)
         }
         float cgv = -1.f;
@@ -705,11 +1020,7 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lbfgs_kernel(FoldState s)
             mode = 1;
             if (gg == 0.f) {   // stationary: the run is over
                 run++;
-                if (run >= s.nruns) status = ST_DONE;
-                else {
-                    status = ST_INIT;
-                    for (int k = 0; k < TRX_NTERM; ++k) s.wl[(size_t)k * Npad + n] = s.runs[run].w[k];
-                }
+                enter(run);
                 mode = 3;
             }
         }
@@ -807,6 +1118,7 @@ __global__ void init_state_kernel(FoldState s, const float *__restrict__ tors_na
         x[k * LANES] = v;
         xt[k * LANES] = v;
     }
+    s.held[n] = 0;
     s.status[n] = n < s.N ? ST_INIT : ST_DONE;
     s.run[n] = 0; s.hist[n] = 0; s.head[n] = 0; s.iter[n] = 0; s.bt[n] = 0; s.restart[n] = 1; s.nmem[n] = 0;
     s.f[n] = 0.0; s.alpha[n] = 0.f; s.slope[n] = 0.f; s.evals[n] = 0; s.iters[n] = 0;
@@ -828,7 +1140,8 @@ __global__ void export_kernel(FoldState s, float *__restrict__ tors_nat, double 
     if (n >= s.N) return;
     const float *x = s.x + (size_t)g * s.ndof * LANES + lane;
     for (int k = 0; k < s.ndof; ++k) tors_nat[(size_t)n * s.ndof + k] = x[k * LANES];
-    for (int k = 0; k < TRX_NTERM; ++k) terms_nat[(size_t)n * TRX_NTERM + k] = s.terms[(size_t)k * s.Npad + n];
+    const double *tv = s.held[n] ? s.theld : s.terms;
+    for (int k = 0; k < TRX_NTERM; ++k) terms_nat[(size_t)n * TRX_NTERM + k] = tv[(size_t)k * s.Npad + n];
     stats[(size_t)n * 2] = s.evals[n];
     stats[(size_t)n * 2 + 1] = s.iters[n];
 }
@@ -886,6 +1199,7 @@ __global__ void mc_begin_kernel(FoldState s, McOpts o)
     if (warp == 0) {
         if (o.cycle == 0) s.naccept[n] = 0;
         s.fsave[n] = s.f[n];
+        s.held[n] = 0;
         s.status[n] = ST_INIT; s.run[n] = o.mc_run; s.hist[n] = 0; s.head[n] = 0; s.iter[n] = 0; s.bt[n] = 0;
         s.restart[n] = 1; s.nmem[n] = 0;
         for (int k = 0; k < TRX_NTERM; ++k) s.wl[(size_t)k * s.Npad + n] = s.runs[o.mc_run].w[k];
@@ -939,6 +1253,9 @@ struct trx_fold_batch {
     int *d_aa = nullptr;
     Run *d_runs = nullptr;
     size_t vdw_smem = 0, lb_smem = 0;
+    struct Segment { int lo, hi, cart; };
+    std::vector<Segment> segs;   // maximal stretches of torsion-space / Cartesian runs
+    bool has_cart = false;
 };
 
 extern "C" {
@@ -977,22 +1294,32 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
         G += num_groups(ndecoys[t]);
     }
     for (int i = 0; i < L; ++i) TRX_REQUIRE(aa[i] >= 0 && aa[i] < 20, "trx_fold_create: aa[%d]=%d out of range", i, aa[i]);
-    for (int r = 0; r < nruns; ++r)
+    for (int r = 0; r < nruns; ++r) {
         TRX_REQUIRE(runs[r].max_iter >= 0 && (!runs[r].clash_check || (runs[r].skip_to > r && runs[r].skip_to <= nruns)),
                     "trx_fold_create: run %d has a bad skip_to/max_iter", r);
+        if (b->segs.empty() || b->segs.back().cart != (runs[r].cartesian ? 1 : 0)) b->segs.push_back({r, r + 1, runs[r].cartesian ? 1 : 0});
+        else b->segs.back().hi = r + 1;
+        b->has_cart = b->has_cart || runs[r].cartesian;
+    }
+    for (int r = 0; r < nruns; ++r)   // a clash check may not jump over a Cartesian run
+        if (runs[r].clash_check)
+            for (int q = r + 1; q < runs[r].skip_to; ++q)
+                TRX_REQUIRE(!runs[q].cartesian || runs[r].cartesian, "trx_fold_create: run %d skips over the Cartesian run %d", r, q);
     int N = 0;
     for (int t = 0; t < ntab; ++t) N += ndecoys[t];
     FoldState &s = b->s;
     s.N = (G - 1) * LANES + ((ndecoys[ntab - 1] - 1) % LANES + 1);
     TRX_REQUIRE(s.N == N, "trx_fold_create: internal decoy count mismatch");
     s.G = G; s.Npad = G * LANES; s.L = L; s.Lpad = padded_length(L); s.ndof = 3 * L; s.m = lbfgs_m; s.nruns = nruns;
+    s.ndof_t = 3 * L; s.ndof_c = NAT3 * s.Lpad; s.cart = 0; s.seg_hi = nruns;
+    const int ndof_max = b->has_cart ? s.ndof_c : s.ndof_t;
     b->vdw_smem = sizeof(float4) * 6 * L + ((sizeof(int) * 18 * L + 15) / 16) * 16 + sizeof(float4) * L;
     TRX_REQUIRE(b->vdw_smem <= 220 * 1024, "trx_fold_create: L=%d exceeds the shared-memory budget of the vdw kernel", L);
     TRX_REQUIRE(L < 65536, "trx_fold_create: L too large");
     // one arena, carved into aligned pieces
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
-    const size_t vec = (size_t)G * s.ndof * LANES * sizeof(float), np = (size_t)s.Npad;
+    const size_t vec = (size_t)G * ndof_max * LANES * sizeof(float), np = (size_t)s.Npad;
     size_t o_x = carve(vec), o_g = carve(vec), o_d = carve(vec), o_xt = carve(vec), o_gt = carve(vec);
     const int lbM = lbfgs_m <= 8 ? 8 : (lbfgs_m <= 16 ? 16 : 24);
     size_t o_S = carve(vec * s.m), o_Y = carve(vec * s.m), o_rho = carve((size_t)G * 2 * lbM * lbM * LANES * sizeof(float));
@@ -1005,6 +1332,7 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     size_t o_ga = carve((size_t)G * 4), o_na = carve(256);
     size_t o_xs = carve(vec), o_fs = carve(np * 8), o_nacc = carve(np * 4);
     size_t o_perm = carve(np * 4), o_gs = carve((size_t)G * 4), o_ns = carve(256), o_ws = carve(np * 4 * TRX_NTERM);
+    size_t o_held = carve(np * 4), o_xh = carve(b->has_cart ? np * L * NAT3 * 4 : 256), o_th = carve(np * 8 * TRX_NTERM);
     cudaError_t e = cudaMalloc(&b->arena, off);
     if (e != cudaSuccess) {
         set_error("trx_fold_create: cudaMalloc(%zu bytes) failed: %s", off, cudaGetErrorString(e));
@@ -1025,6 +1353,7 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     s.E3 = (double *)(A + o_E3); s.Evdw = (double *)(A + o_Ev); s.gactive = (int *)(A + o_ga); s.nactive = (int *)(A + o_na);
     s.xsave = (float *)(A + o_xs); s.fsave = (double *)(A + o_fs); s.naccept = (int *)(A + o_nacc);
     s.perm = (int *)(A + o_perm); s.gslot = (int *)(A + o_gs); s.nslot = (int *)(A + o_ns); s.wslot = (float *)(A + o_ws);
+    s.held = (int *)(A + o_held); s.xheld = (float *)(A + o_xh); s.theld = (double *)(A + o_th);
     s.ntab = ntab;
     for (int t = 0; t < ntab; ++t) { s.tab_d0[t] = b->tab_g0[t] * LANES; s.tab_n[t] = ndecoys[t]; }
     TRX_CUDA(cudaMalloc(&b->d_aa, L * sizeof(int)));
@@ -1033,7 +1362,7 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     for (int r = 0; r < nruns; ++r) {
         for (int k = 0; k < TRX_NTERM; ++k) hr[r].w[k] = (float)runs[r].w[k];
         hr[r].max_iter = runs[r].max_iter; hr[r].tol = (float)runs[r].tol; hr[r].clash_check = runs[r].clash_check;
-        hr[r].clash_thr = (float)runs[r].clash_thr; hr[r].skip_to = runs[r].skip_to;
+        hr[r].clash_thr = (float)runs[r].clash_thr; hr[r].skip_to = runs[r].skip_to; hr[r].cartesian = runs[r].cartesian ? 1 : 0;
     }
     TRX_CUDA(cudaMalloc(&b->d_runs, nruns * sizeof(Run)));
     TRX_CUDA(cudaMemcpy(b->d_runs, hr.data(), nruns * sizeof(Run), cudaMemcpyHostToDevice));
@@ -1057,9 +1386,15 @@ static int fold_eval(trx_fold_batch *b, const int *ng_tab, bool identity)
     ctx->time_begin("compact");
     compact_kernel<<<s.ntab, 1024, 0, ctx->stream>>>(s, identity ? 1 : 0);
     ctx->time_end("compact");
-    ctx->time_begin("nerf");
-    nerf_kernel<<<s.G, SEG_THREADS, 0, ctx->stream>>>(s);
-    ctx->time_end("nerf");
+    if (s.cart) {
+        ctx->time_begin("cart_gather");
+        cart_gather_kernel<<<s.G, 256, 0, ctx->stream>>>(s);
+        ctx->time_end("cart_gather");
+    } else {
+        ctx->time_begin("nerf");
+        nerf_kernel<<<s.G, SEG_THREADS, 0, ctx->stream>>>(s);
+        ctx->time_end("nerf");
+    }
     for (size_t t = 0; t < b->tabs.size(); ++t) {
         const int ng = ng_tab ? std::min(ng_tab[t], b->tab_ng[t]) : b->tab_ng[t];
         if (ng <= 0) continue;
@@ -1069,9 +1404,15 @@ static int fold_eval(trx_fold_batch *b, const int *ng_tab, bool identity)
     ctx->time_begin("centroid");
     vdw_kernel<<<s.N, VDW_THREADS, b->vdw_smem, ctx->stream>>>(s);
     ctx->time_end("centroid");
-    ctx->time_begin("torsion_grad");
-    torsion_grad_kernel<<<s.G, SEG_THREADS, 0, ctx->stream>>>(s);
-    ctx->time_end("torsion_grad");
+    if (s.cart) {
+        ctx->time_begin("cart_grad");
+        cart_grad_kernel<<<s.G, SEG_THREADS, 0, ctx->stream>>>(s);
+        ctx->time_end("cart_grad");
+    } else {
+        ctx->time_begin("torsion_grad");
+        torsion_grad_kernel<<<s.G, SEG_THREADS, 0, ctx->stream>>>(s);
+        ctx->time_end("torsion_grad");
+    }
     TRX_CUDA(cudaGetLastError());
     return TRX_OK;
 }
@@ -1109,9 +1450,48 @@ static int run_rounds(trx_fold_batch *b, int max_rounds, int check_every, int *r
     return TRX_OK;
 }
 
+// The whole schedule: segment by segment, changing the degrees of freedom at the boundaries.
+static int run_schedule(trx_fold_batch *b, int max_rounds, int check_every, int *rounds_io)
+{
+    trx_ctx *ctx = b->ctx;
+    FoldState &s = b->s;
+    int rc;
+    for (const auto &sg : b->segs) {
+        if (sg.cart) {
+            // coordinates of the accepted torsions (identity slots), then x = xt = coordinates
+            ctx->time_begin("segment");
+            restore_kernel<<<s.G, 256, 0, ctx->stream>>>(s);
+            ctx->time_end("segment");
+            if ((rc = fold_eval(b, nullptr, true))) return rc;
+            ctx->time_begin("segment");
+            cart_begin_kernel<<<s.G, 256, 0, ctx->stream>>>(s);
+            ctx->time_end("segment");
+            s.cart = 1; s.ndof = s.ndof_c;
+        }
+        s.seg_hi = sg.hi;
+        ctx->time_begin("segment");
+        seg_begin_kernel<<<(s.Npad + 255) / 256, 256, 0, ctx->stream>>>(s, sg.lo, sg.hi);
+        ctx->time_end("segment");
+        if ((rc = run_rounds(b, max_rounds, check_every, rounds_io))) return rc;
+        if (sg.cart) {
+            ctx->time_begin("segment");
+            restore_kernel<<<s.G, 256, 0, ctx->stream>>>(s);
+            ctx->time_end("segment");
+            if ((rc = fold_eval(b, nullptr, true))) return rc;
+            ctx->time_begin("segment");
+            cart_end_kernel<<<s.G, 256, 0, ctx->stream>>>(s);
+            ctx->time_end("segment");
+            s.cart = 0; s.ndof = s.ndof_t;
+        }
+    }
+    s.seg_hi = s.nruns;
+    TRX_CUDA(cudaGetLastError());
+    return TRX_OK;
+}
+
 /* Runs the schedule to completion (or max_rounds evaluation rounds).  tors: host [N][L][3]
  * float, in: start torsions, out: final torsions.  xyz (may be NULL): host [N][L][5][3] float,
- * atoms N,CA,CB,C,O.  terms (may be NULL): [N][6] double.  stats (may be NULL): [N][2]
+ * atoms N,CA,CB,C,O.  terms (may be NULL): [N][7] double.  stats (may be NULL): [N][2]
  * evaluations, accepted iterations.  *rounds_out (may be NULL): evaluation rounds executed. */
 int trx_fold_run(trx_fold_batch *b, float *tors, float *xyz, double *terms, long long *stats, int max_rounds,
                  int check_every, int *rounds_out)
@@ -1130,11 +1510,12 @@ int trx_fold_run(trx_fold_batch *b, float *tors, float *xyz, double *terms, long
     TRX_CUDA(cudaMemcpyAsync(d_tors, tors, tb, cudaMemcpyHostToDevice, ctx->stream));
     ctx->time_begin("fold_device");   // device time of the whole fold, inputs resident (H2D done, D2H not started)
     --ctx->launches;
+    s.cart = 0; s.ndof = s.ndof_t; s.seg_hi = s.nruns;
     ctx->time_begin("fold_init");
     init_state_kernel<<<s.G, 32, 0, ctx->stream>>>(s, (const float *)d_tors);
     ctx->time_end("fold_init");
     int rounds = 0;
-    if ((rc = run_rounds(b, max_rounds, check_every, &rounds))) return rc;
+    if ((rc = run_schedule(b, max_rounds, check_every, &rounds))) return rc;
     // final coordinates / terms at the accepted point x: one more evaluation with xt = x for everyone
     ctx->time_begin("export");
     restore_kernel<<<s.G, 256, 0, ctx->stream>>>(s);
@@ -1143,6 +1524,11 @@ int trx_fold_run(trx_fold_batch *b, float *tors, float *xyz, double *terms, long
     ctx->time_begin("export");
     export_kernel<<<s.G, 32, 0, ctx->stream>>>(s, (float *)d_tors, (double *)d_terms, (long long *)d_stats);
     ctx->time_end("export");
+    if (b->has_cart) {
+        ctx->time_begin("export");
+        held_xyz_kernel<<<s.N, 128, 0, ctx->stream>>>(s);
+        ctx->time_end("export");
+    }
     ctx->time_end("fold_device");
     TRX_CUDA(cudaGetLastError());
     TRX_CUDA(cudaMemcpyAsync(tors, d_tors, tb, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1180,11 +1566,13 @@ int trx_fold_mc(trx_fold_batch *b, float *tors, float *xyz, double *terms, long 
     TRX_CUDA(cudaMemcpyAsync(d_tors, tors, tb, cudaMemcpyHostToDevice, ctx->stream));
     ctx->time_begin("fold_device");
     --ctx->launches;
+    TRX_REQUIRE(!b->segs.back().cart, "trx_fold_mc: the Monte-Carlo run must be a torsion-space run");
+    s.cart = 0; s.ndof = s.ndof_t; s.seg_hi = s.nruns;
     init_state_kernel<<<s.G, 32, 0, ctx->stream>>>(s, (const float *)d_tors);
     ++ctx->launches;
     int rounds = 0;
     // runs [0, mc_run] once: the last one scores the minimised decoy under the MC weights
-    if ((rc = run_rounds(b, max_rounds, check_every, &rounds))) return rc;
+    if ((rc = run_schedule(b, max_rounds, check_every, &rounds))) return rc;
     McOpts o;
     o.seed = seed; o.id_offset = id_offset; o.block_min = block_min; o.block_max = block_max; o.mc_run = mc_run;
     o.sigma = (float)(sigma_deg * TRX_DEG); o.kT = (float)kT; o.cycle = 0;
@@ -1203,6 +1591,10 @@ int trx_fold_mc(trx_fold_batch *b, float *tors, float *xyz, double *terms, long 
     if ((rc = fold_eval(b, nullptr, true))) return rc;
     export_kernel<<<s.G, 32, 0, ctx->stream>>>(s, (float *)d_tors, (double *)d_terms, (long long *)d_stats);
     ++ctx->launches;
+    if (b->has_cart) {
+        held_xyz_kernel<<<s.N, 128, 0, ctx->stream>>>(s);
+        ++ctx->launches;
+    }
     ctx->time_end("fold_device");
     TRX_CUDA(cudaGetLastError());
     std::vector<long long> st2((size_t)s.N * 2);
@@ -1224,13 +1616,14 @@ int trx_fold_mc(trx_fold_batch *b, float *tors, float *xyz, double *terms, long 
 }
 
 /* Single evaluation at given torsions under uniform weights (parity tests of K2-K4):
- * tors host [N][L][3] float -> total [N], terms [N][6], gtors [N][L][3] float, xyz [N][L][5][3] float. */
-int trx_fold_eval(trx_fold_batch *b, const float *tors, const double w[6], double *total, double *terms, float *gtors, float *xyz)
+ * tors host [N][L][3] float -> total [N], terms [N][7], gtors [N][L][3] float, xyz [N][L][5][3] float. */
+int trx_fold_eval(trx_fold_batch *b, const float *tors, const double w[TRX_NTERM], double *total, double *terms, float *gtors, float *xyz)
 {
     TRX_REQUIRE(b && tors && w, "trx_fold_eval: NULL argument");
     trx_ctx *ctx = b->ctx;
     FoldState &s = b->s;
     TRX_CUDA(cudaSetDevice(ctx->device));
+    s.cart = 0; s.ndof = s.ndof_t; s.seg_hi = s.nruns;
     void *d_tors = nullptr;
     int rc;
     const size_t tb = (size_t)s.N * s.ndof * sizeof(float);
@@ -1253,6 +1646,62 @@ int trx_fold_eval(trx_fold_batch *b, const float *tors, const double w[6], doubl
         if (total) total[n] = ft[n];
         if (terms) for (int k = 0; k < TRX_NTERM; ++k) terms[(size_t)n * TRX_NTERM + k] = tr[(size_t)k * s.Npad + n];
         if (gtors) for (int k = 0; k < s.ndof; ++k) gtors[(size_t)n * s.ndof + k] = gt[((size_t)(n / LANES) * s.ndof + k) * LANES + n % LANES];
+    }
+    return TRX_OK;
+}
+
+/* Single Cartesian-mode evaluation (parity entry of the Cartesian stage): xyz host
+ * [N][L][5][3] float are the degrees of freedom -> total [N], terms [N][7], grad [N][L][5][3]
+ * float (gradient of the weighted total w.r.t. every coordinate), tors [N][L][3] float (the
+ * torsions read back from the coordinates).  Any output may be NULL.  The batch must have
+ * been created with a schedule that contains a Cartesian run. */
+int trx_fold_eval_cart(trx_fold_batch *b, const float *xyz, const double w[TRX_NTERM], double *total, double *terms, float *grad,
+                       float *tors)
+{
+    TRX_REQUIRE(b && xyz && w, "trx_fold_eval_cart: NULL argument");
+    TRX_REQUIRE(b->has_cart, "trx_fold_eval_cart: the batch's schedule has no Cartesian run (buffers are sized for torsions)");
+    trx_ctx *ctx = b->ctx;
+    FoldState &s = b->s;
+    TRX_CUDA(cudaSetDevice(ctx->device));
+    void *d_tors = nullptr, *d_xyz = nullptr;
+    int rc;
+    const size_t tb = (size_t)s.N * s.ndof_t * sizeof(float), xb = (size_t)s.N * s.L * NAT3 * sizeof(float);
+    if ((rc = ctx->get_scratch("fold_tors", tb, &d_tors))) return rc;
+    if ((rc = ctx->get_scratch("fold_xyz", xb, &d_xyz))) return rc;
+    TRX_CUDA(cudaMemsetAsync(d_tors, 0, tb, ctx->stream));
+    TRX_CUDA(cudaMemcpyAsync(d_xyz, xyz, xb, cudaMemcpyHostToDevice, ctx->stream));
+    s.cart = 0; s.ndof = s.ndof_t; s.seg_hi = s.nruns;
+    init_state_kernel<<<s.G, 32, 0, ctx->stream>>>(s, (const float *)d_tors);
+    std::vector<float> wl((size_t)TRX_NTERM * s.Npad);
+    for (int k = 0; k < TRX_NTERM; ++k) for (int n = 0; n < s.Npad; ++n) wl[(size_t)k * s.Npad + n] = (float)w[k];
+    TRX_CUDA(cudaMemcpyAsync(s.wl, wl.data(), wl.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    s.cart = 1; s.ndof = s.ndof_c;
+    TRX_CUDA(cudaMemsetAsync(s.xt, 0, (size_t)s.G * s.ndof_c * LANES * sizeof(float), ctx->stream));
+    if ((rc = trx_to_grouped(ctx, s.N, s.L, TRX_NAT, TRX_F32, d_xyz, s.xt))) return rc;
+    ctx->launches += 1;
+    rc = fold_eval(b, nullptr, true);
+    if (!rc && tors) {
+        cart_end_kernel<<<s.G, 256, 0, ctx->stream>>>(s);
+        ctx->launches += 1;
+    }
+    s.cart = 0; s.ndof = s.ndof_t;
+    if (rc) return rc;
+    std::vector<double> ft(s.Npad), tr((size_t)TRX_NTERM * s.Npad);
+    std::vector<float> gt((size_t)s.G * s.ndof_c * LANES), tx;
+    TRX_CUDA(cudaMemcpyAsync(ft.data(), s.ft, ft.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    TRX_CUDA(cudaMemcpyAsync(tr.data(), s.terms, tr.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    TRX_CUDA(cudaMemcpyAsync(gt.data(), s.gt, gt.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (tors) {
+        tx.resize((size_t)s.G * s.ndof_t * LANES);
+        TRX_CUDA(cudaMemcpyAsync(tx.data(), s.x, tx.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    TRX_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int n = 0; n < s.N; ++n) {
+        const size_t gb = (size_t)(n / LANES), ln = n % LANES;
+        if (total) total[n] = ft[n];
+        if (terms) for (int k = 0; k < TRX_NTERM; ++k) terms[(size_t)n * TRX_NTERM + k] = tr[(size_t)k * s.Npad + n];
+        if (grad) for (int k = 0; k < s.L * NAT3; ++k) grad[(size_t)n * s.L * NAT3 + k] = gt[(gb * s.ndof_c + k) * LANES + ln];
+        if (tors) for (int k = 0; k < s.ndof_t; ++k) tors[(size_t)n * s.ndof_t + k] = tx[(gb * s.ndof_t + k) * LANES + ln];
     }
     return TRX_OK;
 }

@@ -5,17 +5,18 @@ folding/folding.py:74-104 builds four ScoreFunctions from data/*.wts and four Mi
 :118-119 and :164-171 (mode 2) apply them:
     remove_clash(sf_vdw, min_mover_vdw)        <= 5 x { if sf_vdw(pose) < 10: break; minimise }
     RepeatMover(min_mover, 3)                  3 x minimise under scorefxn.wts
-    min_mover_cart                             Cartesian stage (NOT built in this round)
+    min_mover_cart                             Cartesian stage: xyz are the degrees of freedom (scorefxn_cart.wts)
     remove_clash(sf_vdw, min_mover1)           <= 5 x { ...; minimise under scorefxn1.wts }
 Terms the library implements: atom_pair_constraint, dihedral_constraint, angle_constraint,
-vdw, rama, omega.  cen_hb / hbond_* / cart_bonded weights are read and ignored (no database)."""
+vdw, rama, omega, cart_bonded (the non-restraint ones as stated approximations).  cen_hb /
+hbond_* weights are read and ignored (database-driven terms, not in the reference tree)."""
 from __future__ import annotations
 
 import os
 
 from .capi import Run, NTERM
 
-TERMS = ("atom_pair_constraint", "dihedral_constraint", "angle_constraint", "vdw", "rama", "omega")
+TERMS = ("atom_pair_constraint", "dihedral_constraint", "angle_constraint", "vdw", "rama", "omega", "cart_bonded")
 _DATA = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "folding", "data")
 
 
@@ -30,48 +31,49 @@ def read_wts(name, data_dir=None):
     return [w[t] for t in TERMS]
 
 
-def make_run(w, max_iter, tol=1e-4, clash_check=False, clash_thr=10.0, skip_to=0):
+def make_run(w, max_iter, tol=1e-4, clash_check=False, clash_thr=10.0, skip_to=0, cartesian=False):
     r = Run()
     for k in range(NTERM):
         r.w[k] = w[k]
     r.max_iter, r.tol = int(max_iter), float(tol)
-    r.clash_check, r.clash_thr, r.skip_to = int(clash_check), float(clash_thr), int(skip_to)
+    r.clash_check, r.clash_thr, r.skip_to, r.cartesian = int(clash_check), float(clash_thr), int(skip_to), int(cartesian)
     return r
 
 
-def reference_schedule(data_dir=None, stages=1):
-    """Mode-2 schedule (stages=1).  Modes 0 and 1 of folding.py:125-160 repeat the
-    {repeat_mover, cart, remove_clash} block per separation window; the host driver
-    then calls the fold once per window with the window's tables."""
+def _stage(runs, data_dir, cartesian):
+    """{RepeatMover(min_mover,3); min_mover_cart; remove_clash(sf_vdw, min_mover1)} appended to runs
+    (folding.py:129-171: the block every mode repeats after add_rst)."""
     sf = read_wts("scorefxn.wts", data_dir)
     sf1 = read_wts("scorefxn1.wts", data_dir)
-    sf_vdw = read_wts("scorefxn_vdw.wts", data_dir)
-    runs = []
-    first = [make_run(sf_vdw, 500, clash_check=True, skip_to=5) for _ in range(5)]
-    runs += first
     runs += [make_run(sf, 1000) for _ in range(3)]
+    if cartesian:
+        runs.append(make_run(read_wts("scorefxn_cart.wts", data_dir), 1000, cartesian=True))
     end = len(runs) + 5
     runs += [make_run(sf1, 1000, clash_check=True, skip_to=end) for _ in range(5)]
     return runs
 
 
-def window_schedule(data_dir=None, initial_clash=False):
-    """One separation window of modes 0/1/3: RepeatMover(min_mover,3) + remove_clash(min_mover1)."""
-    sf = read_wts("scorefxn.wts", data_dir)
-    sf1 = read_wts("scorefxn1.wts", data_dir)
+def reference_schedule(data_dir=None, cartesian=True):
+    """Mode-2 schedule.  Modes 0 and 1 of folding.py:125-160 repeat the {repeat_mover, cart,
+    remove_clash} block per separation window; the host driver then calls the fold once per
+    window with the window's tables (window_schedule)."""
+    sf_vdw = read_wts("scorefxn_vdw.wts", data_dir)
+    runs = [make_run(sf_vdw, 500, clash_check=True, skip_to=5) for _ in range(5)]
+    return _stage(runs, data_dir, cartesian)
+
+
+def window_schedule(data_dir=None, initial_clash=False, cartesian=True):
+    """One separation window of modes 0/1/3: RepeatMover(min_mover,3) + min_mover_cart + remove_clash(min_mover1)."""
     sf_vdw = read_wts("scorefxn_vdw.wts", data_dir)
     runs = []
     if initial_clash:
         runs += [make_run(sf_vdw, 500, clash_check=True, skip_to=5) for _ in range(5)]
-    runs += [make_run(sf, 1000) for _ in range(3)]
-    end = len(runs) + 5
-    runs += [make_run(sf1, 1000, clash_check=True, skip_to=end) for _ in range(5)]
-    return runs
+    return _stage(runs, data_dir, cartesian)
 
 
-def mc_schedule(data_dir=None, mc_max_iter=200):
+def mc_schedule(data_dir=None, mc_max_iter=200, cartesian=True):
     """reference_schedule() followed by the run Monte-Carlo cycles re-minimise with and score
     on (scorefxn.wts, shorter cap).  An extension: the reference has no MC step in folding/."""
-    runs = reference_schedule(data_dir)
+    runs = reference_schedule(data_dir, cartesian)
     runs.append(make_run(read_wts("scorefxn.wts", data_dir), mc_max_iter))
     return runs
