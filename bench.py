@@ -293,7 +293,7 @@ def run_b200_fold(args):
         dt = one_fold(1000 * rank + 100 + k)
         if world > 1:
             # the path's only exchange: all-gather of per-decoy energies (NCCL) for pool selection
-            score = (terms_h.numpy() * np.array([5.0, 4.0, 4.0, 1.0, 1.0, 0.5, 0.0])).sum(1)
+            score = (terms_h.numpy() * np.array([5.0, 4.0, 4.0, 1.0, 1.0, 0.5, 0.1])).sum(1)
             full = parallel.gather_scalars(score, N * world, rank, world, device="cuda")
             pool = parallel.select_pool(full[:, 0], 10)
             dt = time.perf_counter() - t0
@@ -312,7 +312,7 @@ def run_b200_fold(args):
     t_dev = max(lane_dev)
     k1_ms = sum(ln["ctx"].timing("restraints")[0] for ln in lanes)
     k1_n = sum(ln["ctx"].timing("restraints")[1] for ln in lanes)
-    busy = {name: sum(ln["ctx"].timing(name)[0] for ln in lanes) for name in ("restraints", "reduce", "nerf", "centroid", "torsion_grad", "lbfgs")}
+    busy = {name: sum(ln["ctx"].timing(name)[0] for ln in lanes) for name in ("restraints", "reduce", "nerf", "centroid", "torsion_grad", "lbfgs", "cart_gather", "cart_grad", "segment", "compact", "activity")}
     tot_busy = sum(busy.values())
     shares = {name: v / tot_busy for name, v in busy.items()}
     for ln in lanes:
@@ -341,7 +341,7 @@ def run_b200_fold(args):
             "config": {"workload": "synthetic L=300 dist+omega+theta+phi, two-model mixing, %d decoys per GPU, full mode-2 centroid schedule (configs[2])" % N,
                        "restraints_per_decoy": R, "l2": "working set per step (%.1f GB of decoy state) exceeds L2" % (batch_bytes(N, L_TARGET, args.lbfgs_m) / 1e9),
                        "streams": S,
-                       "mode": "fold", "lbfgs_m": args.lbfgs_m, "cartesian_stage": "not built (DESIGN.md)",
+                       "mode": "fold", "lbfgs_m": args.lbfgs_m, "cartesian_stage": "min_mover_cart built: coordinates as degrees of freedom, cart_bonded-like springs (stated approximation; hbond_* terms dropped)",
                        "collective": "all-gather of per-decoy energies for pool selection (N>1 only)"},
             "restraint_decoy_evals_per_sec": evals_total * world / t_dev,
             "restraint_evals_per_sec": rest_evals * world / t_dev,

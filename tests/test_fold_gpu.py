@@ -172,8 +172,18 @@ def test_cartesian_stage_in_the_schedule(ctx):
     batch = capi.FoldBatch(ctx, [tb], [64], aa, runs)
     held = batch.run(t0)
     bond = np.linalg.norm(held["xyz"][:, :, 1] - held["xyz"][:, :, 0], axis=-1)
-    assert np.abs(bond - 1.458).max() > 1e-3 and np.abs(bond - 1.458).mean() < 0.1
-    assert np.all(held["terms"][:, 6] > 0.0)
+    # cart_bonded carries weight 0.1 against restraint weights 5/4/4 (scorefxn_cart.wts) and this synthetic
+    # target's distograms are sharp: bonds give visibly.  Same distribution as the oracle's Cartesian stage.
+    assert np.abs(bond - 1.458).max() > 1e-3 and np.all(held["terms"][:, 6] > 0.0)
+    oruns = fo.reference_schedule(cartesian=True)
+    for r in oruns[9:]:
+        r.clash_thr = 1e9
+    o = F.fold(t0[:8].astype(np.float64), oruns, m=20, nthreads=8)
+    obond = np.linalg.norm(o["xyz"][:, :, 1] - o["xyz"][:, :, 0], axis=-1)
+    assert abs(np.abs(bond - 1.458).mean() - np.abs(obond - 1.458).mean()) < 0.05
+    assert abs(np.median(held["terms"][:, 6]) - np.median(o["terms"][:, 6])) < 0.3 * np.median(o["terms"][:, 6])
+    wc = np.array(list(runs[8].w))
+    assert abs(np.median(held["terms"] @ wc) - np.median(o["terms"] @ wc)) < 0.03 * abs(np.median(o["terms"] @ wc))
     assert np.all(held["evals"] > base["evals"]) and np.all(held["iters"] > base["iters"])
     w = np.array(list(runs[8].w))
     e_start = np.array([F.eval_cart(base["xyz"][n].astype(np.float64), w)[0] for n in range(0, 64, 7)])
