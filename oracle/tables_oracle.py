@@ -127,3 +127,207 @@ def select_oracle(rst, sep1, sep2, pcut, seq=None, nogly=False):
             m[k] = ok
         sel[name] = m
     return sel
+
+
+# ---------------------------------------------------------------------------------------------
+# Restraint variants: -r idp / af2 / gpcr and the mode-3 selection.
+# Restated with explicit loops where the reference loops, so that this file stays a plain
+# reading of utils_ros.py; the product (trx2dyn.tables) is vectorised and tested against it.
+
+def _pack(i, j, p, knots, tab, fmt, bin_size):
+    xs, x = _fmt_rows(knots, fmt)
+    ys, y = _fmt_rows(tab, fmt)
+    return dict(a=i, b=j, p=p, x=x, y=y, xs=xs, ys=ys, bin_size=float("%.5f" % bin_size))
+
+
+def _periodic_pad(e):      # [E23,E24 ; E1..E24 ; E1,E2]  (utils_ros.py:87)
+    return np.concatenate([e[..., -2:], e[..., 1:], e[..., 1:3]], axis=-1)
+
+
+def _mirror_pad(e):        # [E2,E1 ; E1..E12 ; E12,E11]  (utils_ros.py:130)
+    return np.concatenate([np.flip(e[..., 1:3], axis=-1), e[..., 1:], np.flip(e[..., -2:], axis=-1)], axis=-1)
+
+
+def gen_idp_rst_oracle(npz, use_orient=True, params=PARAMS):
+    """gen_idp_rst (utils_ros.py:196-373): as gen_rst, but pairs flagged in npz['idr'] take their
+    energies relative to the MOST PROBABLE bin instead of the last one."""
+    MEFF, DCUT, ALPHA, EBASE = params["MEFF"], params["DCUT"], params["ALPHA"], params["EBASE"]
+    EREP, DREP, DSTEP = params["EREP"], params["DREP"], params["DSTEP"]
+    ASTEP = np.deg2rad(params["ASTEP"])
+    PCUT = 0.05
+    idr = np.asarray(npz["idr"])
+    out = {}
+    dist = npz["dist"]
+    bins = np.array([4.25 + DSTEP * i for i in range(32)])
+    prob = np.sum(dist[:, :, 5:], axis=-1)
+    top = np.argmax(dist[:, :, 5:], axis=-1)
+    idr_bkgr = (bins[None, None, :] / bins[top][:, :, None]) ** ALPHA                     # (:249)
+    idr_attr = -np.log((dist[:, :, 5:] + MEFF) / (np.max(dist[:, :, 5:], axis=-1)[:, :, None] * idr_bkgr + 1e-6)) + EBASE
+    bkgr = (bins / DCUT) ** ALPHA
+    attr = -np.log((dist[:, :, 5:] + MEFF) / (dist[:, :, -1][:, :, None] * bkgr[None, None, :] + 1e-6)) + EBASE
+    repul = np.maximum(attr[:, :, 0], 0.0)[:, :, None] + np.array(EREP)[None, None, :]   # from the LAST-bin table for both (:254)
+    tab_n = np.concatenate([repul, attr], axis=-1)
+    tab_i = np.concatenate([repul, idr_attr], axis=-1)
+    knots = np.concatenate([DREP, bins])
+    i, j = np.where(prob > PCUT)
+    keep = j > i
+    i, j = i[keep], j[keep]
+    rows = np.array([tab_i[a, b] if idr[a, b] else tab_n[a, b] for a, b in zip(i, j)]).reshape(len(i), 35)
+    out["dist"] = _pack(i, j, prob[i, j], knots, rows, "%.3f", 0.5)
+    if not use_orient:
+        return out
+    for name, fmt, unordered, pad in (("omega", "%.5f", True, _periodic_pad), ("theta", "%.3f", False, _periodic_pad),
+                                      ("phi", "%.3f", False, _mirror_pad)):
+        arr = npz[name]
+        nk = arr.shape[2] + 3
+        lo = -1.5 * ASTEP if name == "phi" else -np.pi - 1.5 * ASTEP
+        knots = np.linspace(lo, np.pi + 1.5 * ASTEP, nk)
+        prob = np.sum(arr[:, :, 1:], axis=-1)
+        e_i = pad(-np.log((arr + MEFF) / (np.max(arr, axis=-1) + MEFF)[:, :, None]))     # max over ALL bins, bin 0 included
+        e_n = pad(-np.log((arr + MEFF) / (arr[:, :, -1] + MEFF)[:, :, None]))
+        i, j = np.where(prob > PCUT)
+        keep = (j > i) if unordered else (j != i)
+        i, j = i[keep], j[keep]
+        rows = np.array([e_i[a, b] if idr[a, b] else e_n[a, b] for a, b in zip(i, j)]).reshape(len(i), nk)
+        out[name] = _pack(i, j, prob[i, j], knots, rows, fmt, ASTEP)
+    return out
+
+
+def gen_rst_af2_oracle(npz, params=PARAMS):
+    """gen_rst_af2 (utils_ros.py:148-194): AlphaFold-style 64-bin CA-CA distogram, distance only.
+    Quirk kept: the background of EVERY bin is the last bin's (bkgr[None,None,-1], :172)."""
+    MEFF, DCUT, ALPHA, EBASE, EREP = params["MEFF"], params["DCUT"], params["ALPHA"], params["EBASE"], params["EREP"]
+    PCUT = 0.0025
+    dist, af_bins = npz["dist"], np.asarray(npz["bins"])
+    bins = af_bins[5:-1]
+    prob = np.sum(dist[:, :, 6:-1], axis=-1)
+    bkgr = (bins / DCUT) ** ALPHA
+    attr = -np.log((dist[:, :, 6:-1] + MEFF) / (dist[:, :, -2][:, :, None] * bkgr[None, None, -1] + 1e-6)) + EBASE
+    repul = np.maximum(attr[:, :, 0], 0.0)[:, :, None] + np.array(EREP)[None, None, :]
+    tab = np.concatenate([repul, attr], axis=-1)
+    knots = np.concatenate([[0.0, 2.325, 3.575], bins])
+    assert tab.shape[-1] == 60 and len(knots) == 60     # the reference formats exactly 60 values (:181-187)
+    i, j = np.where(prob > PCUT)
+    keep = j > i
+    i, j = i[keep], j[keep]
+    rec = _pack(i, j, prob[i, j], knots, tab[i, j], "%.3f", 0.3125)
+    rec["atom"] = "CA"
+    return {"dist": rec}
+
+
+def _bin_templates(known, use_orient):
+    """pros (utils_ros.py:395-450): real-valued template maps -> one-hot bins.  Quirk kept: phi is
+    binned from the THETA values (:433)."""
+    d = np.asarray(known["dist"])
+    edges = np.arange(2, 20.5, 0.5)
+    J = (edges[None, None, None, :] < d[..., None]).sum(-1)
+    J = np.where(J >= 37, 0, J)
+    oh = {"dist": np.eye(37)[J]}
+    if use_orient:
+        ae = np.arange(-np.pi, np.pi, np.pi / 12)
+        for name, key in (("omega", "omega"), ("theta", "theta_asym")):
+            Ja = (ae[None, None, None, :] < np.asarray(known[key])[..., None]).sum(-1)
+            oh[name] = np.eye(25)[np.where(J == 0, 0, Ja)]
+        pe = np.arange(0, np.pi, np.pi / 12)
+        Jp = (pe[None, None, None, :] < np.asarray(known["theta_asym"])[..., None]).sum(-1)
+        oh["phi"] = np.eye(13)[np.where(J == 0, 0, Jp)]
+    return oh
+
+
+def _template_histogram(onehot):
+    """get_sample (utils_ros.py:456-482): every template vote is spread as a Gaussian over bin
+    indices, narrower (std .5) when > 2/3 of the templates agree, wider (1.5) when < 1/3 do."""
+    M, H, W, Cn = onehot.shape
+    count = onehot.sum(axis=0)
+    out = np.zeros((H, W, Cn))
+    x = np.arange(Cn)
+    for i in range(H):
+        for j in range(W):
+            for k in np.where(count[i, j] != 0)[0]:
+                c = count[i, j, k]
+                std = 1.5 if c < M / 3 else (0.5 if c > 2 * M / 3 else 1.0)
+                g = (1 / (np.sqrt(2 * np.pi * std ** 2)) * np.exp(-((x - k) ** 2) / (2 * std ** 2)))
+                for _ in range(int(c)):
+                    out[i, j, :] += g
+    return out / M
+
+
+def _blend(test, tmpl, knots, mask, rg=5):
+    """ling_sumlt (utils_ros.py:375-394): on masked pairs the rg lowest-energy knots of the TEMPLATE
+    table are replaced, in the predicted table, by the straight line between the knots just outside
+    them.  Ties: the padded angular tables repeat knots, so ties are common; the reference calls
+    numpy's default (unstable) argsort, whose tie order depends on the numpy build / CPU -- the same
+    call is made here, and tests accept either order on rows whose 5th/6th lowest values tie."""
+    t = test.copy()
+    for i in range(test.shape[0]):
+        for j in range(test.shape[1]):
+            if mask[i, j]:
+                idx = np.argsort(tmpl[i, j])[:rg]
+                lo, hi = idx.min() - 1, idx.max() + 1
+                if lo < 0:
+                    lo += 1
+                if hi >= len(knots):
+                    hi -= 1
+                t[i, j][idx] = (knots[idx] - knots[hi]) / (knots[lo] - knots[hi]) * (t[i, j][lo] - t[i, j][hi]) + t[i, j][hi]
+    return t
+
+
+def gen_gpcr_rst_oracle(npz, known, use_orient=True, params=PARAMS):
+    """gen_gpcr_rst (utils_ros.py:484-654): predicted tables blended with a histogram of known
+    (template) structures on the pairs flagged in npz['idr']."""
+    MEFF, DCUT, ALPHA, EBASE = params["MEFF"], params["DCUT"], params["ALPHA"], params["EBASE"]
+    EREP, DREP, DSTEP = params["EREP"], params["DREP"], params["DSTEP"]
+    ASTEP = np.deg2rad(params["ASTEP"])
+    PCUT = 0.05
+    idr = np.asarray(npz["idr"])
+    oh = _bin_templates(known, use_orient)
+    out = {}
+    dist = npz["dist"]
+    bins = np.array([4.25 + DSTEP * i for i in range(32)])
+    prob = np.sum(dist[:, :, 5:], axis=-1)
+    bkgr = (bins / DCUT) ** ALPHA
+
+    def table(d):
+        attr = -np.log((d[:, :, 5:] + MEFF) / (d[:, :, -1][:, :, None] * bkgr[None, None, :] + 1e-6)) + EBASE
+        repul = np.maximum(attr[:, :, 0], 0.0)[:, :, None] + np.array(EREP)[None, None, :]
+        return np.concatenate([repul, attr], axis=-1)
+    knots = np.concatenate([DREP, bins])
+    tab = _blend(table(dist), table(_template_histogram(oh["dist"])), knots, idr)
+    i, j = np.where(prob > PCUT)
+    keep = j > i
+    i, j = i[keep], j[keep]
+    out["dist"] = _pack(i, j, prob[i, j], knots, tab[i, j], "%.3f", 0.5)
+    if not use_orient:
+        return out
+    for name, fmt, unordered, pad in (("omega", "%.5f", True, _periodic_pad), ("theta", "%.3f", False, _periodic_pad),
+                                      ("phi", "%.3f", False, _mirror_pad)):
+        arr = npz[name]
+        nk = arr.shape[2] + 3
+        lo = -1.5 * ASTEP if name == "phi" else -np.pi - 1.5 * ASTEP
+        knots = np.linspace(lo, np.pi + 1.5 * ASTEP, nk)
+        prob = np.sum(arr[:, :, 1:], axis=-1)
+        e = pad(-np.log((arr + MEFF) / (arr[:, :, -1] + MEFF)[:, :, None]))               # float32
+        cate = _template_histogram(oh[name])
+        ce = pad(-np.log((cate + MEFF) / (cate[:, :, -1] + MEFF)[:, :, None]))            # float64
+        tab = _blend(e, ce, knots, idr)                                                    # stays float32 (t = test.copy())
+        i, j = np.where(prob > PCUT)
+        keep = (j > i) if unordered else (j != i)
+        i, j = i[keep], j[keep]
+        out[name] = _pack(i, j, prob[i, j], knots, tab[i, j], fmt, ASTEP)
+    return out
+
+
+def select_idr_oracle(rst, idr, pcut, seq=None, nogly=False):
+    """add_idr_rst's list filters (utils_ros.py:745-760): pairs flagged in `idr` (any sequence
+    separation) above the probability thresholds of add_rst."""
+    thr = {"dist": pcut, "omega": pcut + 0.5, "theta": pcut + 0.5, "phi": pcut + 0.6}
+    sel = {}
+    for name, rec in rst.items():
+        m = np.zeros(len(rec["a"]), dtype=bool)
+        for k, (a, b, p) in enumerate(zip(rec["a"], rec["b"], rec["p"])):
+            ok = bool(idr[a, b]) and p >= thr[name]
+            if nogly and ok:
+                ok = seq[a] != "G" and seq[b] != "G"
+            m[k] = ok
+        sel[name] = m
+    return sel

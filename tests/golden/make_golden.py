@@ -12,6 +12,8 @@ Outputs
   gen_rst_example_NMR.npz                      a,b,p per type + sha256 of all text lines + every 7th table
   gen_rst_random24.npz                         full tables for a random L=24 input (edge cases: p near cutoffs)
   geometry_random.npz                          reference get_dihedrals/get_angles on random points
+  gen_rst_variants24.npz                       gen_idp_rst / gen_gpcr_rst / gen_rst_af2 tables on random L=24 inputs
+  dynamics_example48.npz                       outer-loop arithmetic (get_neighbors, pros, process_distribution...)
 """
 import hashlib, os, shutil, sys, tempfile, types
 import numpy as np
@@ -59,6 +61,79 @@ def run_gen_rst(utils_ros, npz, seq, use_orient=True):
         res[name] = dict(a=a, b=b, p=p, texts=texts, lines=lines)
     tmp.cleanup()
     return res
+
+
+def run_variant(utils_ros, fn_name, npz, seq, use_orient, known=None):
+    """gen_idp_rst / gen_rst_af2 / gen_gpcr_rst of the reference (utils_ros.py:148-654), same packing as run_gen_rst."""
+    import json
+    params = json.load(open(os.path.join(REF, "folding/data/params.json")))
+    params["USE_ORIENT"] = use_orient
+    params["seq"] = seq
+    tmp = tempfile.TemporaryDirectory(prefix="/dev/shm/")
+    fn = getattr(utils_ros, fn_name)
+    rst = fn(npz, known, tmp, params) if known is not None else fn(npz, tmp, params)
+    res = {}
+    for name, recs in rst.items():
+        if name == "rep":
+            continue
+        a = np.array([r[0] for r in recs], dtype=np.int32)
+        b = np.array([r[1] for r in recs], dtype=np.int32)
+        p = np.array([r[2] for r in recs], dtype=np.float32)
+        lines, texts = [], []
+        for r in recs:
+            toks = r[3].split()
+            f = [t for t in toks if t.startswith(tmp.name)][0]
+            texts.append(open(f).read())
+            lines.append(r[3].replace(tmp.name, "TMP"))
+        res[name] = dict(a=a, b=b, p=p, texts=texts, lines=lines)
+    tmp.cleanup()
+    return res
+
+
+def make_variant_golden():
+    """Restraint variants of SURVEY 8a row 15 on a random L=24 input: -r idp (idr mask picks the
+    max-bin energy reference), -r af2 (64-bin CA-CA distogram, 60 knots), -r gpcr (template-blended
+    tables), plus add_idr_rst's selection for mode 3."""
+    ur = load_reference_gen_rst()
+    g = np.load(f"{HERE}/gen_rst_random24.npz")
+    rnd = {k: g[f"in_{k}"] for k in ("dist", "omega", "theta", "phi")}
+    L = rnd["dist"].shape[0]
+    rng = np.random.default_rng(2424)
+    idr = rng.random((L, L)) < 0.3
+    idr = idr | idr.T
+    inp = dict(rnd, idr=idr)
+    out = {"in_idr": idr}
+    for orient in (True, False):
+        tag = "idp" if orient else "idp_noorient"
+        for k, v in pack(run_variant(ur, "gen_idp_rst", inp, "A" * L, orient), every=1).items():
+            out[f"{tag}__{k}"] = v
+    # gpcr: 5 templates given as real-valued maps (distance in A, angles in rad)
+    M = 5
+    base = np.abs(rng.normal(size=(L, L))) * 6 + 3.0
+    base = 0.5 * (base + base.T)
+    known = dict(dist=np.stack([base + rng.normal(size=(L, L)) * 1.0 for _ in range(M)]).astype(np.float64),
+                 omega=rng.uniform(-np.pi, np.pi, size=(M, L, L)),
+                 theta_asym=rng.uniform(-np.pi, np.pi, size=(M, L, L)),
+                 phi_asym=rng.uniform(0, np.pi, size=(M, L, L)))
+    known["dist"][:, rng.random((L, L)) < 0.2] = 25.0      # beyond the last bin -> 'no contact'
+    for k, v in known.items():
+        out[f"in_known_{k}"] = v
+    for orient in (True, False):
+        tag = "gpcr" if orient else "gpcr_noorient"
+        for k, v in pack(run_variant(ur, "gen_gpcr_rst", inp, "A" * L, orient, known=known), every=1).items():
+            out[f"{tag}__{k}"] = v
+    # af2: 64-bin distogram over CA-CA, bin edges linspace(2.3125, 21.6875, 63)
+    a = rng.dirichlet(np.full(64, 0.3), size=(L, L)).astype(np.float32)
+    w = rng.uniform(0, 1, size=(L, L, 1)).astype(np.float32) ** 2
+    e_last = np.zeros(64, dtype=np.float32); e_last[-1] = 1
+    d64 = (w * a + (1 - w) * e_last).astype(np.float32)
+    d64 = (0.5 * (d64 + d64.transpose(1, 0, 2))).astype(np.float32)
+    bins = np.linspace(2.3125, 21.6875, 63)
+    out["in_af2_dist"], out["in_af2_bins"] = d64, bins
+    for k, v in pack(run_variant(ur, "gen_rst_af2", dict(dist=d64, bins=bins), "A" * L, False), every=1).items():
+        out[f"af2__{k}"] = v
+    np.savez_compressed(f"{HERE}/gen_rst_variants24.npz", **out)
+    print("variant golden written")
 
 
 def pack(res, every=1):
@@ -161,6 +236,10 @@ def make_dynamics_golden():
 
 
 if __name__ == "__main__":
+    if "--variants-only" in sys.argv:
+        make_variant_golden()
+        sys.exit(0)
     if "--dynamics-only" not in sys.argv:
         main()
+        make_variant_golden()
     make_dynamics_golden()

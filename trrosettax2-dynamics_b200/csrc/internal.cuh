@@ -14,8 +14,12 @@ namespace trx {
 constexpr int LANES = 32;        // decoys per group: one warp lane per decoy
 constexpr int TILE = 16;         // residues per block row / block column
 constexpr int REC_ELEMS = TILE * 9 * LANES;  // one partial-gradient record (N,CA,CB x xyz)
-constexpr int MAXK = 40;         // max spline knots per restraint
-constexpr int K1_WARPS = 8;
+constexpr int MAXK = 64;         // max spline knots per restraint: distance tables (af2 variant: 60 listed + 2 end knots)
+constexpr int MAXK_ANG = 32;     // ... and of the three angular types (28 / 28 / 16 listed + 2)
+// The restraint kernel runs 4-warp CTAs: a step of the per-tile schedule is a matching of <= 4
+// residue pairs, which fills ~91 % of the warp slots on protein-like contact maps (8-warp steps:
+// 72 %, bounded by the busiest row/column of a tile).
+constexpr int K1_WARPS = 4;
 constexpr int K1_THREADS = K1_WARPS * 32;
 
 void set_error(const char *fmt, ...);
@@ -76,9 +80,6 @@ struct alignas(4 * sizeof(T)) Coef {
 template <typename T>
 struct KnotGeom {
     T x[MAXK];      // knot abscissae
-    T rh[MAXK];     // 1/(x[k+1]-x[k])           (kept for reference/debug)
-    T h2_6[MAXK];
-    T h_6[MAXK];
     T gx0, ginv;    // interval guess: k = floor((x-gx0)*ginv)+goff
     int goff;
     int K;

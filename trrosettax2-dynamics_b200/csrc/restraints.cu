@@ -8,25 +8,47 @@
 // Mapping (B200): lane = decoy (32 decoys per group, coordinates stored
 // [group][residue][9][32] so every load/store is one full 128 B / 256 B line and
 // all 32 lanes walk the SAME restraint => the spline table of a restraint is read
-// once per warp from L1/L2, never per decoy from HBM).  A CTA of 8 warps owns a
-// block row of 16 residues for one decoy group and walks its active 16x16 tiles;
-// warp w owns rows w and w+8 (row gradients live in registers), column gradients
-// are accumulated in shared memory with a staggered column schedule
-// (warp w touches column (2w+s)&15 at step s) so that no two warps ever touch the
-// same column in a step: no atomics, bit-reproducible sums.  Per-tile column
-// gradients and per-CTA row gradients are written as partial records that the
-// reduce kernel sums in a fixed order.
+// once per warp from L1/L2, never per decoy from HBM).  A CTA of K1_WARPS warps owns
+// a block row of 16 residues for one decoy group and walks its active 16x16 tiles
+// through a host-built step schedule: in a step every warp evaluates one residue pair
+// and the pairs of a step have distinct rows and distinct columns, so row and column
+// gradients are accumulated in shared memory with plain read-modify-writes: no
+// atomics, bit-reproducible sums.  Per-tile column gradients and per-CTA row
+// gradients are written as partial records that the reduce kernel sums in a fixed order.
+#include <cstdlib>
+
 #include "internal.cuh"
 
+// Register budget of the fp32 kernel: 5 CTAs/SM -> 96 registers, no spills.  Measured on B200
+// (tools/k1_bench.py, L=300): 6 CTAs (80 regs, spills) 1.42 / 5.11 ms sparse / dense, 5 CTAs 1.25 / 4.52 ms,
+// 4 CTAs (124 regs) 1.33 / 4.80 ms.
 #ifndef TRX_K1_MINBLOCKS
-#define TRX_K1_MINBLOCKS 3
+#define TRX_K1_MINBLOCKS 5
+#endif
+// Shared-memory carve-out (percent of the 256 KB L1/shared array): 72 % = 164 KB keeps FOUR CTAs
+// (16 warps) resident and leaves ~90 KB of L1 for the coordinate lines the warps of a tile re-read;
+// the maximum carve-out (5 CTAs resident, ~28 KB of L1) is 2 % slower.
+#ifndef TRX_K1_CARVEOUT
+#define TRX_K1_CARVEOUT 72
 #endif
 
 namespace trx {
 
-__device__ __forceinline__ float t_rsqrt(float x) { return rsqrtf(x); }
+// every argument is clamped to >= 1e-12 before it gets here, so the denormal rescaling of rsqrtf
+// (4 extra instructions per call, ~7 calls per pair) is dead weight: MUFU.RSQ directly
+__device__ __forceinline__ float t_rsqrt(float x)
+{
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ double t_rsqrt(double x) { return 1.0 / sqrt(x); }
-__device__ __forceinline__ float t_rcp(float x) { return __fdividef(1.0f, x); }
+__device__ __forceinline__ float t_rcp(float x)   // same reasoning: MUFU.RCP without the denormal path
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ double t_rcp(double x) { return 1.0 / x; }
 #define ATAN_C0 9.999993354e-01f
 #define ATAN_C1 -3.332986002e-01f
@@ -44,7 +66,7 @@ __device__ __forceinline__ float t_atan2(float y, float x)
 {
     const float ax = fabsf(x), ay = fabsf(y);
     const float mx = fmaxf(fmaxf(ax, ay), 1e-30f), mn = fminf(ax, ay);
-    const float a = __fdividef(mn, mx), s = a * a;
+    const float a = mn * t_rcp(mx), s = a * a;
     float r = ATAN_C7;
     r = r * s + ATAN_C6; r = r * s + ATAN_C5; r = r * s + ATAN_C4; r = r * s + ATAN_C3;
     r = r * s + ATAN_C2; r = r * s + ATAN_C1; r = r * s + ATAN_C0;
@@ -59,6 +81,16 @@ __device__ __forceinline__ double t_floor(double x) { return floor(x); }
 template <typename T> __device__ __forceinline__ T t_tiny();
 template <> __device__ __forceinline__ float t_tiny<float>() { return 1e-12f; }
 template <> __device__ __forceinline__ double t_tiny<double>() { return 1e-24; }
+
+// What the kernel keeps of a KnotGeom in shared memory: the scalars of the interval guess and
+// (in one array for the four types) the knot abscissae.  Sized so that six CTAs fit an SM.
+template <typename T>
+struct KnotHead {
+    T gx0, ginv;
+    int goff, K, urun0, pad;
+};
+constexpr int KX_TOTAL = MAXK + 3 * MAXK_ANG;
+__host__ __device__ constexpr int kx_off(int type) { return type == 0 ? 0 : MAXK + (type - 1) * MAXK_ANG; }
 
 template <typename T>
 struct K1Params {
@@ -89,14 +121,14 @@ struct K1Params {
 // rounding makes the angular grids uneven at the 5e-4 level); fp32 only below the uniform run.
 // Split in two so that a pair can issue the table loads of all its restraints together.
 template <typename T>
-__device__ __forceinline__ int spline_locate_exact(const KnotGeom<T> &kn, T x, T &u)
+__device__ __forceinline__ int spline_locate_exact(const KnotHead<T> &kn, const T *__restrict__ kx, T x, T &u)
 {
     const int K = kn.K;
     int k = (int)t_floor((x - kn.gx0) * kn.ginv) + kn.goff;
     k = min(max(k, 0), K - 1);
-    while (k > 0 && x < kn.x[k]) --k;
-    while (k < K - 1 && x >= kn.x[k + 1]) ++k;
-    u = x - kn.x[k];
+    while (k > 0 && x < kx[k]) --k;
+    while (k < K - 1 && x >= kx[k + 1]) ++k;
+    u = x - kx[k];
     if (k == 0) u = max(u, (T)0);   // below the first knot: clamped spline => value y_0, slope 0
     return k;
 }
@@ -106,25 +138,34 @@ __device__ __forceinline__ int spline_locate_exact(const KnotGeom<T> &kn, T x, T
 // its interval: error ~1e-8, the spline being C2); the few uneven intervals below the run
 // (the 0 / 2 / 3.5 A knots of the distance grid; at most 6, checked at table creation) are
 // counted with compares.
-__device__ __forceinline__ int spline_locate(const KnotGeom<float> &kn, float x, float &u)
+// HEAD: the grid may have uneven leading intervals (the distance grid); the angular grids are
+// uniform from their first knot (checked at table creation), so their lookups skip the test.
+template <bool HEAD>
+__device__ __forceinline__ int spline_locate(const KnotHead<float> &kn, const float *__restrict__ kx, float x, float &u)
 {
-    const int K = kn.K, r0 = kn.urun0;
+    const int K = kn.K, r0 = HEAD ? kn.urun0 : 0;
     int k = (int)floorf((x - kn.gx0) * kn.ginv) + kn.goff;
-    if (r0 > 0 && __any_sync(0xffffffffu, k < r0)) {   // rare: some decoy below the uniform run (d < 4.25 A)
+    if (HEAD && r0 > 0 && __any_sync(0xffffffffu, k < r0)) {   // rare: some decoy below the uniform run (d < 4.25 A)
         int kh = 0;
 #pragma unroll
-        for (int m = 1; m <= 6; ++m) kh += (m <= r0 && x >= kn.x[m]) ? 1 : 0;
+        for (int m = 1; m <= 6; ++m) kh += (m <= r0 && x >= kx[m]) ? 1 : 0;
         k = k >= r0 ? k : kh;
     }
     k = min(max(k, 0), K - 1);
-    u = x - kn.x[k];
+    u = x - kx[k];
     u = k == 0 ? fmaxf(u, 0.f) : u;
     return k;
 }
-__device__ __forceinline__ int spline_locate(const KnotGeom<double> &kn, double x, double &u) { return spline_locate_exact(kn, x, u); }
+template <bool HEAD>
+__device__ __forceinline__ int spline_locate(const KnotHead<double> &kn, const double *__restrict__ kx, double x, double &u)
+{
+    return spline_locate_exact(kn, kx, x, u);
+}
 
+// off = element offset of the restraint's first interval (< 2^31 by construction): one
+// 32-bit add and one widening multiply-add instead of 64-bit pointer arithmetic per load
 template <typename T>
-__device__ __forceinline__ Coef<T> spline_load(const Coef<T> *__restrict__ tab, int k) { return tab[k]; }
+__device__ __forceinline__ Coef<T> spline_load(const Coef<T> *__restrict__ tab, int off, int k) { return tab[(unsigned)(off + k)]; }
 
 #define SPLINE_F(c, u) ((c).c0 + (u) * ((c).c1 + (u) * ((c).c2 + (u) * (c).c3)))
 #define SPLINE_DF(c, u) ((c).c1 + (u) * ((T)2 * (c).c2 + (T)3 * (c).c3 * (u)))
@@ -157,7 +198,7 @@ struct ColGeom {
 // get_dihedrals (utils_trX2dy/utils.py:97-110); angle: get_angles (:113-122).
 // row: CB_i(0..2) P(3..5) U=N_i-CA_i(6..8); rg/cg: gradient accumulators N(0..2) CA(3..5) CB(6..8).
 template <typename T, bool ALL>
-__device__ __forceinline__ void pair_eval(const K1Params<T> &p, const KnotGeom<T> *geom, const int4 ia, const int4 ib,
+__device__ __forceinline__ void pair_eval(const K1Params<T> &p, const KnotHead<T> *geom, const T *__restrict__ kx, const int4 ia, const int4 ib,
                                           const T *row, const ColGeom<T> &c, T *rg, T *cg, const T w0, const T w1, const T w2,
                                           T &e0, T &e1, T &e2)
 {
@@ -186,18 +227,18 @@ __device__ __forceinline__ void pair_eval(const K1Params<T> &p, const KnotGeom<T
     // ---- phase 1: values, intervals, loads
     T u0 = (T)0, u1 = (T)0, u2 = (T)0, u3 = (T)0, u4 = (T)0, u5 = (T)0;
     Coef<T> c0 = {(T)0, (T)0, (T)0, (T)0}, c1 = c0, c2 = c0, c3 = c0, c4 = c0, c5 = c0;
-    if (ALL || (mask & 1)) c0 = spline_load(p.tab[0] + ia.y, spline_locate(geom[0], d, u0));
+    if (ALL || (mask & 1)) c0 = spline_load(p.tab[0], ia.y, spline_locate<true>(geom[0], kx + kx_off(0), d, u0));
     if (ALL || (mask & 2))    // omega: F = P, G = -D, H = Q  =>  A = X, B = Y
-        c1 = spline_load(p.tab[1] + ia.z, spline_locate(geom[1], t_atan2(-d * DOT(P, Y), DOT(X, Y)), u1));
+        c1 = spline_load(p.tab[1], ia.z, spline_locate<false>(geom[1], kx + kx_off(1), t_atan2(-d * DOT(P, Y), DOT(X, Y)), u1));
     if (ALL || (mask & 4))    // theta(i,j): F = U_i, G = P, H = D  =>  A = U_i x P, B = X
-        c2 = spline_load(p.tab[2] + ia.w, spline_locate(geom[2], t_atan2(-np_ * DOT(U, X), DOT(W, X)), u2));
+        c2 = spline_load(p.tab[2], ia.w, spline_locate<false>(geom[2], kx + kx_off(2), t_atan2(-np_ * DOT(U, X), DOT(W, X)), u2));
     if (ALL || (mask & 8))    // theta(j,i): F = U_j, G = Q, H = -D  =>  A = W_j, B = -Y
-        c3 = spline_load(p.tab[2] + ib.x,
-                         spline_locate(geom[2], t_atan2(nq * (c.Ux * Yx + c.Uy * Yy + c.Uz * Yz), -(c.Wx * Yx + c.Wy * Yy + c.Wz * Yz)), u3));
+        c3 = spline_load(p.tab[2], ib.x,
+                         spline_locate<false>(geom[2], kx + kx_off(2), t_atan2(nq * (c.Ux * Yx + c.Uy * Yy + c.Uz * Yz), -(c.Wx * Yx + c.Wy * Yy + c.Wz * Yz)), u3));
     if (ALL || (mask & 16))   // phi(i,j): angle between P and D at CB_i; sin = |X| / (|P||D|)
-        c4 = spline_load(p.tab[3] + ib.y, spline_locate(geom[3], t_atan2(xx * rX, pd), u4));
+        c4 = spline_load(p.tab[3], ib.y, spline_locate<false>(geom[3], kx + kx_off(3), t_atan2(xx * rX, pd), u4));
     if (ALL || (mask & 32))   // phi(j,i): angle between Q and -D at CB_j; sin = |Y| / (|Q||D|)
-        c5 = spline_load(p.tab[3] + ib.z, spline_locate(geom[3], t_atan2(yy * rY, -qd), u5));
+        c5 = spline_load(p.tab[3], ib.z, spline_locate<false>(geom[3], kx + kx_off(3), t_atan2(yy * rY, -qd), u5));
 
     // ---- phase 2: energies and gradients
     const T ixx = rX * rX, iyy = rY * rY;
@@ -257,7 +298,8 @@ __device__ __forceinline__ void pair_eval(const K1Params<T> &p, const KnotGeom<T
 template <typename T>
 __global__ void __launch_bounds__(K1_THREADS, (sizeof(T) == 4 ? TRX_K1_MINBLOCKS : 1)) restraints_kernel(const K1Params<T> p)
 {
-    __shared__ KnotGeom<T> geom[4];
+    __shared__ KnotHead<T> geom[4];
+    __shared__ T kx[KX_TOTAL];
     extern __shared__ __align__(16) unsigned char k1_dyn[];
     T *colg = reinterpret_cast<T *>(k1_dyn);      // column-block gradient of the current tile
     T *rowg = colg + REC_ELEMS;                    // row-block gradient of the whole work item
@@ -267,14 +309,24 @@ __global__ void __launch_bounds__(K1_THREADS, (sizeof(T) == 4 ? TRX_K1_MINBLOCKS
     const int q = blockIdx.y, g = p.g0 + blockIdx.x;   // group is the fast grid index: co-resident CTAs share tiles
     if (p.gactive && !p.gactive[g]) return;
     {
-        const int *src = reinterpret_cast<const int *>(p.geom);
-        int *dst = reinterpret_cast<int *>(geom);
-        for (int e = threadIdx.x; e < (int)(sizeof(geom) / sizeof(int)); e += K1_THREADS) dst[e] = src[e];
+        if (threadIdx.x < 4) {
+            const KnotGeom<T> &gs = p.geom[threadIdx.x];
+            KnotHead<T> h;
+            h.gx0 = gs.gx0; h.ginv = gs.ginv; h.goff = gs.goff; h.K = gs.K; h.urun0 = gs.urun0; h.pad = 0;
+            geom[threadIdx.x] = h;
+        }
+        for (int e = threadIdx.x; e < KX_TOTAL; e += K1_THREADS) {
+            const int t = e < MAXK ? 0 : 1 + (e - MAXK) / MAXK_ANG, k = e - kx_off(t);
+            kx[e] = p.geom[t].x[k];
+        }
         for (int e = threadIdx.x; e < REC_ELEMS; e += K1_THREADS) { colg[e] = (T)0; rowg[e] = (T)0; }
     }
     const int I = p.work[q * 4 + 0], t0 = p.work[q * 4 + 1], nt = p.work[q * 4 + 2], rowrec = p.work[q * 4 + 3];
     const int xs = p.xstride;
-    const T *__restrict__ Xg = p.X + (size_t)g * p.Lpad * xs * LANES + lane;
+    size_t gbase = (size_t)g * p.Lpad * xs * LANES + lane;
+    asm volatile("" : "+l"(gbase));   // keep the group offset in registers (the compiler otherwise rebuilds it from %ctaid every step)
+    const T *__restrict__ Xg = p.X + gbase;
+    const unsigned xrow = (unsigned)xs * LANES;   // elements per residue; offsets within a group fit 32 bits
     T w0 = p.w0, w1 = p.w1, w2 = p.w2;
     if (p.wl) {
         w0 = (T)p.wl[0 * (size_t)p.Npad + g * LANES + lane];
@@ -288,7 +340,7 @@ __global__ void __launch_bounds__(K1_THREADS, (sizeof(T) == 4 ? TRX_K1_MINBLOCKS
         const int J = p.tileJ[t];
         const int *__restrict__ rec_t = p.pairrec + (size_t)t * TILE * TILE * 8;
         T f0 = (T)0, f1 = (T)0, f2 = (T)0;   // per-tile partial energies
-        // host-built schedule: the (<= 8) pairs of a step have distinct rows and distinct columns,
+        // host-built schedule: the (<= K1_WARPS) pairs of a step have distinct rows and distinct columns,
         // so one warp per pair can add its row and column gradients to shared memory without atomics
         const int s0 = p.nsteps[t], s1 = p.nsteps[t + 1];
         for (int s = s0; s < s1; ++s) {
@@ -298,11 +350,11 @@ __global__ void __launch_bounds__(K1_THREADS, (sizeof(T) == 4 ? TRX_K1_MINBLOCKS
                 const int4 *rp = reinterpret_cast<const int4 *>(rec_t + (r * TILE + c) * 8);
                 const int4 ia = __ldg(rp), ib = __ldg(rp + 1);
                 T ri[9], cj[9], rg[9], cg[9];
-                const int ires = I * TILE + r, jres = J * TILE + c;
+                const T *__restrict__ xr = Xg + (unsigned)(I * TILE + r) * xrow, *__restrict__ xc = Xg + (unsigned)(J * TILE + c) * xrow;
 #pragma unroll
                 for (int k = 0; k < 9; ++k) {
-                    ri[k] = Xg[((size_t)ires * xs + k) * LANES];
-                    cj[k] = Xg[((size_t)jres * xs + k) * LANES];
+                    ri[k] = xr[k * LANES];
+                    cj[k] = xc[k * LANES];
                     rg[k] = (T)0;
                     cg[k] = (T)0;
                 }
@@ -324,8 +376,8 @@ __global__ void __launch_bounds__(K1_THREADS, (sizeof(T) == 4 ? TRX_K1_MINBLOCKS
                 cgm.ww = max(cgm.Wx * cgm.Wx + cgm.Wy * cgm.Wy + cgm.Wz * cgm.Wz, t_tiny<T>());
                 cgm.uq = cgm.Ux * cgm.Qx + cgm.Uy * cgm.Qy + cgm.Uz * cgm.Qz;
                 // pairs carrying all six restraints take a straight-line path (no per-restraint branches)
-                if (ia.x == 63) pair_eval<T, true>(p, geom, ia, ib, row, cgm, rg, cg, w0, w1, w2, f0, f1, f2);
-                else pair_eval<T, false>(p, geom, ia, ib, row, cgm, rg, cg, w0, w1, w2, f0, f1, f2);
+                if (ia.x == 63) pair_eval<T, true>(p, geom, kx, ia, ib, row, cgm, rg, cg, w0, w1, w2, f0, f1, f2);
+                else pair_eval<T, false>(p, geom, kx, ia, ib, row, cgm, rg, cg, w0, w1, w2, f0, f1, f2);
 #pragma unroll
                 for (int k = 0; k < 9; ++k) {
                     rowg[(r * 9 + k) * LANES + lane] += rg[k];
@@ -430,6 +482,9 @@ int k1_launch(trx_ctx *ctx, trx_tables *tb, int Gtot, int g0, int ng, const T *d
         static bool attr_set[2] = {false, false};
         if (!attr_set[sizeof(T) == 8]) {
             TRX_CUDA(cudaFuncSetAttribute(restraints_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            int carve = TRX_K1_CARVEOUT;
+            if (const char *ev = getenv("TRX_K1_CARVEOUT")) carve = atoi(ev);   // development knob: percent of the L1/shared array
+            TRX_CUDA(cudaFuncSetAttribute(restraints_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
             attr_set[sizeof(T) == 8] = true;
         }
         restraints_kernel<T><<<dim3(ng, plan->nwork), K1_THREADS, dyn, ctx->stream>>>(p);
@@ -455,6 +510,16 @@ template int k1_launch<double>(trx_ctx *, trx_tables *, int, int, int, const dou
 using namespace trx;
 
 extern "C" {
+
+/* Development aid (not part of include/trx2dyn.h): resident CTAs per SM of the fp32 restraint kernel. */
+int trx_debug_k1_occupancy(int *out)
+{
+    const size_t dyn = 2 * REC_ELEMS * sizeof(float);
+    TRX_CUDA(cudaFuncSetAttribute(restraints_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    TRX_CUDA(cudaFuncSetAttribute(restraints_kernel<float>, cudaFuncAttributePreferredSharedMemoryCarveout, TRX_K1_CARVEOUT));
+    TRX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, restraints_kernel<float>, K1_THREADS, dyn));
+    return TRX_OK;
+}
 
 int trx_energy_grad_device(trx_ctx *ctx, trx_tables *tb, int N, int precision, const void *d_xyz, const double w[3],
                            double *d_E, void *d_grad)

@@ -62,12 +62,6 @@ static void fill_geom(KnotGeom<T> &g, int K, const double *x)
     g.K = K;
     if (K < 2) return;
     for (int k = 0; k < K; ++k) g.x[k] = (T)x[k];
-    for (int k = 0; k + 1 < K; ++k) {
-        double h = x[k + 1] - x[k];
-        g.rh[k] = (T)(1.0 / h);
-        g.h2_6[k] = (T)(h * h / 6.0);
-        g.h_6[k] = (T)(h / 6.0);
-    }
     // interval guess anchored on the longest run of (nearly) equal spacings -- the
     // uniform part of the grid; the kernel corrects the guess against the true knots
     int best = 0, bestlen = 0;
@@ -94,7 +88,7 @@ int trx_tables::get_plan(int groups, Plan **out)
 {
     // chunk tiles of one block row so that the grid has a few waves of CTAs; plans are
     // cached by chunk size (the only thing the group count changes)
-    const long long want_ctas = 148LL * 3 * 4;
+    const long long want_ctas = 148LL * 4 * 6;   // 4 resident CTAs per SM, a few waves
     long long chunk = std::max(1LL, (long long)ntiles * groups / want_ctas);
     chunk = std::min<long long>(chunk, std::max(1, nb));
     auto it = plans.find((int)chunk);
@@ -154,7 +148,8 @@ int trx_tables_create(trx_ctx *ctx, int L, const trx_rst_set sets[4], trx_tables
         TRX_REQUIRE(s.n >= 0, "trx_tables_create: sets[%d].n < 0", t);
         if (s.n == 0) continue;
         TRX_REQUIRE(s.a && s.b && s.x && s.y, "trx_tables_create: sets[%d] has NULL arrays", t);
-        TRX_REQUIRE(s.K >= 3 && s.K <= MAXK, "trx_tables_create: sets[%d].K=%d out of range [3,%d]", t, s.K, MAXK);
+        const int kmax = t == TRX_DIST ? MAXK : MAXK_ANG;
+        TRX_REQUIRE(s.K >= 3 && s.K <= kmax, "trx_tables_create: sets[%d].K=%d out of range [3,%d]", t, s.K, kmax);
         for (int k = 0; k + 1 < s.K; ++k)
             TRX_REQUIRE(s.x[k + 1] > s.x[k], "trx_tables_create: sets[%d].x not strictly increasing at %d", t, k);
         for (int r = 0; r < s.n; ++r)
@@ -181,6 +176,11 @@ int trx_tables_create(trx_ctx *ctx, int L, const trx_rst_set sets[4], trx_tables
         if (s.n && (g32[t].urun0 > 6 || g32[t].urun1 < s.K - 1)) {
             set_error("trx_tables_create: sets[%d].x must be uniformly spaced after at most 6 leading uneven intervals "
                       "(uniform run found: intervals [%d,%d) of %d)", t, g32[t].urun0, g32[t].urun1, s.K - 1);
+            trx_tables_destroy(T);
+            return TRX_ERR_INVALID;
+        }
+        if (s.n && t != TRX_DIST && g32[t].urun0 != 0) {   // the fp32 kernel looks angular intervals up without a head search
+            set_error("trx_tables_create: sets[%d].x (angular grid) must be uniformly spaced from its first knot", t);
             trx_tables_destroy(T);
             return TRX_ERR_INVALID;
         }
@@ -251,11 +251,11 @@ int trx_tables_create(trx_ctx *ctx, int L, const trx_rst_set sets[4], trx_tables
             rec[p] |= 1 << slot;
             rec[p + 1 + slot] = r * sets[t].K;   // element offset of the restraint's first interval
         }
-    // ---- per-tile step schedule.  In one step each of the 8 warps of the restraint kernel
+    // ---- per-tile step schedule.  In one step each of the K1_WARPS warps of the restraint kernel
     // evaluates one residue pair; row and column gradients are accumulated in shared memory
     // without atomics, so the pairs of a step must have distinct rows and distinct columns
     // (a matching of the tile's rows x columns graph).  Greedy list scheduling, busiest
-    // rows/columns first: sparse tiles take about max(pairs/8, max degree) steps.
+    // rows/columns first: sparse tiles take about max(pairs/K1_WARPS, max degree) steps.
     std::vector<unsigned short> sched;
     std::vector<int> step_ptr(std::max(1, T->ntiles) + 1, 0);
     for (int t = 0; t < T->ntiles; ++t) {
