@@ -9,9 +9,9 @@ through libtrx2dyn.so.  With --ndecoy N the N independent decoys the reference w
 produce with N processes (folding_with_pred_npz(repeat=N)) come out of ONE launch
 (-OUT then holds a '{i}' placeholder).  There is no CPU fallback.
 
-Not built: the Cartesian min_mover_cart stage and the full-atom FastRelax
-stage (--fastrelax is accepted and ignored; decoys are centroid backbone + CB), and the
-idp / af2 / gpcr restraint variants."""
+The staged schedule includes the Cartesian min_mover_cart stage.  Not built: the
+full-atom FastRelax stage (--fastrelax is accepted and ignored; decoys are centroid backbone + CB) and
+Rosetta's database-driven cen_hb / hbond terms."""
 import os
 import sys
 import time
@@ -46,44 +46,57 @@ def main(argv=None):
     params = tables.load_params()
     args = get_args(params, argv)
     print(args)
-    if args.rst != "no-idp":
-        raise SystemExit("folding.py: restraint variant '-r %s' is not built in this version (only no-idp)" % args.rst)
     npz = np.load(args.NPZ)
     seq = read_fasta(args.FASTA)
     L = len(seq)
     params["seq"] = seq
     ctx = capi.Context(max(args.gpu, 0))
-    rst = tables.gen_rst(npz, params)
+    # restraint tables of the requested variant (folding.py:60-68)
+    known = None
+    if args.rst == "gpcr":
+        if not args.KNOWN:
+            raise SystemExit("folding.py: -r gpcr needs -KNOWN (npz of template maps: dist, omega, theta_asym, phi_asym)")
+        known = np.load(args.KNOWN)
+    rst = tables.gen_rst(npz, params, variant=args.rst, known=known)
     for name in ("dist", "omega", "theta", "phi"):
         if name in rst:
             print("%-6s restraints: %d" % (name, len(rst[name]["a"])))
 
-    # separation windows of the modes (folding.py:125-171); restraints accumulate
-    # (ConstraintSetMover.add_constraints(True)), so window k scores [first sep1, sep2_k)
+    # restraint sets of the stages (folding.py:125-186); restraints accumulate
+    # (ConstraintSetMover.add_constraints(True)), so stage k scores the union of stages <= k
     if args.mode == 0:
-        windows = [(1, 12), (1, 24), (1, L)]
+        stages = [tables.select(rst, 1, s2, params) for s2 in (12, 24, L)]
     elif args.mode == 1:
-        windows = [(3, 24), (3, L)]
+        stages = [tables.select(rst, 3, s2, params) for s2 in (24, L)]
     elif args.mode == 2:
-        windows = [(1, L)]
-    else:
-        raise SystemExit("folding.py: mode 3 needs the 'idr' order/disorder split, not built in this version")
+        stages = [tables.select(rst, 1, L, params)]
+    else:   # mode 3: ordered pairs first (odr = 1 - idr), then the disordered ones on top (folding.py:173-186)
+        if "idr" not in npz:
+            raise SystemExit("folding.py: -m 3 needs the 'idr' order/disorder map in the npz")
+        idr = np.asarray(npz["idr"])
+        first = tables.select_idr(rst, 1 - idr, params)
+        second = tables.select_idr(rst, idr, params)
+        stages = [first, {k: first[k] | second[k] for k in first}]
 
     n = args.ndecoy
     seed = args.seed if args.seed is not None else int.from_bytes(os.urandom(4), "little")
     tors = sampler.random_torsions(n, L, seed)
     aa = sampler.aa_index(seq)  # Gly -> Ala for the centroid stage (folding.py:112-115)
     out = None
-    for k, (s1, s2) in enumerate(windows):
-        masks = tables.select(rst, s1, s2, params)
+    for k, masks in enumerate(stages):
+        if not any(m.any() for m in masks.values()):
+            continue                                   # nothing selected up to this stage (add_rst returns early, utils_ros.py:725)
         tb = capi.Tables(ctx, L, tables.active_restraints(rst, masks, args.spline_end_rule))
-        runs = schedule.reference_schedule() if k == 0 and len(windows) == 1 else schedule.window_schedule(initial_clash=(k == 0))
+        # remove_clash(sf_vdw, min_mover_vdw) runs once, before the first stage (folding.py:119)
+        runs = schedule.reference_schedule() if len(stages) == 1 else schedule.window_schedule(initial_clash=(out is None))
         batch = capi.FoldBatch(ctx, [tb], [n], aa, runs)
         out = batch.run(tors)
         tors = out["tors"]
         batch.close()
         tb.close()
-    names = ("atom_pair_constraint", "dihedral_constraint", "angle_constraint", "vdw", "rama", "omega")
+    if out is None:
+        raise SystemExit("folding.py: no restraint passed the probability thresholds; nothing to fold against")
+    names = schedule.TERMS
     for i in range(n):
         path = args.OUT.replace("{i}", str(args.start_id + i)) if n > 1 or "{i}" in args.OUT else args.OUT
         os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)

@@ -79,6 +79,11 @@ long long trx_ctx_launch_count(trx_ctx *ctx);
  * parsing the .cst file and fitting one SplineFunc per line.  sets[t].n may be 0. */
 int trx_tables_create(trx_ctx *ctx, int L, const trx_rst_set sets[4], trx_tables **out);
 int trx_tables_destroy(trx_tables *t);
+/* Atom the AtomPair (distance) restraints sit on: TRX_ATOM_CB (default; 'AtomPair CB a CB b',
+ * utils_ros.py:73) or TRX_ATOM_CA ('AtomPair CA a CA b' of the -r af2 variant, utils_ros.py:191).
+ * CA is only accepted for tables without angular restraints, as gen_rst_af2 produces. */
+enum { TRX_ATOM_CA = 1, TRX_ATOM_CB = 2 };
+int trx_tables_set_dist_atom(trx_tables *t, int atom);
 /* counts[4] = restraints per type; *tiles = active 16x16 residue-pair tiles. */
 int trx_tables_info(const trx_tables *t, int *L, int counts[4], int *tiles);
 /* Copies the fitted second derivatives of type `type` back: y2[n][K] (for parity tests). */

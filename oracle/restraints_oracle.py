@@ -72,6 +72,10 @@ class RestraintSetOracle:
 
     def __init__(self, rst, sel=None, rule="H1"):
         self.sets = {}
+        # 'AtomPair CA a CA b' of the af2 variant (utils_ros.py:191): distance-only sets; the C code scores
+        # the CB slot, so CA is presented there and the gradient moved back (energy_grad only)
+        self.dist_atom = rst.get("dist", {}).get("atom", "CB")
+        assert self.dist_atom == "CB" or set(rst) == {"dist"}
         for name in TYPES:
             if name not in rst:
                 continue
@@ -113,6 +117,17 @@ class RestraintSetOracle:
     def energy_grad(self, xyz, w=(1.0, 1.0, 1.0)):
         """xyz (L,3,3) float64 [res][N,CA,CB][xyz] -> (E[3] unweighted, grad (L,3,3) of w.E)."""
         xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+        if self.dist_atom == "CA":
+            swapped = xyz.copy()
+            swapped[:, 2] = xyz[:, 1]
+            self.dist_atom = "CB"
+            try:
+                E, g = self.energy_grad(swapped, w)
+            finally:
+                self.dist_atom = "CA"
+            grad = np.zeros_like(g)
+            grad[:, 1] = g[:, 2]
+            return E, grad
         L = xyz.shape[0]
         args = [C.c_int(L), _p(xyz)]
         empty_i = np.zeros(1, dtype=np.int32)

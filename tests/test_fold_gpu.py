@@ -234,6 +234,39 @@ def test_folding_cli_drop_in(tmp_path, golden_dir, example):
     assert files == ["initial%d.pdb" % i for i in (10, 3, 4, 5, 6, 7, 8, 9)]
 
 
+def test_folding_cli_variants(tmp_path, golden_dir):
+    """-r idp -m 3 (order / disorder stages, folding.py:173-186), -r gpcr with -KNOWN, -r af2 --no-orient."""
+    import os, subprocess, sys
+    from trx2dyn import pdbio
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    g = np.load(f"{golden_dir}/gen_rst_variants24.npz")
+    r = np.load(f"{golden_dir}/gen_rst_random24.npz")
+    L = 24
+    seq = "MKTAYIAKQRQISFVKSHFSRQLE"
+    (tmp_path / "s.fasta").write_text(">s\n%s\n" % seq)
+    np.savez(tmp_path / "idp.npz", idr=g["in_idr"], **{k: r[f"in_{k}"] for k in ("dist", "omega", "theta", "phi")})
+    np.savez(tmp_path / "known.npz", **{k: g[f"in_known_{k}"] for k in ("dist", "omega", "theta_asym", "phi_asym")})
+    np.savez(tmp_path / "af2.npz", dist=g["in_af2_dist"], bins=g["in_af2_bins"])
+    base = [sys.executable, "./folding/folding.py", "-FASTA", str(tmp_path / "s.fasta"), "--seed", "3", "--no-fastrelax"]
+    runs = {"idp3": ["-NPZ", str(tmp_path / "idp.npz"), "-r", "idp", "-m", "3"],
+            "gpcr": ["-NPZ", str(tmp_path / "idp.npz"), "-r", "gpcr", "-KNOWN", str(tmp_path / "known.npz"), "-m", "1"],
+            "af2": ["-NPZ", str(tmp_path / "af2.npz"), "-r", "af2", "--no-orient"]}
+    for tag, extra in runs.items():
+        out = tmp_path / (tag + ".pdb")
+        res = subprocess.run(base + extra + ["-OUT", str(out)], cwd=root, capture_output=True, text=True)
+        assert res.returncode == 0, (tag, res.stderr[-2000:])
+        s2, at = pdbio.read_backbone(str(out))
+        assert s2 == seq and np.isfinite(at["CA"]).all()
+        pep = np.linalg.norm(at["N"][1:] - at["C"][:-1], axis=1)
+        assert np.all(pep < 1.8)                                      # bonded peptide C-N for PPBuilder
+    res = subprocess.run(base + ["-NPZ", str(tmp_path / "af2.npz"), "-r", "af2", "--orient", "-OUT", str(tmp_path / "x.pdb")],
+                         cwd=root, capture_output=True, text=True)
+    assert res.returncode != 0 and "AF2 Not support" in res.stderr   # the reference's own refusal (utils_ros.py:150)
+    res = subprocess.run(base + ["-NPZ", str(tmp_path / "idp.npz"), "-r", "gpcr", "-OUT", str(tmp_path / "x.pdb")],
+                         cwd=root, capture_output=True, text=True)
+    assert res.returncode != 0 and "-KNOWN" in res.stderr
+
+
 def test_monte_carlo_extension(ctx):
     """Extension with no reference behaviour: checks the invariants it can have --
     Metropolis never loses the best state at kT -> 0, counters are sane, trajectories are

@@ -143,3 +143,53 @@ def test_bad_arguments_fail_loudly(ctx):
     tb = capi.Tables(ctx, 10, {})  # empty restraint set is legal: zero energy, zero gradient
     E, g = tb.energy_grad(synth.random_backbones(2, 10, 0))
     assert np.all(E == 0) and np.all(g == 0)
+
+
+@pytest.mark.parametrize("rule", ["H1", "H2"])
+def test_af2_variant_ca_ca_parity(ctx, golden_dir, rule):
+    """-r af2 (utils_ros.py:148-194): 'AtomPair CA a CA b' restraints with 60 (+2) knots on the uneven
+    0 / 2.325 / 3.575 / 3.875+0.3125k grid; fp64 and fp32 against the oracle."""
+    from oracle.tables_oracle import gen_rst_af2_oracle
+    g = np.load(f"{golden_dir}/gen_rst_variants24.npz")
+    af2 = dict(dist=g["in_af2_dist"], bins=g["in_af2_bins"])
+    L = af2["dist"].shape[0]
+    rst_o = gen_rst_af2_oracle(af2)
+    rs = ro.RestraintSetOracle(rst_o, select_oracle(rst_o, 1, L, 0.05), rule)
+    params = tables.load_params()
+    rst = tables.gen_rst(af2, params, False, "af2")
+    tb = capi.Tables(ctx, L, tables.active_restraints(rst, tables.select(rst, 1, L, params), rule))
+    assert tb.info()["counts"][1:] == [0, 0, 0] and tb.K[0] == (62 if rule == "H1" else 60)
+    xyz = synth.random_backbones(40, L, seed=3) * 0.6          # compact: many CA-CA distances inside the knot range
+    w = np.array([5.0, 4.0, 4.0])
+    _compare(rs, tb, xyz, w, 1e-10, 1e-9, capi.F64)
+    _compare(rs, tb, xyz, w, 2e-6, 2e-3, capi.F32)
+    E, grad = tb.energy_grad(xyz, w, capi.F64)
+    assert np.abs(grad[:, :, 1]).max() > 0 and np.all(grad[:, :, 0] == 0) and np.all(grad[:, :, 2] == 0)   # forces on CA only
+    # CA-CA cannot be combined with angular restraints
+    full = tables.gen_rst(np.load(f"{golden_dir}/example_NMR.npz"), params)
+    act = tables.active_restraints(full, None)
+    with pytest.raises(RuntimeError, match="angular"):
+        capi.Tables(ctx, 90, act, dist_atom="CA")
+    tb.close()
+
+
+def test_idp_and_gpcr_tables_on_device(ctx, golden_dir):
+    """The idp / gpcr variants only change knot values: same kernel, parity against the oracle's tables."""
+    from oracle.tables_oracle import gen_idp_rst_oracle, gen_gpcr_rst_oracle
+    g = np.load(f"{golden_dir}/gen_rst_variants24.npz")
+    r = np.load(f"{golden_dir}/gen_rst_random24.npz")
+    inp = {k: r[f"in_{k}"] for k in tables.TYPES}
+    inp["idr"] = g["in_idr"]
+    known = {k: g[f"in_known_{k}"] for k in ("dist", "omega", "theta_asym", "phi_asym")}
+    L = 24
+    params = tables.load_params()
+    xyz = synth.random_backbones(33, L, seed=8)
+    for variant, rst_o in (("idp", gen_idp_rst_oracle(inp, True)), ("gpcr", gen_gpcr_rst_oracle(inp, known, True))):
+        rs = ro.RestraintSetOracle(rst_o, select_oracle(rst_o, 1, L, 0.05), "H1")
+        rst = tables.gen_rst(inp, params, True, variant, known)
+        tb = capi.Tables(ctx, L, tables.active_restraints(rst, tables.select(rst, 1, L, params), "H1"))
+        _compare(rs, tb, xyz, np.array([5.0, 4.0, 4.0]), 1e-10, 1e-9, capi.F64)
+        # fp32: these Dirichlet tables are far rougher than network output (slopes of tens of units per
+        # radian), so the 1e-6 rad that fp32 coordinates cost an angle shows up at 1e-5 of the term
+        _compare(rs, tb, xyz, np.array([5.0, 4.0, 4.0]), 2e-5, 5e-3, capi.F32)
+        tb.close()

@@ -72,3 +72,60 @@ def test_spline_knots_rules(golden_dir):
     act = tables.active_restraints(rst, tables.select(rst, 1, 90, params))
     assert [len(act[t][0]) for t in tables.TYPES] == [3226, 2562, 5142, 2541]
     assert [len(act[t][2]) for t in tables.TYPES] == [37, 30, 30, 18]
+
+
+# ---- restraint variants: product == oracle (the oracle is pinned on the reference's bytes in test_oracle_tables.py)
+
+def _variant_inputs(golden_dir):
+    g = np.load(f"{golden_dir}/gen_rst_variants24.npz")
+    r = np.load(f"{golden_dir}/gen_rst_random24.npz")
+    inp = {k: r[f"in_{k}"] for k in tables.TYPES}
+    inp["idr"] = g["in_idr"]
+    known = {k: g[f"in_known_{k}"] for k in ("dist", "omega", "theta_asym", "phi_asym")}
+    return inp, known, dict(dist=g["in_af2_dist"], bins=g["in_af2_bins"])
+
+
+def _same(got, want):
+    assert list(got) == list(want)
+    for name in want:
+        for key in ("a", "b", "p", "x", "y"):
+            np.testing.assert_array_equal(got[name][key], want[name][key], err_msg=f"{name} {key}")
+        assert got[name]["bin_size"] == want[name]["bin_size"]
+
+
+@pytest.mark.parametrize("orient", [True, False])
+def test_variants_equal_oracle(golden_dir, orient):
+    from oracle.tables_oracle import gen_idp_rst_oracle, gen_gpcr_rst_oracle
+    params = tables.load_params()
+    inp, known, af2 = _variant_inputs(golden_dir)
+    _same(tables.gen_rst(inp, params, orient, "idp"), gen_idp_rst_oracle(inp, orient))
+    _same(tables.gen_rst(inp, params, orient, "gpcr", known), gen_gpcr_rst_oracle(inp, known, orient))
+
+
+def test_af2_variant_equals_oracle_and_flags_ca(golden_dir):
+    from oracle.tables_oracle import gen_rst_af2_oracle
+    params = tables.load_params()
+    inp, known, af2 = _variant_inputs(golden_dir)
+    got = tables.gen_rst(af2, params, False, "af2")
+    _same(got, gen_rst_af2_oracle(af2))
+    act = tables.active_restraints(got, None)
+    assert act["dist_atom"] == "CA" and len(act["dist"][2]) == 62          # 60 listed knots + the two end knots of rule H1
+    with pytest.raises(RuntimeError):                                       # the reference refuses orientations here (utils_ros.py:150)
+        tables.gen_rst(af2, params, True, "af2")
+    with pytest.raises(ValueError):
+        tables.gen_rst(inp, params, True, "gpcr")                           # no -KNOWN
+
+
+def test_select_idr_equals_oracle(golden_dir):
+    from oracle.tables_oracle import gen_idp_rst_oracle, select_idr_oracle
+    params = tables.load_params()
+    inp, known, af2 = _variant_inputs(golden_dir)
+    rst = tables.gen_rst(inp, params, True, "idp")
+    seq = "AG" * 12
+    for idr in (inp["idr"], 1 - inp["idr"]):
+        for pcut, nogly in ((0.05, False), (0.15, True)):
+            params["PCUT"] = pcut
+            got = tables.select_idr(rst, idr, params, seq, nogly)
+            want = select_idr_oracle(gen_idp_rst_oracle(inp, True), idr, pcut, seq, nogly)
+            for name in got:
+                np.testing.assert_array_equal(got[name], want[name])

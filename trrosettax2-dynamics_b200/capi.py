@@ -90,9 +90,11 @@ class Context:
 class Tables:
     """Device-resident spline tables of one target (one restraint set)."""
 
-    def __init__(self, ctx, L, active):
-        """active: {type: (a, b, x, y)} as tables.active_restraints returns."""
+    def __init__(self, ctx, L, active, dist_atom="CB"):
+        """active: {type: (a, b, x, y)} as tables.active_restraints returns.  dist_atom: 'CB', or 'CA' for
+        the distance-only tables of the -r af2 variant (also taken from active['dist_atom'] if present)."""
         self.ctx, self.L = ctx, L
+        dist_atom = active.get("dist_atom", dist_atom)
         sets = (RstSet * 4)()
         keep = []
         for t, name in enumerate(("dist", "omega", "theta", "phi")):
@@ -112,6 +114,10 @@ class Tables:
         check(lib().trx_tables_create(ctx._h, C.c_int(L), sets, C.byref(self._h)))
         self.counts = [int(s.n) for s in sets]
         self.K = [int(s.K) for s in sets]
+        if dist_atom not in ("CA", "CB"):
+            raise ValueError("dist_atom must be 'CA' or 'CB'")
+        if dist_atom == "CA":
+            check(lib().trx_tables_set_dist_atom(self._h, C.c_int(1)))
 
     def close(self):
         if self._h:

@@ -108,6 +108,7 @@ struct trx_tables {
     double *d_y2[4] = {nullptr, nullptr, nullptr, nullptr};     // [n][K] fitted second derivatives (parity tests)
     trx::KnotGeom<double> *d_geom64 = nullptr;                  // [4]
     trx::KnotGeom<float> *d_geom32 = nullptr;                   // [4]
+    int dist_ca = 0;                 // AtomPair restraints on CA instead of CB (af2 variant; no angular restraints then)
     int ntiles = 0;
     std::vector<int> tileI, tileJ;   // host copies, tiles sorted by (I, J)
     int *d_tileJ = nullptr;          // [ntiles]

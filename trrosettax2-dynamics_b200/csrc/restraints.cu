@@ -106,6 +106,7 @@ struct K1Params {
     double *Epart;                               // [G][nwork][3][32]
     int Lpad, nrec, nwork;
     int xstride;                                 // values per residue in X (9: N,CA,CB; 15: fold layout)
+    int dist_ca;                                 // distance restraints on CA-CA (af2 variant, distance-only tables)
     int g0;                                      // first decoy group of this launch
     const int *gactive;                          // per-group flag or NULL (all active)
     const float *wl;                             // per-decoy weights [3][Npad] or NULL (use w0..w2)
@@ -375,6 +376,16 @@ __global__ void __launch_bounds__(K1_THREADS, (sizeof(T) == 4 ? TRX_K1_MINBLOCKS
                 cgm.qq = max(cgm.Qx * cgm.Qx + cgm.Qy * cgm.Qy + cgm.Qz * cgm.Qz, t_tiny<T>());
                 cgm.ww = max(cgm.Wx * cgm.Wx + cgm.Wy * cgm.Wy + cgm.Wz * cgm.Wz, t_tiny<T>());
                 cgm.uq = cgm.Ux * cgm.Qx + cgm.Uy * cgm.Qy + cgm.Uz * cgm.Qz;
+                if (p.dist_ca) {   // 'AtomPair CA a CA b' (utils_ros.py:191): the only restraint of such a pair
+                    const T Dx = cj[3] - ri[3], Dy = cj[4] - ri[4], Dz = cj[5] - ri[5];
+                    const T dd = max(DOT(D, D), t_tiny<T>()), rd = t_rsqrt(dd);
+                    T u0;
+                    const Coef<T> c0 = spline_load(p.tab[0], ia.y, spline_locate<true>(geom[0], kx + kx_off(0), dd * rd, u0));
+                    f0 += SPLINE_F(c0, u0);
+                    const T sg = w0 * SPLINE_DF(c0, u0) * rd;
+                    cg[3] += sg * Dx; cg[4] += sg * Dy; cg[5] += sg * Dz;
+                    rg[3] -= sg * Dx; rg[4] -= sg * Dy; rg[5] -= sg * Dz;
+                } else
                 // pairs carrying all six restraints take a straight-line path (no per-restraint branches)
                 if (ia.x == 63) pair_eval<T, true>(p, geom, kx, ia, ib, row, cgm, rg, cg, w0, w1, w2, f0, f1, f2);
                 else pair_eval<T, false>(p, geom, kx, ia, ib, row, cgm, rg, cg, w0, w1, w2, f0, f1, f2);
@@ -469,6 +480,7 @@ int k1_launch(trx_ctx *ctx, trx_tables *tb, int Gtot, int g0, int ng, const T *d
     p.nrec = plan->nrec;
     p.nwork = plan->nwork;
     p.xstride = xstride;
+    p.dist_ca = tb->dist_ca;
     p.g0 = g0;
     p.gactive = gactive;
     p.wl = wl;

@@ -72,7 +72,9 @@ static void fill_geom(KnotGeom<T> &g, int K, const double *x)
         if (m - k > bestlen) { bestlen = m - k; best = k; }
         k = m;
     }
-    double h = x[best + 1] - x[best];
+    // mean spacing of the run: the reference's %.3f rounding makes single intervals uneven at the 5e-4
+    // level (0.3125 -> 0.312 / 0.313); taking one of them as THE spacing would let the guess drift
+    double h = (x[best + bestlen] - x[best]) / bestlen;
     g.gx0 = (T)x[best];
     g.ginv = (T)(1.0 / h);
     g.goff = best;
@@ -323,6 +325,16 @@ int trx_tables_destroy(trx_tables *T)
         cudaFree(kv.second.d_blk_rec);
     }
     delete T;
+    return TRX_OK;
+}
+
+int trx_tables_set_dist_atom(trx_tables *t, int atom)
+{
+    TRX_REQUIRE(t, "trx_tables_set_dist_atom: NULL tables");
+    TRX_REQUIRE(atom == TRX_ATOM_CA || atom == TRX_ATOM_CB, "trx_tables_set_dist_atom: atom must be TRX_ATOM_CA or TRX_ATOM_CB");
+    TRX_REQUIRE(atom == TRX_ATOM_CB || (t->n[1] == 0 && t->n[2] == 0 && t->n[3] == 0),
+                "trx_tables_set_dist_atom: CA-CA distance restraints cannot be combined with angular restraints");
+    t->dist_ca = atom == TRX_ATOM_CA;
     return TRX_OK;
 }
 
