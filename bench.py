@@ -315,6 +315,7 @@ def run_b200_fold(args):
     busy = {name: sum(ln["ctx"].timing(name)[0] for ln in lanes) for name in ("restraints", "reduce", "nerf", "centroid", "torsion_grad", "lbfgs", "cart_gather", "cart_grad", "segment", "compact", "activity")}
     tot_busy = sum(busy.values())
     shares = {name: v / tot_busy for name, v in busy.items()}
+    counts = {name: sum(ln["ctx"].timing(name)[1] for ln in lanes) for name in busy}
     for ln in lanes:
         ln["ctx"].set_timing(False)
     t_e2e = float(sum(t_wall))
@@ -355,7 +356,8 @@ def run_b200_fold(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "restraints_kernel<float>", "kernel_ms": k1_ms / max(k1_n, 1),
                          "kernel_share_of_step": shares["restraints"], "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes / max(k1_n, 1), "kernel_shares": shares}}
+                         "algorithmic_bytes_per_launch": alg_bytes / max(k1_n, 1), "kernel_shares": shares,
+                         "kernel_ms_total": {k: round(v, 2) for k, v in busy.items()}, "kernel_launches": counts}}
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         rate, dt, ev = cpu_fold_rate(npzs, seq, threads, threads, SEED)

@@ -172,6 +172,18 @@ int trx_fold_eval(trx_fold_batch *b, const float *tors, const double w[7], doubl
 int trx_fold_eval_cart(trx_fold_batch *b, const float *xyz, const double w[7], double *total, double *terms, float *grad,
                        float *tors);
 
+/* ------------------------------------------------------------------ decoy-set metrics
+ * GloCon matrix of M decoys of L residues: out[M][M], out[i][j] = mean over residue pairs a<b of
+ * |d_i(a,b) - d_j(a,b)| where that exceeds thr (3 A), d = CB-CB distance or 0 beyond dmax (20 A).
+ * cb: host [M][L][3] double (virtual CB for Gly, as get_neighbors builds it).
+ * Replaces: get_glocon_matrix (utils_trX2dy/utils.py:543-567). */
+int trx_glocon_matrix(trx_ctx *ctx, int M, int L, const double *cb, double dmax, double thr, double *out);
+/* TM-score and RMSD of every ordered decoy pair from CA traces with identical residue numbering:
+ * tm[i][j] = TM-score of decoy i superposed on decoy j normalised by L, rmsd[i][j] = Kabsch RMSD.
+ * ca: host [M][L][3] double.  Replaces: get_tmscore_and_rmsd_matrix (utils_trX2dy/utils.py:514-540),
+ * i.e. one `./bin/TMscore a.pdb b.pdb` subprocess per pair. */
+int trx_tmscore_matrix(trx_ctx *ctx, int M, int L, const double *ca, double *tm, double *rmsd);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,6 +13,7 @@ Outputs
   gen_rst_random24.npz                         full tables for a random L=24 input (edge cases: p near cutoffs)
   geometry_random.npz                          reference get_dihedrals/get_angles on random points
   gen_rst_variants24.npz                       gen_idp_rst / gen_gpcr_rst / gen_rst_af2 tables on random L=24 inputs
+  example_tmscore.npz                          bin/TMscore (TM-score, RMSD) + GloCon on the 8 example decoys and 2 natives
   dynamics_example48.npz                       outer-loop arithmetic (get_neighbors, pros, process_distribution...)
 """
 import hashlib, os, shutil, sys, tempfile, types
@@ -235,11 +236,72 @@ def make_dynamics_golden():
     print("dynamics golden written")
 
 
+def make_tmscore_golden():
+    """The reference's structure-comparison step (utils_trX2dy/utils.py:514-540) shells out to the
+    prebuilt bin/TMscore.  Run it here on the reference's 8 example decoys + the two natives (all
+    45 pairs, both normalisations) and keep TM-score / RMSD next to the CA and CB traces."""
+    import itertools, re, subprocess
+    exe = "/tmp/TMscore_ref"
+    shutil.copy(f"{REF}/bin/TMscore", exe)
+    os.chmod(exe, 0o755)
+    names = ["apo", "holo"] + [f"conf_{a}_{b}" for a in (1, 2) for b in (1, 2, 3, 4)]
+    paths = [f"{REF}/example/{n}.pdb" if n in ("apo", "holo") else f"{REF}/example/output/seq/pred_pdb/{n}.pdb" for n in names]
+    ug = load_reference_geometry()
+
+    def backbone(pdb):
+        at = {}
+        for ln in open(pdb):
+            if ln.startswith("ATOM") and ln[12:16].strip() in ("N", "CA", "C", "CB"):
+                at.setdefault(int(ln[22:26]), {})[ln[12:16].strip()] = [float(ln[30:38]), float(ln[38:46]), float(ln[46:54])]
+        ids = sorted(at)
+        n, ca, c = (np.array([at[i][k] for i in ids]) for k in ("N", "CA", "C"))
+        b, cc = ca - n, c - ca
+        cb = -0.58273431 * np.cross(b, cc) + 0.56802827 * b - 0.54067466 * cc + ca      # virtual CB (utils.py:132-135)
+        for k, i in enumerate(ids):
+            if "CB" in at[i]:
+                cb[k] = at[i]["CB"]
+        return ca, cb
+
+    ca, cb = zip(*[backbone(p) for p in paths])
+    M = len(names)
+    tm, rm = np.zeros((M, M)), np.zeros((M, M))
+    for i, j in itertools.product(range(M), repeat=2):
+        if i == j:
+            continue
+        out = subprocess.run([exe, paths[i], paths[j]], stdout=subprocess.PIPE, universal_newlines=True).stdout
+        rm[i, j] = float(re.search(r"RMSD of  the common residues=\s+([\d.]+)", out).group(1))
+        tm[i, j] = float(re.search(r"TM-score    =\s+([\d.]+)", out).group(1))       # normalised by structure j
+    # GloCon of the same set, by the reference's own arithmetic (utils.py:543-567) on get_neighbors' dist maps
+    seq = "".join(l.strip() for l in open(f"{REF}/example/seq.fasta") if not l.startswith(">"))
+    L = len(seq)
+    glocon = np.zeros((M, M))
+    dmaps = []
+    for k in range(M):
+        d = np.linalg.norm(cb[k][:, None] - cb[k][None], axis=-1)
+        d[d > 20.0] = 0.0
+        np.fill_diagonal(d, 0.0)
+        dmaps.append(d)
+    for i, j in itertools.product(range(M), repeat=2):
+        if i <= j:
+            continue
+        diff = np.abs(dmaps[i] - dmaps[j])
+        diff[diff <= 3] = 0
+        glocon[i, j] = np.sum(np.triu(diff)) / (len(diff) * (len(diff) - 1) / 2)
+    glocon = glocon + glocon.T
+    np.savez_compressed(f"{HERE}/example_tmscore.npz", names=np.array(names), ca=np.stack(ca), cb=np.stack(cb),
+                        tm=tm, rmsd=rm, glocon=glocon)
+    print("TMscore golden written:", tm[2, 0], rm[2, 0])
+
+
 if __name__ == "__main__":
+    if "--tmscore-only" in sys.argv:
+        make_tmscore_golden()
+        sys.exit(0)
     if "--variants-only" in sys.argv:
         make_variant_golden()
         sys.exit(0)
     if "--dynamics-only" not in sys.argv:
         main()
         make_variant_golden()
+        make_tmscore_golden()
     make_dynamics_golden()

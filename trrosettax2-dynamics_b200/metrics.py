@@ -55,3 +55,47 @@ def tm_score(model, native, lnorm=None):
                 idx = new
         frag //= 2
     return best
+
+
+# ---- all pairs of a decoy set on the GPU (libtrx2dyn.so: csrc/metrics.cu) ---------------------
+
+def virtual_cb(n, ca, c):
+    """CB rebuilt from N, CA, C (utils_trX2dy/utils.py:132-135); arrays (..., 3)."""
+    b, cc = ca - n, c - ca
+    return -0.58273431 * np.cross(b, cc) + 0.56802827 * b - 0.54067466 * cc + ca
+
+
+def glocon_matrix(ctx, cb, dmax=20.0, thr=3.0):
+    """get_glocon_matrix (utils_trX2dy/utils.py:543-567) for M decoys at once: cb (M, L, 3) -> (M, M)."""
+    import ctypes as C
+    from . import capi
+    cb = np.ascontiguousarray(cb, dtype=np.float64)
+    M, L = cb.shape[:2]
+    out = np.zeros((M, M))
+    capi.check(capi.lib().trx_glocon_matrix(ctx._h, C.c_int(M), C.c_int(L), cb.ctypes.data_as(C.POINTER(C.c_double)),
+                                            C.c_double(dmax), C.c_double(thr), out.ctypes.data_as(C.POINTER(C.c_double))))
+    return out
+
+
+def tmscore_matrix(ctx, ca):
+    """get_tmscore_and_rmsd_matrix (utils_trX2dy/utils.py:514-540) without the per-pair subprocess:
+    ca (M, L, 3) -> (tm (M, M), rmsd (M, M)); tm[i, j] is normalised by L (all decoys share the sequence)."""
+    import ctypes as C
+    from . import capi
+    ca = np.ascontiguousarray(ca, dtype=np.float64)
+    M, L = ca.shape[:2]
+    tm, rm = np.zeros((M, M)), np.zeros((M, M))
+    P = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    capi.check(capi.lib().trx_tmscore_matrix(ctx._h, C.c_int(M), C.c_int(L), P(ca), P(tm), P(rm)))
+    return tm, rm
+
+
+def kmeans_clusters(matrix, names, n_clusters=10):
+    """kmeans_clustering (utils_trX2dy/utils.py:570-580): KMeans(n_clusters, n_init=10, random_state=0) on the
+    rows of a GloCon / TM / RMSD matrix; returns {label: [names]} in first-seen order like the reference."""
+    from sklearn.cluster import KMeans
+    labels = KMeans(n_clusters=n_clusters, n_init=10, random_state=0).fit(matrix).labels_
+    clusters = {}
+    for i, label in enumerate(labels):
+        clusters.setdefault(int(label), []).append(names[i])
+    return clusters
