@@ -55,8 +55,10 @@ struct FoldState {
     int seg_hi;              // first run after the segment in progress
     // vectors [G][ndof][32]
     float *x, *g, *d, *xt, *gt;
-    float *S, *Y;            // [G][m][ndof][32]
+    float *S, *Y;            // [G][ndof][m][32]
     float *gram;             // [G][2][M*M][32]: s_i.y_j and y_i.y_j of the stored pairs (M = padded history)
+    float *lbpart;           // [G][LB_MAXCH][5M+8][32] partial sums of the chunks of sweep A
+    float *lbcoef;           // [G][2M+3][32] coefficients of sweep B
     // per decoy [Npad]
     double *f, *fmem;        // accepted energy, last 3 accepted energies [3][Npad]
     float *alpha, *slope;
@@ -766,9 +768,8 @@ __global__ void held_xyz_kernel(FoldState s)
     for (int k = threadIdx.x; k < s.L * NAT3; k += blockDim.x) s.xnat[base + k] = s.xheld[base + k];
 }
 
-// K5: batched L-BFGS with non-monotone Armijo back-tracking, one CTA per decoy group
-// (lane = decoy, 8 warps split the torsion vector).  Consumes the evaluation of the trial
-// point (ft, gt) and produces the next trial point.
+// K5: batched L-BFGS with non-monotone Armijo back-tracking (lane = decoy).  Consumes the
+// evaluation of the trial point (ft, gt) and produces the next trial point.
 //
 // The two-loop recursion is done on Gram matrices: per decoy we keep SY[i][j] = s_i.y_j and
 // YY[i][j] = y_i.y_j of the stored pairs.  One streaming pass over the history computes every
@@ -776,16 +777,28 @@ __global__ void held_xyz_kernel(FoldState s)
 // 5 accumulators per slot, all loads independent), the m-dimensional recursion then runs on
 // scalars, and a second streaming pass forms d = c_g g + sum a_j s_j + sum b_j y_j and the
 // trial point.  2 bandwidth-bound sweeps instead of 4m latency-bound dependent ones.
+//
+// Three launches per round so that a decoy group is streamed by SEVERAL CTAs (one CTA per
+// group leaves most of the HBM bandwidth idle: a group's history is 4.6 MB per sweep in
+// torsion space, 23 MB in Cartesian space):
+//   lbfgs_dots_kernel    grid (G, nch): sweep A over a chunk of the vector -> partial sums
+//   lbfgs_step_kernel    grid  G      : sums the partials in chunk order (deterministic), step
+//                                       logic on scalars, coefficients of the new direction
+//   lbfgs_update_kernel  grid (G, nch): sweep B over the chunk
+// History layout [G][ndof][m][32]: the m slots of one vector element are contiguous, so a
+// sweep reads each group's history as one sequential stream.
 constexpr int LB_WARPS = 8;
 constexpr int LB_THREADS = LB_WARPS * 32;
 constexpr float LS_SIGMA = 0.1f;
 constexpr int LS_MAXBACK = 20;
 constexpr int LB_NSCAL = 8;   // ss, sy, yy, gg, s.g, y.g (+2 spare)
+constexpr int LB_MAXCH = 16;  // most chunks a group's vector is cut into
 
 template <int M>
 struct LbSmem {
     static constexpr int NRED = 5 * M + LB_NSCAL;
-    // phase A: per-warp partial sums; afterwards the same storage holds the Gram matrices
+    static constexpr int NCOEF = 2 * M + 3;   // coefS[M], coefY[M], cg, alpha, mode
+    // sweep A: per-warp partial sums; the step kernel keeps the Gram matrices in the same storage
     union {
         float red[LB_WARPS][NRED][LANES];
         float gram[2][M * M][LANES];
@@ -793,64 +806,66 @@ struct LbSmem {
     float sum[NRED][LANES];      // reduced sums: YG, YYn, YSn, SG, SYn (M each) then the scalars
     float coefS[M][LANES], coefY[M][LANES];
     float cg[LANES], alpha[LANES];
-    int mode[LANES];             // what pass B does for the lane: 0 nothing, 1 new direction, 2 x + alpha d, 3 xt = x
-    int slot[LANES];             // slot the new pair was written to (accepted steps)
+    int mode[LANES];             // what sweep B does for the lane: 0 nothing, 1 new direction, 2 x + alpha d, 3 xt = x
 };
 
-template <int M>
-__global__ void __launch_bounds__(LB_THREADS, 1) lbfgs_kernel(FoldState s)
+// What the evaluation just made means for decoy n: 0 none, 1 start run here (steepest descent),
+// 2 accepted step, 3 rejected step, 4 run skipped (clash check).  Pure function of the per-decoy
+// scalars, so the dots kernel and the step kernel agree on it.
+__device__ __forceinline__ int lb_action(const FoldState &s, int n, int status)
 {
-    extern __shared__ __align__(16) unsigned char lb_raw[];
-    LbSmem<M> &sm = *reinterpret_cast<LbSmem<M> *>(lb_raw);
-    constexpr int NRED = LbSmem<M>::NRED;
-    const int g = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = g * LANES + lane;
-    if (!s.gactive[g]) return;
-    const int nd = s.ndof, m = s.m, Npad = s.Npad;
-    const size_t vb = (size_t)g * nd * LANES + lane;
-    float *__restrict__ x = s.x + vb, *__restrict__ gv = s.g + vb, *__restrict__ d = s.d + vb;
-    float *__restrict__ xt = s.xt + vb;
-    const float *__restrict__ gt = s.gt + vb;
-    float *__restrict__ S = s.S + (size_t)g * m * nd * LANES + lane, *__restrict__ Y = s.Y + (size_t)g * m * nd * LANES + lane;
-    float *__restrict__ gram = s.gram + (size_t)g * 2 * M * M * LANES;
-
-    // ---- per-decoy decision (replicated in every warp)
-    int status = n < s.N ? s.status[n] : ST_DONE;
-    int run = s.run[n], hist = s.hist[n], head = s.head[n], iter = s.iter[n], bt = s.bt[n], restart = s.restart[n], nmem = s.nmem[n];
-    double f = s.f[n];
-    float alpha = s.alpha[n], slope = s.slope[n];
-    const double ft = s.ft[n];
-    const bool fin = isfinite(ft);
-    // action: 0 none, 1 start run here (steepest descent), 2 accepted step, 3 rejected step, 4 run skipped (clash check)
-    int action = 0;
+    const int Npad = s.Npad;
     if (status == ST_INIT) {
-        const Run &r = s.runs[run];
+        const Run &r = s.runs[s.run[n]];
         bool skip = false;
         if (r.clash_check) {   // a decoy holding Cartesian coordinates is judged on those
             const double *tv = s.held[n] ? s.theld : s.terms;
             skip = (float)(tv[(size_t)TRX_T_VDW * Npad + n] + tv[(size_t)TRX_T_RAMA * Npad + n]) < r.clash_thr;
         }
-        action = skip ? 4 : 1;
-    } else if (status == ST_LS) {
+        return skip ? 4 : 1;
+    }
+    if (status == ST_LS) {
+        const double ft = s.ft[n];
+        const int nmem = s.nmem[n];
         double fref = s.fmem[n];
         for (int q = 1; q < min(nmem, 3); ++q) fref = fmax(fref, s.fmem[(size_t)q * Npad + n]);
-        action = (fin && ft <= fref + (double)(LS_SIGMA * alpha * slope)) ? 2 : 3;
+        return (isfinite(ft) && ft <= fref + (double)(LS_SIGMA * s.alpha[n] * s.slope[n])) ? 2 : 3;
     }
+    return 0;
+}
+
+template <int M>
+__global__ void __launch_bounds__(LB_THREADS, 1) lbfgs_dots_kernel(FoldState s)
+{
+    extern __shared__ __align__(16) unsigned char lb_raw[];
+    LbSmem<M> &sm = *reinterpret_cast<LbSmem<M> *>(lb_raw);
+    constexpr int NRED = LbSmem<M>::NRED;
+    const int g = blockIdx.x, ch = blockIdx.y, nch = gridDim.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = g * LANES + lane;
+    if (!s.gactive[g]) return;
+    const int nd = s.ndof, m = s.m;
+    const int per = (nd + nch - 1) / nch, k0 = ch * per, k1 = min(nd, k0 + per);
+    const size_t vb = (size_t)g * nd * LANES + lane;
+    float *__restrict__ x = s.x + vb, *__restrict__ gv = s.g + vb;
+    const float *__restrict__ xt = s.xt + vb, *__restrict__ gt = s.gt + vb;
+    float *__restrict__ S = s.S + (size_t)g * m * nd * LANES + lane, *__restrict__ Y = s.Y + (size_t)g * m * nd * LANES + lane;
+    const int status = n < s.N ? s.status[n] : ST_DONE;
+    const int action = lb_action(s, n, status), head = s.head[n];
     const bool is_acc = action == 2, is_new = action == 1 || action == 2;
 
-    // ---- pass A: every dot product of the step in one sweep over the history
     float aYG[M], aYY[M], aYS[M], aSG[M], aSY[M], sc[LB_NSCAL];
 #pragma unroll
     for (int j = 0; j < M; ++j) { aYG[j] = 0.f; aYY[j] = 0.f; aYS[j] = 0.f; aSG[j] = 0.f; aSY[j] = 0.f; }
 #pragma unroll
     for (int j = 0; j < LB_NSCAL; ++j) sc[j] = 0.f;
-    for (int k = warp; k < nd; k += LB_WARPS) {
+    for (int k = k0 + warp; k < k1; k += LB_WARPS) {
         const float xk = x[(size_t)k * LANES], xtk = xt[(size_t)k * LANES], gk = gv[(size_t)k * LANES], gtk = gt[(size_t)k * LANES];
         const float sn = xtk - xk, yn = gtk - gk, gn = is_new ? gtk : gk;
         float yj[M], sj[M];
 #pragma unroll
         for (int j = 0; j < M; ++j) {
-            yj[j] = j < m ? Y[((size_t)j * nd + k) * LANES] : 0.f;
-            sj[j] = j < m ? S[((size_t)j * nd + k) * LANES] : 0.f;
+            yj[j] = j < m ? Y[((size_t)k * m + j) * LANES] : 0.f;
+            sj[j] = j < m ? S[((size_t)k * m + j) * LANES] : 0.f;
         }
 #pragma unroll
         for (int j = 0; j < M; ++j) {
@@ -859,8 +874,8 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lbfgs_kernel(FoldState s)
         }
         sc[0] += sn * sn; sc[1] += sn * yn; sc[2] += yn * yn; sc[3] += gn * gn; sc[4] += sn * gn; sc[5] += yn * gn;
         if (is_acc) {
-            S[((size_t)head * nd + k) * LANES] = sn;
-            Y[((size_t)head * nd + k) * LANES] = yn;
+            S[((size_t)k * m + head) * LANES] = sn;
+            Y[((size_t)k * m + head) * LANES] = yn;
         }
         if (is_new) {
             x[(size_t)k * LANES] = xtk;
@@ -875,17 +890,46 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lbfgs_kernel(FoldState s)
 #pragma unroll
     for (int j = 0; j < LB_NSCAL; ++j) sm.u.red[warp][5 * M + j][lane] = sc[j];
     __syncthreads();
+    float *__restrict__ part = s.lbpart + ((size_t)g * LB_MAXCH + ch) * NRED * LANES;
     for (int e = threadIdx.x; e < NRED * LANES; e += LB_THREADS) {
         const int idx = e / LANES, l = e % LANES;
         float t = 0.f;
 #pragma unroll
         for (int w = 0; w < LB_WARPS; ++w) t += sm.u.red[w][idx][l];
-        sm.sum[idx][l] = t;
+        part[e] = t;
     }
-    __syncthreads();
-    // Gram matrices into shared memory (the partial sums are no longer needed)
+}
+
+template <int M>
+__global__ void __launch_bounds__(LB_THREADS, 1) lbfgs_step_kernel(FoldState s, int nch)
+{
+    extern __shared__ __align__(16) unsigned char lb_raw[];
+    LbSmem<M> &sm = *reinterpret_cast<LbSmem<M> *>(lb_raw);
+    constexpr int NRED = LbSmem<M>::NRED;
+    const int g = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = g * LANES + lane;
+    if (!s.gactive[g]) return;
+    const int m = s.m, Npad = s.Npad;
+    float *__restrict__ gram = s.gram + (size_t)g * 2 * M * M * LANES;
+    {   // partial sums of the chunks, in chunk order
+        const float *__restrict__ part = s.lbpart + (size_t)g * LB_MAXCH * NRED * LANES;
+        for (int e = threadIdx.x; e < NRED * LANES; e += LB_THREADS) {
+            float t = 0.f;
+            for (int c = 0; c < nch; ++c) t += part[(size_t)c * NRED * LANES + e];
+            (&sm.sum[0][0])[e] = t;
+        }
+    }
+    // Gram matrices into shared memory
     for (int e = threadIdx.x; e < 2 * M * M * LANES; e += LB_THREADS) (&sm.u.gram[0][0][0])[e] = gram[e];
     __syncthreads();
+
+    // ---- per-decoy decision
+    int status = n < s.N ? s.status[n] : ST_DONE;
+    int run = s.run[n], hist = s.hist[n], head = s.head[n], iter = s.iter[n], bt = s.bt[n], restart = s.restart[n], nmem = s.nmem[n];
+    double f = s.f[n];
+    float alpha = s.alpha[n], slope = s.slope[n];
+    const double ft = s.ft[n];
+    const bool fin = isfinite(ft);
+    const int action = lb_action(s, n, status);
 
     // ---- per-decoy step logic on scalars (warp 0, one lane per decoy)
     if (warp == 0) {
@@ -1034,25 +1078,48 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lbfgs_kernel(FoldState s)
         }
     }
     __syncthreads();
-    // Gram matrices back to global memory
+    // Gram matrices back to global memory; coefficients of sweep B
     for (int e = threadIdx.x; e < 2 * M * M * LANES; e += LB_THREADS) gram[e] = (&sm.u.gram[0][0][0])[e];
+    float *__restrict__ coef = s.lbcoef + (size_t)g * LbSmem<M>::NCOEF * LANES;
+    for (int e = threadIdx.x; e < M * LANES; e += LB_THREADS) {
+        coef[e] = (&sm.coefS[0][0])[e];
+        coef[M * LANES + e] = (&sm.coefY[0][0])[e];
+    }
+    if (warp == 0) {
+        coef[(2 * M) * LANES + lane] = sm.cg[lane];
+        coef[(2 * M + 1) * LANES + lane] = sm.alpha[lane];
+        coef[(2 * M + 2) * LANES + lane] = __int_as_float(sm.mode[lane]);
+    }
+}
 
-    // ---- pass B: new direction and next trial point
-    const int mode = sm.mode[lane];
-    const float cgv = sm.cg[lane], al = sm.alpha[lane];
+template <int M>
+__global__ void __launch_bounds__(LB_THREADS, 1) lbfgs_update_kernel(FoldState s)
+{
+    const int g = blockIdx.x, ch = blockIdx.y, nch = gridDim.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (!s.gactive[g]) return;
+    const int nd = s.ndof, m = s.m;
+    const int per = (nd + nch - 1) / nch, k0 = ch * per, k1 = min(nd, k0 + per);
+    const size_t vb = (size_t)g * nd * LANES + lane;
+    const float *__restrict__ x = s.x + vb, *__restrict__ gv = s.g + vb;
+    float *__restrict__ d = s.d + vb, *__restrict__ xt = s.xt + vb;
+    const float *__restrict__ S = s.S + (size_t)g * m * nd * LANES + lane, *__restrict__ Y = s.Y + (size_t)g * m * nd * LANES + lane;
+    const float *__restrict__ coef = s.lbcoef + (size_t)g * LbSmem<M>::NCOEF * LANES + lane;
+    const int mode = __float_as_int(coef[(2 * M + 2) * LANES]);
+    const float cgv = coef[(2 * M) * LANES], al = coef[(2 * M + 1) * LANES];
     float cS[M], cY[M];
 #pragma unroll
-    for (int j = 0; j < M; ++j) { cS[j] = sm.coefS[j][lane]; cY[j] = sm.coefY[j][lane]; }
+    for (int j = 0; j < M; ++j) { cS[j] = coef[j * LANES]; cY[j] = coef[(M + j) * LANES]; }
     const int anydir = __syncthreads_or(mode == 1);
-    for (int k = warp; k < nd; k += LB_WARPS) {
+    for (int k = k0 + warp; k < k1; k += LB_WARPS) {
         const float xk = x[(size_t)k * LANES];
         if (anydir) {
             float dk = cgv * gv[(size_t)k * LANES];
             float yj[M], sj[M];
 #pragma unroll
             for (int j = 0; j < M; ++j) {
-                yj[j] = j < m ? Y[((size_t)j * nd + k) * LANES] : 0.f;
-                sj[j] = j < m ? S[((size_t)j * nd + k) * LANES] : 0.f;
+                yj[j] = j < m ? Y[((size_t)k * m + j) * LANES] : 0.f;
+                sj[j] = j < m ? S[((size_t)k * m + j) * LANES] : 0.f;
             }
 #pragma unroll
             for (int j = 0; j < M; ++j) dk += cS[j] * sj[j] + cY[j] * yj[j];
@@ -1323,6 +1390,7 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     size_t o_x = carve(vec), o_g = carve(vec), o_d = carve(vec), o_xt = carve(vec), o_gt = carve(vec);
     const int lbM = lbfgs_m <= 8 ? 8 : (lbfgs_m <= 16 ? 16 : 24);
     size_t o_S = carve(vec * s.m), o_Y = carve(vec * s.m), o_rho = carve((size_t)G * 2 * lbM * lbM * LANES * sizeof(float));
+    size_t o_lbp = carve((size_t)G * 16 * (5 * lbM + 8) * LANES * sizeof(float)), o_lbc = carve((size_t)G * (2 * lbM + 3) * LANES * sizeof(float));
     size_t o_f = carve(np * 8), o_al = carve(np * 4), o_sl = carve(np * 4), o_fm = carve(np * 24);
     size_t o_i[10];
     for (int k = 0; k < 10; ++k) o_i[k] = carve(np * 4);
@@ -1344,6 +1412,7 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     char *A = (char *)b->arena;
     s.x = (float *)(A + o_x); s.g = (float *)(A + o_g); s.d = (float *)(A + o_d); s.xt = (float *)(A + o_xt); s.gt = (float *)(A + o_gt);
     s.S = (float *)(A + o_S); s.Y = (float *)(A + o_Y); s.gram = (float *)(A + o_rho); s.lb_M = lbM;
+    s.lbpart = (float *)(A + o_lbp); s.lbcoef = (float *)(A + o_lbc);
     s.f = (double *)(A + o_f); s.alpha = (float *)(A + o_al); s.slope = (float *)(A + o_sl); s.fmem = (double *)(A + o_fm);
     s.nmem = (int *)(A + o_i[0]); s.hist = (int *)(A + o_i[1]); s.head = (int *)(A + o_i[2]); s.iter = (int *)(A + o_i[3]);
     s.run = (int *)(A + o_i[4]); s.bt = (int *)(A + o_i[5]); s.status = (int *)(A + o_i[6]); s.restart = (int *)(A + o_i[7]);
@@ -1370,9 +1439,18 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     s.runs = b->d_runs;
     upload_model();
     TRX_CUDA(cudaFuncSetAttribute(vdw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->vdw_smem));
-    if (lbM == 8) { b->lb_smem = sizeof(LbSmem<8>); TRX_CUDA(cudaFuncSetAttribute(lbfgs_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->lb_smem)); }
-    else if (lbM == 16) { b->lb_smem = sizeof(LbSmem<16>); TRX_CUDA(cudaFuncSetAttribute(lbfgs_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->lb_smem)); }
-    else { b->lb_smem = sizeof(LbSmem<24>); TRX_CUDA(cudaFuncSetAttribute(lbfgs_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->lb_smem)); }
+    static_assert(LB_MAXCH == 16, "lbpart is carved for 16 chunks");
+    auto lb_attr = [&](auto dots, auto step, size_t bytes) -> int {
+        b->lb_smem = bytes;
+        TRX_CUDA(cudaFuncSetAttribute(dots, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        TRX_CUDA(cudaFuncSetAttribute(step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        return TRX_OK;
+    };
+    int rc_attr;
+    if (lbM == 8) rc_attr = lb_attr(lbfgs_dots_kernel<8>, lbfgs_step_kernel<8>, sizeof(LbSmem<8>));
+    else if (lbM == 16) rc_attr = lb_attr(lbfgs_dots_kernel<16>, lbfgs_step_kernel<16>, sizeof(LbSmem<16>));
+    else rc_attr = lb_attr(lbfgs_dots_kernel<24>, lbfgs_step_kernel<24>, sizeof(LbSmem<24>));
+    if (rc_attr) return rc_attr;
     *out = b;
     return TRX_OK;
 }
@@ -1435,9 +1513,25 @@ static int run_rounds(trx_fold_batch *b, int max_rounds, int check_every, int *r
             ctx->time_end("activity");
             if ((rc = fold_eval(b, ng.data(), false))) { cudaFreeHost(h_nslot); return rc; }
             ctx->time_begin("lbfgs");
-            if (s.lb_M == 8) lbfgs_kernel<8><<<s.G, LB_THREADS, b->lb_smem, ctx->stream>>>(s);
-            else if (s.lb_M == 16) lbfgs_kernel<16><<<s.G, LB_THREADS, b->lb_smem, ctx->stream>>>(s);
-            else lbfgs_kernel<24><<<s.G, LB_THREADS, b->lb_smem, ctx->stream>>>(s);
+            {   // enough CTAs for ~3 per SM, at least 4 vector elements per warp and chunk
+                int nch = std::max(1, (3 * 148 + s.G - 1) / s.G);
+                nch = std::min(nch, std::min(LB_MAXCH, std::max(1, s.ndof / (4 * LB_WARPS))));
+                const dim3 grid(s.G, nch);
+                if (s.lb_M == 8) {
+                    lbfgs_dots_kernel<8><<<grid, LB_THREADS, b->lb_smem, ctx->stream>>>(s);
+                    lbfgs_step_kernel<8><<<s.G, LB_THREADS, b->lb_smem, ctx->stream>>>(s, nch);
+                    lbfgs_update_kernel<8><<<grid, LB_THREADS, 0, ctx->stream>>>(s);
+                } else if (s.lb_M == 16) {
+                    lbfgs_dots_kernel<16><<<grid, LB_THREADS, b->lb_smem, ctx->stream>>>(s);
+                    lbfgs_step_kernel<16><<<s.G, LB_THREADS, b->lb_smem, ctx->stream>>>(s, nch);
+                    lbfgs_update_kernel<16><<<grid, LB_THREADS, 0, ctx->stream>>>(s);
+                } else {
+                    lbfgs_dots_kernel<24><<<grid, LB_THREADS, b->lb_smem, ctx->stream>>>(s);
+                    lbfgs_step_kernel<24><<<s.G, LB_THREADS, b->lb_smem, ctx->stream>>>(s, nch);
+                    lbfgs_update_kernel<24><<<grid, LB_THREADS, 0, ctx->stream>>>(s);
+                }
+                ctx->launches += 2;
+            }
             ctx->time_end("lbfgs");
         }
         TRX_CUDA(cudaMemcpyAsync(h_nslot, s.nslot, 16 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
