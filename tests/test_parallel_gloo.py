@@ -66,3 +66,27 @@ def test_single_rank_is_identity():
     np.testing.assert_array_equal(parallel.gather_scalars(x, 6, 0, 1), x)
     assert parallel.shard_counts(10, 4) == [3, 3, 2, 2]
     assert parallel.select_pool([3.0, 1.0, 1.0, 2.0], 3).tolist() == [1, 2, 3]
+
+
+def test_batch_mode_assignment_is_a_balanced_partition():
+    """BASELINE config 5: 64 targets L in [100, 500], 100 decoys each, on 8 ranks."""
+    sys.path.insert(0, ROOT)
+    import trx2dyn  # noqa: F401
+    from trx2dyn import parallel
+    rng = np.random.default_rng(5)
+    lengths = rng.integers(100, 501, size=64)
+    n_dec = [100] * 64
+    plan = parallel.assign_blocks(lengths, n_dec, 8)
+    seen = np.zeros((64, 100), dtype=int)
+    load = []
+    for r in range(8):
+        cost = 0.0
+        for t, d0, cnt in plan[r]:
+            seen[t, d0:d0 + cnt] += 1
+            cost += float(lengths[t]) ** 2 * cnt
+        load.append(cost)
+    assert np.all(seen == 1)                                          # every decoy of every target exactly once
+    assert max(load) / (sum(load) / 8) < 1.02                         # within 2 % of perfect balance
+    assert plan == parallel.assign_blocks(lengths, n_dec, 8)          # deterministic: ranks agree without talking
+    one = parallel.assign_blocks([50], [7], 4)
+    assert one[0] == [(0, 0, 7)] and one[1:] == [[], [], []]

@@ -49,3 +49,34 @@ def select_pool(scores, k, lower_is_better=True):
     key = scores if lower_is_better else -scores
     order = np.lexsort((np.arange(len(key)), key))
     return order[:k]
+
+
+def assign_blocks(lengths, n_decoys, world, block=32):
+    """Batch mode (name_lst; BASELINE config 5): targets of different length, `n_decoys[t]` decoys each.
+    The unit of work is a (target, decoy block) pair -- a block is up to `block` decoys, one warp-wide
+    decoy group on the device -- with estimated cost ~ L^2 x decoys (restraint evaluations dominate).
+    Blocks are dealt longest-first to the least loaded rank (ties: lowest rank), so every rank derives the
+    same assignment without communication.  Returns per rank a list of (target, first decoy, count)."""
+    items = []
+    for t, (L, n) in enumerate(zip(lengths, n_decoys)):
+        for d0 in range(0, int(n), block):
+            cnt = min(block, int(n) - d0)
+            items.append((float(L) * float(L) * cnt, t, d0, cnt))
+    items.sort(key=lambda it: (-it[0], it[1], it[2]))
+    load = [0.0] * world
+    out = [[] for _ in range(world)]
+    for cost, t, d0, cnt in items:
+        r = min(range(world), key=lambda k: (load[k], k))
+        load[r] += cost
+        out[r].append((t, d0, cnt))
+    merged = []
+    for r in range(world):   # contiguous blocks of one target become one fold call
+        blocks = sorted(out[r])
+        m = []
+        for t, d0, cnt in blocks:
+            if m and m[-1][0] == t and m[-1][1] + m[-1][2] == d0:
+                m[-1] = (t, m[-1][1], m[-1][2] + cnt)
+            else:
+                m.append((t, d0, cnt))
+        merged.append(m)
+    return merged
