@@ -68,6 +68,14 @@ static const double TRX_RAMA[2][TRX_RAMA_NB][5] = {
     {{-65.0, -35.0, 20.0, 9.0, 0.40}, {-65.0, 145.0, 20.0, 8.0, 0.55}, {-85.0, 70.0, 12.0, 6.0, 0.05},
      {-65.0, -35.0, 20.0, 9.0, 0.0}, {-65.0, -35.0, 20.0, 9.0, 0.0}}};
 #define TRX_RAMA_FLOOR 1e-4
+/* Rosetta's rama energy of a residue is -ln P(bin) MINUS the entropy of the map (Ramachandran.cc:
+ * ram_energ = -log(prob) + sum P log P), i.e. negative in favourable regions and zero on average
+ * over the map.  The same normalisation for the mixture above, over 10 x 10 degree bins:
+ * E = -ln P(phi,psi) - TRX_RAMA_OFFSET[class], offset = ln(bin area / integral of P) + entropy
+ * (2.125 general, 1.956 proline; minimum of E = -1.34 at the helix centre).  A constant: it moves
+ * no gradient, but it is what lets remove_clash's test rama + vdw < 10 (utils_ros.py:699-703) pass
+ * for a clash-free chain, as it does in the reference. */
+static const double TRX_RAMA_OFFSET[2] = {2.125029287790165, 1.956450144676099};
 /* omega tether: 0.01 * (deviation from 180 in degrees)^2 */
 #define TRX_OMEGA_K 0.01
 

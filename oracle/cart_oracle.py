@@ -29,6 +29,8 @@ def _consts():
     rama = re.search(r"TRX_RAMA\[2\]\[TRX_RAMA_NB\]\[5\] = \{(.*?)\};", src, flags=re.S).group(1)
     nums = [float(x) for x in re.findall(r"-?\d+\.\d+", rama)]
     env["RAMA"] = np.array(nums).reshape(2, 5, 5)
+    off = re.search(r"TRX_RAMA_OFFSET\[2\] = \{(.*?)\};", src, flags=re.S).group(1)
+    env["RAMA_OFFSET"] = np.array([float(x) for x in off.split(",")])
     return env
 
 
@@ -80,7 +82,8 @@ def cart_terms(xyz, aa):
     dphi = phi[:, None] - R[:, :, 0] * K["TRX_DEG"]
     dpsi = psi[:, None] - R[:, :, 1] * K["TRX_DEG"]
     P = K["TRX_RAMA_FLOOR"] + (R[:, :, 4] * torch.exp(R[:, :, 2] * (torch.cos(dphi) - 1) + R[:, :, 3] * (torch.cos(dpsi) - 1))).sum(-1)
-    e_rama = (-torch.log(P)).sum()
+    off = torch.as_tensor(K["RAMA_OFFSET"])[cls]
+    e_rama = (-torch.log(P) - off).sum()
     return {"cart": e, "rama": e_rama, "omega": e_omega}
 
 

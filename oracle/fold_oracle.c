@@ -144,7 +144,7 @@ void trxo_rama_omega(int L, const int *aa, const double *tors, double w_rama, do
                 dP_dphi += -e * b[2] * sin(dphi);
                 dP_dpsi += -e * b[3] * sin(dpsi);
             }
-            *E_rama += -log(P);
+            *E_rama += -log(P) - TRX_RAMA_OFFSET[cls];
             if (gtors) { gtors[(size_t)i * 3 + 0] += -w_rama * dP_dphi / P; gtors[(size_t)i * 3 + 1] += -w_rama * dP_dpsi / P; }
         }
         if (i < L - 1) {
@@ -359,7 +359,7 @@ void trxo_cart_terms(int L, const int *aa, const double *xyz, double w_cart, dou
                 dP_dphi += -e * b[2] * sin(dphi);
                 dP_dpsi += -e * b[3] * sin(dpsi);
             }
-            er += -log(P);
+            er += -log(P) - TRX_RAMA_OFFSET[cls];
             if (grad) {
                 add_dihedral_grad(Cp, N, CA, Cc, -w_rama * dP_dphi / P, GRD(i - 1, TRX_AT_C), gN, gCA, gC);
                 add_dihedral_grad(N, CA, Cc, N1, -w_rama * dP_dpsi / P, gN, gCA, gC, GRD(i + 1, TRX_AT_N));

@@ -42,6 +42,7 @@ struct Run {
 struct Model {   // centroid model constants in device-friendly (float) form
     float cen_s[20], r_cen[20], r_bb[5];
     float rama[2][TRX_RAMA_NB][5];
+    float rama_off[2];
 };
 __constant__ Model c_model;
 
@@ -422,7 +423,7 @@ __global__ void __launch_bounds__(SEG_THREADS) torsion_grad_kernel(FoldState s)
                 dPphi -= e * b[2] * s1;
                 dPpsi -= e * b[3] * s2;
             }
-            e_rama += (double)(-logf(P));
+            e_rama += (double)(-logf(P) - c_model.rama_off[cls]);
             gphi -= w_rama * dPphi / P;
             gpsi -= w_rama * dPpsi / P;
         }
@@ -658,7 +659,7 @@ __global__ void __launch_bounds__(SEG_THREADS) cart_grad_kernel(FoldState s)
                         dPphi -= e * b[2] * s1;
                         dPpsi -= e * b[3] * s2;
                     }
-                    er = -logf(P);
+                    er = -logf(P) - c_model.rama_off[cls];
                     const float fphi = -w_rama * dPphi / P, fpsi = -w_rama * dPpsi / P;
                     axpy(gp[TRX_AT_C], fphi, a1); axpy(gc[TRX_AT_N], fphi, a2); axpy(gc[TRX_AT_CA], fphi, a3); axpy(gc[TRX_AT_C], fphi, a4);
                     axpy(gc[TRX_AT_N], fpsi, b1); axpy(gc[TRX_AT_CA], fpsi, b2); axpy(gc[TRX_AT_C], fpsi, b3); axpy(gx[0], fpsi, b4);
@@ -1302,6 +1303,7 @@ static void upload_model()
     for (int k = 0; k < 20; ++k) { mdl.cen_s[k] = (float)TRX_CEN_S[k]; mdl.r_cen[k] = (float)TRX_R_CEN[k]; }
     for (int k = 0; k < 5; ++k) mdl.r_bb[k] = (float)TRX_R_BB[k];
     for (int c = 0; c < 2; ++c) for (int k = 0; k < TRX_RAMA_NB; ++k) for (int j = 0; j < 5; ++j) mdl.rama[c][k][j] = (float)TRX_RAMA[c][k][j];
+    mdl.rama_off[0] = (float)TRX_RAMA_OFFSET[0]; mdl.rama_off[1] = (float)TRX_RAMA_OFFSET[1];
     cudaMemcpyToSymbol(c_model, &mdl, sizeof(mdl));
     done[dev] = true;
 }
