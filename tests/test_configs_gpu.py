@@ -76,3 +76,28 @@ def test_config4_batch_of_targets(ctx):
         assert out["xyz"].shape == (32, L, 5, 3) and np.all(np.isfinite(out["terms"]))
         tm = np.array([metrics.tm_score(c, nat[:, 1]) for c in out["xyz"][:8, :, 1].astype(np.float64)])
         assert tm.max() > 0.5
+
+
+def test_config5_batch_mode_is_sharding_invariant(ctx, tmp_path):
+    """name_lst batch mode, target-and-decoy sharded: the union of what 2 ranks fold equals what 1 rank folds,
+    bit for bit, and every (target, decoy) is folded exactly once."""
+    from trx2dyn import pipeline, pdbio
+    targets = []
+    for name, Ls, seed in (("t0", 48, 2000), ("t1", 77, 2001), ("t2", 33, 2002)):
+        seq, npzs, nat = synth.target(Ls, seed=seed, two_model=(name == "t1"))
+        targets.append((name, seq, npzs))
+    n_dec = [40, 70, 33]
+    one = pipeline.fold_batch(ctx, targets, n_dec, 0, 1, seed=5, out_dir=str(tmp_path))
+    assert sorted(one) == [(t, d) for t in range(3) for d in range(n_dec[t])]
+    two = {}
+    for r in range(2):
+        part = pipeline.fold_batch(ctx, targets, n_dec, r, 2, seed=5)
+        assert not set(part) & set(two)
+        two.update(part)
+    assert sorted(two) == sorted(one)
+    for key in one:
+        np.testing.assert_array_equal(one[key]["tors"], two[key]["tors"])
+        np.testing.assert_array_equal(one[key]["xyz"], two[key]["xyz"])
+    assert {one[(1, d)]["model"] for d in range(70)} == {0, 1}          # two-model target: both models used
+    s2, at = pdbio.read_backbone(str(tmp_path / "t2" / "initial32.pdb"))
+    assert s2 == targets[2][1]

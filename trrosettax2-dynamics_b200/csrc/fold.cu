@@ -28,6 +28,24 @@
 namespace trx {
 
 constexpr int NAT3 = TRX_NAT * 3;  // 15 values per residue
+constexpr int NATP = 16;           // ... padded to 64 B in the natural-layout copies (xnat, gnat): a decoy's residue is four float4
+
+// 15 values of one residue of one decoy <-> the padded natural layout, as four 16 B accesses
+__device__ __forceinline__ void nat_store(float *__restrict__ p, const float *v)
+{
+    float4 *q = reinterpret_cast<float4 *>(p);
+    q[0] = make_float4(v[0], v[1], v[2], v[3]);
+    q[1] = make_float4(v[4], v[5], v[6], v[7]);
+    q[2] = make_float4(v[8], v[9], v[10], v[11]);
+    q[3] = make_float4(v[12], v[13], v[14], 0.f);
+}
+__device__ __forceinline__ void nat_load(const float *__restrict__ p, float *v)
+{
+    const float4 *q = reinterpret_cast<const float4 *>(p);
+    const float4 a = q[0], b = q[1], c = q[2], d = q[3];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w; v[12] = d.x; v[13] = d.y; v[14] = d.z;
+}
 
 struct Run {
     float w[TRX_NTERM];
@@ -71,7 +89,7 @@ struct FoldState {
     float *wl;               // [TRX_NTERM][Npad] weights in force per decoy
     // geometry
     float *X;                // [G][Lpad][15][32]
-    float *xnat, *gnat;      // [Npad][L][15]
+    float *xnat, *gnat;      // [Npad][L][16] (15 values + pad)
     float *gk1;              // [G][Lpad][9][32]
     double *E3;              // [3][Npad]
     double *Evdw;            // [Npad]
@@ -140,7 +158,7 @@ __global__ void __launch_bounds__(SEG_THREADS) nerf_kernel(FoldState s)
     const int dn = live ? dec : 0;      // empty slots replay decoy 0's torsions: finite, ignored
     const float *__restrict__ t = s.xt + (size_t)(dn / LANES) * s.ndof * LANES + dn % LANES;
     float *__restrict__ X = s.X + (size_t)g * s.Lpad * NAT3 * LANES + lane;
-    float *__restrict__ xn = s.xnat + (size_t)n * s.L * NAT3;
+    float *__restrict__ xn = s.xnat + (size_t)n * s.L * NATP;
     if (warp == 0) {
 #pragma unroll
         for (int k = 0; k < TRX_NTERM; ++k) s.wslot[(size_t)k * s.Npad + n] = live ? s.wl[(size_t)k * s.Npad + dec] : 0.f;
@@ -217,11 +235,11 @@ __global__ void __launch_bounds__(SEG_THREADS) nerf_kernel(FoldState s)
             v[a * 3 + 1] = R[3] * x + R[4] * y + R[5] * z + T[1];
             v[a * 3 + 2] = R[6] * x + R[7] * y + R[8] * z + T[2];
         }
+        if (warp > 0) {
 #pragma unroll
-        for (int k = 0; k < NAT3; ++k) {
-            if (warp > 0) X[((size_t)i * NAT3 + k) * LANES] = v[k];
-            if (live) xn[(size_t)i * NAT3 + k] = v[k];
+            for (int k = 0; k < NAT3; ++k) X[((size_t)i * NAT3 + k) * LANES] = v[k];
         }
+        if (live) nat_store(xn + (size_t)i * NATP, v);
     }
 }
 
@@ -243,12 +261,11 @@ __global__ void __launch_bounds__(VDW_THREADS) vdw_kernel(FoldState s)
     int *acc = reinterpret_cast<int *>(smem_raw + sizeof(float4) * 6 * L);               // [L][6][3]
     float4 *bsph = reinterpret_cast<float4 *>(smem_raw + sizeof(float4) * 6 * L + ((sizeof(int) * 18 * L + 15) / 16) * 16);   // [L] bounding spheres
     __shared__ double ered[VDW_THREADS / 32];
-    const float *__restrict__ xn = s.xnat + (size_t)n * L * NAT3;
+    const float *__restrict__ xn = s.xnat + (size_t)n * L * NATP;
     for (int i = threadIdx.x; i < L; i += VDW_THREADS) {
         const int aa = s.aa[i];
         float v[NAT3];
-#pragma unroll
-        for (int k = 0; k < NAT3; ++k) v[k] = xn[(size_t)i * NAT3 + k];
+        nat_load(xn + (size_t)i * NATP, v);
 #pragma unroll
         for (int a = 0; a < 5; ++a) at[i * 6 + a] = make_float4(v[a * 3], v[a * 3 + 1], v[a * 3 + 2], c_model.r_bb[a]);
         const float cs = c_model.cen_s[aa];
@@ -275,21 +292,33 @@ __global__ void __launch_bounds__(VDW_THREADS) vdw_kernel(FoldState s)
     // per-warp queue of close residue pairs
     __shared__ int queue[VDW_THREADS / 32][64];
     int qn = 0;
+    // lane -> (queued pair q = lane / 6, atom a = lane % 6 of residue i), fixed for the whole kernel; a pass
+    // takes 5 queued residue pairs (30 lanes) and every lane tests its atom against the 6 atoms of residue j
+    // (broadcast reads): 180 atom pairs per pass with no index arithmetic in the loop
+    const int fq = lane / 6, fa = lane - 6 * fq;
     auto flush = [&](int count) {
-        for (int item = lane; item < count * 36; item += 32) {
-            const int pr = queue[warp][item / 36], ab = item % 36;
-            const int i = pr >> 16, j = pr & 0xffff, a = ab / 6, b = ab % 6;
-            const float4 pa = at[i * 6 + a], pb = at[j * 6 + b];
-            const float dx = pa.x - pb.x, dy = pa.y - pb.y, dz = pa.z - pb.z;
-            const float r = pa.w + pb.w, r2 = r * r, d2 = dx * dx + dy * dy + dz * dz;
-            if (d2 < r2) {
-                const float c = r2 - d2, ir2 = 1.0f / r2;
-                e_thread += (double)((float)TRX_VDW_SCALE * c * c * ir2);
-                const float f = -4.0f * (float)TRX_VDW_SCALE * c * ir2;
-                const int gx = __float2int_rn(f * dx * VDW_FIX), gy = __float2int_rn(f * dy * VDW_FIX), gz = __float2int_rn(f * dz * VDW_FIX);
-                int *pi = acc + (i * 6 + a) * 3, *pj = acc + (j * 6 + b) * 3;
-                atomicAdd(pi + 0, gx); atomicAdd(pi + 1, gy); atomicAdd(pi + 2, gz);
-                atomicAdd(pj + 0, -gx); atomicAdd(pj + 1, -gy); atomicAdd(pj + 2, -gz);
+        for (int base = 0; base < count; base += 5) {
+            const int q = base + fq;
+            if (fq < 5 && q < count) {
+                const int pr = queue[warp][q];
+                const int i = pr >> 16, j = pr & 0xffff;
+                const float4 pa = at[i * 6 + fa];
+                int *pi = acc + (i * 6 + fa) * 3;
+#pragma unroll
+                for (int b = 0; b < 6; ++b) {
+                    const float4 pb = at[j * 6 + b];
+                    const float dx = pa.x - pb.x, dy = pa.y - pb.y, dz = pa.z - pb.z;
+                    const float r = pa.w + pb.w, r2 = r * r, d2 = dx * dx + dy * dy + dz * dz;
+                    if (d2 < r2) {
+                        const float c = r2 - d2, ir2 = 1.0f / r2;
+                        e_thread += (double)((float)TRX_VDW_SCALE * c * c * ir2);
+                        const float f = -4.0f * (float)TRX_VDW_SCALE * c * ir2;
+                        const int gx = __float2int_rn(f * dx * VDW_FIX), gy = __float2int_rn(f * dy * VDW_FIX), gz = __float2int_rn(f * dz * VDW_FIX);
+                        int *pj = acc + (j * 6 + b) * 3;
+                        atomicAdd(pi + 0, gx); atomicAdd(pi + 1, gy); atomicAdd(pi + 2, gz);
+                        atomicAdd(pj + 0, -gx); atomicAdd(pj + 1, -gy); atomicAdd(pj + 2, -gz);
+                    }
+                }
             }
         }
     };
@@ -309,14 +338,13 @@ __global__ void __launch_bounds__(VDW_THREADS) vdw_kernel(FoldState s)
                 if (close) queue[warp][pos] = (i << 16) | j;
                 qn += __popc(m);
                 __syncwarp();
-                if (qn >= 32) {   // 32 pairs = 1152 atom pairs = 36 full warp passes
-                    flush(32);
+                if (qn >= 30) {   // 30 pairs = 6 full passes of 5 pairs
+                    flush(30);
                     __syncwarp();
-                    const int rest = qn - 32;
-                    if (lane < rest) {
-                        const int v = queue[warp][32 + lane];
-                        queue[warp][lane] = v;
-                    }
+                    const int rest = qn - 30;   // < 32: at most 31 queued before this scan step
+                    const int v = lane < rest ? queue[warp][30 + lane] : 0;
+                    __syncwarp();
+                    if (lane < rest) queue[warp][lane] = v;
                     qn = rest;
                     __syncwarp();
                 }
@@ -335,7 +363,7 @@ __global__ void __launch_bounds__(VDW_THREADS) vdw_kernel(FoldState s)
     }
     // gradient out (weighted), CEN folded into CA and CB
     const float w = s.wslot[(size_t)TRX_T_VDW * s.Npad + n];
-    float *__restrict__ gn = s.gnat + (size_t)n * L * NAT3;
+    float *__restrict__ gn = s.gnat + (size_t)n * L * NATP;
     for (int i = threadIdx.x; i < L; i += VDW_THREADS) {
         const float cs = c_model.cen_s[s.aa[i]];
         float gv[18];
@@ -346,8 +374,7 @@ __global__ void __launch_bounds__(VDW_THREADS) vdw_kernel(FoldState s)
             gv[TRX_AT_CA * 3 + k] += (1.0f - cs) * gv[15 + k];
             gv[TRX_AT_CB * 3 + k] += cs * gv[15 + k];
         }
-#pragma unroll
-        for (int k = 0; k < NAT3; ++k) gn[(size_t)i * NAT3 + k] = gv[k];
+        nat_store(gn + (size_t)i * NATP, gv);
     }
 }
 
@@ -369,7 +396,7 @@ __global__ void __launch_bounds__(SEG_THREADS) torsion_grad_kernel(FoldState s)
     const int L = s.L, Npad = s.Npad;
     const float *__restrict__ X = s.X + (size_t)g * s.Lpad * NAT3 * LANES + lane;
     const float *__restrict__ G1 = s.gk1 + (size_t)g * s.Lpad * 9 * LANES + lane;
-    const float *__restrict__ gn = s.gnat + (size_t)n * L * NAT3;
+    const float *__restrict__ gn = s.gnat + (size_t)n * L * NATP;
     const size_t dvb = (size_t)(dn / LANES) * s.ndof * LANES + dn % LANES;
     const float *__restrict__ t = s.xt + dvb;
     float *__restrict__ gt = s.gt + dvb;
@@ -383,10 +410,14 @@ __global__ void __launch_bounds__(SEG_THREADS) torsion_grad_kernel(FoldState s)
     auto dtor = [&](f3 p, f3 q, f3 A1, f3 A2) -> float { f3 u = unit(q - p); return dot(u, A1 - cross(p, A2)); };
     for (int i = r1 - 1; i >= r0; --i) {
         f3 xa[TRX_NAT], ga[TRX_NAT];
+        float gvn[NAT3];
+#pragma unroll
+        for (int k = 0; k < NAT3; ++k) gvn[k] = 0.f;
+        if (live) nat_load(gn + (size_t)i * NATP, gvn);
 #pragma unroll
         for (int a = 0; a < TRX_NAT; ++a) {
             xa[a] = load(i, a);
-            ga[a] = live ? f3{gn[(size_t)i * NAT3 + a * 3], gn[(size_t)i * NAT3 + a * 3 + 1], gn[(size_t)i * NAT3 + a * 3 + 2]} : f3{0.f, 0.f, 0.f};
+            ga[a] = f3{gvn[a * 3], gvn[a * 3 + 1], gvn[a * 3 + 2]};
         }
 #pragma unroll
         for (int a = 0; a < 3; ++a) {   // restraint gradient lives on N, CA, CB
@@ -495,15 +526,19 @@ __global__ void __launch_bounds__(256) cart_gather_kernel(FoldState s)
     const int dn = live ? dec : 0;
     const float *__restrict__ xt = s.xt + (size_t)(dn / LANES) * s.ndof * LANES + dn % LANES;
     float *__restrict__ X = s.X + (size_t)g * s.Lpad * NAT3 * LANES + lane;
-    float *__restrict__ xn = s.xnat + (size_t)n * s.L * NAT3;
+    float *__restrict__ xn = s.xnat + (size_t)n * s.L * NATP;
     if (warp == 0) {
 #pragma unroll
         for (int k = 0; k < TRX_NTERM; ++k) s.wslot[(size_t)k * s.Npad + n] = live ? s.wl[(size_t)k * s.Npad + dec] : 0.f;
     }
-    for (int k = warp; k < s.L * NAT3; k += nw) {
-        const float v = xt[(size_t)k * LANES];
-        X[(size_t)k * LANES] = v;
-        if (live) xn[k] = v;
+    for (int i = warp; i < s.L; i += nw) {
+        float v[NAT3];
+#pragma unroll
+        for (int k = 0; k < NAT3; ++k) {
+            v[k] = xt[((size_t)i * NAT3 + k) * LANES];
+            X[((size_t)i * NAT3 + k) * LANES] = v[k];
+        }
+        if (live) nat_store(xn + (size_t)i * NATP, v);
     }
 }
 
@@ -569,7 +604,7 @@ __global__ void __launch_bounds__(CART_THREADS) cart_grad_kernel(FoldState s)
     const int L = s.L, Npad = s.Npad;
     const float *__restrict__ X = s.X + (size_t)g * s.Lpad * NAT3 * LANES + lane;
     const float *__restrict__ G1 = s.gk1 + (size_t)g * s.Lpad * 9 * LANES + lane;
-    const float *__restrict__ gn = s.gnat + (size_t)n * L * NAT3;
+    const float *__restrict__ gn = s.gnat + (size_t)n * L * NATP;
     float *__restrict__ gt = s.gt + (size_t)(dn / LANES) * s.ndof * LANES + dn % LANES;
     const float w_cart = s.wslot[(size_t)TRX_T_CART * Npad + n], w_rama = s.wslot[(size_t)TRX_T_RAMA * Npad + n];
     const float w_omega = s.wslot[(size_t)TRX_T_OMEGA * Npad + n];
@@ -589,8 +624,10 @@ __global__ void __launch_bounds__(CART_THREADS) cart_grad_kernel(FoldState s)
             float v[NAT3];
 #pragma unroll
             for (int a = 0; a < TRX_NAT; ++a) { v[a * 3] = gr[a].x; v[a * 3 + 1] = gr[a].y; v[a * 3 + 2] = gr[a].z; }
+            float gvn[NAT3];
+            nat_load(gn + (size_t)i * NATP, gvn);
 #pragma unroll
-            for (int k = 0; k < NAT3; ++k) v[k] += gn[(size_t)i * NAT3 + k];
+            for (int k = 0; k < NAT3; ++k) v[k] += gvn[k];
 #pragma unroll
             for (int k = 0; k < 9; ++k) v[k] += G1[((size_t)i * 9 + k) * LANES];
 #pragma unroll
@@ -772,8 +809,8 @@ __global__ void held_xyz_kernel(FoldState s)
 {
     const int n = blockIdx.x;
     if (!s.held[n]) return;
-    const size_t base = (size_t)n * s.L * NAT3;
-    for (int k = threadIdx.x; k < s.L * NAT3; k += blockDim.x) s.xnat[base + k] = s.xheld[base + k];
+    const size_t base = (size_t)n * s.L;
+    for (int k = threadIdx.x; k < s.L * NAT3; k += blockDim.x) s.xnat[(base + k / NAT3) * NATP + k % NAT3] = s.xheld[base * NAT3 + k];
 }
 
 // K5: batched L-BFGS with non-monotone Armijo back-tracking (lane = decoy).  Consumes the
@@ -1404,7 +1441,7 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     size_t o_i[10];
     for (int k = 0; k < 10; ++k) o_i[k] = carve(np * 4);
     size_t o_terms = carve(np * 8 * TRX_NTERM), o_ft = carve(np * 8), o_wl = carve(np * 4 * TRX_NTERM);
-    size_t o_X = carve((size_t)G * s.Lpad * NAT3 * LANES * 4), o_xn = carve(np * L * NAT3 * 4), o_gn = carve(np * L * NAT3 * 4);
+    size_t o_X = carve((size_t)G * s.Lpad * NAT3 * LANES * 4), o_xn = carve(np * L * NATP * 4), o_gn = carve(np * L * NATP * 4);
     size_t o_gk = carve((size_t)G * s.Lpad * 9 * LANES * 4), o_E3 = carve(np * 8 * 3), o_Ev = carve(np * 8);
     size_t o_ga = carve((size_t)G * 4), o_na = carve(256);
     size_t o_xs = carve(vec), o_fs = carve(np * 8), o_nacc = carve(np * 4);
@@ -1637,7 +1674,7 @@ int trx_fold_run(trx_fold_batch *b, float *tors, float *xyz, double *terms, long
     TRX_CUDA(cudaMemcpyAsync(tors, d_tors, tb, cudaMemcpyDeviceToHost, ctx->stream));
     if (terms) TRX_CUDA(cudaMemcpyAsync(terms, d_terms, (size_t)s.N * TRX_NTERM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (stats) TRX_CUDA(cudaMemcpyAsync(stats, d_stats, (size_t)s.N * 2 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
-    if (xyz) TRX_CUDA(cudaMemcpyAsync(xyz, s.xnat, (size_t)s.N * s.L * NAT3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (xyz) TRX_CUDA(cudaMemcpy2DAsync(xyz, NAT3 * sizeof(float), s.xnat, NATP * sizeof(float), NAT3 * sizeof(float), (size_t)s.N * s.L, cudaMemcpyDeviceToHost, ctx->stream));
     TRX_CUDA(cudaStreamSynchronize(ctx->stream));
     if (rounds_out) *rounds_out = rounds;
     return TRX_OK;
@@ -1706,7 +1743,7 @@ int trx_fold_mc(trx_fold_batch *b, float *tors, float *xyz, double *terms, long 
     if (terms) TRX_CUDA(cudaMemcpyAsync(terms, d_terms, (size_t)s.N * TRX_NTERM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     TRX_CUDA(cudaMemcpyAsync(st2.data(), d_stats, st2.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
     TRX_CUDA(cudaMemcpyAsync(acc.data(), s.naccept, acc.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    if (xyz) TRX_CUDA(cudaMemcpyAsync(xyz, s.xnat, (size_t)s.N * s.L * NAT3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (xyz) TRX_CUDA(cudaMemcpy2DAsync(xyz, NAT3 * sizeof(float), s.xnat, NATP * sizeof(float), NAT3 * sizeof(float), (size_t)s.N * s.L, cudaMemcpyDeviceToHost, ctx->stream));
     TRX_CUDA(cudaStreamSynchronize(ctx->stream));
     if (stats)
         for (int n = 0; n < s.N; ++n) {
@@ -1743,7 +1780,7 @@ int trx_fold_eval(trx_fold_batch *b, const float *tors, const double w[TRX_NTERM
     TRX_CUDA(cudaMemcpyAsync(ft.data(), s.ft, ft.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
     TRX_CUDA(cudaMemcpyAsync(tr.data(), s.terms, tr.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
     TRX_CUDA(cudaMemcpyAsync(gt.data(), s.gt, gt.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (xyz) TRX_CUDA(cudaMemcpyAsync(xyz, s.xnat, (size_t)s.N * s.L * NAT3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (xyz) TRX_CUDA(cudaMemcpy2DAsync(xyz, NAT3 * sizeof(float), s.xnat, NATP * sizeof(float), NAT3 * sizeof(float), (size_t)s.N * s.L, cudaMemcpyDeviceToHost, ctx->stream));
     TRX_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int n = 0; n < s.N; ++n) {
         if (total) total[n] = ft[n];

@@ -78,5 +78,54 @@ def main(argv=None):
     print("wrote %d decoys under %s" % (len(files), os.path.join(a.save_dir, a.name, "pred_pdb")))
 
 
+def fold_batch(ctx, targets, n_decoys, rank=0, world=1, seed=0, out_dir=None, params=None, rule="H1"):
+    """Batch mode (the reference's name_lst loop, run_inference.py:339-354; BASELINE config 5): many
+    targets of different length, n_decoys[t] decoys each, target-and-decoy sharded over `world` ranks.
+    targets: [(name, seq, [npz, ...]), ...]; decoys of a target are dealt to its npz models in equal
+    contiguous shares.  Every rank derives the same assignment (parallel.assign_blocks) and folds its
+    blocks; a decoy's start (and therefore its result, bit for bit) depends only on (seed, target, global
+    decoy index), not on the sharding.  Returns {(t, decoy): dict(xyz, tors, terms, model)} for this rank's
+    decoys and writes out_dir/name/initial{decoy}.pdb when out_dir is given."""
+    from . import parallel
+    params = params or tables.load_params()
+    plan = parallel.assign_blocks([len(t[1]) for t in targets], n_decoys, world)[rank]
+    results = {}
+    cache = {}
+    for t, d0, cnt in plan:
+        name, seq, npzs = targets[t]
+        L, n_t, nm = len(seq), int(n_decoys[t]), len(npzs)
+        if t not in cache:   # one target's tables on the device at a time (the plan lists a rank's blocks target by target)
+            for old in cache.values():
+                for tb in old:
+                    tb.close()
+            cache = {t: [sampler.build_tables(ctx, z, seq, params, rule=rule) for z in npzs]}
+        tabs = cache[t]
+        starts = sampler.random_torsions(n_t, L, seed + 104729 * t)
+        model = np.minimum(np.arange(n_t) * nm // max(n_t, 1), nm - 1)
+        ids = np.arange(d0, d0 + cnt)
+        for m in range(nm):
+            sel = ids[model[ids] == m]
+            if len(sel) == 0:
+                continue
+            batch = capi.FoldBatch(ctx, [tabs[m]], [len(sel)], sampler.aa_index(seq), schedule_for(params))
+            out = batch.run(starts[sel])
+            batch.close()
+            for k, d in enumerate(sel):
+                results[(t, int(d))] = dict(xyz=out["xyz"][k], tors=out["tors"][k], terms=out["terms"][k], model=m)
+                if out_dir:
+                    p = os.path.join(out_dir, name, "initial%d.pdb" % d)
+                    os.makedirs(os.path.dirname(p), exist_ok=True)
+                    pdbio.write_pdb(p, seq, out["xyz"][k], ["target %s decoy %d model %d" % (name, d, m)])
+    for tabs in cache.values():
+        for tb in tabs:
+            tb.close()
+    return results
+
+
+def schedule_for(params):
+    from . import schedule
+    return schedule.reference_schedule()
+
+
 if __name__ == "__main__":
     main()
