@@ -203,6 +203,36 @@ def test_cartesian_stage_in_the_schedule(ctx):
     half.close(); batch.close(); tb.close()
 
 
+def test_packing_of_unfinished_decoys_changes_nothing(ctx, monkeypatch):
+    """The device packs the unfinished decoys of a block to the front when they fill less than half of it
+    (migration: positions are swapped, results go back to the caller's order).  Bit-identical to a run with the
+    packing disabled -- torsions, coordinates, terms, counters, MC acceptance -- for two table blocks, a block
+    size that is not a multiple of 32, the Cartesian segment and Monte-Carlo cycles."""
+    seq, npzs, nat = synth.target(48, seed=12, two_model=True)
+    params = tables.load_params()
+    tabs = [sampler.build_tables(ctx, z, seq, params) for z in npzs]
+    aa = sampler.aa_index(seq)
+    nd = [160, 75]
+    t0 = sampler.random_torsions(sum(nd), 48, seed=4)
+    res = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("TRX_NO_MIGRATE", flag)
+        batch = capi.FoldBatch(ctx, tabs, nd, aa, schedule.reference_schedule())
+        res["fold" + flag] = batch.run(t0)
+        batch.close()
+        batch = capi.FoldBatch(ctx, tabs, nd, aa, schedule.mc_schedule(mc_max_iter=60))
+        res["mc" + flag] = batch.run_mc(t0, cycles=3, kT=2.0, sigma_deg=25.0, seed=5)
+        batch.close()
+    for kind in ("fold", "mc"):
+        a, b = res[kind + "1"], res[kind + "0"]
+        for key in a:
+            if key != "rounds":
+                np.testing.assert_array_equal(a[key], b[key], err_msg="%s %s" % (kind, key))
+    assert res["mc0"]["accepted"].sum() > 0 and len(set(res["fold0"]["evals"].tolist())) > 20   # decoys do finish at different times
+    for t in tabs:
+        t.close()
+
+
 def test_folding_cli_drop_in(tmp_path, golden_dir, example):
     """The exact command utils_trX2dy/utils.py:491-498 builds (+ seed), and the batched form."""
     import os, subprocess, sys

@@ -20,6 +20,7 @@
 // The same L-BFGS kernel serves both: it only sees a vector of ndof floats per decoy.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "internal.cuh"
@@ -71,6 +72,7 @@ struct FoldState {
     int N, Npad, G, L, Lpad, ndof, m, nruns;
     int ndof_t, ndof_c;      // torsion space: 3 L; Cartesian: 15 Lpad (the layout of X)
     int cart;                // the segment in progress is Cartesian
+    int has_cart;            // the schedule has a Cartesian run (xheld is allocated)
     int seg_hi;              // first run after the segment in progress
     // vectors [G][ndof][32]
     float *x, *g, *d, *xt, *gt;
@@ -112,6 +114,13 @@ struct FoldState {
     int *held;               // [Npad]
     float *xheld;            // [Npad][L][15]
     double *theld;           // [TRX_NTERM][Npad]
+    // Migration: the position of a decoy in the arrays above is not its identity.  When fewer than
+    // half of a table block's positions hold unfinished decoys, the unfinished ones are moved to the
+    // front of the block (swapped with finished ones), so the L-BFGS kernels -- which stream a whole
+    // 32-decoy group if any of its decoys is unfinished -- stream only ~live/32 groups.
+    int *orig;               // [Npad] decoy id (index into the caller's arrays) held at each position
+    int *mig_a, *mig_b;      // [Npad] position pairs to swap (per table block, from its first position)
+    int *mig_n;              // [16] pairs per table block
     const int *aa;           // [L]
     const Run *runs;
 };
@@ -804,15 +813,6 @@ __global__ void seg_begin_kernel(FoldState s, int lo, int hi)
     s.status[n] = (n < s.N && s.run[n] >= lo && s.run[n] < hi) ? ST_INIT : ST_DONE;
 }
 
-// Held coordinates replace the (ideal-geometry) rebuild in the natural-layout output.
-__global__ void held_xyz_kernel(FoldState s)
-{
-    const int n = blockIdx.x;
-    if (!s.held[n]) return;
-    const size_t base = (size_t)n * s.L;
-    for (int k = threadIdx.x; k < s.L * NAT3; k += blockDim.x) s.xnat[(base + k / NAT3) * NATP + k % NAT3] = s.xheld[base * NAT3 + k];
-}
-
 // K5: batched L-BFGS with non-monotone Armijo back-tracking (lane = decoy).  Consumes the
 // evaluation of the trial point (ft, gt) and produces the next trial point.
 //
@@ -1231,6 +1231,7 @@ __global__ void init_state_kernel(FoldState s, const float *__restrict__ tors_na
         xt[k * LANES] = v;
     }
     s.held[n] = 0;
+    s.orig[n] = n;
     s.status[n] = n < s.N ? ST_INIT : ST_DONE;
     s.run[n] = 0; s.hist[n] = 0; s.head[n] = 0; s.iter[n] = 0; s.bt[n] = 0; s.restart[n] = 1; s.nmem[n] = 0;
     s.f[n] = 0.0; s.alpha[n] = 0.f; s.slope[n] = 0.f; s.evals[n] = 0; s.iters[n] = 0;
@@ -1246,18 +1247,123 @@ __global__ void restore_kernel(FoldState s)
     for (int e = threadIdx.x; e < s.ndof * LANES; e += blockDim.x) s.xt[base + e] = s.x[base + e];
 }
 
-__global__ void export_kernel(FoldState s, float *__restrict__ tors_nat, double *__restrict__ terms_nat, long long *__restrict__ stats)
+__global__ void export_kernel(FoldState s, float *__restrict__ tors_nat, double *__restrict__ terms_nat, long long *__restrict__ stats,
+                              float *__restrict__ xyz_nat)
 {
-    const int g = blockIdx.x, lane = threadIdx.x, n = g * LANES + lane;
+    // position n holds decoy o = orig[n]: results go to the caller's row o.  xyz_nat (may be NULL): [N][L][15]
+    // from the identity-slot evaluation just made (held Cartesian coordinates take precedence).
+    const int g = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, n = g * LANES + lane;
     if (n >= s.N) return;
+    const int o = s.orig[n];
     const float *x = s.x + (size_t)g * s.ndof * LANES + lane;
-    for (int k = 0; k < s.ndof; ++k) tors_nat[(size_t)n * s.ndof + k] = x[k * LANES];
-    const double *tv = s.held[n] ? s.theld : s.terms;
-    for (int k = 0; k < TRX_NTERM; ++k) terms_nat[(size_t)n * TRX_NTERM + k] = tv[(size_t)k * s.Npad + n];
-    stats[(size_t)n * 2] = s.evals[n];
-    stats[(size_t)n * 2 + 1] = s.iters[n];
+    for (int k = warp; k < s.ndof; k += nw) tors_nat[(size_t)o * s.ndof + k] = x[(size_t)k * LANES];
+    if (xyz_nat) {
+        const bool hd = s.held[n];
+        const float *src = hd ? s.xheld + (size_t)n * s.L * NAT3 : s.xnat + (size_t)n * s.L * NATP;
+        for (int k = warp; k < s.L * NAT3; k += nw)
+            xyz_nat[(size_t)o * s.L * NAT3 + k] = hd ? src[k] : src[(k / NAT3) * NATP + k % NAT3];
+    }
+    if (warp == 0) {
+        const double *tv = s.held[n] ? s.theld : s.terms;
+        for (int k = 0; k < TRX_NTERM; ++k) terms_nat[(size_t)o * TRX_NTERM + k] = tv[(size_t)k * s.Npad + n];
+        stats[(size_t)o * 2] = s.evals[n];
+        stats[(size_t)o * 2 + 1] = s.iters[n];
+    }
 }
 
+__global__ void scatter_int_kernel(FoldState s, const int *__restrict__ by_pos, int *__restrict__ by_id)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < s.N) by_id[s.orig[n]] = by_pos[n];
+}
+
+// Which positions swap: in table block t, the k-th finished decoy among the first `nlive` positions
+// with the k-th unfinished decoy behind them (nlive = unfinished decoys of the block).  One CTA per block.
+__global__ void __launch_bounds__(1024) migrate_plan_kernel(FoldState s)
+{
+    __shared__ int wsum[32];
+    __shared__ int tot_s, base_s;
+    const int t = blockIdx.x, d0 = s.tab_d0[t], nt = s.tab_n[t];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int span = (nt + 1023) / 1024 * 1024;
+    int cnt = 0;
+    for (int i = threadIdx.x; i < nt; i += 1024) cnt += s.status[d0 + i] != ST_DONE;
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) wsum[warp] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) { int a = 0; for (int w = 0; w < 32; ++w) a += wsum[w]; tot_s = a; }
+    __syncthreads();
+    const int nlive = tot_s;
+    // pass 0: finished decoys in front of nlive -> mig_a; pass 1: unfinished ones behind it -> mig_b; by position
+    for (int pass = 0; pass < 2; ++pass) {
+        __syncthreads();
+        if (threadIdx.x == 0) base_s = 0;
+        __syncthreads();
+        for (int c0 = 0; c0 < span; c0 += 1024) {
+            const int i = c0 + threadIdx.x;
+            bool pick = false;
+            if (i < nt) {
+                const bool live = s.status[d0 + i] != ST_DONE;
+                pick = pass == 0 ? (i < nlive && !live) : (i >= nlive && live);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, pick);
+            if (lane == 0) wsum[warp] = __popc(m);
+            __syncthreads();
+            int off = base_s;
+            for (int w = 0; w < warp; ++w) off += wsum[w];
+            if (pick) (pass == 0 ? s.mig_a : s.mig_b)[d0 + off + __popc(m & ((1u << lane) - 1))] = d0 + i;
+            __syncthreads();
+            if (threadIdx.x == 0) { int a = 0; for (int w = 0; w < 32; ++w) a += wsum[w]; base_s += a; }
+            __syncthreads();
+        }
+        if (pass == 1 && threadIdx.x == 0) s.mig_n[t] = base_s;
+    }
+}
+
+// Swaps everything a position carries between a (finished, front) and b (unfinished, back); the
+// L-BFGS history and Gram matrices only travel b -> a (a finished decoy's history is dead).
+__global__ void __launch_bounds__(256) migrate_swap_kernel(FoldState s)
+{
+    const int t = blockIdx.y, k = blockIdx.x;
+    if (k >= s.mig_n[t]) return;
+    const int a = s.mig_a[s.tab_d0[t] + k], b = s.mig_b[s.tab_d0[t] + k];
+    const int nd = s.ndof, m = s.m, Npad = s.Npad;
+    const size_t va = (size_t)(a / LANES) * nd * LANES + a % LANES, vb = (size_t)(b / LANES) * nd * LANES + b % LANES;
+    float *vecs[6] = {s.x, s.g, s.d, s.xt, s.gt, s.xsave};
+    for (int e = threadIdx.x; e < nd; e += blockDim.x) {
+#pragma unroll
+        for (int v = 0; v < 6; ++v) {
+            float *p = vecs[v];
+            const float ta = p[va + (size_t)e * LANES], tb = p[vb + (size_t)e * LANES];
+            p[va + (size_t)e * LANES] = tb;
+            p[vb + (size_t)e * LANES] = ta;
+        }
+    }
+    {
+        const size_t ha = (size_t)(a / LANES) * nd * m * LANES + a % LANES, hb = (size_t)(b / LANES) * nd * m * LANES + b % LANES;
+        for (size_t e = threadIdx.x; e < (size_t)nd * m; e += blockDim.x) {
+            s.S[ha + e * LANES] = s.S[hb + e * LANES];
+            s.Y[ha + e * LANES] = s.Y[hb + e * LANES];
+        }
+        const int MM = 2 * s.lb_M * s.lb_M;
+        const size_t ga = (size_t)(a / LANES) * MM * LANES + a % LANES, gb = (size_t)(b / LANES) * MM * LANES + b % LANES;
+        for (int e = threadIdx.x; e < MM; e += blockDim.x) s.gram[ga + (size_t)e * LANES] = s.gram[gb + (size_t)e * LANES];
+    }
+    if (s.has_cart) for (int e = threadIdx.x; e < s.L * NAT3; e += blockDim.x) {
+        const float ta = s.xheld[(size_t)a * s.L * NAT3 + e], tb = s.xheld[(size_t)b * s.L * NAT3 + e];
+        s.xheld[(size_t)a * s.L * NAT3 + e] = tb;
+        s.xheld[(size_t)b * s.L * NAT3 + e] = ta;
+    }
+    if (threadIdx.x == 0) {
+        auto swp_d = [&](double *p, size_t stride, int cnt) { for (int q = 0; q < cnt; ++q) { const double u = p[q * stride + a]; p[q * stride + a] = p[q * stride + b]; p[q * stride + b] = u; } };
+        auto swp_f = [&](float *p, size_t stride, int cnt) { for (int q = 0; q < cnt; ++q) { const float u = p[q * stride + a]; p[q * stride + a] = p[q * stride + b]; p[q * stride + b] = u; } };
+        auto swp_i = [&](int *p) { const int u = p[a]; p[a] = p[b]; p[b] = u; };
+        swp_d(s.f, 0, 1); swp_d(s.fmem, Npad, 3); swp_d(s.fsave, 0, 1); swp_d(s.terms, Npad, TRX_NTERM); swp_d(s.ft, 0, 1); swp_d(s.theld, Npad, TRX_NTERM);
+        swp_f(s.alpha, 0, 1); swp_f(s.slope, 0, 1); swp_f(s.wl, Npad, TRX_NTERM);
+        swp_i(s.nmem); swp_i(s.hist); swp_i(s.head); swp_i(s.iter); swp_i(s.run); swp_i(s.bt); swp_i(s.status); swp_i(s.restart);
+        swp_i(s.evals); swp_i(s.iters); swp_i(s.naccept); swp_i(s.held); swp_i(s.orig);
+    }
+}
 
 // ---- Monte-Carlo extension (no reference behaviour: BASELINE config 4 / SURVEY 8a row 16).
 // A cycle = perturb a block of consecutive residues' phi/psi, re-minimise through one run of
@@ -1290,7 +1396,7 @@ __global__ void mc_begin_kernel(FoldState s, McOpts o)
     if (n >= s.N) return;
     const size_t vb = (size_t)g * s.ndof * LANES + lane;
     float *x = s.x + vb, *xt = s.xt + vb, *xs = s.xsave + vb;
-    const unsigned long long id = o.id_offset + n;
+    const unsigned long long id = o.id_offset + s.orig[n];
     const int L = s.L;
     const int blk = o.block_min + (int)(u01(o.seed, id, o.cycle, 0) * (o.block_max - o.block_min + 1));
     const int len = min(max(blk, 1), L - 2);
@@ -1327,7 +1433,7 @@ __global__ void mc_accept_kernel(FoldState s, McOpts o, int first)
     const double fnew = s.f[n], fold = s.fsave[n];
     bool keep = true;
     if (!first) {
-        keep = isfinite(fnew) && (fnew <= fold || u01(o.seed, o.id_offset + n, o.cycle, 0x7fffffffu) < expf((float)((fold - fnew) / (double)o.kT)));
+        keep = isfinite(fnew) && (fnew <= fold || u01(o.seed, o.id_offset + s.orig[n], o.cycle, 0x7fffffffu) < expf((float)((fold - fnew) / (double)o.kT)));
         if (warp == 0 && keep) s.naccept[n] += 1;
     }
     if (!keep) {
@@ -1369,6 +1475,7 @@ struct trx_fold_batch {
     struct Segment { int lo, hi, cart; };
     std::vector<Segment> segs;   // maximal stretches of torsion-space / Cartesian runs
     bool has_cart = false;
+    bool migrate = true;         // TRX_NO_MIGRATE=1 disables the packing of unfinished decoys (same results, bit for bit)
 };
 
 extern "C" {
@@ -1397,6 +1504,7 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     int G = 0;
     trx_fold_batch *b = new trx_fold_batch();
     b->ctx = ctx;
+    if (const char *ev = getenv("TRX_NO_MIGRATE")) b->migrate = !(ev[0] && ev[0] != '0');
     for (int t = 0; t < ntab; ++t) {
         TRX_REQUIRE(tabs[t] && tabs[t]->ctx == ctx && tabs[t]->L == L, "trx_fold_create: tables %d: NULL, other context or other L", t);
         TRX_REQUIRE(ndecoys[t] > 0, "trx_fold_create: ndecoys[%d] must be positive", t);
@@ -1426,6 +1534,7 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     s.G = G; s.Npad = G * LANES; s.L = L; s.Lpad = padded_length(L); s.ndof = 3 * L; s.m = lbfgs_m; s.nruns = nruns;
     s.ndof_t = 3 * L; s.ndof_c = NAT3 * s.Lpad; s.cart = 0; s.seg_hi = nruns;
     const int ndof_max = b->has_cart ? s.ndof_c : s.ndof_t;
+    s.has_cart = b->has_cart ? 1 : 0;
     b->vdw_smem = sizeof(float4) * 6 * L + ((sizeof(int) * 18 * L + 15) / 16) * 16 + sizeof(float4) * L;
     TRX_REQUIRE(b->vdw_smem <= 220 * 1024, "trx_fold_create: L=%d exceeds the shared-memory budget of the vdw kernel", L);
     TRX_REQUIRE(L < 65536, "trx_fold_create: L too large");
@@ -1446,6 +1555,7 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     size_t o_ga = carve((size_t)G * 4), o_na = carve(256);
     size_t o_xs = carve(vec), o_fs = carve(np * 8), o_nacc = carve(np * 4);
     size_t o_perm = carve(np * 4), o_gs = carve((size_t)G * 4), o_ns = carve(256), o_ws = carve(np * 4 * TRX_NTERM);
+    size_t o_orig = carve(np * 4), o_ma = carve(np * 4), o_mb = carve(np * 4), o_mn = carve(256);
     size_t o_held = carve(np * 4), o_xh = carve(b->has_cart ? np * L * NAT3 * 4 : 256), o_th = carve(np * 8 * TRX_NTERM);
     cudaError_t e = cudaMalloc(&b->arena, off);
     if (e != cudaSuccess) {
@@ -1468,6 +1578,7 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     s.E3 = (double *)(A + o_E3); s.Evdw = (double *)(A + o_Ev); s.gactive = (int *)(A + o_ga); s.nactive = (int *)(A + o_na);
     s.xsave = (float *)(A + o_xs); s.fsave = (double *)(A + o_fs); s.naccept = (int *)(A + o_nacc);
     s.perm = (int *)(A + o_perm); s.gslot = (int *)(A + o_gs); s.nslot = (int *)(A + o_ns); s.wslot = (float *)(A + o_ws);
+    s.orig = (int *)(A + o_orig); s.mig_a = (int *)(A + o_ma); s.mig_b = (int *)(A + o_mb); s.mig_n = (int *)(A + o_mn);
     s.held = (int *)(A + o_held); s.xheld = (float *)(A + o_xh); s.theld = (double *)(A + o_th);
     s.ntab = ntab;
     for (int t = 0; t < ntab; ++t) { s.tab_d0[t] = b->tab_g0[t] * LANES; s.tab_n[t] = ndecoys[t]; }
@@ -1550,6 +1661,8 @@ static int run_rounds(trx_fold_batch *b, int max_rounds, int check_every, int *r
     int *h_nslot = nullptr;
     TRX_CUDA(cudaMallocHost(&h_nslot, 16 * sizeof(int)));
     std::vector<int> ng(b->tab_ng);   // live slot groups per table block: an upper bound between polls
+    std::vector<int> cap(s.ntab);     // positions of each block its unfinished decoys are spread over (all, until a migration)
+    for (int t = 0; t < s.ntab; ++t) cap[t] = s.tab_n[t];
     dim3 ablk(32, 8), agrd((s.G + 7) / 8);
     while (active > 0 && rounds < max_rounds) {
         for (int k = 0; k < check_every && rounds < max_rounds; ++k, ++rounds) {
@@ -1583,7 +1696,23 @@ static int run_rounds(trx_fold_batch *b, int max_rounds, int check_every, int *r
         TRX_CUDA(cudaMemcpyAsync(h_nslot, s.nslot, 16 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         TRX_CUDA(cudaStreamSynchronize(ctx->stream));
         active = 0;   // counts at the start of the last round; they only ever decrease
-        for (int t = 0; t < s.ntab; ++t) { active += h_nslot[t]; ng[t] = num_groups(h_nslot[t]); }
+        bool migrate = false;
+        for (int t = 0; t < s.ntab; ++t) {
+            active += h_nslot[t];
+            ng[t] = num_groups(h_nslot[t]);
+            // unfinished decoys fill less than half of the positions they are spread over: pack them
+            if (b->migrate && h_nslot[t] > 0 && 2 * h_nslot[t] <= cap[t] && cap[t] >= 2 * LANES) { migrate = true; cap[t] = h_nslot[t]; }
+        }
+        if (migrate && active > 0) {
+            int maxn = 0;
+            for (int t = 0; t < s.ntab; ++t) maxn = std::max(maxn, s.tab_n[t]);
+            ctx->time_begin("migrate");
+            migrate_plan_kernel<<<s.ntab, 1024, 0, ctx->stream>>>(s);
+            ctx->time_end("migrate");
+            ctx->time_begin("migrate");
+            migrate_swap_kernel<<<dim3((maxn + 1) / 2, s.ntab), 256, 0, ctx->stream>>>(s);
+            ctx->time_end("migrate");
+        }
     }
     cudaFreeHost(h_nslot);
     *rounds_io += rounds;
@@ -1661,20 +1790,17 @@ int trx_fold_run(trx_fold_batch *b, float *tors, float *xyz, double *terms, long
     restore_kernel<<<s.G, 256, 0, ctx->stream>>>(s);
     ctx->time_end("export");
     if ((rc = fold_eval(b, nullptr, true))) return rc;
+    void *d_xyz = nullptr;
+    if (xyz && (rc = ctx->get_scratch("fold_xyz_out", (size_t)s.N * s.L * NAT3 * sizeof(float), &d_xyz))) return rc;
     ctx->time_begin("export");
-    export_kernel<<<s.G, 32, 0, ctx->stream>>>(s, (float *)d_tors, (double *)d_terms, (long long *)d_stats);
+    export_kernel<<<s.G, 256, 0, ctx->stream>>>(s, (float *)d_tors, (double *)d_terms, (long long *)d_stats, (float *)d_xyz);
     ctx->time_end("export");
-    if (b->has_cart) {
-        ctx->time_begin("export");
-        held_xyz_kernel<<<s.N, 128, 0, ctx->stream>>>(s);
-        ctx->time_end("export");
-    }
     ctx->time_end("fold_device");
     TRX_CUDA(cudaGetLastError());
     TRX_CUDA(cudaMemcpyAsync(tors, d_tors, tb, cudaMemcpyDeviceToHost, ctx->stream));
     if (terms) TRX_CUDA(cudaMemcpyAsync(terms, d_terms, (size_t)s.N * TRX_NTERM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (stats) TRX_CUDA(cudaMemcpyAsync(stats, d_stats, (size_t)s.N * 2 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
-    if (xyz) TRX_CUDA(cudaMemcpy2DAsync(xyz, NAT3 * sizeof(float), s.xnat, NATP * sizeof(float), NAT3 * sizeof(float), (size_t)s.N * s.L, cudaMemcpyDeviceToHost, ctx->stream));
+    if (xyz) TRX_CUDA(cudaMemcpyAsync(xyz, d_xyz, (size_t)s.N * s.L * NAT3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     TRX_CUDA(cudaStreamSynchronize(ctx->stream));
     if (rounds_out) *rounds_out = rounds;
     return TRX_OK;
@@ -1729,12 +1855,13 @@ int trx_fold_mc(trx_fold_batch *b, float *tors, float *xyz, double *terms, long 
     restore_kernel<<<s.G, 256, 0, ctx->stream>>>(s);
     ++ctx->launches;
     if ((rc = fold_eval(b, nullptr, true))) return rc;
-    export_kernel<<<s.G, 32, 0, ctx->stream>>>(s, (float *)d_tors, (double *)d_terms, (long long *)d_stats);
+    void *d_xyz = nullptr, *d_acc = nullptr;
+    if (xyz && (rc = ctx->get_scratch("fold_xyz_out", (size_t)s.N * s.L * NAT3 * sizeof(float), &d_xyz))) return rc;
+    if ((rc = ctx->get_scratch("fold_acc_out", (size_t)s.Npad * sizeof(int), &d_acc))) return rc;
+    export_kernel<<<s.G, 256, 0, ctx->stream>>>(s, (float *)d_tors, (double *)d_terms, (long long *)d_stats, (float *)d_xyz);
     ++ctx->launches;
-    if (b->has_cart) {
-        held_xyz_kernel<<<s.N, 128, 0, ctx->stream>>>(s);
-        ++ctx->launches;
-    }
+    scatter_int_kernel<<<(s.N + 255) / 256, 256, 0, ctx->stream>>>(s, s.naccept, (int *)d_acc);
+    ++ctx->launches;
     ctx->time_end("fold_device");
     TRX_CUDA(cudaGetLastError());
     std::vector<long long> st2((size_t)s.N * 2);
@@ -1742,8 +1869,8 @@ int trx_fold_mc(trx_fold_batch *b, float *tors, float *xyz, double *terms, long 
     TRX_CUDA(cudaMemcpyAsync(tors, d_tors, tb, cudaMemcpyDeviceToHost, ctx->stream));
     if (terms) TRX_CUDA(cudaMemcpyAsync(terms, d_terms, (size_t)s.N * TRX_NTERM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     TRX_CUDA(cudaMemcpyAsync(st2.data(), d_stats, st2.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
-    TRX_CUDA(cudaMemcpyAsync(acc.data(), s.naccept, acc.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    if (xyz) TRX_CUDA(cudaMemcpy2DAsync(xyz, NAT3 * sizeof(float), s.xnat, NATP * sizeof(float), NAT3 * sizeof(float), (size_t)s.N * s.L, cudaMemcpyDeviceToHost, ctx->stream));
+    TRX_CUDA(cudaMemcpyAsync(acc.data(), d_acc, (size_t)s.N * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (xyz) TRX_CUDA(cudaMemcpyAsync(xyz, d_xyz, (size_t)s.N * s.L * NAT3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     TRX_CUDA(cudaStreamSynchronize(ctx->stream));
     if (stats)
         for (int n = 0; n < s.N; ++n) {
