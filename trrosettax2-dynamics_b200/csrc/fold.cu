@@ -1476,6 +1476,7 @@ struct trx_fold_batch {
     std::vector<Segment> segs;   // maximal stretches of torsion-space / Cartesian runs
     bool has_cart = false;
     bool migrate = true;         // TRX_NO_MIGRATE=1 disables the packing of unfinished decoys (same results, bit for bit)
+    int mig_num = 3, mig_den = 4; // pack when unfinished <= mig_num/mig_den of the positions they are spread over (1/2: 1246, 3/4: 1257 decoys/s)
 };
 
 extern "C" {
@@ -1505,6 +1506,7 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     trx_fold_batch *b = new trx_fold_batch();
     b->ctx = ctx;
     if (const char *ev = getenv("TRX_NO_MIGRATE")) b->migrate = !(ev[0] && ev[0] != '0');
+    if (const char *ev = getenv("TRX_MIGRATE_AT")) { int p = atoi(ev); if (p > 0 && p < 100) { b->mig_num = p; b->mig_den = 100; } }   // development knob (percent)
     for (int t = 0; t < ntab; ++t) {
         TRX_REQUIRE(tabs[t] && tabs[t]->ctx == ctx && tabs[t]->L == L, "trx_fold_create: tables %d: NULL, other context or other L", t);
         TRX_REQUIRE(ndecoys[t] > 0, "trx_fold_create: ndecoys[%d] must be positive", t);
@@ -1701,7 +1703,7 @@ static int run_rounds(trx_fold_batch *b, int max_rounds, int check_every, int *r
             active += h_nslot[t];
             ng[t] = num_groups(h_nslot[t]);
             // unfinished decoys fill less than half of the positions they are spread over: pack them
-            if (b->migrate && h_nslot[t] > 0 && 2 * h_nslot[t] <= cap[t] && cap[t] >= 2 * LANES) { migrate = true; cap[t] = h_nslot[t]; }
+            if (b->migrate && h_nslot[t] > 0 && b->mig_den * h_nslot[t] <= b->mig_num * cap[t] && cap[t] >= 2 * LANES) { migrate = true; cap[t] = h_nslot[t]; }
         }
         if (migrate && active > 0) {
             int maxn = 0;
