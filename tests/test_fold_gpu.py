@@ -203,6 +203,32 @@ def test_cartesian_stage_in_the_schedule(ctx):
     half.close(); batch.close(); tb.close()
 
 
+def test_decoy_distributions_match_the_oracle(ctx, example):
+    """north_star: 'the RMSD/TM-score distribution of final decoys statistically matched'.  The device folds in fp32
+    with its own summation orders, so trajectories differ from the fp64 oracle's; the DISTRIBUTIONS over random
+    starts must not.  Two-sample Kolmogorov-Smirnov tests, 128 device decoys against 32 oracle decoys of the
+    reference's example target: TM-score and RMSD to the closer native, restraint energy, evaluations spent."""
+    from scipy.stats import ks_2samp
+    seq, npzs, nat = example
+    L = len(seq)
+    out = sampler.fold(ctx, [npzs[0]], seq, [128], seed=21)
+    F = _oracle(npzs[0], seq)
+    o = F.fold(sampler.random_torsions(32, L, 77).astype(np.float64), fo.reference_schedule(), m=20, nthreads=16)
+
+    def quality(ca):
+        tm = np.array([max(metrics.tm_score(c, nat["apo"]), metrics.tm_score(c, nat["holo"])) for c in ca])
+        rm = np.array([min(metrics.rmsd(c, nat["apo"]), metrics.rmsd(c, nat["holo"])) for c in ca])
+        return tm, rm
+    tm_d, rm_d = quality(out["xyz"][:, :, 1].astype(np.float64))
+    tm_o, rm_o = quality(o["xyz"][:, :, 1])
+    w = np.array([5.0, 4.0, 4.0, 1.0, 1.0, 0.5, 0.0])
+    for name, a, b in (("TM", tm_d, tm_o), ("RMSD", rm_d, rm_o), ("score", out["terms"] @ w, o["terms"] @ w),
+                       ("evals", out["evals"].astype(float), o["evals"].astype(float))):
+        p = ks_2samp(a, b).pvalue
+        assert p > 0.01, (name, p, np.median(a), np.median(b))
+    assert abs(np.median(tm_d) - np.median(tm_o)) < 0.03 and abs(np.median(rm_d) - np.median(rm_o)) < 0.5
+
+
 def test_packing_of_unfinished_decoys_changes_nothing(ctx, monkeypatch):
     """The device packs the unfinished decoys of a block to the front when they fill less than half of it
     (migration: positions are swapped, results go back to the caller's order).  Bit-identical to a run with the
