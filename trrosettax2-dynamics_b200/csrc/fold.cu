@@ -838,6 +838,7 @@ constexpr float LS_SIGMA = 0.1f;
 constexpr int LS_MAXBACK = 20;
 constexpr int LB_NSCAL = 8;   // ss, sy, yy, gg, s.g, y.g (+2 spare)
 constexpr int LB_MAXCH = 16;  // most chunks a group's vector is cut into
+constexpr int LB_STEP_THREADS = 512;
 
 template <int M>
 struct LbSmem {
@@ -946,7 +947,7 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lbfgs_dots_kernel(FoldState s)
 }
 
 template <int M>
-__global__ void __launch_bounds__(LB_THREADS, 1) lbfgs_step_kernel(FoldState s, int nch)
+__global__ void __launch_bounds__(LB_STEP_THREADS, 1) lbfgs_step_kernel(FoldState s, int nch)
 {
     extern __shared__ __align__(16) unsigned char lb_raw[];
     LbSmem<M> &sm = *reinterpret_cast<LbSmem<M> *>(lb_raw);
@@ -957,14 +958,19 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lbfgs_step_kernel(FoldState s, 
     float *__restrict__ gram = s.gram + (size_t)g * 2 * M * M * LANES;
     {   // partial sums of the chunks, in chunk order
         const float *__restrict__ part = s.lbpart + (size_t)g * LB_MAXCH * NRED * LANES;
-        for (int e = threadIdx.x; e < NRED * LANES; e += LB_THREADS) {
+        for (int e = threadIdx.x; e < NRED * LANES; e += LB_STEP_THREADS) {
             float t = 0.f;
             for (int c = 0; c < nch; ++c) t += part[(size_t)c * NRED * LANES + e];
             (&sm.sum[0][0])[e] = t;
         }
     }
-    // Gram matrices into shared memory
-    for (int e = threadIdx.x; e < 2 * M * M * LANES; e += LB_THREADS) (&sm.u.gram[0][0][0])[e] = gram[e];
+    // Gram matrices into shared memory (147 KB per group at M = 24: 16-byte copies by 512 threads; with
+    // 4-byte copies by 256 threads this staging was the longest part of the kernel, ~90 us per round)
+    {
+        const float4 *__restrict__ src = reinterpret_cast<const float4 *>(gram);
+        float4 *dst = reinterpret_cast<float4 *>(&sm.u.gram[0][0][0]);
+        for (int e = threadIdx.x; e < 2 * M * M * LANES / 4; e += LB_STEP_THREADS) dst[e] = src[e];
+    }
     __syncthreads();
 
     // ---- per-decoy decision
@@ -1124,9 +1130,13 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lbfgs_step_kernel(FoldState s, 
     }
     __syncthreads();
     // Gram matrices back to global memory; coefficients of sweep B
-    for (int e = threadIdx.x; e < 2 * M * M * LANES; e += LB_THREADS) gram[e] = (&sm.u.gram[0][0][0])[e];
+    {
+        float4 *__restrict__ dst = reinterpret_cast<float4 *>(gram);
+        const float4 *src = reinterpret_cast<const float4 *>(&sm.u.gram[0][0][0]);
+        for (int e = threadIdx.x; e < 2 * M * M * LANES / 4; e += LB_STEP_THREADS) dst[e] = src[e];
+    }
     float *__restrict__ coef = s.lbcoef + (size_t)g * LbSmem<M>::NCOEF * LANES;
-    for (int e = threadIdx.x; e < M * LANES; e += LB_THREADS) {
+    for (int e = threadIdx.x; e < M * LANES; e += LB_STEP_THREADS) {
         coef[e] = (&sm.coefS[0][0])[e];
         coef[M * LANES + e] = (&sm.coefY[0][0])[e];
     }
@@ -1138,7 +1148,7 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lbfgs_step_kernel(FoldState s, 
 }
 
 template <int M>
-__global__ void __launch_bounds__(LB_THREADS, 1) lbfgs_update_kernel(FoldState s)
+__global__ void __launch_bounds__(LB_THREADS, 2) lbfgs_update_kernel(FoldState s)   // <= 128 registers: two CTAs per SM keep more of the stream in flight
 {
     const int g = blockIdx.x, ch = blockIdx.y, nch = gridDim.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1680,15 +1690,15 @@ static int run_rounds(trx_fold_batch *b, int max_rounds, int check_every, int *r
                 const dim3 grid(s.G, nch);
                 if (s.lb_M == 8) {
                     lbfgs_dots_kernel<8><<<grid, LB_THREADS, b->lb_smem, ctx->stream>>>(s);
-                    lbfgs_step_kernel<8><<<s.G, LB_THREADS, b->lb_smem, ctx->stream>>>(s, nch);
+                    lbfgs_step_kernel<8><<<s.G, LB_STEP_THREADS, b->lb_smem, ctx->stream>>>(s, nch);
                     lbfgs_update_kernel<8><<<grid, LB_THREADS, 0, ctx->stream>>>(s);
                 } else if (s.lb_M == 16) {
                     lbfgs_dots_kernel<16><<<grid, LB_THREADS, b->lb_smem, ctx->stream>>>(s);
-                    lbfgs_step_kernel<16><<<s.G, LB_THREADS, b->lb_smem, ctx->stream>>>(s, nch);
+                    lbfgs_step_kernel<16><<<s.G, LB_STEP_THREADS, b->lb_smem, ctx->stream>>>(s, nch);
                     lbfgs_update_kernel<16><<<grid, LB_THREADS, 0, ctx->stream>>>(s);
                 } else {
                     lbfgs_dots_kernel<24><<<grid, LB_THREADS, b->lb_smem, ctx->stream>>>(s);
-                    lbfgs_step_kernel<24><<<s.G, LB_THREADS, b->lb_smem, ctx->stream>>>(s, nch);
+                    lbfgs_step_kernel<24><<<s.G, LB_STEP_THREADS, b->lb_smem, ctx->stream>>>(s, nch);
                     lbfgs_update_kernel<24><<<grid, LB_THREADS, 0, ctx->stream>>>(s);
                 }
                 ctx->launches += 2;

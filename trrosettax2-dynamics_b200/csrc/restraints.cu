@@ -306,6 +306,11 @@ __global__ void __launch_bounds__(K1_THREADS, (sizeof(T) == 4 ? TRX_K1_MINBLOCKS
     T *rowg = colg + REC_ELEMS;                    // row-block gradient of the whole work item
     double(*ered)[3][LANES] = reinterpret_cast<double(*)[3][LANES]>(colg);  // reused after the last flush
     static_assert(sizeof(double) * K1_WARPS * 3 * LANES <= sizeof(T) * REC_ELEMS, "energy scratch must fit");
+    constexpr int KV = 16 / sizeof(T);
+    struct alignas(16) KVec { T v[KV]; };
+    KVec kzero;
+#pragma unroll
+    for (int k = 0; k < KV; ++k) kzero.v[k] = (T)0;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int q = blockIdx.y, g = p.g0 + blockIdx.x;   // group is the fast grid index: co-resident CTAs share tiles
     if (p.gactive && !p.gactive[g]) return;
@@ -399,15 +404,16 @@ __global__ void __launch_bounds__(K1_THREADS, (sizeof(T) == 4 ? TRX_K1_MINBLOCKS
         }
         e0 += (double)f0; e1 += (double)f1; e2 += (double)f2;
         T *__restrict__ dst = p.recs + ((size_t)g * p.nrec + t) * REC_ELEMS;
-        for (int e = threadIdx.x; e < REC_ELEMS; e += K1_THREADS) {
-            dst[e] = colg[e];
-            colg[e] = (T)0;
+        for (int e = threadIdx.x * KV; e < REC_ELEMS; e += K1_THREADS * KV) {   // 16-byte copies
+            *reinterpret_cast<KVec *>(dst + e) = *reinterpret_cast<const KVec *>(colg + e);
+            *reinterpret_cast<KVec *>(colg + e) = kzero;
         }
         __syncthreads();
     }
     {
         T *__restrict__ dst = p.recs + ((size_t)g * p.nrec + rowrec) * REC_ELEMS;
-        for (int e = threadIdx.x; e < REC_ELEMS; e += K1_THREADS) dst[e] = rowg[e];
+        for (int e = threadIdx.x * KV; e < REC_ELEMS; e += K1_THREADS * KV)
+            *reinterpret_cast<KVec *>(dst + e) = *reinterpret_cast<const KVec *>(rowg + e);
     }
     ered[w][0][lane] = e0;
     ered[w][1][lane] = e1;
@@ -443,10 +449,21 @@ __global__ void __launch_bounds__(256) reduce_kernel(const T *__restrict__ recs,
     const int B = blockIdx.x;
     const int r0 = blk_ptr[B], r1 = blk_ptr[B + 1];
     T *__restrict__ dst = grad + ((size_t)g * Lpad + (size_t)B * TILE) * 9 * LANES;
-    for (int e = threadIdx.x; e < REC_ELEMS; e += 256) {
-        T s = accumulate ? dst[e] : (T)0;
-        for (int r = r0; r < r1; ++r) s += recs[((size_t)g * nrec + blk_rec[r]) * REC_ELEMS + e];
-        dst[e] = s;
+    // 16-byte accesses: V elements of a record per thread and load (records are REC_ELEMS contiguous values)
+    constexpr int V = 16 / sizeof(T);
+    struct alignas(16) Vec { T v[V]; };
+    for (int e = threadIdx.x * V; e < REC_ELEMS; e += 256 * V) {
+        Vec s;
+        if (accumulate) s = *reinterpret_cast<const Vec *>(dst + e);
+        else
+#pragma unroll
+            for (int k = 0; k < V; ++k) s.v[k] = (T)0;
+        for (int r = r0; r < r1; ++r) {
+            const Vec x = *reinterpret_cast<const Vec *>(recs + ((size_t)g * nrec + blk_rec[r]) * REC_ELEMS + e);
+#pragma unroll
+            for (int k = 0; k < V; ++k) s.v[k] += x.v[k];
+        }
+        *reinterpret_cast<Vec *>(dst + e) = s;
     }
 }
 
