@@ -358,7 +358,7 @@ def run_b200_fold(args):
                          "kernel_share_of_step": shares["restraints"], "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes / max(k1_n, 1), "kernel_shares": shares,
                          "kernel_ms_total": {k: round(v, 2) for k, v in busy.items()}, "kernel_launches": counts}}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:   # rank 0 at N=1 only (the other ranks of an N>1 run would wait on it)
         threads = os.cpu_count() or 1
         rate, dt, ev = cpu_fold_rate(npzs, seq, threads, threads, SEED)
         line["cpu_baseline"] = {"value": rate, "unit": "decoys/s", "cores": threads, "kind": "port",
@@ -509,7 +509,7 @@ def run_b200(args):
                          "traffic": None, "kernel": "restraints_kernel<float>" if prec == 32 else "restraints_kernel<double>",
                          "kernel_ms": k1_avg_ms, "kernel_share_of_step": k1_ms / (1e3 * t_dev), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_per_launch}}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
         n_sample = max(2 * threads, 64)
         rate, dt = cpu_restraint_rate(npzs, xyz, n_sample, threads)
