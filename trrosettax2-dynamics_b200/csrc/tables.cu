@@ -8,6 +8,8 @@
 #include <cmath>
 #include <cstring>
 
+#include <cstdlib>
+
 #include "internal.cuh"
 
 namespace trx {
@@ -90,7 +92,8 @@ int trx_tables::get_plan(int groups, Plan **out)
 {
     // chunk tiles of one block row so that the grid has a few waves of CTAs; plans are
     // cached by chunk size (the only thing the group count changes)
-    const long long want_ctas = 148LL * 4 * 6;   // 4 resident CTAs per SM, a few waves
+    static const int waves = [] { const char *ev = getenv("TRX_K1_WAVES"); const int v = ev ? atoi(ev) : 0; return v > 0 ? v : 6; }();
+    const long long want_ctas = 148LL * 4 * waves;   // 4 resident CTAs per SM, a few waves (TRX_K1_WAVES: development knob)
     long long chunk = std::max(1LL, (long long)ntiles * groups / want_ctas);
     chunk = std::min<long long>(chunk, std::max(1, nb));
     auto it = plans.find((int)chunk);
