@@ -101,6 +101,15 @@ def test_full_size_fold_is_reproducible_and_batch_independent(ctx, full):
     small.close()
     w = np.array([5.0, 4.0, 4.0, 1.0, 1.0, 0.5, 0.0])
     assert np.median(a["terms"] @ w) < -100000 and np.all(a["iters"] > 50)
+    # ... also inside a bench-sized batch (2048 decoys on this table: many more decoy groups per launch, decoys packed
+    # and re-packed as they finish); the restraint kernel's summation order must not follow the live-decoy count
+    huge = capi.FoldBatch(ctx, [tb], [2048], aa, runs)
+    t1 = sampler.random_torsions(2048, L, seed=9)
+    t1[1000:1064] = t0[128:192]
+    h = huge.run(t1)
+    huge.close()
+    np.testing.assert_array_equal(h["tors"][1000:1064], c["tors"])
+    np.testing.assert_array_equal(h["xyz"][1000:1064], c["xyz"])
 
 
 def test_degenerate_inputs(ctx):

@@ -73,6 +73,7 @@ struct FoldState {
     int ndof_t, ndof_c;      // torsion space: 3 L; Cartesian: 15 Lpad (the layout of X)
     int cart;                // the segment in progress is Cartesian
     int has_cart;            // the schedule has a Cartesian run (xheld is allocated)
+    int k1skip;              // skip the restraint kernel for slot groups whose runs do not score restraints
     int seg_hi;              // first run after the segment in progress
     // vectors [G][ndof][32]
     float *x, *g, *d, *xt, *gt;
@@ -101,6 +102,7 @@ struct FoldState {
     // block every round, so the evaluation kernels only touch live lanes
     int *perm;               // [Npad] slot -> decoy, -1 for an empty slot
     int *gslot;              // [G] slot group holds a live slot
+    int *gneedk1;            // [G] ... and one whose run scores the restraints (others skip the restraint kernel)
     int *nslot;              // [16] live slots per table block
     float *wslot;            // [TRX_NTERM][Npad] weights in slot order
     int ntab;
@@ -410,6 +412,7 @@ __global__ void __launch_bounds__(SEG_THREADS) torsion_grad_kernel(FoldState s)
     const float *__restrict__ t = s.xt + dvb;
     float *__restrict__ gt = s.gt + dvb;
     const float w_rama = s.wslot[(size_t)TRX_T_RAMA * Npad + n], w_omega = s.wslot[(size_t)TRX_T_OMEGA * Npad + n];
+    const bool k1 = s.gneedk1[g] != 0;
     const int Lseg = (L + SEG_WARPS - 1) / SEG_WARPS;
     const int r0 = warp * Lseg, r1 = min(L, r0 + Lseg);
     f3 F1 = {0.f, 0.f, 0.f}, F2 = {0.f, 0.f, 0.f};
@@ -428,11 +431,13 @@ __global__ void __launch_bounds__(SEG_THREADS) torsion_grad_kernel(FoldState s)
             xa[a] = load(i, a);
             ga[a] = f3{gvn[a * 3], gvn[a * 3 + 1], gvn[a * 3 + 2]};
         }
+        if (k1) {   // restraint gradient lives on N, CA, CB (absent when the group's runs do not score restraints)
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {   // restraint gradient lives on N, CA, CB
-            ga[a].x += G1[((size_t)i * 9 + a * 3) * LANES];
-            ga[a].y += G1[((size_t)i * 9 + a * 3 + 1) * LANES];
-            ga[a].z += G1[((size_t)i * 9 + a * 3 + 2) * LANES];
+            for (int a = 0; a < 3; ++a) {
+                ga[a].x += G1[((size_t)i * 9 + a * 3) * LANES];
+                ga[a].y += G1[((size_t)i * 9 + a * 3 + 1) * LANES];
+                ga[a].z += G1[((size_t)i * 9 + a * 3 + 2) * LANES];
+            }
         }
         const float phi = t[(i * 3 + 0) * LANES], psi = t[(i * 3 + 1) * LANES];
         float gphi = 0.f, gpsi = 0.f;
@@ -502,9 +507,9 @@ __global__ void __launch_bounds__(SEG_THREADS) torsion_grad_kernel(FoldState s)
         double er = 0.0, eo = 0.0;
         for (int w2 = 0; w2 < SEG_WARPS; ++w2) { er += esum[w2][0][lane]; eo += esum[w2][1][lane]; }
         double term[TRX_NTERM];
-        term[TRX_T_APC] = s.E3[0 * (size_t)Npad + n];
-        term[TRX_T_DIH] = s.E3[1 * (size_t)Npad + n];
-        term[TRX_T_ANG] = s.E3[2 * (size_t)Npad + n];
+        term[TRX_T_APC] = k1 ? s.E3[0 * (size_t)Npad + n] : 0.0;
+        term[TRX_T_DIH] = k1 ? s.E3[1 * (size_t)Npad + n] : 0.0;
+        term[TRX_T_ANG] = k1 ? s.E3[2 * (size_t)Npad + n] : 0.0;
         term[TRX_T_VDW] = s.Evdw[n];
         term[TRX_T_RAMA] = er;
         term[TRX_T_OMEGA] = eo;
@@ -618,6 +623,7 @@ __global__ void __launch_bounds__(CART_THREADS) cart_grad_kernel(FoldState s)
     const float w_cart = s.wslot[(size_t)TRX_T_CART * Npad + n], w_rama = s.wslot[(size_t)TRX_T_RAMA * Npad + n];
     const float w_omega = s.wslot[(size_t)TRX_T_OMEGA * Npad + n];
     const float kb2 = w_cart * 2.0f * (float)TRX_CART_KB, ka2 = w_cart * 2.0f * (float)TRX_CART_KA;
+    const bool k1 = s.gneedk1[g] != 0;
     const int Lseg = (L + CART_WARPS - 1) / CART_WARPS;
     const int r0 = warp * Lseg, r1 = min(L, r0 + Lseg);
     auto load = [&](int i, int a) -> f3 { return {X[((size_t)i * NAT3 + a * 3) * LANES], X[((size_t)i * NAT3 + a * 3 + 1) * LANES], X[((size_t)i * NAT3 + a * 3 + 2) * LANES]}; };
@@ -637,8 +643,10 @@ __global__ void __launch_bounds__(CART_THREADS) cart_grad_kernel(FoldState s)
             nat_load(gn + (size_t)i * NATP, gvn);
 #pragma unroll
             for (int k = 0; k < NAT3; ++k) v[k] += gvn[k];
+            if (k1) {
 #pragma unroll
-            for (int k = 0; k < 9; ++k) v[k] += G1[((size_t)i * 9 + k) * LANES];
+                for (int k = 0; k < 9; ++k) v[k] += G1[((size_t)i * 9 + k) * LANES];
+            }
 #pragma unroll
             for (int k = 0; k < NAT3; ++k) gt[((size_t)i * NAT3 + k) * LANES] = v[k];
         };
@@ -736,9 +744,9 @@ __global__ void __launch_bounds__(CART_THREADS) cart_grad_kernel(FoldState s)
         double ec = 0.0, er = 0.0, eo = 0.0;
         for (int w2 = 0; w2 < CART_WARPS; ++w2) { ec += esum[w2][0][lane]; er += esum[w2][1][lane]; eo += esum[w2][2][lane]; }
         double term[TRX_NTERM];
-        term[TRX_T_APC] = s.E3[0 * (size_t)Npad + n];
-        term[TRX_T_DIH] = s.E3[1 * (size_t)Npad + n];
-        term[TRX_T_ANG] = s.E3[2 * (size_t)Npad + n];
+        term[TRX_T_APC] = k1 ? s.E3[0 * (size_t)Npad + n] : 0.0;
+        term[TRX_T_DIH] = k1 ? s.E3[1 * (size_t)Npad + n] : 0.0;
+        term[TRX_T_ANG] = k1 ? s.E3[2 * (size_t)Npad + n] : 0.0;
         term[TRX_T_VDW] = s.Evdw[n];
         term[TRX_T_RAMA] = er;
         term[TRX_T_OMEGA] = eo;
@@ -826,10 +834,10 @@ __global__ void seg_begin_kernel(FoldState s, int lo, int hi)
 // Three launches per round so that a decoy group is streamed by SEVERAL CTAs (one CTA per
 // group leaves most of the HBM bandwidth idle: a group's history is 4.6 MB per sweep in
 // torsion space, 23 MB in Cartesian space):
-//   lbfgs_dots_kernel    grid (G, nch): sweep A over a chunk of the vector -> partial sums
-//   lbfgs_step_kernel    grid  G      : sums the partials in chunk order (deterministic), step
-//                                       logic on scalars, coefficients of the new direction
-//   lbfgs_update_kernel  grid (G, nch): sweep B over the chunk
+//   lbfgs_dots_kernel    grid (G, nch): sweep A -> partial sums of the 16 fixed chunks of the vector
+//   lbfgs_step_kernel    grid  G      : sums the partials in chunk order (deterministic and the same
+//                                       in any batch), step logic on scalars, coefficients of the new direction
+//   lbfgs_update_kernel  grid (G, nch): sweep B over a share of the vector
 // History layout [G][ndof][m][32]: the m slots of one vector element are contiguous, so a
 // sweep reads each group's history as one sequential stream.
 constexpr int LB_WARPS = 8;
@@ -886,11 +894,10 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lbfgs_dots_kernel(FoldState s)
     extern __shared__ __align__(16) unsigned char lb_raw[];
     LbSmem<M> &sm = *reinterpret_cast<LbSmem<M> *>(lb_raw);
     constexpr int NRED = LbSmem<M>::NRED;
-    const int g = blockIdx.x, ch = blockIdx.y, nch = gridDim.y;
+    const int g = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = g * LANES + lane;
     if (!s.gactive[g]) return;
     const int nd = s.ndof, m = s.m;
-    const int per = (nd + nch - 1) / nch, k0 = ch * per, k1 = min(nd, k0 + per);
     const size_t vb = (size_t)g * nd * LANES + lane;
     float *__restrict__ x = s.x + vb, *__restrict__ gv = s.g + vb;
     const float *__restrict__ xt = s.xt + vb, *__restrict__ gt = s.gt + vb;
@@ -898,51 +905,58 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lbfgs_dots_kernel(FoldState s)
     const int status = n < s.N ? s.status[n] : ST_DONE;
     const int action = lb_action(s, n, status), head = s.head[n];
     const bool is_acc = action == 2, is_new = action == 1 || action == 2;
-
-    float aYG[M], aYY[M], aYS[M], aSG[M], aSY[M], sc[LB_NSCAL];
+    // The vector is ALWAYS cut into LB_MAXCH chunks and each chunk's sums are formed by the 8 warps of one CTA in a
+    // fixed order; only the number of CTAs that share the chunks (gridDim.y) follows the batch size.  The sums a
+    // decoy sees are therefore the same bits in any batch.
+    const int per = (nd + LB_MAXCH - 1) / LB_MAXCH;
+    for (int ch = blockIdx.y; ch < LB_MAXCH; ch += gridDim.y) {
+        const int k0 = ch * per, k1 = min(nd, k0 + per);
+        float aYG[M], aYY[M], aYS[M], aSG[M], aSY[M], sc[LB_NSCAL];
 #pragma unroll
-    for (int j = 0; j < M; ++j) { aYG[j] = 0.f; aYY[j] = 0.f; aYS[j] = 0.f; aSG[j] = 0.f; aSY[j] = 0.f; }
+        for (int j = 0; j < M; ++j) { aYG[j] = 0.f; aYY[j] = 0.f; aYS[j] = 0.f; aSG[j] = 0.f; aSY[j] = 0.f; }
 #pragma unroll
-    for (int j = 0; j < LB_NSCAL; ++j) sc[j] = 0.f;
-    for (int k = k0 + warp; k < k1; k += LB_WARPS) {
-        const float xk = x[(size_t)k * LANES], xtk = xt[(size_t)k * LANES], gk = gv[(size_t)k * LANES], gtk = gt[(size_t)k * LANES];
-        const float sn = xtk - xk, yn = gtk - gk, gn = is_new ? gtk : gk;
-        float yj[M], sj[M];
+        for (int j = 0; j < LB_NSCAL; ++j) sc[j] = 0.f;
+        for (int k = k0 + warp; k < k1; k += LB_WARPS) {
+            const float xk = x[(size_t)k * LANES], xtk = xt[(size_t)k * LANES], gk = gv[(size_t)k * LANES], gtk = gt[(size_t)k * LANES];
+            const float sn = xtk - xk, yn = gtk - gk, gn = is_new ? gtk : gk;
+            float yj[M], sj[M];
 #pragma unroll
-        for (int j = 0; j < M; ++j) {
-            yj[j] = j < m ? Y[((size_t)k * m + j) * LANES] : 0.f;
-            sj[j] = j < m ? S[((size_t)k * m + j) * LANES] : 0.f;
+            for (int j = 0; j < M; ++j) {
+                yj[j] = j < m ? Y[((size_t)k * m + j) * LANES] : 0.f;
+                sj[j] = j < m ? S[((size_t)k * m + j) * LANES] : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < M; ++j) {
+                aYG[j] += yj[j] * gn; aYY[j] += yj[j] * yn; aYS[j] += yj[j] * sn;
+                aSG[j] += sj[j] * gn; aSY[j] += sj[j] * yn;
+            }
+            sc[0] += sn * sn; sc[1] += sn * yn; sc[2] += yn * yn; sc[3] += gn * gn; sc[4] += sn * gn; sc[5] += yn * gn;
+            if (is_acc) {
+                S[((size_t)k * m + head) * LANES] = sn;
+                Y[((size_t)k * m + head) * LANES] = yn;
+            }
+            if (is_new) {
+                x[(size_t)k * LANES] = xtk;
+                gv[(size_t)k * LANES] = gtk;
+            }
         }
 #pragma unroll
         for (int j = 0; j < M; ++j) {
-            aYG[j] += yj[j] * gn; aYY[j] += yj[j] * yn; aYS[j] += yj[j] * sn;
-            aSG[j] += sj[j] * gn; aSY[j] += sj[j] * yn;
+            sm.u.red[warp][j][lane] = aYG[j]; sm.u.red[warp][M + j][lane] = aYY[j]; sm.u.red[warp][2 * M + j][lane] = aYS[j];
+            sm.u.red[warp][3 * M + j][lane] = aSG[j]; sm.u.red[warp][4 * M + j][lane] = aSY[j];
         }
-        sc[0] += sn * sn; sc[1] += sn * yn; sc[2] += yn * yn; sc[3] += gn * gn; sc[4] += sn * gn; sc[5] += yn * gn;
-        if (is_acc) {
-            S[((size_t)k * m + head) * LANES] = sn;
-            Y[((size_t)k * m + head) * LANES] = yn;
+#pragma unroll
+        for (int j = 0; j < LB_NSCAL; ++j) sm.u.red[warp][5 * M + j][lane] = sc[j];
+        __syncthreads();
+        float *__restrict__ part = s.lbpart + ((size_t)g * LB_MAXCH + ch) * NRED * LANES;
+        for (int e = threadIdx.x; e < NRED * LANES; e += LB_THREADS) {
+            const int idx = e / LANES, l = e % LANES;
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < LB_WARPS; ++w) t += sm.u.red[w][idx][l];
+            part[e] = t;
         }
-        if (is_new) {
-            x[(size_t)k * LANES] = xtk;
-            gv[(size_t)k * LANES] = gtk;
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < M; ++j) {
-        sm.u.red[warp][j][lane] = aYG[j]; sm.u.red[warp][M + j][lane] = aYY[j]; sm.u.red[warp][2 * M + j][lane] = aYS[j];
-        sm.u.red[warp][3 * M + j][lane] = aSG[j]; sm.u.red[warp][4 * M + j][lane] = aSY[j];
-    }
-#pragma unroll
-    for (int j = 0; j < LB_NSCAL; ++j) sm.u.red[warp][5 * M + j][lane] = sc[j];
-    __syncthreads();
-    float *__restrict__ part = s.lbpart + ((size_t)g * LB_MAXCH + ch) * NRED * LANES;
-    for (int e = threadIdx.x; e < NRED * LANES; e += LB_THREADS) {
-        const int idx = e / LANES, l = e % LANES;
-        float t = 0.f;
-#pragma unroll
-        for (int w = 0; w < LB_WARPS; ++w) t += sm.u.red[w][idx][l];
-        part[e] = t;
+        __syncthreads();   // the next chunk reuses the buffer
     }
 }
 
@@ -1199,34 +1213,53 @@ __global__ void activity_kernel(FoldState s)
     if (lane == 0) s.gactive[g] = m != 0;
 }
 
-// Slot assignment: the unfinished decoys of table block t, in decoy order, fill the slots
-// from the start of the block (one CTA per block, chunked block-wide exclusive scan).
-// identity != 0: every decoy gets its own slot (final consistent pass / parity entry).
+// Slot assignment: the unfinished decoys of table block t fill the slots from the start of the
+// block (one CTA per block, chunked block-wide exclusive scans): first, in decoy order, those
+// whose run in force scores the restraints, then those whose run does not (the vdw-only runs of
+// remove_clash, folding.py:119: all restraint weights zero) -- the restraint kernel and its
+// reduction skip the slot groups of the second kind (12 % of the evaluations of a fold).
+// identity != 0: every decoy gets its own slot and every group is scored (final consistent
+// pass / parity entries: the reported terms are unweighted and must be complete).
 __global__ void __launch_bounds__(1024) compact_kernel(FoldState s, int identity)
 {
     __shared__ int wsum[32];
-    __shared__ int base_s;
+    __shared__ int base_s, nk1_s;
     const int t = blockIdx.x, d0 = s.tab_d0[t], nt = s.tab_n[t];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int span = (nt + LANES - 1) / LANES * LANES;
+    const int span = (nt + LANES - 1) / LANES * LANES, Npad = s.Npad;
     if (threadIdx.x == 0) base_s = 0;
     __syncthreads();
-    for (int c0 = 0; c0 < span; c0 += 1024) {
-        const int i = c0 + threadIdx.x;
-        const bool live = i < nt && (identity || s.status[d0 + i] != ST_DONE);
-        const unsigned m = __ballot_sync(0xffffffffu, live);
-        if (lane == 0) wsum[warp] = __popc(m);
-        __syncthreads();
-        int off = base_s;
-        for (int w = 0; w < warp; ++w) off += wsum[w];
-        if (live) s.perm[d0 + off + __popc(m & ((1u << lane) - 1))] = d0 + i;
-        __syncthreads();
-        if (threadIdx.x == 0) { int tot = 0; for (int w = 0; w < 32; ++w) tot += wsum[w]; base_s += tot; }
+    for (int pass = 0; pass < (identity ? 1 : 2); ++pass) {
+        for (int c0 = 0; c0 < span; c0 += 1024) {
+            const int i = c0 + threadIdx.x;
+            bool pick = false;
+            if (i < nt) {
+                const int n = d0 + i;
+                if (identity) pick = true;
+                else if (s.status[n] != ST_DONE) {
+                    const bool k1 = !s.k1skip || s.wl[n] != 0.f || s.wl[(size_t)Npad + n] != 0.f || s.wl[(size_t)2 * Npad + n] != 0.f;
+                    pick = pass == 0 ? k1 : !k1;
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, pick);
+            if (lane == 0) wsum[warp] = __popc(m);
+            __syncthreads();
+            int off = base_s;
+            for (int w = 0; w < warp; ++w) off += wsum[w];
+            if (pick) s.perm[d0 + off + __popc(m & ((1u << lane) - 1))] = d0 + i;
+            __syncthreads();
+            if (threadIdx.x == 0) { int tot = 0; for (int w = 0; w < 32; ++w) tot += wsum[w]; base_s += tot; }
+            __syncthreads();
+        }
+        if (pass == 0 && threadIdx.x == 0) nk1_s = base_s;
         __syncthreads();
     }
-    const int nlive = base_s;
+    const int nlive = base_s, nk1 = identity ? nlive : nk1_s;
     for (int i = nlive + threadIdx.x; i < span; i += 1024) s.perm[d0 + i] = -1;
-    for (int g = threadIdx.x; g < span / LANES; g += 1024) s.gslot[d0 / LANES + g] = g * LANES < nlive;
+    for (int g = threadIdx.x; g < span / LANES; g += 1024) {
+        s.gslot[d0 / LANES + g] = g * LANES < nlive;
+        s.gneedk1[d0 / LANES + g] = g * LANES < nk1;
+    }
     if (threadIdx.x == 0) { s.nslot[t] = nlive; atomicAdd(s.nactive, nlive); }
 }
 
@@ -1547,6 +1580,8 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     s.ndof_t = 3 * L; s.ndof_c = NAT3 * s.Lpad; s.cart = 0; s.seg_hi = nruns;
     const int ndof_max = b->has_cart ? s.ndof_c : s.ndof_t;
     s.has_cart = b->has_cart ? 1 : 0;
+    s.k1skip = 1;
+    if (const char *ev = getenv("TRX_NO_K1SKIP")) s.k1skip = !(ev[0] && ev[0] != '0');   // A/B and tests: same results, bit for bit
     b->vdw_smem = sizeof(float4) * 6 * L + ((sizeof(int) * 18 * L + 15) / 16) * 16 + sizeof(float4) * L;
     TRX_REQUIRE(b->vdw_smem <= 220 * 1024, "trx_fold_create: L=%d exceeds the shared-memory budget of the vdw kernel", L);
     TRX_REQUIRE(L < 65536, "trx_fold_create: L too large");
@@ -1567,6 +1602,7 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     size_t o_ga = carve((size_t)G * 4), o_na = carve(256);
     size_t o_xs = carve(vec), o_fs = carve(np * 8), o_nacc = carve(np * 4);
     size_t o_perm = carve(np * 4), o_gs = carve((size_t)G * 4), o_ns = carve(256), o_ws = carve(np * 4 * TRX_NTERM);
+    size_t o_gk1f = carve((size_t)G * 4);
     size_t o_orig = carve(np * 4), o_ma = carve(np * 4), o_mb = carve(np * 4), o_mn = carve(256);
     size_t o_held = carve(np * 4), o_xh = carve(b->has_cart ? np * L * NAT3 * 4 : 256), o_th = carve(np * 8 * TRX_NTERM);
     cudaError_t e = cudaMalloc(&b->arena, off);
@@ -1590,6 +1626,7 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     s.E3 = (double *)(A + o_E3); s.Evdw = (double *)(A + o_Ev); s.gactive = (int *)(A + o_ga); s.nactive = (int *)(A + o_na);
     s.xsave = (float *)(A + o_xs); s.fsave = (double *)(A + o_fs); s.naccept = (int *)(A + o_nacc);
     s.perm = (int *)(A + o_perm); s.gslot = (int *)(A + o_gs); s.nslot = (int *)(A + o_ns); s.wslot = (float *)(A + o_ws);
+    s.gneedk1 = (int *)(A + o_gk1f);
     s.orig = (int *)(A + o_orig); s.mig_a = (int *)(A + o_ma); s.mig_b = (int *)(A + o_mb); s.mig_n = (int *)(A + o_mn);
     s.held = (int *)(A + o_held); s.xheld = (float *)(A + o_xh); s.theld = (double *)(A + o_th);
     s.ntab = ntab;
@@ -1645,7 +1682,7 @@ static int fold_eval(trx_fold_batch *b, const int *ng_tab, bool identity)
     for (size_t t = 0; t < b->tabs.size(); ++t) {
         const int ng = ng_tab ? std::min(ng_tab[t], b->tab_ng[t]) : b->tab_ng[t];
         if (ng <= 0) continue;
-        int rc = k1_launch<float>(ctx, b->tabs[t], s.G, b->tab_g0[t], ng, s.X, NAT3, s.wslot, nullptr, s.gslot, s.E3, s.gk1);
+        int rc = k1_launch<float>(ctx, b->tabs[t], s.G, b->tab_g0[t], ng, s.X, NAT3, s.wslot, nullptr, s.gneedk1, s.E3, s.gk1);
         if (rc) return rc;
     }
     ctx->time_begin("centroid");
@@ -1685,20 +1722,20 @@ static int run_rounds(trx_fold_batch *b, int max_rounds, int check_every, int *r
             if ((rc = fold_eval(b, ng.data(), false))) { cudaFreeHost(h_nslot); return rc; }
             ctx->time_begin("lbfgs");
             {   // enough CTAs for ~3 per SM, at least 4 vector elements per warp and chunk
-                int nch = std::max(1, (3 * 148 + s.G - 1) / s.G);
-                nch = std::min(nch, std::min(LB_MAXCH, std::max(1, s.ndof / (4 * LB_WARPS))));
+                int nch = std::max(1, (3 * 148 + s.G - 1) / s.G);   // CTAs that share a group's LB_MAXCH chunks
+                nch = std::min(nch, LB_MAXCH);
                 const dim3 grid(s.G, nch);
                 if (s.lb_M == 8) {
                     lbfgs_dots_kernel<8><<<grid, LB_THREADS, b->lb_smem, ctx->stream>>>(s);
-                    lbfgs_step_kernel<8><<<s.G, LB_STEP_THREADS, b->lb_smem, ctx->stream>>>(s, nch);
+                    lbfgs_step_kernel<8><<<s.G, LB_STEP_THREADS, b->lb_smem, ctx->stream>>>(s, LB_MAXCH);
                     lbfgs_update_kernel<8><<<grid, LB_THREADS, 0, ctx->stream>>>(s);
                 } else if (s.lb_M == 16) {
                     lbfgs_dots_kernel<16><<<grid, LB_THREADS, b->lb_smem, ctx->stream>>>(s);
-                    lbfgs_step_kernel<16><<<s.G, LB_STEP_THREADS, b->lb_smem, ctx->stream>>>(s, nch);
+                    lbfgs_step_kernel<16><<<s.G, LB_STEP_THREADS, b->lb_smem, ctx->stream>>>(s, LB_MAXCH);
                     lbfgs_update_kernel<16><<<grid, LB_THREADS, 0, ctx->stream>>>(s);
                 } else {
                     lbfgs_dots_kernel<24><<<grid, LB_THREADS, b->lb_smem, ctx->stream>>>(s);
-                    lbfgs_step_kernel<24><<<s.G, LB_STEP_THREADS, b->lb_smem, ctx->stream>>>(s, nch);
+                    lbfgs_step_kernel<24><<<s.G, LB_STEP_THREADS, b->lb_smem, ctx->stream>>>(s, LB_MAXCH);
                     lbfgs_update_kernel<24><<<grid, LB_THREADS, 0, ctx->stream>>>(s);
                 }
                 ctx->launches += 2;

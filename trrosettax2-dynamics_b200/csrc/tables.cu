@@ -90,12 +90,17 @@ using namespace trx;
 
 int trx_tables::get_plan(int groups, Plan **out)
 {
-    // chunk tiles of one block row so that the grid has a few waves of CTAs; plans are
-    // cached by chunk size (the only thing the group count changes)
-    static const int waves = [] { const char *ev = getenv("TRX_K1_WAVES"); const int v = ev ? atoi(ev) : 0; return v > 0 ? v : 6; }();
-    const long long want_ctas = 148LL * 4 * waves;   // 4 resident CTAs per SM, a few waves (TRX_K1_WAVES: development knob)
-    long long chunk = std::max(1LL, (long long)ntiles * groups / want_ctas);
-    chunk = std::min<long long>(chunk, std::max(1, nb));
+    // A work item is `chunk` consecutive tiles of one block row.  The chunk is a constant of the tables, NOT a
+    // function of the number of decoy groups: a CTA adds the row gradients of its tiles in shared memory before
+    // writing one row record, so the chunk fixes the order of those fp32 sums -- with a chunk that followed the
+    // live-decoy count (as an earlier version did, to keep a few waves of CTAs in flight) a decoy's gradient
+    // bits, and then its whole trajectory, depended on how many other decoys were still running.
+    // One tile per CTA (145 CTAs per decoy group on the L=300 bench tables): measured best inside a fold, where most
+    // launches carry a few hundred live decoys (chunk 1 / 2 / 3: 1379 / 1347 / 1294 decoys/s; standalone at 4096
+    // decoys 1.27 / 1.26 / 1.23 ms).  TRX_K1_CHUNK: development knob.
+    (void)groups;
+    static const int fixed_chunk = [] { const char *ev = getenv("TRX_K1_CHUNK"); const int v = ev ? atoi(ev) : 0; return v > 0 ? v : 1; }();
+    long long chunk = std::min<long long>(fixed_chunk, std::max(1, nb));
     auto it = plans.find((int)chunk);
     if (it != plans.end()) { *out = &it->second; return TRX_OK; }
     Plan p;
