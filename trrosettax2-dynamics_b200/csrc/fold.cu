@@ -84,7 +84,7 @@ struct FoldState {
     // per decoy [Npad]
     double *f, *fmem;        // accepted energy, last 3 accepted energies [3][Npad]
     float *alpha, *slope;
-    int lb_M;                // compile-time history bound of the L-BFGS kernel in use (8, 16 or 24)
+    int lb_M;                // compile-time history bound of the L-BFGS kernel in use (8, 16, 20 or 24)
     int *nmem, *hist, *head, *iter, *run, *bt, *status, *restart;
     int *evals, *iters;
     double *terms;           // [TRX_NTERM][Npad] unweighted terms of the last evaluation
@@ -1590,7 +1590,7 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
     const size_t vec = (size_t)G * ndof_max * LANES * sizeof(float), np = (size_t)s.Npad;
     size_t o_x = carve(vec), o_g = carve(vec), o_d = carve(vec), o_xt = carve(vec), o_gt = carve(vec);
-    const int lbM = lbfgs_m <= 8 ? 8 : (lbfgs_m <= 16 ? 16 : 24);
+    const int lbM = lbfgs_m <= 8 ? 8 : (lbfgs_m <= 16 ? 16 : (lbfgs_m <= 20 ? 20 : 24));
     size_t o_S = carve(vec * s.m), o_Y = carve(vec * s.m), o_rho = carve((size_t)G * 2 * lbM * lbM * LANES * sizeof(float));
     size_t o_lbp = carve((size_t)G * 16 * (5 * lbM + 8) * LANES * sizeof(float)), o_lbc = carve((size_t)G * (2 * lbM + 3) * LANES * sizeof(float));
     size_t o_f = carve(np * 8), o_al = carve(np * 4), o_sl = carve(np * 4), o_fm = carve(np * 24);
@@ -1655,6 +1655,7 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     int rc_attr;
     if (lbM == 8) rc_attr = lb_attr(lbfgs_dots_kernel<8>, lbfgs_step_kernel<8>, sizeof(LbSmem<8>));
     else if (lbM == 16) rc_attr = lb_attr(lbfgs_dots_kernel<16>, lbfgs_step_kernel<16>, sizeof(LbSmem<16>));
+    else if (lbM == 20) rc_attr = lb_attr(lbfgs_dots_kernel<20>, lbfgs_step_kernel<20>, sizeof(LbSmem<20>));
     else rc_attr = lb_attr(lbfgs_dots_kernel<24>, lbfgs_step_kernel<24>, sizeof(LbSmem<24>));
     if (rc_attr) return rc_attr;
     *out = b;
@@ -1733,6 +1734,10 @@ static int run_rounds(trx_fold_batch *b, int max_rounds, int check_every, int *r
                     lbfgs_dots_kernel<16><<<grid, LB_THREADS, b->lb_smem, ctx->stream>>>(s);
                     lbfgs_step_kernel<16><<<s.G, LB_STEP_THREADS, b->lb_smem, ctx->stream>>>(s, LB_MAXCH);
                     lbfgs_update_kernel<16><<<grid, LB_THREADS, 0, ctx->stream>>>(s);
+                } else if (s.lb_M == 20) {
+                    lbfgs_dots_kernel<20><<<grid, LB_THREADS, b->lb_smem, ctx->stream>>>(s);
+                    lbfgs_step_kernel<20><<<s.G, LB_STEP_THREADS, b->lb_smem, ctx->stream>>>(s, LB_MAXCH);
+                    lbfgs_update_kernel<20><<<grid, LB_THREADS, 0, ctx->stream>>>(s);
                 } else {
                     lbfgs_dots_kernel<24><<<grid, LB_THREADS, b->lb_smem, ctx->stream>>>(s);
                     lbfgs_step_kernel<24><<<s.G, LB_STEP_THREADS, b->lb_smem, ctx->stream>>>(s, LB_MAXCH);
