@@ -374,7 +374,7 @@ void trxo_cart_terms(int L, const int *aa, const double *xyz, double w_cart, dou
 double trxo_eval_cart(const trxo_target *T, const double *w, const double *xyz, double *terms, double *g)
 {
     const int L = T->L;
-    double *x9 = (double *)malloc(sizeof(double) * (size_t)L * 9), *g9 = (double *)malloc(sizeof(double) * (size_t)L * 9);
+    double *x9 = (double *)calloc((size_t)L * 9, sizeof(double)), *g9 = (double *)malloc(sizeof(double) * (size_t)L * 9);
     memset(g, 0, sizeof(double) * (size_t)L * TRX_NAT * 3);
     for (int i = 0; i < L; ++i) memcpy(x9 + (size_t)i * 9, XYZ(i, 0), 9 * sizeof(double));
     trxo_energy_grad(L, x9, T->sets[0], T->sets[1], T->sets[2], T->sets[3], w, terms, g9, NULL, NULL);
