@@ -14,6 +14,7 @@ Outputs
   geometry_random.npz                          reference get_dihedrals/get_angles on random points
   gen_rst_variants24.npz                       gen_idp_rst / gen_gpcr_rst / gen_rst_af2 tables on random L=24 inputs
   example_tmscore.npz                          bin/TMscore (TM-score, RMSD) + GloCon on the 8 example decoys and 2 natives
+  example_backbone_stats.npz                   bond / angle statistics of the reference's 8 example decoys (Rosetta-written)
   dynamics_example48.npz                       outer-loop arithmetic (get_neighbors, pros, process_distribution...)
 """
 import hashlib, os, shutil, sys, tempfile, types
@@ -293,7 +294,50 @@ def make_tmscore_golden():
     print("TMscore golden written:", tm[2, 0], rm[2, 0])
 
 
+def make_backbone_stats_golden():
+    """Ideal backbone geometry is a [ROSETTA-RECALL] item.  The reference's example decoys were
+    written by Rosetta after IdealizeMover + a final minimisation, so their bond lengths and angles sit on
+    Rosetta's ideal values: keep their means / standard deviations as the fixture the constants of
+    include/trx_centroid_model.h are checked against."""
+    import glob
+
+    def ang(a, b, c):
+        u, v = a - b, c - b
+        return np.degrees(np.arccos(np.dot(u, v) / np.linalg.norm(u) / np.linalg.norm(v)))
+
+    def dih(p1, p2, p3, p4):
+        b0, b1, b2 = p1 - p2, p3 - p2, p4 - p3
+        b1 = b1 / np.linalg.norm(b1)
+        v, w = b0 - np.dot(b0, b1) * b1, b2 - np.dot(b2, b1) * b1
+        return np.degrees(np.arctan2(np.dot(np.cross(b1, v), w), np.dot(v, w)))
+    keys = ("N-CA", "CA-C", "C-N", "C-O", "CA-CB", "N-CA-C", "CA-C-N", "C-N-CA", "CA-C-O", "O-C-N", "abs_omega", "N-C-CA-CB")
+    S = {k: [] for k in keys}
+    for f in sorted(glob.glob(f"{REF}/example/output/seq/pred_pdb/conf_*.pdb")):
+        at = {}
+        for ln in open(f):
+            if ln.startswith("ATOM") and ln[12:16].strip() in ("N", "CA", "C", "O", "CB"):
+                at.setdefault(int(ln[22:26]), {})[ln[12:16].strip()] = np.array([float(ln[30:38]), float(ln[38:46]), float(ln[46:54])])
+        r = [at[i] for i in sorted(at)]
+        for i, a in enumerate(r):
+            S["N-CA"].append(np.linalg.norm(a["CA"] - a["N"])); S["CA-C"].append(np.linalg.norm(a["C"] - a["CA"]))
+            S["C-O"].append(np.linalg.norm(a["O"] - a["C"]))
+            S["N-CA-C"].append(ang(a["N"], a["CA"], a["C"])); S["CA-C-O"].append(ang(a["CA"], a["C"], a["O"]))
+            if "CB" in a:
+                S["CA-CB"].append(np.linalg.norm(a["CB"] - a["CA"])); S["N-C-CA-CB"].append(dih(a["N"], a["C"], a["CA"], a["CB"]))
+            if i + 1 < len(r):
+                b = r[i + 1]
+                S["C-N"].append(np.linalg.norm(b["N"] - a["C"])); S["CA-C-N"].append(ang(a["CA"], a["C"], b["N"]))
+                S["C-N-CA"].append(ang(a["C"], b["N"], b["CA"])); S["O-C-N"].append(ang(a["O"], a["C"], b["N"]))
+                S["abs_omega"].append(abs(dih(a["CA"], a["C"], b["N"], b["CA"])))
+    np.savez_compressed(f"{HERE}/example_backbone_stats.npz", keys=np.array(keys), mean=np.array([np.mean(S[k]) for k in keys]),
+                        sd=np.array([np.std(S[k]) for k in keys]), n=np.array([len(S[k]) for k in keys]))
+    print("backbone statistics written")
+
+
 if __name__ == "__main__":
+    if "--backbone-only" in sys.argv:
+        make_backbone_stats_golden()
+        sys.exit(0)
     if "--tmscore-only" in sys.argv:
         make_tmscore_golden()
         sys.exit(0)
@@ -304,4 +348,5 @@ if __name__ == "__main__":
         main()
         make_variant_golden()
         make_tmscore_golden()
+        make_backbone_stats_golden()
     make_dynamics_golden()

@@ -141,3 +141,28 @@ def test_cartesian_run_is_held_until_a_torsion_run_starts(small):
     no_cart = F.fold(t0, fo.reference_schedule(cartesian=False)[:8], m=20, nthreads=3)
     e0 = np.array([F.eval_cart(no_cart["xyz"][n], w)[0] for n in range(3)])
     assert np.all(held["terms"] @ w < e0)
+
+
+def test_ideal_geometry_constants_match_rosetta_written_structures(golden_dir, small):
+    """SURVEY 8a row 12 lists the ideal backbone geometry as recalled from Rosetta.  The reference's own example
+    decoys (idealised and minimised by Rosetta 2023.42) pin it: mean bond lengths within 0.01 A, mean angles
+    within 1 degree of the constants NeRF builds with (include/trx_centroid_model.h)."""
+    g = np.load(f"{golden_dir}/example_backbone_stats.npz")
+    stat = dict(zip([str(k) for k in g["keys"]], g["mean"]))
+    seq, nat, F = small
+    xyz = F.nerf(fo.random_torsions(1, len(seq), 3)[0])
+    N, CA, CB, Cc, O = (xyz[:, k] for k in range(5))
+
+    def ang(a, b, c):
+        u, v = a - b, c - b
+        return np.degrees(np.arccos(np.sum(u * v, -1) / np.linalg.norm(u, axis=-1) / np.linalg.norm(v, axis=-1)))
+    ours = {"N-CA": np.linalg.norm(CA - N, axis=1).mean(), "CA-C": np.linalg.norm(Cc - CA, axis=1).mean(),
+            "C-N": np.linalg.norm(N[1:] - Cc[:-1], axis=1).mean(), "C-O": np.linalg.norm(O - Cc, axis=1).mean(),
+            "CA-CB": np.linalg.norm(CB - CA, axis=1).mean(), "N-CA-C": ang(N, CA, Cc).mean(),
+            "CA-C-N": ang(CA[:-1], Cc[:-1], N[1:]).mean(), "C-N-CA": ang(Cc[:-1], N[1:], CA[1:]).mean(),
+            "CA-C-O": ang(CA, Cc, O).mean(), "O-C-N": ang(O[:-1], Cc[:-1], N[1:]).mean()}
+    for k in ("N-CA", "CA-C", "C-N", "C-O", "CA-CB"):
+        assert abs(ours[k] - stat[k]) < 0.01, (k, ours[k], stat[k])
+    for k in ("N-CA-C", "CA-C-N", "C-N-CA", "CA-C-O", "O-C-N"):
+        assert abs(ours[k] - stat[k]) < 1.0, (k, ours[k], stat[k])
+    assert stat["abs_omega"] > 175.0      # trans peptides: the omega tether's minimum
