@@ -261,9 +261,9 @@ def make_tmscore_golden():
         for k, i in enumerate(ids):
             if "CB" in at[i]:
                 cb[k] = at[i]["CB"]
-        return ca, cb
+        return ca, cb, n
 
-    ca, cb = zip(*[backbone(p) for p in paths])
+    ca, cb, nn = zip(*[backbone(p) for p in paths])
     M = len(names)
     tm, rm = np.zeros((M, M)), np.zeros((M, M))
     for i, j in itertools.product(range(M), repeat=2):
@@ -289,7 +289,7 @@ def make_tmscore_golden():
         diff[diff <= 3] = 0
         glocon[i, j] = np.sum(np.triu(diff)) / (len(diff) * (len(diff) - 1) / 2)
     glocon = glocon + glocon.T
-    np.savez_compressed(f"{HERE}/example_tmscore.npz", names=np.array(names), ca=np.stack(ca), cb=np.stack(cb),
+    np.savez_compressed(f"{HERE}/example_tmscore.npz", names=np.array(names), ca=np.stack(ca), cb=np.stack(cb), n=np.stack(nn),
                         tm=tm, rmsd=rm, glocon=glocon)
     print("TMscore golden written:", tm[2, 0], rm[2, 0])
 

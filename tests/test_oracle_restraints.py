@@ -94,3 +94,35 @@ def test_energy_terms_sum_of_restraints(golden_dir):
     d = np.linalg.norm(xyz[s["a"], 2] - xyz[s["b"], 2], axis=-1)
     e = sum(ro.splinefunc(s["x"], s["y"][r], s["y2"][r], d[r])[0] for r in range(len(d)))
     assert abs(e - E[0]) < 1e-9 * abs(e)
+
+
+def test_reference_decoys_sit_in_the_minimum_of_our_restraint_score(golden_dir):
+    """An indirect pin against Rosetta's output.  The reference's 8 example decoys were minimised by PyRosetta
+    against the restraints of the example npz files; scored with THIS oracle's tables, conventions and splines
+    they must sit where a minimiser of the same objective ends up: far below a random start and below the
+    natives, at the level this repository's own fold reaches, and each decoy family must prefer the
+    distograms it was folded from (wrong dihedral signs or atom orders would destroy all of that)."""
+    from oracle import fold_oracle as fo
+    from oracle.tables_oracle import gen_rst_oracle, select_oracle
+    g = np.load(f"{golden_dir}/example_tmscore.npz")
+    names = [str(x) for x in g["names"]]
+    xyz = np.stack([g["n"], g["ca"], g["cb"]], axis=2)                       # (10, 90, 3 atoms, 3)
+    seq = open(f"{golden_dir}/example_seq.fasta").read().split("\n")[1]
+    w = np.array([5.0, 4.0, 4.0])
+    tot = {}
+    for tag in ("NMR", "Xray"):
+        rst = gen_rst_oracle(np.load(f"{golden_dir}/example_{tag}.npz"))
+        rs = ro.RestraintSetOracle(rst, select_oracle(rst, 1, 90, 0.05), "H1")
+        tot[tag] = np.array([rs.energy_grad(x, w)[0] @ w for x in xyz])
+        if tag == "NMR":
+            F = fo.FoldOracle(rs, seq)
+            start = np.array([rs.energy_grad(F.nerf(t)[:, :3], w)[0] @ w for t in fo.random_torsions(4, 90, 1)])
+            ours = F.fold(fo.random_torsions(8, 90, 5), fo.reference_schedule(), m=20, nthreads=8)["terms"][:, :3] @ w
+    dec, natives = tot["NMR"][2:], tot["NMR"][:2]
+    assert dec.max() < -240000 and natives.max() < -190000 and start.min() > -100000
+    assert dec.max() < natives.min()                                          # minimised decoys beat the natives on the predicted restraints
+    assert abs(np.median(ours) - np.median(dec)) < 0.03 * abs(np.median(dec))  # our minimiser ends at the same level
+    fam_a = [names.index(n) for n in ("conf_1_1", "conf_1_2", "conf_2_3", "conf_2_4")]   # apo-like family (BASELINE.md section 2)
+    fam_h = [names.index(n) for n in ("conf_1_3", "conf_1_4", "conf_2_1", "conf_2_2")]   # holo-like family
+    assert tot["Xray"][fam_a].max() < tot["Xray"][fam_h].min()               # apo-like decoys fit the X-ray-model distograms better
+    assert tot["NMR"][fam_h].max() < tot["NMR"][fam_a].min()                 # holo-like decoys fit the NMR-model distograms better
