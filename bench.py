@@ -82,6 +82,11 @@ class ClockSampler:
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        late = False
+        t0 = time.time()
+        while not self.rows and time.time() - t0 < 1.5:   # timed region shorter than the 100 ms sampling period
+            late = True
+            time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -91,8 +96,11 @@ class ClockSampler:
         mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for k, n in enumerate(names) if any(len(r) >= 8 and r[4 + k].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": reasons, "samples": len(sm)}
+        if late:
+            out["note"] = "timed region shorter than the sampling period: first sample taken right after it"
+        return out
 
 
 def build_workload(n_decoys, precision):
