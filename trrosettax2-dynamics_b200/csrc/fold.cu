@@ -1547,6 +1547,17 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     const int L = tabs[0]->L;
     int G = 0;
     trx_fold_batch *b = new trx_fold_batch();
+    struct Guard {   // every early return below releases what has been built so far
+        trx_fold_batch *b;
+        ~Guard()
+        {
+            if (!b) return;
+            if (b->arena) cudaFree(b->arena);
+            if (b->d_aa) cudaFree(b->d_aa);
+            if (b->d_runs) cudaFree(b->d_runs);
+            delete b;
+        }
+    } guard{b};
     b->ctx = ctx;
     if (const char *ev = getenv("TRX_NO_MIGRATE")) b->migrate = !(ev[0] && ev[0] != '0');
     if (const char *ev = getenv("TRX_MIGRATE_AT")) { int p = atoi(ev); if (p > 0 && p < 100) { b->mig_num = p; b->mig_den = 100; } }   // development knob (percent)
@@ -1608,7 +1619,7 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     cudaError_t e = cudaMalloc(&b->arena, off);
     if (e != cudaSuccess) {
         set_error("trx_fold_create: cudaMalloc(%zu bytes) failed: %s", off, cudaGetErrorString(e));
-        delete b;
+        b->arena = nullptr;
         return TRX_ERR_NOMEM;
     }
     b->arena_bytes = off;
@@ -1658,6 +1669,7 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     else if (lbM == 20) rc_attr = lb_attr(lbfgs_dots_kernel<20>, lbfgs_step_kernel<20>, sizeof(LbSmem<20>));
     else rc_attr = lb_attr(lbfgs_dots_kernel<24>, lbfgs_step_kernel<24>, sizeof(LbSmem<24>));
     if (rc_attr) return rc_attr;
+    guard.b = nullptr;
     *out = b;
     return TRX_OK;
 }

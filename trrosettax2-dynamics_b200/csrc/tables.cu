@@ -167,6 +167,10 @@ int trx_tables_create(trx_ctx *ctx, int L, const trx_rst_set sets[4], trx_tables
                         "trx_tables_create: sets[%d] restraint %d has bad residues (%d,%d)", t, r, s.a[r], s.b[r]);
     }
     trx_tables *T = new trx_tables();
+    struct Guard {   // a failing CUDA call below returns early: release what has been built
+        trx_tables *T;
+        ~Guard() { if (T) trx_tables_destroy(T); }
+    } guard{T};
     T->ctx = ctx;
     T->L = L;
     T->Lpad = padded_length(L);
@@ -186,12 +190,10 @@ int trx_tables_create(trx_ctx *ctx, int L, const trx_rst_set sets[4], trx_tables
         if (s.n && (g32[t].urun0 > 6 || g32[t].urun1 < s.K - 1)) {
             set_error("trx_tables_create: sets[%d].x must be uniformly spaced after at most 6 leading uneven intervals "
                       "(uniform run found: intervals [%d,%d) of %d)", t, g32[t].urun0, g32[t].urun1, s.K - 1);
-            trx_tables_destroy(T);
             return TRX_ERR_INVALID;
         }
         if (s.n && t != TRX_DIST && g32[t].urun0 != 0) {   // the fp32 kernel looks angular intervals up without a head search
             set_error("trx_tables_create: sets[%d].x (angular grid) must be uniformly spaced from its first knot", t);
-            trx_tables_destroy(T);
             return TRX_ERR_INVALID;
         }
         if (s.n == 0) continue;
@@ -254,7 +256,6 @@ int trx_tables_create(trx_ctx *ctx, int L, const trx_rst_set sets[4], trx_tables
             size_t p = (((size_t)tile * TILE + i % TILE) * TILE + j % TILE) * 8;
             if (rec[p + 1 + slot] != -1) {
                 set_error("trx_tables_create: duplicate restraint of type %d on pair (%d,%d)", t, sets[t].a[r], sets[t].b[r]);
-                trx_tables_destroy(T);
                 return TRX_ERR_INVALID;
             }
             if (rec[p] == 0) T->active_pairs++;
@@ -307,6 +308,7 @@ int trx_tables_create(trx_ctx *ctx, int L, const trx_rst_set sets[4], trx_tables
     TRX_CUDA(cudaMalloc(&T->d_pairrec, rec.size() * sizeof(int)));
     TRX_CUDA(cudaMemcpy(T->d_tileJ, tj.data(), tj.size() * sizeof(int), cudaMemcpyHostToDevice));
     TRX_CUDA(cudaMemcpy(T->d_pairrec, rec.data(), rec.size() * sizeof(int), cudaMemcpyHostToDevice));
+    guard.T = nullptr;
     *out = T;
     return TRX_OK;
 }
