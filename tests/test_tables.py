@@ -129,3 +129,61 @@ def test_select_idr_equals_oracle(golden_dir):
             want = select_idr_oracle(gen_idp_rst_oracle(inp, True), idr, pcut, seq, nogly)
             for name in got:
                 np.testing.assert_array_equal(got[name], want[name])
+
+
+# ---- edge cases of the table builder (empty / degenerate inputs)
+
+def test_no_contacts_gives_empty_records_and_empty_selection():
+    params = tables.load_params()
+    L = 12
+    def only_bin0(nb):
+        a = np.zeros((L, L, nb), dtype=np.float32)
+        a[..., 0] = 1.0                                     # every pair 'no contact': probability mass in bin 0
+        return a
+    npz = dict(dist=only_bin0(37), omega=only_bin0(25), theta=only_bin0(25), phi=only_bin0(13))
+    rst = tables.gen_rst(npz, params)
+    want = gen_rst_oracle(npz)
+    for name in tables.TYPES:
+        assert len(rst[name]["a"]) == 0 and rst[name]["y"].shape == (0, len(rst[name]["x"]))
+        assert len(want[name]["a"]) == 0
+    masks = tables.select(rst, 1, L, params)
+    assert all(m.shape == (0,) for m in masks.values())
+    act = tables.active_restraints(rst, masks)
+    assert all(len(act[t][0]) == 0 and act[t][3].shape[0] == 0 for t in tables.TYPES)
+
+
+def test_selection_window_edges_and_probability_thresholds(golden_dir):
+    params = tables.load_params()
+    rst = tables.gen_rst(np.load(f"{golden_dir}/example_NMR.npz"), params)
+    # windows are half-open [sep1, sep2): a window of width zero selects nothing, adjacent windows partition
+    assert not any(m.any() for m in tables.select(rst, 5, 5, params).values())
+    a, b, c = (tables.select(rst, s1, s2, params) for s1, s2 in ((1, 12), (12, 24), (24, 90)))
+    full = tables.select(rst, 1, 90, params)
+    for name in tables.TYPES:
+        assert not (a[name] & b[name]).any() and not (b[name] & c[name]).any()
+        np.testing.assert_array_equal(a[name] | b[name] | c[name], full[name])
+    # -pd acts on the selection only (gen_rst hard-codes 0.05, utils_ros.py:18): raising it can only remove restraints
+    params["PCUT"] = 0.45
+    high = tables.select(rst, 1, 90, params)
+    for name in tables.TYPES:
+        assert not (high[name] & ~full[name]).any() and high[name].sum() < full[name].sum()
+    params["PCUT"] = 2.0
+    assert not any(m.any() for m in tables.select(rst, 1, 90, params).values())
+
+
+def test_idr_mask_extremes(golden_dir):
+    from oracle.tables_oracle import gen_idp_rst_oracle
+    params = tables.load_params()
+    inp, known, af2 = _variant_inputs(golden_dir)
+    base = tables.gen_rst(inp, params, True, "no-idp")
+    none = dict(inp, idr=np.zeros_like(inp["idr"]))
+    every = dict(inp, idr=np.ones_like(inp["idr"]))
+    _same(tables.gen_rst(none, params, True, "idp"), base)                       # nothing flagged: gen_idp_rst == gen_rst
+    _same(tables.gen_rst(every, params, True, "idp"), gen_idp_rst_oracle(every, True))
+    # mode 3 with everything ordered: the 'disorder' stage adds nothing, the 'order' stage is add_rst over all separations
+    rst = tables.gen_rst(none, params, True, "idp")
+    first, second = tables.select_idr(rst, 1 - none["idr"], params), tables.select_idr(rst, none["idr"], params)
+    everything = tables.select(rst, 0, 10 ** 6, params)
+    for name in tables.TYPES:
+        assert not second[name].any()
+        np.testing.assert_array_equal(first[name], everything[name])
