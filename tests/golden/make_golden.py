@@ -277,10 +277,17 @@ def make_tmscore_golden():
     L = len(seq)
     glocon = np.zeros((M, M))
     dmaps = []
+    cfull = []
+    for p_ in paths:   # C atoms for the reference's own get_neighbors (utils_trX2dy/utils.py:125-182)
+        at = {}
+        for ln in open(p_):
+            if ln.startswith("ATOM") and ln[12:16].strip() == "C":
+                at[int(ln[22:26])] = [float(ln[30:38]), float(ln[38:46]), float(ln[46:54])]
+        cfull.append(np.array([at[i] for i in sorted(at)]))
     for k in range(M):
-        d = np.linalg.norm(cb[k][:, None] - cb[k][None], axis=-1)
-        d[d > 20.0] = 0.0
-        np.fill_diagonal(d, 0.0)
+        xyzs = {"N": nn[k], "CA": ca[k], "C": cfull[k], "CB": {i: cb[k][i] for i in range(L) if seq[i] != "G"}}
+        key, d, _, _, _ = ug.get_neighbors(xyzs, seq, 20)          # the reference's distance map: 0 beyond 20 A
+        assert key is False
         dmaps.append(d)
     for i, j in itertools.product(range(M), repeat=2):
         if i <= j:
