@@ -28,7 +28,7 @@ _DATA = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def load_params(path=None):
     """folding/data/params.json (same keys as the reference's)."""
     with open(path or os.path.join(_DATA, "params.json")) as fh:
-        return json.load(fh)
+        return {k: v for k, v in json.load(fh).items() if not k.startswith("_")}
 
 
 def round_decimals(v, nd):
