@@ -124,7 +124,9 @@ def gen_rst(npz, params, use_orient=None, variant="no-idp", known=None):
     meff = params["MEFF"]
     astep = np.deg2rad(params["ASTEP"])
     pcut = 0.05  # the reference hard-codes this here (utils_ros.py:18); -pd only acts in select()
-    idr = np.asarray(npz["idr"]).astype(bool) if variant != "no-idp" else None
+    if variant == "no-idp":
+        return _gen_rst_plain(npz, params, use_orient, meff, astep, pcut)
+    idr = np.asarray(npz["idr"]).astype(bool)
     rst = {}
 
     d = npz["dist"]
@@ -171,6 +173,39 @@ def gen_rst(npz, params, use_orient=None, variant="no-idp", known=None):
         i, j = i[m], j[m]
         rst[name] = dict(a=i.astype(np.int32), b=j.astype(np.int32), p=p[i, j],
                          x=round_decimals(knots, nd), y=round_decimals(e[i, j], nd), bin_size=astep5)
+    return rst
+
+
+def _gen_rst_plain(npz, params, use_orient, meff, astep, pcut):
+    """gen_rst proper (utils_ros.py:6-146), the variant the dynamics loop calls once per iteration: the pairs are
+    selected first and the energies evaluated for those rows only (elementwise the same float32 / float64
+    operations as on the full (L, L, bins) arrays: identical knots, ~5 x less work at L = 300)."""
+    rst = {}
+    d = npz["dist"]
+    centres = 4.25 + params["DSTEP"] * np.arange(32)
+    p = d[..., 5:].sum(axis=-1)
+    i, j = np.nonzero(p > pcut)
+    m = j > i
+    i, j = i[m], j[m]
+    rst["dist"] = dict(a=i.astype(np.int32), b=j.astype(np.int32), p=p[i, j],
+                       x=round_decimals(np.concatenate([params["DREP"], centres]), 3),
+                       y=round_decimals(_dist_table(d[i, j], params, centres), 3), bin_size=0.5)
+    if not use_orient:
+        return rst
+    astep5 = float(round_decimals(astep, 5))
+    for name, nd, unordered in (("omega", 5, True), ("theta", 3, False), ("phi", 3, False)):
+        t = npz[name]
+        nb = t.shape[2]
+        lo = -1.5 * astep if name == "phi" else -np.pi - 1.5 * astep
+        p = t[..., 1:].sum(axis=-1)
+        i, j = np.nonzero(p > pcut)
+        m = (j > i) if unordered else (j != i)
+        i, j = i[m], j[m]
+        ts = t[i, j]
+        e = _pad(-np.log((ts + meff) / (ts[..., -1:] + meff)), name)          # float32 throughout
+        rst[name] = dict(a=i.astype(np.int32), b=j.astype(np.int32), p=p[i, j],
+                         x=round_decimals(np.linspace(lo, np.pi + 1.5 * astep, nb + 3), nd), y=round_decimals(e, nd),
+                         bin_size=astep5)
     return rst
 
 
