@@ -33,3 +33,22 @@ def test_no_cpu_fallback_without_gpu():
         pytest.skip("GPU present")
     with pytest.raises(capi.TrxError, match="no CUDA device|CPU fallback"):
         capi.Context(0)
+
+
+def test_headers_are_plain_c(tmp_path):
+    """The boundary is a C ABI: both headers must compile as C99 (no C++-isms, no torch types), and every entry
+    point must say which reference code it replaces."""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('#include "trx2dyn.h"\n#include "trx_centroid_model.h"\nint main(void) { return trx_abi_version() * 0; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    text = open(os.path.join(ROOT, "include", "trx2dyn.h")).read()
+    code = re.sub(r"/\*.*?\*/", "", text, flags=re.S)                  # comments may mention torch streams
+    assert "torch" not in code.lower() and "std::" not in code and "at::" not in code
+    # the compute entry points cite the reference lines they replace
+    for fn in ("trx_tables_create", "trx_energy_grad", "trx_fold_create", "trx_fold_run", "trx_glocon_matrix", "trx_tmscore_matrix"):
+        head = text[:text.index("int " + fn + "(")]
+        comment = head[head.rindex("/*"):]
+        assert "Replaces" in comment and (".py:" in comment), fn
