@@ -508,7 +508,8 @@ int k1_launch(trx_ctx *ctx, trx_tables *tb, int Gtot, int g0, int ng, const T *d
     if (plan->nwork > 0) {
         ctx->time_begin("restraints");
         const size_t dyn = 2 * REC_ELEMS * sizeof(T);
-        static bool attr_set[2] = {false, false};
+        static bool attr_set_dev[64][2] = {};   // function attributes are per device
+        bool *attr_set = attr_set_dev[ctx->device & 63];
         if (!attr_set[sizeof(T) == 8]) {
             TRX_CUDA(cudaFuncSetAttribute(restraints_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
             int carve = TRX_K1_CARVEOUT;
