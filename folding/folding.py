@@ -50,6 +50,20 @@ def main(argv=None):
     seq = read_fasta(args.FASTA)
     L = len(seq)
     params["seq"] = seq
+    odd = sorted(set(seq) - set(sampler.AA_ORDER))
+    if odd:
+        print("warning: non-standard residue letter(s) %s are scored as Ala" % ", ".join(odd), file=sys.stderr)
+    n = args.ndecoy
+    if n > 1 and "{i}" not in args.OUT:
+        raise SystemExit("folding.py: --ndecoy %d needs a '{i}' placeholder in -OUT (every decoy would be written to %s)" % (n, args.OUT))
+    # what differs from the reference's energy function, said where a user sees it (and in the PDB REMARKs)
+    dropped = schedule.ignored_terms()
+    model_note = ["energy function: atom_pair/dihedral/angle constraints as the reference; vdw, rama, omega, cart_bonded are",
+                  "stated approximations of Rosetta's centroid terms (include/trx_centroid_model.h); no full-atom FastRelax"]
+    if dropped:
+        model_note.append("weight-file terms NOT scored: " + ", ".join("%s %g (%s)" % (t, w, f) for f, t, w in dropped))
+    for ln in model_note:
+        print("note: " + ln, file=sys.stderr)
     ctx = capi.Context(max(args.gpu, 0))
     # restraint tables of the requested variant (folding.py:60-68)
     known = None
@@ -78,14 +92,13 @@ def main(argv=None):
         second = tables.select_idr(rst, idr, params)
         stages = [first, {k: first[k] | second[k] for k in first}]
 
-    n = args.ndecoy
     seed = args.seed if args.seed is not None else int.from_bytes(os.urandom(4), "little")
     tors = sampler.random_torsions(n, L, seed)
     aa = sampler.aa_index(seq)  # Gly -> Ala for the centroid stage (folding.py:112-115)
     out = None
     for k, masks in enumerate(stages):
-        if not any(m.any() for m in masks.values()):
-            continue                                   # nothing selected up to this stage (add_rst returns early, utils_ros.py:725)
+        # a stage with nothing selected still runs its movers (add_rst returns early, utils_ros.py:725, but
+        # repeat_mover / min_mover_cart / remove_clash follow, folding.py:129-171): empty tables
         tb = capi.Tables(ctx, L, tables.active_restraints(rst, masks, args.spline_end_rule))
         # remove_clash(sf_vdw, min_mover_vdw) runs once, before the first stage (folding.py:119)
         runs = schedule.reference_schedule() if len(stages) == 1 else schedule.window_schedule(initial_clash=(out is None))
@@ -94,13 +107,11 @@ def main(argv=None):
         tors = out["tors"]
         batch.close()
         tb.close()
-    if out is None:
-        raise SystemExit("folding.py: no restraint passed the probability thresholds; nothing to fold against")
     names = schedule.TERMS
     for i in range(n):
         path = args.OUT.replace("{i}", str(args.start_id + i)) if n > 1 or "{i}" in args.OUT else args.OUT
         os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
-        remark = ["%s %.3f" % (nm, v) for nm, v in zip(names, out["terms"][i])]
+        remark = ["%s %.3f" % (nm, v) for nm, v in zip(names, out["terms"][i])] + model_note
         pdbio.write_pdb(path, seq, out["xyz"][i], remark)
     print("\ndone: %d decoy(s), %d energy evaluations each on average" % (n, int(out["evals"].mean())))
 

@@ -147,6 +147,21 @@ int trx_fold_destroy(trx_fold_batch *b);
  * Replaces: remove_clash + repeat_mover.apply + remove_clash (folding.py:119,164-171). */
 int trx_fold_run(trx_fold_batch *b, float *tors, float *xyz, double *terms, long long *stats, int max_rounds,
                  int check_every, int *rounds_out);
+/* Continuous batching: folds nq[t] decoys against table block t -- any number, normally many more than the
+ * batch has positions (ndecoys[t] of trx_fold_create) -- keeping the positions full: a position whose decoy
+ * has finished the schedule segment in progress (torsion-space runs | min_mover_cart | torsion-space runs)
+ * is refilled with the next waiting decoy in the same evaluation round; between segments a decoy lives in a
+ * device-side queue record (torsions, held coordinates, terms, counters).  Arrays as trx_fold_run with
+ * N = sum nq[t], the decoys of block 0 first.  A decoy's result does not depend on the position it occupied,
+ * on nq or on the batch size, bit for bit.
+ * Replaces: folding_with_pred_npz(repeat=N) (utils_trX2dy/utils.py:484-505), whose ThreadPoolExecutor keeps
+ * min(32, cpu+4) one-decoy processes in flight until the N decoys are done. */
+int trx_fold_run_queue(trx_fold_batch *b, const int *nq, float *tors, float *xyz, double *terms, long long *stats,
+                       int max_rounds, int check_every, int *rounds_out);
+/* Restraint-kernel work of the last trx_fold_run / trx_fold_run_queue / trx_fold_mc call on this batch: decoy
+ * evaluations the restraint kernel made per table block (evaluations of vdw-only runs skip it).  out: [ntab].
+ * Measurement aid (roofline accounting of bench.py); no reference counterpart. */
+int trx_fold_k1_evals(trx_fold_batch *b, long long *out);
 /* Monte-Carlo sampling on top of the fold -- an EXTENSION with no reference behaviour
  * (BASELINE config 4; the reference's folding/ has no Metropolis step).
  * Minimises through the whole schedule, whose LAST run (index mc_run) defines the MC score;
@@ -158,6 +173,12 @@ int trx_fold_run(trx_fold_batch *b, float *tors, float *xyz, double *terms, long
 int trx_fold_mc(trx_fold_batch *b, float *tors, float *xyz, double *terms, long long *stats, int mc_run, int cycles,
                 double kT, int block_min, int block_max, double sigma_deg, unsigned long long seed,
                 unsigned long long id_offset, int max_rounds, int check_every, int *rounds_out);
+/* trx_fold_mc over a queue of nq[t] decoys per table block (see trx_fold_run_queue; nq NULL = one decoy per
+ * position).  The Monte-Carlo cycles are part of each decoy's own state machine: a decoy that finishes a
+ * minimisation is judged, perturbed and restarted in the same evaluation round. */
+int trx_fold_mc_queue(trx_fold_batch *b, const int *nq, float *tors, float *xyz, double *terms, long long *stats, int mc_run,
+                      int cycles, double kT, int block_min, int block_max, double sigma_deg, unsigned long long seed,
+                      unsigned long long id_offset, int max_rounds, int check_every, int *rounds_out);
 /* One evaluation at given torsions under uniform weights (parity entry for the NeRF /
  * vdw / rama / omega / torsion-gradient kernels): total[N], terms[N][7], gtors[N][L][3],
  * xyz[N][L][5][3] (any output may be NULL). */

@@ -65,3 +65,24 @@ def test_generate_loop_with_a_stub_folder():
     decoys = dynamics.generate(fold_fn, npz0, L, n_init=4, n_max=5)
     assert calls[0] == 4 and all(c == 1 for c in calls[1:])
     assert len(decoys) == 4 + len(calls) - 1 and len(calls) - 1 <= 5
+
+
+def test_generate_uses_the_decoys_own_cb_like_the_reference(gold):
+    # the product loop (pipeline.run_single_from_npz -> dynamics.generate) must take the decoy's real CB for
+    # every non-Gly residue, as the reference does when it re-reads the PDB (utils.py:145-150): the
+    # distograms handed to the second fold are the reference-run golden ones
+    seq = str(gold["seq"])
+    L = len(seq)
+    npz0 = {k: gold[f"in_{k}"] for k in ("dist", "omega", "theta", "phi")}
+    seen = []
+
+    def fold_fn(npz, n):
+        seen.append(npz)
+        xyz = np.stack([gold["n"], gold["ca"], np.nan_to_num(gold["cb"]), gold["c"], gold["c"] + 1.0], axis=1)
+        return dict(xyz=np.repeat(xyz[None], n, 0), tors=np.zeros((n, L, 3)))
+
+    dynamics.generate(fold_fn, npz0, L, n_init=2, n_max=1, seq=seq)
+    assert len(seen) == 2
+    for k in ("dist", "omega", "theta", "phi"):
+        np.testing.assert_array_equal(seen[1][k], gold[f"proc_{k}"])
+    np.testing.assert_array_equal(seen[1]["tmp"], gold["tmp"])

@@ -324,6 +324,72 @@ def test_folding_cli_variants(tmp_path, golden_dir):
     assert res.returncode != 0 and "-KNOWN" in res.stderr
 
 
+def test_continuous_batching_is_bit_identical(ctx):
+    """trx_fold_run_queue: 235 decoys of two table blocks folded through 96 positions (a position is refilled as
+    soon as its decoy leaves the schedule segment in progress) give, decoy for decoy and bit for bit, what one
+    resident batch of 235 positions gives -- torsions, coordinates, terms, counters, MC acceptance -- through the
+    torsion | Cartesian | torsion segments and through Monte-Carlo cycles.  Also a queue shorter than the batch."""
+    seq, npzs, nat = synth.target(48, seed=12, two_model=True)
+    params = tables.load_params()
+    tabs = [sampler.build_tables(ctx, z, seq, params) for z in npzs]
+    aa = sampler.aa_index(seq)
+    nd = [160, 75]
+    t0 = sampler.random_torsions(sum(nd), 48, seed=4)
+    big = capi.FoldBatch(ctx, tabs, nd, aa, schedule.reference_schedule())
+    ref = big.run(t0)
+    k1_ref = big.k1_evals()
+    big.close()
+    small = capi.FoldBatch(ctx, tabs, [64, 32], aa, schedule.reference_schedule())
+    got = small.run_queue(t0, nd)
+    for key in ref:
+        if key != "rounds":
+            np.testing.assert_array_equal(got[key], ref[key], err_msg=key)
+    assert got["rounds"] > ref["rounds"]                      # fewer positions, more rounds
+    assert small.k1_evals() == k1_ref                         # the same restraint-kernel work, decoy for decoy
+    assert 0 < k1_ref[0] < ref["evals"][:160].sum() + 3 * 160  # vdw-only evaluations skip the kernel; 3 closing evaluations per decoy
+    few = small.run_queue(np.concatenate([t0[:20], t0[160:165]]), [20, 5])
+    np.testing.assert_array_equal(few["tors"], np.concatenate([ref["tors"][:20], ref["tors"][160:165]]))
+    np.testing.assert_array_equal(few["xyz"], np.concatenate([ref["xyz"][:20], ref["xyz"][160:165]]))
+    small.close()
+    runs = schedule.mc_schedule(mc_max_iter=60)
+    big = capi.FoldBatch(ctx, tabs, nd, aa, runs)
+    ref = big.run_mc(t0, cycles=3, kT=2.0, sigma_deg=25.0, seed=5)
+    big.close()
+    small = capi.FoldBatch(ctx, tabs, [64, 32], aa, runs)
+    got = small.run_mc(t0, cycles=3, kT=2.0, sigma_deg=25.0, seed=5, nq=nd)
+    for key in ref:
+        if key != "rounds":
+            np.testing.assert_array_equal(got[key], ref[key], err_msg="mc " + key)
+    assert ref["accepted"].sum() > 0
+    small.close()
+    for t in tabs:
+        t.close()
+
+
+def test_round_budget_closes_every_decoy(ctx):
+    """max_rounds exhausted mid-schedule: every decoy (running, or still waiting in the queue) is closed at its
+    accepted point with one consistent evaluation -- finite coordinates whose NeRF rebuild is the torsions
+    returned, terms of those coordinates."""
+    seq, npzs, nat = synth.target(40, seed=3)
+    params = tables.load_params()
+    tb = sampler.build_tables(ctx, npzs[0], seq, params)
+    runs = schedule.reference_schedule()
+    batch = capi.FoldBatch(ctx, [tb], [32], sampler.aa_index(seq), runs)
+    t0 = sampler.random_torsions(80, 40, seed=1)
+    out = batch.run_queue(t0, [80], max_rounds=48)
+    assert np.all(np.isfinite(out["xyz"])) and np.all(np.isfinite(out["terms"]))
+    assert out["evals"][:32].min() > 0 and out["evals"][64:].max() == 0      # the tail of the queue never started
+    np.testing.assert_array_equal(out["tors"][64:], t0[64:])
+    chk = capi.FoldBatch(ctx, [tb], [80], sampler.aa_index(seq), runs)
+    w = np.array(list(runs[5].w))
+    _, terms, _, xyz = chk.eval(out["tors"], w)
+    assert np.abs(xyz - out["xyz"]).max() < 1e-4
+    assert np.allclose(terms, out["terms"], rtol=1e-6, atol=1e-6)
+    full = batch.run_queue(t0, [80])
+    assert np.all((full["terms"] @ w) < (out["terms"] @ w)[:80] + 1e-6)
+    chk.close(); batch.close(); tb.close()
+
+
 def test_monte_carlo_extension(ctx):
     """Extension with no reference behaviour: checks the invariants it can have --
     Metropolis never loses the best state at kT -> 0, counters are sane, trajectories are

@@ -38,6 +38,8 @@ def lib():
         L.trx_last_error.restype = C.c_char_p
         L.trx_ctx_launch_count.restype = C.c_longlong
         L.trx_ctx_launch_count.argtypes = [C.c_void_p]
+        for fn in (L.trx_fold_run_queue, L.trx_fold_mc_queue, L.trx_fold_k1_evals):
+            fn.restype = C.c_int
         _lib = L
     return _lib
 
@@ -226,19 +228,51 @@ class FoldBatch:
                                  C.c_int(check_every), C.byref(rounds)))
         return dict(tors=tors, xyz=xyz, terms=terms, evals=stats[:, 0], iters=stats[:, 1], rounds=rounds.value)
 
-    def run_mc(self, tors, cycles, kT=2.0, block=(3, 9), sigma_deg=20.0, seed=0, id_offset=0, max_rounds=20000,
-               check_every=16):
-        """Fold, then `cycles` Monte-Carlo cycles (perturb / re-minimise with the schedule's LAST run /
-        Metropolis) on device.  Returns the dict of run() plus 'accepted' (N,)."""
+    def _nq(self, tors, nq):
+        nq = self.ndecoys if nq is None else [int(n) for n in nq]
+        if len(nq) != len(self.ndecoys):
+            raise ValueError("nq must give a decoy count per table block")
         tors = np.ascontiguousarray(tors, dtype=np.float32).copy()
-        xyz = np.zeros((self.N, self.L, 5, 3), dtype=np.float32)
-        terms = np.zeros((self.N, NTERM))
-        stats = np.zeros((self.N, 3), dtype=np.int64)
+        if tors.shape != (sum(nq), self.L, 3):
+            raise ValueError("tors must be (%d, %d, 3)" % (sum(nq), self.L))
+        return tors, nq, (C.c_int * len(nq))(*nq)
+
+    def run_queue(self, tors, nq, max_rounds=1 << 30, check_every=16, want_xyz=True):
+        """Continuous batching (trx_fold_run_queue): folds nq[t] decoys against table block t through the
+        batch's positions, refilling a position as soon as its decoy has left the schedule segment in
+        progress.  tors (sum nq, L, 3), the decoys of block 0 first.  Same dict as run()."""
+        tors, nq, arr = self._nq(tors, nq)
+        n = sum(nq)
+        xyz = np.zeros((n, self.L, 5, 3), dtype=np.float32) if want_xyz else None
+        terms = np.zeros((n, NTERM))
+        stats = np.zeros((n, 2), dtype=np.int64)
         rounds = C.c_int()
-        check(lib().trx_fold_mc(self._h, _ptr(tors, C.c_float), _ptr(xyz, C.c_float), _ptr(terms, C.c_double),
-                                _ptr(stats, C.c_longlong), C.c_int(self.nruns - 1), C.c_int(cycles), C.c_double(kT),
-                                C.c_int(block[0]), C.c_int(block[1]), C.c_double(sigma_deg), C.c_ulonglong(seed),
-                                C.c_ulonglong(id_offset), C.c_int(max_rounds), C.c_int(check_every), C.byref(rounds)))
+        check(lib().trx_fold_run_queue(self._h, arr, _ptr(tors, C.c_float), _ptr(xyz, C.c_float) if want_xyz else None,
+                                       _ptr(terms, C.c_double), _ptr(stats, C.c_longlong), C.c_int(max_rounds),
+                                       C.c_int(check_every), C.byref(rounds)))
+        return dict(tors=tors, xyz=xyz, terms=terms, evals=stats[:, 0], iters=stats[:, 1], rounds=rounds.value)
+
+    def k1_evals(self):
+        """Decoy evaluations the restraint kernel made in the last run*/run_mc call, per table block."""
+        out = (C.c_longlong * len(self.ndecoys))()
+        check(lib().trx_fold_k1_evals(self._h, out))
+        return [int(v) for v in out]
+
+    def run_mc(self, tors, cycles, kT=2.0, block=(3, 9), sigma_deg=20.0, seed=0, id_offset=0, max_rounds=1 << 30,
+               check_every=16, nq=None):
+        """Fold, then `cycles` Monte-Carlo cycles (perturb / re-minimise with the schedule's LAST run /
+        Metropolis) on device.  nq: decoys per table block (continuous batching), default one per position.
+        Returns the dict of run() plus 'accepted' (N,)."""
+        tors, nq, arr = self._nq(tors, nq)
+        n = sum(nq)
+        xyz = np.zeros((n, self.L, 5, 3), dtype=np.float32)
+        terms = np.zeros((n, NTERM))
+        stats = np.zeros((n, 3), dtype=np.int64)
+        rounds = C.c_int()
+        check(lib().trx_fold_mc_queue(self._h, arr, _ptr(tors, C.c_float), _ptr(xyz, C.c_float), _ptr(terms, C.c_double),
+                                      _ptr(stats, C.c_longlong), C.c_int(self.nruns - 1), C.c_int(cycles), C.c_double(kT),
+                                      C.c_int(block[0]), C.c_int(block[1]), C.c_double(sigma_deg), C.c_ulonglong(seed),
+                                      C.c_ulonglong(id_offset), C.c_int(max_rounds), C.c_int(check_every), C.byref(rounds)))
         return dict(tors=tors, xyz=xyz, terms=terms, evals=stats[:, 0], iters=stats[:, 1], accepted=stats[:, 2],
                     rounds=rounds.value)
 

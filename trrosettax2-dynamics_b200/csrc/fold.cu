@@ -22,6 +22,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "internal.cuh"
 #include "../../include/trx_centroid_model.h"
@@ -65,16 +66,27 @@ struct Model {   // centroid model constants in device-friendly (float) form
 };
 __constant__ Model c_model;
 
-// status of a decoy between evaluation rounds
-enum { ST_INIT = 0, ST_LS = 1, ST_DONE = 2 };
+// status of a position between evaluation rounds.  ST_FINAL: the decoy has left the segment in progress; its
+// accepted point is evaluated once more (all terms, trial point = accepted point) so that what is parked --
+// torsions, coordinates, terms -- is one consistent evaluation; ST_DONE: nothing to do (finished or empty).
+enum { ST_INIT = 0, ST_LS = 1, ST_DONE = 2, ST_FINAL = 3 };
+
+// Monte-Carlo extension (trx_fold_mc): options of the call; cycles == 0 switches it off
+struct McOpts {
+    unsigned long long seed, id_offset;
+    int cycles, block_min, block_max, mc_run;
+    float sigma, kT;
+};
 
 struct FoldState {
     int N, Npad, G, L, Lpad, ndof, m, nruns;
     int ndof_t, ndof_c;      // torsion space: 3 L; Cartesian: 15 Lpad (the layout of X)
     int cart;                // the segment in progress is Cartesian
-    int has_cart;            // the schedule has a Cartesian run (xheld is allocated)
+    int has_cart;            // the schedule has a Cartesian run (the queue keeps held coordinates)
     int k1skip;              // skip the restraint kernel for slot groups whose runs do not score restraints
-    int seg_hi;              // first run after the segment in progress
+    int seg_lo, seg_hi;      // runs of the segment in progress: [seg_lo, seg_hi)
+    int seg_last;            // ... it is the last one: a decoy that leaves it is finished (results are written)
+    int park_X;              // ... the next one is Cartesian: a decoy that leaves it parks its coordinates too
     // vectors [G][ndof][32]
     float *x, *g, *d, *xt, *gt;
     float *S, *Y;            // [G][ndof][m][32]
@@ -100,7 +112,9 @@ struct FoldState {
     int *nactive;            // [1]
     // slot space: the unfinished decoys of each table block, compacted to the front of the
     // block every round, so the evaluation kernels only touch live lanes
-    int *perm;               // [Npad] slot -> decoy, -1 for an empty slot
+    int *perm;               // [Npad] slot -> position, -1 for an empty slot
+    int *slot_of;            // [Npad] position -> slot of the evaluation round just made
+    long long *k1count;      // [16] decoy evaluations the restraint kernel made per table block (roofline accounting)
     int *gslot;              // [G] slot group holds a live slot
     int *gneedk1;            // [G] ... and one whose run scores the restraints (others skip the restraint kernel)
     int *nslot;              // [16] live slots per table block
@@ -111,16 +125,36 @@ struct FoldState {
     float *xsave;            // [G][ndof][32]
     double *fsave;           // [Npad]
     int *naccept;            // [Npad]
-    // a decoy that went through a Cartesian run HOLDS those coordinates (and their terms)
-    // until a torsion-space run starts and rebuilds it with ideal bond geometry
+    int *mccyc;              // [Npad] perturbations made so far
+    McOpts mc;
+    // a decoy that went through a Cartesian run HOLDS those coordinates (in the queue store) and their
+    // terms until a torsion-space run starts and rebuilds it with ideal bond geometry
     int *held;               // [Npad]
-    float *xheld;            // [Npad][L][15]
     double *theld;           // [TRX_NTERM][Npad]
+    // Continuous batching.  A call folds nq_tab[t] decoys per table block through the tab_n[t] POSITIONS of
+    // the block: every round the positions whose decoy has left the segment in progress are parked into
+    // the queue store and refilled with the next waiting decoy, so the batch stays full until the queue
+    // drains.  The schedule is walked segment by segment over the whole queue (a segment changes the
+    // degrees of freedom); between segments a decoy is its queue record: torsions, held coordinates,
+    // terms, run index, counters.  Queue ids are block-major, each block starting at a multiple of 32.
+    int nq_tab[16], qd0[16], qc0[16];   // decoys of the call per block; first queue id; first caller index
+    int Nqpad;
+    int *qcursor;            // [16] queue entries of each block handed out so far
+    int *qocc;               // [16] occupied positions of each block after the last turnover
+    int *newid;              // [Npad] turnover plan: queue id to load, -1 = leave empty, -2 = no change
+    float *q_tors;           // [Nqpad/32][3L][32]
+    float *q_X;              // [Nqpad/32][Lpad*15][32] (only with a Cartesian run)
+    double *q_terms;         // [TRX_NTERM][Nqpad]
+    int *q_run, *q_held, *q_evals, *q_iters;   // [Nqpad]
+    // results in the caller's order
+    float *o_tors, *o_xyz;   // [Nq][3L], [Nq][L][15] (o_xyz may be NULL)
+    double *o_terms;         // [Nq][TRX_NTERM]
+    long long *o_stats;      // [Nq][3] evaluations, accepted iterations, accepted MC moves
     // Migration: the position of a decoy in the arrays above is not its identity.  When fewer than
     // half of a table block's positions hold unfinished decoys, the unfinished ones are moved to the
     // front of the block (swapped with finished ones), so the L-BFGS kernels -- which stream a whole
     // 32-decoy group if any of its decoys is unfinished -- stream only ~live/32 groups.
-    int *orig;               // [Npad] decoy id (index into the caller's arrays) held at each position
+    int *orig;               // [Npad] queue id of the decoy held at each position, -1 = empty
     int *mig_a, *mig_b;      // [Npad] position pairs to swap (per table block, from its first position)
     int *mig_n;              // [16] pairs per table block
     const int *aa;           // [L]
@@ -761,64 +795,92 @@ __global__ void __launch_bounds__(CART_THREADS) cart_grad_kernel(FoldState s)
     }
 }
 
-// Start of a Cartesian segment: x = xt = current coordinates of every decoy (X of the
-// identity-slot evaluation just made, or the coordinates the decoy still holds).
-__global__ void __launch_bounds__(256) cart_begin_kernel(FoldState s)
+// Backbone torsions of residue i read back from coordinates (load(i, atom) -> f3): what a decoy keeps of its
+// Cartesian run when a torsion-space run rebuilds it with ideal bond geometry.
+template <typename LoadFn>
+__device__ __forceinline__ void readback_torsions(LoadFn load, int i, int L, float &phi, float &psi, float &omg)
 {
-    const int g = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, n = g * LANES + lane;
-    const bool hd = n < s.N && s.held[n];
-    const float *__restrict__ X = s.X + (size_t)g * s.Lpad * NAT3 * LANES + lane;
-    const float *__restrict__ xh = s.xheld + (size_t)n * s.L * NAT3;
-    float *__restrict__ x = s.x + (size_t)g * s.ndof_c * LANES + lane, *__restrict__ xt = s.xt + (size_t)g * s.ndof_c * LANES + lane;
-    for (int k = warp; k < s.ndof_c; k += nw) {
-        float v = 0.f;
-        if (k < s.L * NAT3) v = hd ? xh[k] : X[(size_t)k * LANES];
-        x[(size_t)k * LANES] = v;
-        xt[(size_t)k * LANES] = v;
+    const f3 N = load(i, TRX_AT_N), CA = load(i, TRX_AT_CA), C = load(i, TRX_AT_C);
+    f3 d1, d2, d3, d4;
+    phi = (float)TRX_PI; omg = (float)TRX_PI;
+    if (i > 0) phi = cart_dihedral(load(i - 1, TRX_AT_C), N, CA, C, d1, d2, d3, d4);
+    if (i < L - 1) {
+        const f3 N1 = load(i + 1, TRX_AT_N), CA1 = load(i + 1, TRX_AT_CA);
+        psi = cart_dihedral(N, CA, C, N1, d1, d2, d3, d4);
+        omg = cart_dihedral(CA, C, N1, CA1, d1, d2, d3, d4);
+    } else {
+        psi = cart_dihedral(N, CA, C, load(i, TRX_AT_O), d1, d2, d3, d4) - (float)TRX_PI;   // NeRF places O at psi + pi
+        if (psi <= -(float)TRX_PI) psi += 2.0f * (float)TRX_PI;
     }
 }
 
-// End of a Cartesian segment (after the identity-slot evaluation of the accepted points):
-// every decoy now holds its coordinates and terms; its torsions are read back from them.
-__global__ void __launch_bounds__(256) cart_end_kernel(FoldState s)
+// Parity entry (trx_fold_eval_cart): torsions of the coordinates just evaluated (identity slots) -> x.
+__global__ void __launch_bounds__(256) cart_readback_kernel(FoldState s)
 {
     const int g = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, n = g * LANES + lane;
     if (n >= s.N) return;
     const int L = s.L;
     const float *__restrict__ X = s.X + (size_t)g * s.Lpad * NAT3 * LANES + lane;
-    float *__restrict__ xh = s.xheld + (size_t)n * L * NAT3;
-    float *__restrict__ x = s.x + (size_t)g * s.ndof_t * LANES + lane, *__restrict__ xt = s.xt + (size_t)g * s.ndof_t * LANES + lane;
+    float *__restrict__ x = s.x + (size_t)g * s.ndof_t * LANES + lane;
     auto load = [&](int i, int a) -> f3 { return {X[((size_t)i * NAT3 + a * 3) * LANES], X[((size_t)i * NAT3 + a * 3 + 1) * LANES], X[((size_t)i * NAT3 + a * 3 + 2) * LANES]}; };
-    if (warp == 0) {
-        s.held[n] = 1;
-        for (int k = 0; k < TRX_NTERM; ++k) s.theld[(size_t)k * s.Npad + n] = s.terms[(size_t)k * s.Npad + n];
-    }
-    for (int k = warp; k < L * NAT3; k += nw) xh[k] = X[(size_t)k * LANES];
     for (int i = warp; i < L; i += nw) {
-        const f3 N = load(i, TRX_AT_N), CA = load(i, TRX_AT_CA), C = load(i, TRX_AT_C);
-        f3 d1, d2, d3, d4;
-        float phi = (float)TRX_PI, psi, omg = (float)TRX_PI;
-        if (i > 0) phi = cart_dihedral(load(i - 1, TRX_AT_C), N, CA, C, d1, d2, d3, d4);
-        if (i < L - 1) {
-            const f3 N1 = load(i + 1, TRX_AT_N), CA1 = load(i + 1, TRX_AT_CA);
-            psi = cart_dihedral(N, CA, C, N1, d1, d2, d3, d4);
-            omg = cart_dihedral(CA, C, N1, CA1, d1, d2, d3, d4);
-        } else {
-            psi = cart_dihedral(N, CA, C, load(i, TRX_AT_O), d1, d2, d3, d4) - (float)TRX_PI;   // NeRF places O at psi + pi
-            if (psi <= -(float)TRX_PI) psi += 2.0f * (float)TRX_PI;
-        }
-        x[(size_t)(i * 3 + 0) * LANES] = phi; xt[(size_t)(i * 3 + 0) * LANES] = phi;
-        x[(size_t)(i * 3 + 1) * LANES] = psi; xt[(size_t)(i * 3 + 1) * LANES] = psi;
-        x[(size_t)(i * 3 + 2) * LANES] = omg; xt[(size_t)(i * 3 + 2) * LANES] = omg;
+        float phi, psi, omg;
+        readback_torsions(load, i, L, phi, psi, omg);
+        x[(size_t)(i * 3 + 0) * LANES] = phi;
+        x[(size_t)(i * 3 + 1) * LANES] = psi;
+        x[(size_t)(i * 3 + 2) * LANES] = omg;
     }
 }
 
-// Start of a segment [lo, hi) of the schedule: the decoys whose next run lies in it wake up.
-__global__ void seg_begin_kernel(FoldState s, int lo, int hi)
+// ---- Monte-Carlo extension (no reference behaviour: BASELINE config 4 / SURVEY 8a row 16).
+// A cycle = perturb a block of consecutive residues' phi/psi, re-minimise through the schedule's last run,
+// Metropolis accept/reject on that run's weighted score.  It is part of the per-decoy state machine (a decoy
+// that finishes its minimisation is judged, perturbed and restarted in the same round: no batch-wide barrier
+// per cycle); the counter-based generator is keyed by (seed, global decoy id, cycle, draw), so a decoy's
+// trajectory does not depend on the batch, the position or the GPU it sits in.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z)
+{
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ float u01(unsigned long long seed, unsigned long long id, unsigned cycle, unsigned draw)
+{
+    const unsigned long long h = mix64(mix64(seed ^ mix64(id)) ^ ((unsigned long long)cycle << 32 | draw));
+    return ((h >> 40) + 0.5f) * (1.0f / 16777216.0f);
+}
+// index of queue entry q in the caller's arrays (queue ids are block-major with every block 32-aligned)
+__device__ __forceinline__ int caller_index(const FoldState &s, int q)
+{
+    int t = 0;
+    while (t + 1 < s.ntab && q >= s.qd0[t + 1]) ++t;
+    return s.qc0[t] + (q - s.qd0[t]);
+}
+// phi/psi element k of a decoy after the perturbation of cycle `cycle`
+__device__ __noinline__ float mc_perturb(const McOpts o, int L, unsigned long long id, int cycle, int k, float v)
+{
+    const int blk = o.block_min + (int)(u01(o.seed, id, cycle, 0) * (o.block_max - o.block_min + 1));
+    const int len = min(max(blk, 1), L - 2);
+    const int start = 1 + (int)(u01(o.seed, id, cycle, 1) * (L - 1 - len));
+    const int res = k / 3, t = k % 3;
+    if (t < 2 && res >= start && res < start + len) {
+        // Box-Muller from two counter-based uniforms
+        const float a = u01(o.seed, id, cycle, 2 + 2 * k), b = u01(o.seed, id, cycle, 3 + 2 * k);
+        return v + o.sigma * sqrtf(-2.0f * logf(a)) * cospif(2.0f * b);
+    }
+    return v;
+}
+
+// Start of a segment: every position is empty; the first turnover fills them from the head of the queue.
+__global__ void seg_reset_kernel(FoldState s)
 {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < 16) { s.qcursor[n] = 0; s.qocc[n] = 0; }
     if (n >= s.Npad) return;
-    s.status[n] = (n < s.N && s.run[n] >= lo && s.run[n] < hi) ? ST_INIT : ST_DONE;
+    s.status[n] = ST_DONE;
+    s.orig[n] = -1;
+    s.held[n] = 0;
 }
 
 // K5: batched L-BFGS with non-monotone Armijo back-tracking (lane = decoy).  Consumes the
@@ -864,8 +926,9 @@ struct LbSmem {
 };
 
 // What the evaluation just made means for decoy n: 0 none, 1 start run here (steepest descent),
-// 2 accepted step, 3 rejected step, 4 run skipped (clash check).  Pure function of the per-decoy
-// scalars, so the dots kernel and the step kernel agree on it.
+// 2 accepted step, 3 rejected step, 4 run skipped (clash check), 5 the closing evaluation of a decoy that
+// has left the segment.  Pure function of the per-decoy scalars, so the dots kernel and the step kernel
+// agree on it.
 __device__ __forceinline__ int lb_action(const FoldState &s, int n, int status)
 {
     const int Npad = s.Npad;
@@ -885,6 +948,7 @@ __device__ __forceinline__ int lb_action(const FoldState &s, int n, int status)
         for (int q = 1; q < min(nmem, 3); ++q) fref = fmax(fref, s.fmem[(size_t)q * Npad + n]);
         return (isfinite(ft) && ft <= fref + (double)(LS_SIGMA * s.alpha[n] * s.slope[n])) ? 2 : 3;
     }
+    if (status == ST_FINAL) return 5;
     return 0;
 }
 
@@ -1002,16 +1066,42 @@ __global__ void __launch_bounds__(LB_STEP_THREADS, 1) lbfgs_step_kernel(FoldStat
         float(*YYm)[LANES] = sm.u.gram[1];
         const float ss = sm.sum[5 * M + 0][lane], sy = sm.sum[5 * M + 1][lane], yy = sm.sum[5 * M + 2][lane];
         const float gg = sm.sum[5 * M + 3][lane], sgn = sm.sum[5 * M + 4][lane], ygn = sm.sum[5 * M + 5][lane];
-        int evals = s.evals[n] + (status != ST_DONE ? 1 : 0), iters = s.iters[n];
+        int evals = s.evals[n] + ((status == ST_INIT || status == ST_LS) ? 1 : 0), iters = s.iters[n];
         bool run_over = false, need_dir = false;
-        int mode = 0;
-        // the decoy moves on to run r: its weights come into force; beyond the segment in
-        // progress it waits for the batch (DONE until the next segment begins)
+        int mode = 0, mcmode = 0;
+        // the decoy moves on to run r: its weights come into force.  Beyond the segment in progress it
+        // leaves the batch: one closing evaluation at its accepted point (ST_FINAL), then it is parked.
+        // With Monte-Carlo cycles the end of the schedule is instead the Metropolis test on the cycle just
+        // minimised, followed by the next perturbation and a restart of the last run.
         auto enter = [&](int r) {
             if (r < s.nruns)
                 for (int k = 0; k < TRX_NTERM; ++k) s.wl[(size_t)k * Npad + n] = s.runs[r].w[k];
-            status = r < s.seg_hi ? ST_INIT : ST_DONE;
+            if (r < s.seg_hi) { status = ST_INIT; return; }
+            status = ST_FINAL;
+            if (s.mc.cycles > 0 && r >= s.nruns && n < s.N) {
+                const int c = s.mccyc[n];   // perturbations made so far
+                const unsigned long long id = s.mc.id_offset + (unsigned long long)caller_index(s, s.orig[n]);
+                bool keep = true;
+                if (c > 0) {
+                    const double fnew = f, fold = s.fsave[n];
+                    keep = isfinite(fnew) && (fnew <= fold || u01(s.mc.seed, id, c - 1, 0x7fffffffu) < expf((float)((fold - fnew) / (double)s.mc.kT)));
+                    if (keep) s.naccept[n] += 1;
+                    else f = fold;
+                }
+                if (c < s.mc.cycles) {
+                    s.fsave[n] = f;
+                    s.mccyc[n] = c + 1;
+                    s.held[n] = 0;
+                    run = s.mc.mc_run;
+                    for (int k = 0; k < TRX_NTERM; ++k) s.wl[(size_t)k * Npad + n] = s.runs[run].w[k];
+                    status = ST_INIT; hist = 0; head = 0; iter = 0; bt = 0; restart = 1; nmem = 0;
+                    mcmode = keep ? 4 : 5;   // sweep B: (x or the saved x) -> saved x, perturbed -> x, xt
+                } else {
+                    mcmode = keep ? 3 : 6;   // the last cycle was rejected: back to the saved x
+                }
+            }
         };
+        if (action == 5) status = ST_DONE;   // closing evaluation made: the turnover parks the decoy
         if (action == 4) {
             run = s.runs[run].skip_to;
             enter(run);   // xt stays = x; the next round evaluates it under the new weights
@@ -1133,6 +1223,7 @@ __global__ void __launch_bounds__(LB_STEP_THREADS, 1) lbfgs_step_kernel(FoldStat
                 mode = 3;
             }
         }
+        if (mcmode) mode = mcmode;
         sm.cg[lane] = cgv;
         sm.alpha[lane] = alpha;
         sm.mode[lane] = mode;
@@ -1170,11 +1261,27 @@ __global__ void __launch_bounds__(LB_THREADS, 2) lbfgs_update_kernel(FoldState s
     const int nd = s.ndof, m = s.m;
     const int per = (nd + nch - 1) / nch, k0 = ch * per, k1 = min(nd, k0 + per);
     const size_t vb = (size_t)g * nd * LANES + lane;
-    const float *__restrict__ x = s.x + vb, *__restrict__ gv = s.g + vb;
+    float *__restrict__ x = s.x + vb;
+    const float *__restrict__ gv = s.g + vb;
     float *__restrict__ d = s.d + vb, *__restrict__ xt = s.xt + vb;
     const float *__restrict__ S = s.S + (size_t)g * m * nd * LANES + lane, *__restrict__ Y = s.Y + (size_t)g * m * nd * LANES + lane;
     const float *__restrict__ coef = s.lbcoef + (size_t)g * LbSmem<M>::NCOEF * LANES + lane;
     const int mode = __float_as_int(coef[(2 * M + 2) * LANES]);
+    if (__syncthreads_or(mode >= 4)) {   // Monte-Carlo moves (rare rounds): revert and / or perturb, see lbfgs_step_kernel
+        const int n = g * LANES + lane;
+        if (mode >= 4) {
+            float *__restrict__ xs = s.xsave + vb;
+            const unsigned long long id = s.mc.id_offset + (unsigned long long)caller_index(s, s.orig[n]);
+            const int cycle = s.mccyc[n] - 1;
+            for (int k = k0 + warp; k < k1; k += LB_WARPS) {
+                const float base = mode == 4 ? x[(size_t)k * LANES] : xs[(size_t)k * LANES];
+                if (mode == 4) xs[(size_t)k * LANES] = base;
+                const float nv = mode == 6 ? base : mc_perturb(s.mc, s.L, id, cycle, k, base);
+                x[(size_t)k * LANES] = nv;
+                xt[(size_t)k * LANES] = nv;
+            }
+        }
+    }
     const float cgv = coef[(2 * M) * LANES], al = coef[(2 * M + 1) * LANES];
     float cS[M], cY[M];
 #pragma unroll
@@ -1237,7 +1344,8 @@ __global__ void __launch_bounds__(1024) compact_kernel(FoldState s, int identity
                 const int n = d0 + i;
                 if (identity) pick = true;
                 else if (s.status[n] != ST_DONE) {
-                    const bool k1 = !s.k1skip || s.wl[n] != 0.f || s.wl[(size_t)Npad + n] != 0.f || s.wl[(size_t)2 * Npad + n] != 0.f;
+                    // a closing evaluation reports every term, whatever the weights in force
+                    const bool k1 = !s.k1skip || s.status[n] == ST_FINAL || s.wl[n] != 0.f || s.wl[(size_t)Npad + n] != 0.f || s.wl[(size_t)2 * Npad + n] != 0.f;
                     pick = pass == 0 ? k1 : !k1;
                 }
             }
@@ -1246,7 +1354,11 @@ __global__ void __launch_bounds__(1024) compact_kernel(FoldState s, int identity
             __syncthreads();
             int off = base_s;
             for (int w = 0; w < warp; ++w) off += wsum[w];
-            if (pick) s.perm[d0 + off + __popc(m & ((1u << lane) - 1))] = d0 + i;
+            if (pick) {
+                const int slot = d0 + off + __popc(m & ((1u << lane) - 1));
+                s.perm[slot] = d0 + i;
+                s.slot_of[d0 + i] = slot;
+            }
             __syncthreads();
             if (threadIdx.x == 0) { int tot = 0; for (int w = 0; w < 32; ++w) tot += wsum[w]; base_s += tot; }
             __syncthreads();
@@ -1260,7 +1372,10 @@ __global__ void __launch_bounds__(1024) compact_kernel(FoldState s, int identity
         s.gslot[d0 / LANES + g] = g * LANES < nlive;
         s.gneedk1[d0 / LANES + g] = g * LANES < nk1;
     }
-    if (threadIdx.x == 0) { s.nslot[t] = nlive; atomicAdd(s.nactive, nlive); }
+    if (threadIdx.x == 0) {
+        s.nslot[t] = nlive;
+        if (!identity) s.k1count[t] += nk1;
+    }
 }
 
 __global__ void init_state_kernel(FoldState s, const float *__restrict__ tors_nat)
@@ -1274,7 +1389,8 @@ __global__ void init_state_kernel(FoldState s, const float *__restrict__ tors_na
         xt[k * LANES] = v;
     }
     s.held[n] = 0;
-    s.orig[n] = n;
+    s.orig[n] = -1;
+    s.mccyc[n] = 0;
     s.status[n] = n < s.N ? ST_INIT : ST_DONE;
     s.run[n] = 0; s.hist[n] = 0; s.head[n] = 0; s.iter[n] = 0; s.bt[n] = 0; s.restart[n] = 1; s.nmem[n] = 0;
     s.f[n] = 0.0; s.alpha[n] = 0.f; s.slope[n] = 0.f; s.evals[n] = 0; s.iters[n] = 0;
@@ -1283,41 +1399,187 @@ __global__ void init_state_kernel(FoldState s, const float *__restrict__ tors_na
     for (int k = 0; k < 3; ++k) { s.fmem[(size_t)k * s.Npad + n] = 0.0; s.E3[(size_t)k * s.Npad + n] = 0.0; }
 }
 
-__global__ void restore_kernel(FoldState s)
+// ---- continuous batching: queue store, turnover (park + refill) ----------------------------------------
+// Start of a call: the caller's start torsions [Nq][L][3] (block-major, caller order) -> queue records.
+__global__ void __launch_bounds__(256) queue_init_kernel(FoldState s, const float *__restrict__ tors_nat)
 {
-    // xt = x for every decoy (the accepted point), ahead of the final consistent evaluation
-    const size_t base = (size_t)blockIdx.x * s.ndof * LANES;
-    for (int e = threadIdx.x; e < s.ndof * LANES; e += blockDim.x) s.xt[base + e] = s.x[base + e];
+    const int gq = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, q = gq * LANES + lane;
+    int t = 0;
+    while (t + 1 < s.ntab && q >= s.qd0[t + 1]) ++t;
+    const bool real = q - s.qd0[t] < s.nq_tab[t];
+    const int c = s.qc0[t] + (q - s.qd0[t]);
+    float *__restrict__ qt = s.q_tors + (size_t)gq * s.ndof_t * LANES + lane;
+    for (int k = warp; k < s.ndof_t; k += nw) qt[(size_t)k * LANES] = real ? tors_nat[(size_t)c * s.ndof_t + k] : (float)TRX_PI;
+    if (warp == 0) {
+        s.q_run[q] = 0; s.q_held[q] = 0; s.q_evals[q] = 0; s.q_iters[q] = 0;
+        for (int k = 0; k < TRX_NTERM; ++k) s.q_terms[(size_t)k * s.Nqpad + q] = 0.0;
+    }
 }
 
-__global__ void export_kernel(FoldState s, float *__restrict__ tors_nat, double *__restrict__ terms_nat, long long *__restrict__ stats,
-                              float *__restrict__ xyz_nat)
+// Turnover, step 1 (one CTA per table block): the positions whose decoy has left the segment (or that are
+// empty) take the next waiting queue entries, in position order.  Deterministic, and immaterial to the
+// results: a decoy's trajectory does not depend on the position it occupies.
+__global__ void __launch_bounds__(1024) turnover_plan_kernel(FoldState s)
 {
-    // position n holds decoy o = orig[n]: results go to the caller's row o.  xyz_nat (may be NULL): [N][L][15]
-    // from the identity-slot evaluation just made (held Cartesian coordinates take precedence).
+    __shared__ int wsum[32];
+    __shared__ int base_s;
+    const int t = blockIdx.x, d0 = s.tab_d0[t], nt = s.tab_n[t];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int span = (nt + 1023) / 1024 * 1024;
+    const int cursor = s.qcursor[t], nq = s.nq_tab[t];
+    if (threadIdx.x == 0) base_s = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < span; c0 += 1024) {
+        const int i = c0 + threadIdx.x;
+        const bool free_ = i < nt && s.status[d0 + i] == ST_DONE;
+        const unsigned m = __ballot_sync(0xffffffffu, free_);
+        if (lane == 0) wsum[warp] = __popc(m);
+        __syncthreads();
+        int off = base_s;
+        for (int w = 0; w < warp; ++w) off += wsum[w];
+        if (i < nt) {
+            int nid = -2;
+            if (free_) {
+                const int k = cursor + off + __popc(m & ((1u << lane) - 1));
+                nid = k < nq ? s.qd0[t] + k : -1;
+                if (nid == -1 && s.orig[d0 + i] == -1) nid = -2;   // empty stays empty
+            }
+            s.newid[d0 + i] = nid;
+        } else if (i < (nt + LANES - 1) / LANES * LANES) {
+            s.newid[d0 + i] = -2;   // padding positions of the block's last group never hold a decoy
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { int a = 0; for (int w = 0; w < 32; ++w) a += wsum[w]; base_s += a; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const int nfree = base_s, taken = min(nfree, nq - cursor);
+        s.qcursor[t] = cursor + taken;
+        s.qocc[t] = nt - nfree + taken;
+    }
+}
+
+// Turnover, step 2 (one CTA per position that changes hands).  PARK: the decoy's record goes back to the
+// queue store -- torsions (read back from the coordinates after a Cartesian segment), the coordinates it
+// holds or that the next (Cartesian) segment starts from, the terms of its closing evaluation, counters --
+// and, when it has left the LAST segment, its results go to the output arrays in the caller's order.
+// LOAD: the next waiting decoy starts the segment from its record.
+__global__ void __launch_bounds__(128) turnover_move_kernel(FoldState s)
+{
+    const int pos = blockIdx.x;
+    const int nid = s.newid[pos];
+    if (nid == -2) return;
+    const int L = s.L, Npad = s.Npad, Nqpad = s.Nqpad;
+    const int old = s.orig[pos];
+    const size_t vb = (size_t)(pos / LANES) * s.ndof * LANES + pos % LANES;
+    float *__restrict__ x = s.x + vb, *__restrict__ xt = s.xt + vb;
+    if (old >= 0) {
+        float *__restrict__ qt = s.q_tors + (size_t)(old / LANES) * s.ndof_t * LANES + old % LANES;
+        float *__restrict__ qX = s.has_cart ? s.q_X + (size_t)(old / LANES) * s.ndof_c * LANES + old % LANES : nullptr;
+        const int slot = s.slot_of[pos], held = s.held[pos];
+        const int c = caller_index(s, old);
+        if (s.cart) {
+            // the coordinates the decoy holds from now on, and its torsions read back from them
+            for (int e = threadIdx.x; e < L * NAT3; e += blockDim.x) {
+                const float v = x[(size_t)e * LANES];
+                qX[(size_t)e * LANES] = v;
+                if (s.seg_last && s.o_xyz) s.o_xyz[(size_t)c * L * NAT3 + e] = v;
+            }
+            auto load = [&](int i, int a) -> f3 { return {x[((size_t)i * NAT3 + a * 3) * LANES], x[((size_t)i * NAT3 + a * 3 + 1) * LANES], x[((size_t)i * NAT3 + a * 3 + 2) * LANES]}; };
+            for (int i = threadIdx.x; i < L; i += blockDim.x) {
+                float phi, psi, omg;
+                readback_torsions(load, i, L, phi, psi, omg);
+                qt[(size_t)(i * 3 + 0) * LANES] = phi; qt[(size_t)(i * 3 + 1) * LANES] = psi; qt[(size_t)(i * 3 + 2) * LANES] = omg;
+                if (s.seg_last) { s.o_tors[(size_t)c * s.ndof_t + i * 3] = phi; s.o_tors[(size_t)c * s.ndof_t + i * 3 + 1] = psi; s.o_tors[(size_t)c * s.ndof_t + i * 3 + 2] = omg; }
+            }
+        } else {
+            for (int k = threadIdx.x; k < s.ndof_t; k += blockDim.x) {
+                const float v = x[(size_t)k * LANES];
+                qt[(size_t)k * LANES] = v;
+                if (s.seg_last) s.o_tors[(size_t)c * s.ndof_t + k] = v;
+            }
+            // coordinates of the closing evaluation (slot space): the start of a Cartesian segment / the result
+            const float *__restrict__ X = s.X + (size_t)(slot / LANES) * s.Lpad * NAT3 * LANES + slot % LANES;
+            if (s.park_X && !held)
+                for (int e = threadIdx.x; e < L * NAT3; e += blockDim.x) qX[(size_t)e * LANES] = X[(size_t)e * LANES];
+            if (s.seg_last && s.o_xyz)
+                for (int e = threadIdx.x; e < L * NAT3; e += blockDim.x)
+                    s.o_xyz[(size_t)c * L * NAT3 + e] = held ? qX[(size_t)e * LANES] : X[(size_t)e * LANES];
+        }
+        if (threadIdx.x == 0) {
+            const bool keep_terms = !s.cart && held;   // still holding its Cartesian coordinates: their terms stand
+            s.q_run[old] = s.run[pos]; s.q_evals[old] = s.evals[pos]; s.q_iters[old] = s.iters[pos];
+            s.q_held[old] = s.cart ? 1 : held;
+            for (int k = 0; k < TRX_NTERM; ++k) {
+                const double v = keep_terms ? s.theld[(size_t)k * Npad + pos] : s.terms[(size_t)k * Npad + pos];
+                s.q_terms[(size_t)k * Nqpad + old] = v;
+                if (s.seg_last) s.o_terms[(size_t)c * TRX_NTERM + k] = v;
+            }
+            if (s.seg_last) {
+                s.o_stats[(size_t)c * 3] = s.evals[pos];
+                s.o_stats[(size_t)c * 3 + 1] = s.iters[pos];
+                s.o_stats[(size_t)c * 3 + 2] = s.naccept[pos];
+            }
+        }
+    }
+    __syncthreads();   // the old record is out before the position is overwritten
+    if (nid >= 0) {
+        const float *__restrict__ qt = s.q_tors + (size_t)(nid / LANES) * s.ndof_t * LANES + nid % LANES;
+        if (s.cart) {
+            const float *__restrict__ qX = s.q_X + (size_t)(nid / LANES) * s.ndof_c * LANES + nid % LANES;
+            for (int e = threadIdx.x; e < s.ndof_c; e += blockDim.x) {
+                const float v = e < L * NAT3 ? qX[(size_t)e * LANES] : 0.f;
+                x[(size_t)e * LANES] = v;
+                xt[(size_t)e * LANES] = v;
+            }
+        } else {
+            for (int k = threadIdx.x; k < s.ndof_t; k += blockDim.x) {
+                const float v = qt[(size_t)k * LANES];
+                x[(size_t)k * LANES] = v;
+                xt[(size_t)k * LANES] = v;
+            }
+        }
+    }
+    if (threadIdx.x == 0) {
+        const int n = pos;
+        s.orig[n] = nid;
+        s.hist[n] = 0; s.head[n] = 0; s.iter[n] = 0; s.bt[n] = 0; s.restart[n] = 1; s.nmem[n] = 0;
+        s.f[n] = 0.0; s.alpha[n] = 0.f; s.slope[n] = 0.f; s.ft[n] = 0.0; s.Evdw[n] = 0.0;
+        s.mccyc[n] = 0; s.naccept[n] = 0; s.fsave[n] = 0.0;
+        for (int k = 0; k < 3; ++k) { s.fmem[(size_t)k * Npad + n] = 0.0; s.E3[(size_t)k * Npad + n] = 0.0; }
+        if (nid >= 0) {
+            const int run = s.q_run[nid];
+            // a record beyond the segment passes through with one closing evaluation
+            s.status[n] = (run >= s.seg_lo && run < s.seg_hi) ? ST_INIT : ST_FINAL;
+            s.run[n] = run; s.evals[n] = s.q_evals[nid]; s.iters[n] = s.q_iters[nid]; s.held[n] = s.q_held[nid];
+            const Run &r = s.runs[min(run, s.nruns - 1)];
+            for (int k = 0; k < TRX_NTERM; ++k) {
+                s.wl[(size_t)k * Npad + n] = r.w[k];
+                s.terms[(size_t)k * Npad + n] = 0.0;
+                s.theld[(size_t)k * Npad + n] = s.q_terms[(size_t)k * Nqpad + nid];
+            }
+        } else {
+            s.status[n] = ST_DONE; s.run[n] = s.nruns; s.held[n] = 0; s.evals[n] = 0; s.iters[n] = 0;
+        }
+    }
+}
+
+// The round budget ran out: every unfinished decoy stops where it is (its accepted point) and gets its
+// closing evaluation; decoys still waiting in the queue are handed out to be closed too.
+__global__ void __launch_bounds__(256) force_final_kernel(FoldState s)
+{
     const int g = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, n = g * LANES + lane;
     if (n >= s.N) return;
-    const int o = s.orig[n];
-    const float *x = s.x + (size_t)g * s.ndof * LANES + lane;
-    for (int k = warp; k < s.ndof; k += nw) tors_nat[(size_t)o * s.ndof + k] = x[(size_t)k * LANES];
-    if (xyz_nat) {
-        const bool hd = s.held[n];
-        const float *src = hd ? s.xheld + (size_t)n * s.L * NAT3 : s.xnat + (size_t)n * s.L * NATP;
-        for (int k = warp; k < s.L * NAT3; k += nw)
-            xyz_nat[(size_t)o * s.L * NAT3 + k] = hd ? src[k] : src[(k / NAT3) * NATP + k % NAT3];
-    }
-    if (warp == 0) {
-        const double *tv = s.held[n] ? s.theld : s.terms;
-        for (int k = 0; k < TRX_NTERM; ++k) terms_nat[(size_t)o * TRX_NTERM + k] = tv[(size_t)k * s.Npad + n];
-        stats[(size_t)o * 2] = s.evals[n];
-        stats[(size_t)o * 2 + 1] = s.iters[n];
-    }
+    const int st = s.status[n];
+    if (st != ST_INIT && st != ST_LS) return;
+    const size_t vb = (size_t)g * s.ndof * LANES + lane;
+    for (int k = warp; k < s.ndof; k += nw) s.xt[vb + (size_t)k * LANES] = s.x[vb + (size_t)k * LANES];
+    if (warp == 0) { s.status[n] = ST_FINAL; s.run[n] = s.nruns; }
 }
-
-__global__ void scatter_int_kernel(FoldState s, const int *__restrict__ by_pos, int *__restrict__ by_id)
+__global__ void force_final_queue_kernel(FoldState s)
 {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n < s.N) by_id[s.orig[n]] = by_pos[n];
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < s.Nqpad && s.q_run[q] < s.nruns) s.q_run[q] = s.nruns;
 }
 
 // Which positions swap: in table block t, the k-th finished decoy among the first `nlive` positions
@@ -1392,11 +1654,6 @@ __global__ void __launch_bounds__(256) migrate_swap_kernel(FoldState s)
         const size_t ga = (size_t)(a / LANES) * MM * LANES + a % LANES, gb = (size_t)(b / LANES) * MM * LANES + b % LANES;
         for (int e = threadIdx.x; e < MM; e += blockDim.x) s.gram[ga + (size_t)e * LANES] = s.gram[gb + (size_t)e * LANES];
     }
-    if (s.has_cart) for (int e = threadIdx.x; e < s.L * NAT3; e += blockDim.x) {
-        const float ta = s.xheld[(size_t)a * s.L * NAT3 + e], tb = s.xheld[(size_t)b * s.L * NAT3 + e];
-        s.xheld[(size_t)a * s.L * NAT3 + e] = tb;
-        s.xheld[(size_t)b * s.L * NAT3 + e] = ta;
-    }
     if (threadIdx.x == 0) {
         auto swp_d = [&](double *p, size_t stride, int cnt) { for (int q = 0; q < cnt; ++q) { const double u = p[q * stride + a]; p[q * stride + a] = p[q * stride + b]; p[q * stride + b] = u; } };
         auto swp_f = [&](float *p, size_t stride, int cnt) { for (int q = 0; q < cnt; ++q) { const float u = p[q * stride + a]; p[q * stride + a] = p[q * stride + b]; p[q * stride + b] = u; } };
@@ -1404,85 +1661,7 @@ __global__ void __launch_bounds__(256) migrate_swap_kernel(FoldState s)
         swp_d(s.f, 0, 1); swp_d(s.fmem, Npad, 3); swp_d(s.fsave, 0, 1); swp_d(s.terms, Npad, TRX_NTERM); swp_d(s.ft, 0, 1); swp_d(s.theld, Npad, TRX_NTERM);
         swp_f(s.alpha, 0, 1); swp_f(s.slope, 0, 1); swp_f(s.wl, Npad, TRX_NTERM);
         swp_i(s.nmem); swp_i(s.hist); swp_i(s.head); swp_i(s.iter); swp_i(s.run); swp_i(s.bt); swp_i(s.status); swp_i(s.restart);
-        swp_i(s.evals); swp_i(s.iters); swp_i(s.naccept); swp_i(s.held); swp_i(s.orig);
-    }
-}
-
-// ---- Monte-Carlo extension (no reference behaviour: BASELINE config 4 / SURVEY 8a row 16).
-// A cycle = perturb a block of consecutive residues' phi/psi, re-minimise through one run of
-// the schedule, Metropolis accept/reject on the run's weighted score.  Everything below is on
-// device; the counter-based generator is keyed by (seed, global decoy id, cycle, draw), so a
-// decoy's trajectory does not depend on the batch or GPU it sits in.
-__device__ __forceinline__ unsigned long long mix64(unsigned long long z)
-{
-    z += 0x9e3779b97f4a7c15ull;
-    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
-    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
-    return z ^ (z >> 31);
-}
-__device__ __forceinline__ float u01(unsigned long long seed, unsigned long long id, unsigned cycle, unsigned draw)
-{
-    const unsigned long long h = mix64(mix64(seed ^ mix64(id)) ^ ((unsigned long long)cycle << 32 | draw));
-    return ((h >> 40) + 0.5f) * (1.0f / 16777216.0f);
-}
-
-struct McOpts {
-    unsigned long long seed, id_offset;
-    int cycle, block_min, block_max, mc_run;
-    float sigma, kT;
-};
-
-// save (x, f), perturb, and restart the decoy at run mc_run
-__global__ void mc_begin_kernel(FoldState s, McOpts o)
-{
-    const int g = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, n = g * LANES + lane;
-    if (n >= s.N) return;
-    const size_t vb = (size_t)g * s.ndof * LANES + lane;
-    float *x = s.x + vb, *xt = s.xt + vb, *xs = s.xsave + vb;
-    const unsigned long long id = o.id_offset + s.orig[n];
-    const int L = s.L;
-    const int blk = o.block_min + (int)(u01(o.seed, id, o.cycle, 0) * (o.block_max - o.block_min + 1));
-    const int len = min(max(blk, 1), L - 2);
-    const int start = 1 + (int)(u01(o.seed, id, o.cycle, 1) * (L - 1 - len));
-    for (int k = warp; k < s.ndof; k += nw) {
-        const float v = x[(size_t)k * LANES];
-        xs[(size_t)k * LANES] = v;
-        const int res = k / 3, t = k % 3;
-        float nv = v;
-        if (t < 2 && res >= start && res < start + len) {
-            // Box-Muller from two counter-based uniforms
-            const float a = u01(o.seed, id, o.cycle, 2 + 2 * k), b = u01(o.seed, id, o.cycle, 3 + 2 * k);
-            nv = v + o.sigma * sqrtf(-2.0f * logf(a)) * cospif(2.0f * b);
-        }
-        x[(size_t)k * LANES] = nv;
-        xt[(size_t)k * LANES] = nv;
-    }
-    if (warp == 0) {
-        if (o.cycle == 0) s.naccept[n] = 0;
-        s.fsave[n] = s.f[n];
-        s.held[n] = 0;
-        s.status[n] = ST_INIT; s.run[n] = o.mc_run; s.hist[n] = 0; s.head[n] = 0; s.iter[n] = 0; s.bt[n] = 0;
-        s.restart[n] = 1; s.nmem[n] = 0;
-        for (int k = 0; k < TRX_NTERM; ++k) s.wl[(size_t)k * s.Npad + n] = s.runs[o.mc_run].w[k];
-    }
-}
-
-// Metropolis on the minimised score; a rejected decoy returns to its saved state.
-// first != 0: no perturbation preceded (scoring pass under the MC weights), always keep.
-__global__ void mc_accept_kernel(FoldState s, McOpts o, int first)
-{
-    const int g = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, n = g * LANES + lane;
-    if (n >= s.N) return;
-    const double fnew = s.f[n], fold = s.fsave[n];
-    bool keep = true;
-    if (!first) {
-        keep = isfinite(fnew) && (fnew <= fold || u01(o.seed, o.id_offset + s.orig[n], o.cycle, 0x7fffffffu) < expf((float)((fold - fnew) / (double)o.kT)));
-        if (warp == 0 && keep) s.naccept[n] += 1;
-    }
-    if (!keep) {
-        const size_t vb = (size_t)g * s.ndof * LANES + lane;
-        for (int k = warp; k < s.ndof; k += nw) s.x[vb + (size_t)k * LANES] = s.xsave[vb + (size_t)k * LANES];
-        if (warp == 0) s.f[n] = fold;
+        swp_i(s.evals); swp_i(s.iters); swp_i(s.naccept); swp_i(s.held); swp_i(s.orig); swp_i(s.mccyc); swp_i(s.slot_of);
     }
 }
 
@@ -1514,12 +1693,14 @@ struct trx_fold_batch {
     size_t arena_bytes = 0;
     int *d_aa = nullptr;
     Run *d_runs = nullptr;
+    int *h_poll = nullptr;       // pinned: live slots, occupied positions and queue cursors of every table block
     size_t vdw_smem = 0, lb_smem = 0;
     struct Segment { int lo, hi, cart; };
     std::vector<Segment> segs;   // maximal stretches of torsion-space / Cartesian runs
     bool has_cart = false;
     bool migrate = true;         // TRX_NO_MIGRATE=1 disables the packing of unfinished decoys (same results, bit for bit)
     int mig_num = 3, mig_den = 4; // pack when unfinished <= mig_num/mig_den of the positions they are spread over (1/2: 1246, 3/4: 1257 decoys/s)
+    long long k1_decoy_evals[16] = {0};   // restraint-kernel decoy evaluations of the last call, per table block
 };
 
 extern "C" {
@@ -1532,6 +1713,7 @@ int trx_fold_destroy(trx_fold_batch *b)
     if (b->arena) cudaFree(b->arena);
     if (b->d_aa) cudaFree(b->d_aa);
     if (b->d_runs) cudaFree(b->d_runs);
+    if (b->h_poll) cudaFreeHost(b->h_poll);
     delete b;
     return TRX_OK;
 }
@@ -1555,6 +1737,7 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
             if (b->arena) cudaFree(b->arena);
             if (b->d_aa) cudaFree(b->d_aa);
             if (b->d_runs) cudaFree(b->d_runs);
+            if (b->h_poll) cudaFreeHost(b->h_poll);
             delete b;
         }
     } guard{b};
@@ -1615,7 +1798,8 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     size_t o_perm = carve(np * 4), o_gs = carve((size_t)G * 4), o_ns = carve(256), o_ws = carve(np * 4 * TRX_NTERM);
     size_t o_gk1f = carve((size_t)G * 4);
     size_t o_orig = carve(np * 4), o_ma = carve(np * 4), o_mb = carve(np * 4), o_mn = carve(256);
-    size_t o_held = carve(np * 4), o_xh = carve(b->has_cart ? np * L * NAT3 * 4 : 256), o_th = carve(np * 8 * TRX_NTERM);
+    size_t o_held = carve(np * 4), o_th = carve(np * 8 * TRX_NTERM);
+    size_t o_mcc = carve(np * 4), o_sof = carve(np * 4), o_nid = carve(np * 4), o_qc = carve(256), o_qo = carve(256), o_k1c = carve(256);
     cudaError_t e = cudaMalloc(&b->arena, off);
     if (e != cudaSuccess) {
         set_error("trx_fold_create: cudaMalloc(%zu bytes) failed: %s", off, cudaGetErrorString(e));
@@ -1639,7 +1823,11 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     s.perm = (int *)(A + o_perm); s.gslot = (int *)(A + o_gs); s.nslot = (int *)(A + o_ns); s.wslot = (float *)(A + o_ws);
     s.gneedk1 = (int *)(A + o_gk1f);
     s.orig = (int *)(A + o_orig); s.mig_a = (int *)(A + o_ma); s.mig_b = (int *)(A + o_mb); s.mig_n = (int *)(A + o_mn);
-    s.held = (int *)(A + o_held); s.xheld = (float *)(A + o_xh); s.theld = (double *)(A + o_th);
+    s.held = (int *)(A + o_held); s.theld = (double *)(A + o_th);
+    s.mccyc = (int *)(A + o_mcc); s.slot_of = (int *)(A + o_sof); s.newid = (int *)(A + o_nid);
+    s.qcursor = (int *)(A + o_qc); s.qocc = (int *)(A + o_qo); s.k1count = (long long *)(A + o_k1c);
+    s.mc = McOpts{};
+    TRX_CUDA(cudaMallocHost(&b->h_poll, 64 * sizeof(int)));
     s.ntab = ntab;
     for (int t = 0; t < ntab; ++t) { s.tab_d0[t] = b->tab_g0[t] * LANES; s.tab_n[t] = ndecoys[t]; }
     TRX_CUDA(cudaMalloc(&b->d_aa, L * sizeof(int)));
@@ -1655,7 +1843,18 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     s.aa = b->d_aa;
     s.runs = b->d_runs;
     upload_model();
-    TRX_CUDA(cudaFuncSetAttribute(vdw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->vdw_smem));
+    {   // function attributes are per device and the vdw kernel's need follows L: only ever raise it, so that a
+        // batch created later for a shorter chain does not cut the limit of one that is still alive
+        // (batches are created from several host threads in batch mode: one lock)
+        static std::mutex vdw_attr_lock;
+        std::lock_guard<std::mutex> guard_attr(vdw_attr_lock);
+        static size_t vdw_attr_dev[64] = {};
+        size_t &cur = vdw_attr_dev[ctx->device & 63];
+        if (b->vdw_smem > cur) {
+            TRX_CUDA(cudaFuncSetAttribute(vdw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->vdw_smem));
+            cur = b->vdw_smem;
+        }
+    }
     static_assert(LB_MAXCH == 16, "lbpart is carved for 16 chunks");
     auto lb_attr = [&](auto dots, auto step, size_t bytes) -> int {
         b->lb_smem = bytes;
@@ -1714,62 +1913,79 @@ static int fold_eval(trx_fold_batch *b, const int *ng_tab, bool identity)
     return TRX_OK;
 }
 
-// Evaluation rounds until every decoy has finished its schedule (or max_rounds).
+extern "C++" {
+template <int M>
+static void lbfgs_launch(trx_fold_batch *b, const dim3 &grid)
+{
+    trx_ctx *ctx = b->ctx;
+    FoldState &s = b->s;
+    lbfgs_dots_kernel<M><<<grid, LB_THREADS, b->lb_smem, ctx->stream>>>(s);
+    lbfgs_step_kernel<M><<<s.G, LB_STEP_THREADS, b->lb_smem, ctx->stream>>>(s, LB_MAXCH);
+    lbfgs_update_kernel<M><<<grid, LB_THREADS, 0, ctx->stream>>>(s);
+}
+}  // extern "C++"
+
+// Evaluation rounds of the segment in progress until every decoy of the queue has passed through it
+// (or max_rounds).  A round = turnover (park the decoys that left the segment, refill their positions from
+// the queue) -> compact -> evaluate -> L-BFGS step.
 static int run_rounds(trx_fold_batch *b, int max_rounds, int check_every, int *rounds_io)
 {
     trx_ctx *ctx = b->ctx;
     FoldState &s = b->s;
-    int rc, rounds = 0, active = s.N;
-    int *h_nslot = nullptr;
-    TRX_CUDA(cudaMallocHost(&h_nslot, 16 * sizeof(int)));
+    int rc, rounds = 0;
+    bool busy = true;
+    int *h = b->h_poll;          // [0,16) live slots, [16,32) occupied positions, [32,48) queue cursors
     std::vector<int> ng(b->tab_ng);   // live slot groups per table block: an upper bound between polls
     std::vector<int> cap(s.ntab);     // positions of each block its unfinished decoys are spread over (all, until a migration)
     for (int t = 0; t < s.ntab; ++t) cap[t] = s.tab_n[t];
     dim3 ablk(32, 8), agrd((s.G + 7) / 8);
-    while (active > 0 && rounds < max_rounds) {
-        for (int k = 0; k < check_every && rounds < max_rounds; ++k, ++rounds) {
-            TRX_CUDA(cudaMemsetAsync(s.nactive, 0, sizeof(int), ctx->stream));
+    while (busy && *rounds_io + rounds < max_rounds) {
+        for (int k = 0; k < check_every && *rounds_io + rounds < max_rounds; ++k, ++rounds) {
+            ctx->time_begin("turnover");
+            turnover_plan_kernel<<<s.ntab, 1024, 0, ctx->stream>>>(s);
+            ctx->time_end("turnover");
+            ctx->time_begin("turnover");
+            turnover_move_kernel<<<s.Npad, 128, 0, ctx->stream>>>(s);
+            ctx->time_end("turnover");
             ctx->time_begin("activity");
             activity_kernel<<<agrd, ablk, 0, ctx->stream>>>(s);
             ctx->time_end("activity");
-            if ((rc = fold_eval(b, ng.data(), false))) { cudaFreeHost(h_nslot); return rc; }
+            if ((rc = fold_eval(b, ng.data(), false))) return rc;
             ctx->time_begin("lbfgs");
             {   // enough CTAs for ~3 per SM, at least 4 vector elements per warp and chunk
                 int nch = std::max(1, (3 * 148 + s.G - 1) / s.G);   // CTAs that share a group's LB_MAXCH chunks
                 nch = std::min(nch, LB_MAXCH);
                 const dim3 grid(s.G, nch);
-                if (s.lb_M == 8) {
-                    lbfgs_dots_kernel<8><<<grid, LB_THREADS, b->lb_smem, ctx->stream>>>(s);
-                    lbfgs_step_kernel<8><<<s.G, LB_STEP_THREADS, b->lb_smem, ctx->stream>>>(s, LB_MAXCH);
-                    lbfgs_update_kernel<8><<<grid, LB_THREADS, 0, ctx->stream>>>(s);
-                } else if (s.lb_M == 16) {
-                    lbfgs_dots_kernel<16><<<grid, LB_THREADS, b->lb_smem, ctx->stream>>>(s);
-                    lbfgs_step_kernel<16><<<s.G, LB_STEP_THREADS, b->lb_smem, ctx->stream>>>(s, LB_MAXCH);
-                    lbfgs_update_kernel<16><<<grid, LB_THREADS, 0, ctx->stream>>>(s);
-                } else if (s.lb_M == 20) {
-                    lbfgs_dots_kernel<20><<<grid, LB_THREADS, b->lb_smem, ctx->stream>>>(s);
-                    lbfgs_step_kernel<20><<<s.G, LB_STEP_THREADS, b->lb_smem, ctx->stream>>>(s, LB_MAXCH);
-                    lbfgs_update_kernel<20><<<grid, LB_THREADS, 0, ctx->stream>>>(s);
-                } else {
-                    lbfgs_dots_kernel<24><<<grid, LB_THREADS, b->lb_smem, ctx->stream>>>(s);
-                    lbfgs_step_kernel<24><<<s.G, LB_STEP_THREADS, b->lb_smem, ctx->stream>>>(s, LB_MAXCH);
-                    lbfgs_update_kernel<24><<<grid, LB_THREADS, 0, ctx->stream>>>(s);
-                }
+                if (s.lb_M == 8) lbfgs_launch<8>(b, grid);
+                else if (s.lb_M == 16) lbfgs_launch<16>(b, grid);
+                else if (s.lb_M == 20) lbfgs_launch<20>(b, grid);
+                else lbfgs_launch<24>(b, grid);
                 ctx->launches += 2;
             }
             ctx->time_end("lbfgs");
         }
-        TRX_CUDA(cudaMemcpyAsync(h_nslot, s.nslot, 16 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        TRX_CUDA(cudaMemcpyAsync(h, s.nslot, 16 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        TRX_CUDA(cudaMemcpyAsync(h + 16, s.qocc, 16 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        TRX_CUDA(cudaMemcpyAsync(h + 32, s.qcursor, 16 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         TRX_CUDA(cudaStreamSynchronize(ctx->stream));
-        active = 0;   // counts at the start of the last round; they only ever decrease
+        // counts as of the start of the last round: decoys that finished in it are parked by the next turnover
+        busy = false;
         bool migrate = false;
         for (int t = 0; t < s.ntab; ++t) {
-            active += h_nslot[t];
-            ng[t] = num_groups(h_nslot[t]);
-            // unfinished decoys fill less than half of the positions they are spread over: pack them
-            if (b->migrate && h_nslot[t] > 0 && b->mig_den * h_nslot[t] <= b->mig_num * cap[t] && cap[t] >= 2 * LANES) { migrate = true; cap[t] = h_nslot[t]; }
+            const int occ = h[16 + t];
+            const bool waiting = h[32 + t] < s.nq_tab[t];
+            if (occ > 0 || waiting) busy = true;
+            if (waiting) {   // freed positions are refilled: the block stays full
+                ng[t] = b->tab_ng[t];
+                cap[t] = s.tab_n[t];
+                continue;
+            }
+            ng[t] = num_groups(occ);   // the queue is empty: occupied positions only ever decrease
+            const int live = std::min(h[t], occ);
+            // unfinished decoys fill less than mig_num/mig_den of the positions they are spread over: pack them
+            if (b->migrate && live > 0 && b->mig_den * live <= b->mig_num * cap[t] && cap[t] >= 2 * LANES) { migrate = true; cap[t] = live; }
         }
-        if (migrate && active > 0) {
+        if (migrate && busy) {
             int maxn = 0;
             for (int t = 0; t < s.ntab; ++t) maxn = std::max(maxn, s.tab_n[t]);
             ctx->time_begin("migrate");
@@ -1778,174 +1994,195 @@ static int run_rounds(trx_fold_batch *b, int max_rounds, int check_every, int *r
             ctx->time_begin("migrate");
             migrate_swap_kernel<<<dim3((maxn + 1) / 2, s.ntab), 256, 0, ctx->stream>>>(s);
             ctx->time_end("migrate");
+            // a migrated position may hold a finished decoy that is not parked yet: every slot group may be live
+            for (int t = 0; t < s.ntab; ++t) ng[t] = std::max(ng[t], num_groups(h[16 + t]));
         }
     }
-    cudaFreeHost(h_nslot);
     *rounds_io += rounds;
-    return TRX_OK;
+    return busy ? 1 : TRX_OK;   // 1: the round budget ran out with decoys still in the segment
 }
 
-// The whole schedule: segment by segment, changing the degrees of freedom at the boundaries.
+static void begin_segment(trx_fold_batch *b, int lo, int hi, int cart, int last, int park_X)
+{
+    trx_ctx *ctx = b->ctx;
+    FoldState &s = b->s;
+    s.cart = cart; s.ndof = cart ? s.ndof_c : s.ndof_t;
+    s.seg_lo = lo; s.seg_hi = hi; s.seg_last = last; s.park_X = park_X;
+    ctx->time_begin("segment");
+    seg_reset_kernel<<<(s.Npad + 255) / 256, 256, 0, ctx->stream>>>(s);
+    ctx->time_end("segment");
+}
+
+// The whole schedule, segment by segment over the whole queue.
 static int run_schedule(trx_fold_batch *b, int max_rounds, int check_every, int *rounds_io)
 {
     trx_ctx *ctx = b->ctx;
     FoldState &s = b->s;
     int rc;
-    for (const auto &sg : b->segs) {
-        if (sg.cart) {
-            // coordinates of the accepted torsions (identity slots), then x = xt = coordinates
+    for (size_t k = 0; k < b->segs.size(); ++k) {
+        const auto &sg = b->segs[k];
+        const bool last = k + 1 == b->segs.size();
+        begin_segment(b, sg.lo, sg.hi, sg.cart, last ? 1 : 0, (!last && b->segs[k + 1].cart) ? 1 : 0);
+        rc = run_rounds(b, max_rounds, check_every, rounds_io);
+        if (rc < 0) return rc;
+        if (rc == 1) {
+            // Round budget exhausted.  Close the segment in progress: unfinished decoys stop at their accepted
+            // point, waiting ones pass through; then (unless it was the last) one pass in which every record
+            // gets its closing evaluation in torsion space and its results are written.
             ctx->time_begin("segment");
-            restore_kernel<<<s.G, 256, 0, ctx->stream>>>(s);
+            force_final_kernel<<<s.G, 256, 0, ctx->stream>>>(s);
             ctx->time_end("segment");
-            if ((rc = fold_eval(b, nullptr, true))) return rc;
             ctx->time_begin("segment");
-            cart_begin_kernel<<<s.G, 256, 0, ctx->stream>>>(s);
+            force_final_queue_kernel<<<(s.Nqpad + 255) / 256, 256, 0, ctx->stream>>>(s);
             ctx->time_end("segment");
-            s.cart = 1; s.ndof = s.ndof_c;
-        }
-        s.seg_hi = sg.hi;
-        ctx->time_begin("segment");
-        seg_begin_kernel<<<(s.Npad + 255) / 256, 256, 0, ctx->stream>>>(s, sg.lo, sg.hi);
-        ctx->time_end("segment");
-        if ((rc = run_rounds(b, max_rounds, check_every, rounds_io))) return rc;
-        if (sg.cart) {
-            ctx->time_begin("segment");
-            restore_kernel<<<s.G, 256, 0, ctx->stream>>>(s);
-            ctx->time_end("segment");
-            if ((rc = fold_eval(b, nullptr, true))) return rc;
-            ctx->time_begin("segment");
-            cart_end_kernel<<<s.G, 256, 0, ctx->stream>>>(s);
-            ctx->time_end("segment");
-            s.cart = 0; s.ndof = s.ndof_t;
+            int extra = 0;
+            rc = run_rounds(b, 1 << 30, check_every, &extra);
+            if (rc < 0) return rc;
+            if (!last) {
+                begin_segment(b, s.nruns, s.nruns, 0, 1, 0);
+                rc = run_rounds(b, 1 << 30, check_every, &extra);
+                if (rc < 0) return rc;
+            }
+            break;
         }
     }
-    s.seg_hi = s.nruns;
+    s.cart = 0; s.ndof = s.ndof_t; s.seg_lo = 0; s.seg_hi = s.nruns;
     TRX_CUDA(cudaGetLastError());
     return TRX_OK;
 }
 
-/* Runs the schedule to completion (or max_rounds evaluation rounds).  tors: host [N][L][3]
- * float, in: start torsions, out: final torsions.  xyz (may be NULL): host [N][L][5][3] float,
- * atoms N,CA,CB,C,O.  terms (may be NULL): [N][7] double.  stats (may be NULL): [N][2]
- * evaluations, accepted iterations.  *rounds_out (may be NULL): evaluation rounds executed. */
-int trx_fold_run(trx_fold_batch *b, float *tors, float *xyz, double *terms, long long *stats, int max_rounds,
-                 int check_every, int *rounds_out)
+// Folds nq[t] decoys per table block through the batch's positions; MC options in b->s.mc.
+static int fold_queue(trx_fold_batch *b, const int *nq, float *tors, float *xyz, double *terms, long long *stats, int stats_cols,
+                      int max_rounds, int check_every, int *rounds_out)
 {
-    TRX_REQUIRE(b && tors, "trx_fold_run: NULL argument");
     trx_ctx *ctx = b->ctx;
     FoldState &s = b->s;
     TRX_CUDA(cudaSetDevice(ctx->device));
     if (check_every < 1) check_every = 16;
-    void *d_tors = nullptr, *d_terms = nullptr, *d_stats = nullptr;
+    int Nq = 0, Gq = 0;
+    for (int t = 0; t < s.ntab; ++t) {
+        TRX_REQUIRE(nq[t] >= 0, "trx_fold_run: negative decoy count for table block %d", t);
+        s.nq_tab[t] = nq[t]; s.qc0[t] = Nq; s.qd0[t] = Gq * LANES;
+        Nq += nq[t];
+        Gq += num_groups(nq[t]);
+    }
+    TRX_REQUIRE(Nq > 0, "trx_fold_run: no decoys");
+    s.Nqpad = Gq * LANES;
+    const size_t np = (size_t)s.Nqpad;
+    void *d_in = nullptr, *d_q = nullptr, *d_ot = nullptr, *d_ox = nullptr, *d_oe = nullptr, *d_os = nullptr;
     int rc;
-    const size_t tb = (size_t)s.N * s.ndof * sizeof(float);
-    if ((rc = ctx->get_scratch("fold_tors", tb, &d_tors))) return rc;
-    if ((rc = ctx->get_scratch("fold_terms", (size_t)s.N * TRX_NTERM * sizeof(double), &d_terms))) return rc;
-    if ((rc = ctx->get_scratch("fold_stats", (size_t)s.N * 2 * sizeof(long long), &d_stats))) return rc;
-    TRX_CUDA(cudaMemcpyAsync(d_tors, tors, tb, cudaMemcpyHostToDevice, ctx->stream));
+    const size_t tb = (size_t)Nq * s.ndof_t * sizeof(float), xb = (size_t)Nq * s.L * NAT3 * sizeof(float);
+    if ((rc = ctx->get_scratch("fold_tors", tb, &d_in))) return rc;
+    if ((rc = ctx->get_scratch("fold_tors_out", tb, &d_ot))) return rc;
+    if (xyz && (rc = ctx->get_scratch("fold_xyz_out", xb, &d_ox))) return rc;
+    if ((rc = ctx->get_scratch("fold_terms", (size_t)Nq * TRX_NTERM * sizeof(double), &d_oe))) return rc;
+    if ((rc = ctx->get_scratch("fold_stats", (size_t)Nq * 3 * sizeof(long long), &d_os))) return rc;
+    // the queue store, one allocation
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    const size_t o_qt = carve(np * s.ndof_t * 4), o_qx = carve(b->has_cart ? np * s.ndof_c * 4 : 256);
+    const size_t o_qe = carve(np * 8 * TRX_NTERM), o_qr = carve(np * 4), o_qh = carve(np * 4), o_qv = carve(np * 4), o_qi = carve(np * 4);
+    if ((rc = ctx->get_scratch("fold_queue", off, &d_q))) return rc;
+    char *Q = (char *)d_q;
+    s.q_tors = (float *)(Q + o_qt); s.q_X = (float *)(Q + o_qx); s.q_terms = (double *)(Q + o_qe);
+    s.q_run = (int *)(Q + o_qr); s.q_held = (int *)(Q + o_qh); s.q_evals = (int *)(Q + o_qv); s.q_iters = (int *)(Q + o_qi);
+    s.o_tors = (float *)d_ot; s.o_xyz = (float *)d_ox; s.o_terms = (double *)d_oe; s.o_stats = (long long *)d_os;
+    TRX_CUDA(cudaMemcpyAsync(d_in, tors, tb, cudaMemcpyHostToDevice, ctx->stream));
     ctx->time_begin("fold_device");   // device time of the whole fold, inputs resident (H2D done, D2H not started)
     --ctx->launches;
-    s.cart = 0; s.ndof = s.ndof_t; s.seg_hi = s.nruns;
+    TRX_CUDA(cudaMemsetAsync(s.k1count, 0, 16 * sizeof(long long), ctx->stream));
+    TRX_CUDA(cudaMemsetAsync(d_os, 0, (size_t)Nq * 3 * sizeof(long long), ctx->stream));
     ctx->time_begin("fold_init");
-    init_state_kernel<<<s.G, 32, 0, ctx->stream>>>(s, (const float *)d_tors);
+    queue_init_kernel<<<Gq, 256, 0, ctx->stream>>>(s, (const float *)d_in);
     ctx->time_end("fold_init");
     int rounds = 0;
     if ((rc = run_schedule(b, max_rounds, check_every, &rounds))) return rc;
-    // final coordinates / terms at the accepted point x: one more evaluation with xt = x for everyone
-    ctx->time_begin("export");
-    restore_kernel<<<s.G, 256, 0, ctx->stream>>>(s);
-    ctx->time_end("export");
-    if ((rc = fold_eval(b, nullptr, true))) return rc;
-    void *d_xyz = nullptr;
-    if (xyz && (rc = ctx->get_scratch("fold_xyz_out", (size_t)s.N * s.L * NAT3 * sizeof(float), &d_xyz))) return rc;
-    ctx->time_begin("export");
-    export_kernel<<<s.G, 256, 0, ctx->stream>>>(s, (float *)d_tors, (double *)d_terms, (long long *)d_stats, (float *)d_xyz);
-    ctx->time_end("export");
     ctx->time_end("fold_device");
     TRX_CUDA(cudaGetLastError());
-    TRX_CUDA(cudaMemcpyAsync(tors, d_tors, tb, cudaMemcpyDeviceToHost, ctx->stream));
-    if (terms) TRX_CUDA(cudaMemcpyAsync(terms, d_terms, (size_t)s.N * TRX_NTERM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    if (stats) TRX_CUDA(cudaMemcpyAsync(stats, d_stats, (size_t)s.N * 2 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
-    if (xyz) TRX_CUDA(cudaMemcpyAsync(xyz, d_xyz, (size_t)s.N * s.L * NAT3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    TRX_CUDA(cudaMemcpyAsync(tors, d_ot, tb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (terms) TRX_CUDA(cudaMemcpyAsync(terms, d_oe, (size_t)Nq * TRX_NTERM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (xyz) TRX_CUDA(cudaMemcpyAsync(xyz, d_ox, xb, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<long long> st3;
+    if (stats) {
+        if (stats_cols == 3) TRX_CUDA(cudaMemcpyAsync(stats, d_os, (size_t)Nq * 3 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+        else {
+            st3.resize((size_t)Nq * 3);
+            TRX_CUDA(cudaMemcpyAsync(st3.data(), d_os, st3.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+    }
+    TRX_CUDA(cudaMemcpyAsync(b->k1_decoy_evals, s.k1count, 16 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
     TRX_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (stats && stats_cols == 2)
+        for (int n = 0; n < Nq; ++n) { stats[(size_t)n * 2] = st3[(size_t)n * 3]; stats[(size_t)n * 2 + 1] = st3[(size_t)n * 3 + 1]; }
     if (rounds_out) *rounds_out = rounds;
+    return TRX_OK;
+}
+
+/* Runs the schedule to completion (or max_rounds evaluation rounds) for as many decoys as the batch has
+ * positions.  tors: host [N][L][3] float, in: start torsions, out: final torsions.  xyz (may be NULL):
+ * host [N][L][5][3] float, atoms N,CA,CB,C,O.  terms (may be NULL): [N][7] double.  stats (may be NULL):
+ * [N][2] evaluations, accepted iterations.  *rounds_out (may be NULL): evaluation rounds executed. */
+int trx_fold_run(trx_fold_batch *b, float *tors, float *xyz, double *terms, long long *stats, int max_rounds,
+                 int check_every, int *rounds_out)
+{
+    TRX_REQUIRE(b && tors, "trx_fold_run: NULL argument");
+    b->s.mc = McOpts{};
+    return fold_queue(b, b->s.tab_n, tors, xyz, terms, stats, 2, max_rounds, check_every, rounds_out);
+}
+
+/* Continuous batching: folds nq[t] decoys against table block t -- any number, more than the batch has
+ * positions -- keeping the positions full: a position whose decoy has finished the schedule segment in
+ * progress is refilled with the next waiting decoy in the same evaluation round.  Arrays as trx_fold_run
+ * with N = sum nq[t], decoys of block 0 first.  A decoy's result does not depend on the position it
+ * occupied, nor on nq or the batch size (bit for bit). */
+int trx_fold_run_queue(trx_fold_batch *b, const int *nq, float *tors, float *xyz, double *terms, long long *stats,
+                       int max_rounds, int check_every, int *rounds_out)
+{
+    TRX_REQUIRE(b && nq && tors, "trx_fold_run_queue: NULL argument");
+    b->s.mc = McOpts{};
+    return fold_queue(b, nq, tors, xyz, terms, stats, 2, max_rounds, check_every, rounds_out);
+}
+
+/* Restraint-kernel work of the last trx_fold_run* call on this batch: decoy evaluations the kernel made
+ * per table block (the evaluations of vdw-only runs skip it).  out: [ntab]. */
+int trx_fold_k1_evals(trx_fold_batch *b, long long *out)
+{
+    TRX_REQUIRE(b && out, "trx_fold_k1_evals: NULL argument");
+    for (int t = 0; t < b->s.ntab; ++t) out[t] = b->k1_decoy_evals[t];
     return TRX_OK;
 }
 
 /* Monte-Carlo sampling on top of the fold (extension, BASELINE config 4): minimise through
  * runs [0, mc_run) exactly as trx_fold_run, then `cycles` times { perturb phi/psi of a random
  * block of block_min..block_max residues by N(0, sigma_deg); re-minimise with run mc_run;
- * Metropolis at temperature kT on that run's weighted score }.  stats: [N][3] = evaluations,
- * accepted L-BFGS iterations, accepted MC moves.  id_offset: global index of decoy 0 (keeps
- * random streams independent of the sharding). */
+ * Metropolis at temperature kT on that run's weighted score }.  The cycles are part of each decoy's own
+ * state machine: no batch-wide barrier per cycle.  stats: [N][3] = evaluations, accepted L-BFGS
+ * iterations, accepted MC moves.  id_offset: global index of decoy 0 (keeps random streams independent
+ * of the sharding).  nq: decoys per table block as trx_fold_run_queue, or NULL = one per position. */
+int trx_fold_mc_queue(trx_fold_batch *b, const int *nq, float *tors, float *xyz, double *terms, long long *stats, int mc_run,
+                      int cycles, double kT, int block_min, int block_max, double sigma_deg, unsigned long long seed,
+                      unsigned long long id_offset, int max_rounds, int check_every, int *rounds_out)
+{
+    TRX_REQUIRE(b && tors, "trx_fold_mc: NULL argument");
+    FoldState &s = b->s;
+    TRX_REQUIRE(mc_run >= 1 && mc_run == s.nruns - 1, "trx_fold_mc: mc_run must be the last run of the schedule (got %d of %d)", mc_run, s.nruns);
+    TRX_REQUIRE(cycles >= 0 && kT > 0 && block_min >= 1 && block_max >= block_min && sigma_deg >= 0, "trx_fold_mc: bad options");
+    TRX_REQUIRE(!b->segs.back().cart, "trx_fold_mc: the Monte-Carlo run must be a torsion-space run");
+    McOpts o;
+    o.seed = seed; o.id_offset = id_offset; o.block_min = block_min; o.block_max = block_max; o.mc_run = mc_run;
+    o.sigma = (float)(sigma_deg * TRX_DEG); o.kT = (float)kT; o.cycles = cycles;
+    s.mc = o;
+    const int rc = fold_queue(b, nq ? nq : s.tab_n, tors, xyz, terms, stats, 3, max_rounds, check_every, rounds_out);
+    s.mc = McOpts{};
+    return rc;
+}
+
 int trx_fold_mc(trx_fold_batch *b, float *tors, float *xyz, double *terms, long long *stats, int mc_run, int cycles,
                 double kT, int block_min, int block_max, double sigma_deg, unsigned long long seed,
                 unsigned long long id_offset, int max_rounds, int check_every, int *rounds_out)
 {
-    TRX_REQUIRE(b && tors, "trx_fold_mc: NULL argument");
-    trx_ctx *ctx = b->ctx;
-    FoldState &s = b->s;
-    TRX_REQUIRE(mc_run >= 1 && mc_run == s.nruns - 1, "trx_fold_mc: mc_run must be the last run of the schedule (got %d of %d)", mc_run, s.nruns);
-    TRX_REQUIRE(cycles >= 0 && kT > 0 && block_min >= 1 && block_max >= block_min && sigma_deg >= 0, "trx_fold_mc: bad options");
-    TRX_CUDA(cudaSetDevice(ctx->device));
-    if (check_every < 1) check_every = 16;
-    void *d_tors = nullptr, *d_terms = nullptr, *d_stats = nullptr;
-    int rc;
-    const size_t tb = (size_t)s.N * s.ndof * sizeof(float);
-    if ((rc = ctx->get_scratch("fold_tors", tb, &d_tors))) return rc;
-    if ((rc = ctx->get_scratch("fold_terms", (size_t)s.N * TRX_NTERM * sizeof(double), &d_terms))) return rc;
-    if ((rc = ctx->get_scratch("fold_stats", (size_t)s.N * 2 * sizeof(long long), &d_stats))) return rc;
-    TRX_CUDA(cudaMemcpyAsync(d_tors, tors, tb, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->time_begin("fold_device");
-    --ctx->launches;
-    TRX_REQUIRE(!b->segs.back().cart, "trx_fold_mc: the Monte-Carlo run must be a torsion-space run");
-    s.cart = 0; s.ndof = s.ndof_t; s.seg_hi = s.nruns;
-    init_state_kernel<<<s.G, 32, 0, ctx->stream>>>(s, (const float *)d_tors);
-    ++ctx->launches;
-    int rounds = 0;
-    // runs [0, mc_run] once: the last one scores the minimised decoy under the MC weights
-    if ((rc = run_schedule(b, max_rounds, check_every, &rounds))) return rc;
-    McOpts o;
-    o.seed = seed; o.id_offset = id_offset; o.block_min = block_min; o.block_max = block_max; o.mc_run = mc_run;
-    o.sigma = (float)(sigma_deg * TRX_DEG); o.kT = (float)kT; o.cycle = 0;
-    for (int c = 0; c < cycles; ++c) {
-        o.cycle = c;
-        ctx->time_begin("mc");
-        mc_begin_kernel<<<s.G, 256, 0, ctx->stream>>>(s, o);
-        ctx->time_end("mc");
-        if ((rc = run_rounds(b, max_rounds, check_every, &rounds))) return rc;
-        ctx->time_begin("mc");
-        mc_accept_kernel<<<s.G, 256, 0, ctx->stream>>>(s, o, 0);
-        ctx->time_end("mc");
-    }
-    restore_kernel<<<s.G, 256, 0, ctx->stream>>>(s);
-    ++ctx->launches;
-    if ((rc = fold_eval(b, nullptr, true))) return rc;
-    void *d_xyz = nullptr, *d_acc = nullptr;
-    if (xyz && (rc = ctx->get_scratch("fold_xyz_out", (size_t)s.N * s.L * NAT3 * sizeof(float), &d_xyz))) return rc;
-    if ((rc = ctx->get_scratch("fold_acc_out", (size_t)s.Npad * sizeof(int), &d_acc))) return rc;
-    export_kernel<<<s.G, 256, 0, ctx->stream>>>(s, (float *)d_tors, (double *)d_terms, (long long *)d_stats, (float *)d_xyz);
-    ++ctx->launches;
-    scatter_int_kernel<<<(s.N + 255) / 256, 256, 0, ctx->stream>>>(s, s.naccept, (int *)d_acc);
-    ++ctx->launches;
-    ctx->time_end("fold_device");
-    TRX_CUDA(cudaGetLastError());
-    std::vector<long long> st2((size_t)s.N * 2);
-    std::vector<int> acc(s.Npad);
-    TRX_CUDA(cudaMemcpyAsync(tors, d_tors, tb, cudaMemcpyDeviceToHost, ctx->stream));
-    if (terms) TRX_CUDA(cudaMemcpyAsync(terms, d_terms, (size_t)s.N * TRX_NTERM * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    TRX_CUDA(cudaMemcpyAsync(st2.data(), d_stats, st2.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
-    TRX_CUDA(cudaMemcpyAsync(acc.data(), d_acc, (size_t)s.N * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    if (xyz) TRX_CUDA(cudaMemcpyAsync(xyz, d_xyz, (size_t)s.N * s.L * NAT3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    TRX_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (stats)
-        for (int n = 0; n < s.N; ++n) {
-            stats[(size_t)n * 3] = st2[(size_t)n * 2];
-            stats[(size_t)n * 3 + 1] = st2[(size_t)n * 2 + 1];
-            stats[(size_t)n * 3 + 2] = cycles > 0 ? acc[n] : 0;
-        }
-    if (rounds_out) *rounds_out = rounds;
-    return TRX_OK;
+    return trx_fold_mc_queue(b, nullptr, tors, xyz, terms, stats, mc_run, cycles, kT, block_min, block_max, sigma_deg, seed,
+                             id_offset, max_rounds, check_every, rounds_out);
 }
 
 /* Single evaluation at given torsions under uniform weights (parity tests of K2-K4):
@@ -1956,10 +2193,10 @@ int trx_fold_eval(trx_fold_batch *b, const float *tors, const double w[TRX_NTERM
     trx_ctx *ctx = b->ctx;
     FoldState &s = b->s;
     TRX_CUDA(cudaSetDevice(ctx->device));
-    s.cart = 0; s.ndof = s.ndof_t; s.seg_hi = s.nruns;
+    s.cart = 0; s.ndof = s.ndof_t; s.seg_lo = 0; s.seg_hi = s.nruns;
     void *d_tors = nullptr;
     int rc;
-    const size_t tb = (size_t)s.N * s.ndof * sizeof(float);
+    const size_t tb = (size_t)s.N * s.ndof_t * sizeof(float);
     if ((rc = ctx->get_scratch("fold_tors", tb, &d_tors))) return rc;
     TRX_CUDA(cudaMemcpyAsync(d_tors, tors, tb, cudaMemcpyHostToDevice, ctx->stream));
     init_state_kernel<<<s.G, 32, 0, ctx->stream>>>(s, (const float *)d_tors);
@@ -2003,7 +2240,7 @@ int trx_fold_eval_cart(trx_fold_batch *b, const float *xyz, const double w[TRX_N
     if ((rc = ctx->get_scratch("fold_xyz", xb, &d_xyz))) return rc;
     TRX_CUDA(cudaMemsetAsync(d_tors, 0, tb, ctx->stream));
     TRX_CUDA(cudaMemcpyAsync(d_xyz, xyz, xb, cudaMemcpyHostToDevice, ctx->stream));
-    s.cart = 0; s.ndof = s.ndof_t; s.seg_hi = s.nruns;
+    s.cart = 0; s.ndof = s.ndof_t; s.seg_lo = 0; s.seg_hi = s.nruns;
     init_state_kernel<<<s.G, 32, 0, ctx->stream>>>(s, (const float *)d_tors);
     std::vector<float> wl((size_t)TRX_NTERM * s.Npad);
     for (int k = 0; k < TRX_NTERM; ++k) for (int n = 0; n < s.Npad; ++n) wl[(size_t)k * s.Npad + n] = (float)w[k];
@@ -2014,7 +2251,7 @@ int trx_fold_eval_cart(trx_fold_batch *b, const float *xyz, const double w[TRX_N
     ctx->launches += 1;
     rc = fold_eval(b, nullptr, true);
     if (!rc && tors) {
-        cart_end_kernel<<<s.G, 256, 0, ctx->stream>>>(s);
+        cart_readback_kernel<<<s.G, 256, 0, ctx->stream>>>(s);
         ctx->launches += 1;
     }
     s.cart = 0; s.ndof = s.ndof_t;

@@ -111,9 +111,12 @@ def reliability_score(tors):
     return np.mean((phi >= -180.0) & (phi <= 0.0), axis=-1)
 
 
-def generate(fold_fn, initial_npz, L, n_init=10, n_max=300, sigma=1.0, angle=True, on_decoy=None):
+def generate(fold_fn, initial_npz, L, n_init=10, n_max=300, sigma=1.0, angle=True, on_decoy=None, seq=None):
     """generate_npz_and_pdb (run_inference.py:16-143) in memory.  fold_fn(npz, n) -> dict with
     'xyz' (n,L,5,3) [N,CA,CB,C,O] and 'tors' (n,L,3): folds n decoys on the given distograms.
+    seq: the target's sequence.  The reference re-reads every decoy from its PDB file and takes the
+    file's CB for every non-Gly residue (utils.py:145-150), the virtual CB only for Gly; with seq
+    given the decoy's own CB is used the same way (without it every CB is the virtual one).
     Returns the list of decoys [(xyz, tors), ...]: the n_init initial ones, then one per iteration."""
     decoys = []
     out = fold_fn(initial_npz, n_init)
@@ -123,7 +126,7 @@ def generate(fold_fn, initial_npz, L, n_init=10, n_max=300, sigma=1.0, angle=Tru
             on_decoy("initial%d" % k, out["xyz"][k])
     best = int(np.argmax(reliability_score(out["tors"])))     # first maximum, as the reference's loop
     xyz = out["xyz"][best].astype(np.float64)
-    cur = next_npz(initial_npz, xyz[:, 0], xyz[:, 1], xyz[:, 3], sigma=sigma, angle=angle)
+    cur = next_npz(initial_npz, xyz[:, 0], xyz[:, 1], xyz[:, 3], cb=xyz[:, 2] if seq else None, seq=seq, sigma=sigma, angle=angle)
     old_tmp = np.asarray(initial_npz["dist"])
     it = 0
     while True:
@@ -136,7 +139,7 @@ def generate(fold_fn, initial_npz, L, n_init=10, n_max=300, sigma=1.0, angle=Tru
         if it >= n_max:
             break
         xyz = o["xyz"][0].astype(np.float64)
-        cur = next_npz(cur, xyz[:, 0], xyz[:, 1], xyz[:, 3], sigma=sigma, angle=angle)
+        cur = next_npz(cur, xyz[:, 0], xyz[:, 1], xyz[:, 3], cb=xyz[:, 2] if seq else None, seq=seq, sigma=sigma, angle=angle)
         if np.max(np.abs(old_tmp - cur["tmp"])) < 0.01:
             break
     return decoys

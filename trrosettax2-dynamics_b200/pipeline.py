@@ -55,7 +55,7 @@ def run_single_from_npz(name, fasta, npz_paths, save_dir, init_num=10, n_max=300
             pdbio.write_pdb(p, seq, xyz, ["source %s model %d" % (tag, m)])
             written.append(p)
 
-        dynamics.generate(fold_fn, npz0, L, n_init=init_num, n_max=n_max, angle=angle, on_decoy=on_decoy)
+        dynamics.generate(fold_fn, npz0, L, n_init=init_num, n_max=n_max, angle=angle, on_decoy=on_decoy, seq=seq)
     if own:
         ctx.close()
     return written
@@ -84,41 +84,61 @@ def fold_batch(ctx, targets, n_decoys, rank=0, world=1, seed=0, out_dir=None, pa
     targets: [(name, seq, [npz, ...]), ...]; decoys of a target are dealt to its npz models in equal
     contiguous shares.  Every rank derives the same assignment (parallel.assign_blocks) and folds its
     blocks; a decoy's start (and therefore its result, bit for bit) depends only on (seed, target, global
-    decoy index), not on the sharding.  Returns {(t, decoy): dict(xyz, tors, terms, model)} for this rank's
-    decoys and writes out_dir/name/initial{decoy}.pdb when out_dir is given."""
+    decoy index), not on the sharding.  ctx: one context, or a list of contexts (one CUDA stream each):
+    that many targets are then in flight on the GPU at once, one host thread per context -- a batch of
+    100 decoys of one target leaves most of a B200 idle.  Returns {(t, decoy): dict(xyz, tors, terms,
+    model)} for this rank's decoys and writes out_dir/name/initial{decoy}.pdb when out_dir is given."""
+    import queue
+    from concurrent.futures import ThreadPoolExecutor
     from . import parallel
     params = params or tables.load_params()
+    ctxs = list(ctx) if isinstance(ctx, (list, tuple)) else [ctx]
     plan = parallel.assign_blocks([len(t[1]) for t in targets], n_decoys, world)[rank]
-    results = {}
-    cache = {}
+    by_target = {}
     for t, d0, cnt in plan:
+        by_target.setdefault(t, []).append((d0, cnt))
+    free = queue.Queue()
+    for c in ctxs:
+        free.put(c)
+
+    def fold_target(t):
         name, seq, npzs = targets[t]
         L, n_t, nm = len(seq), int(n_decoys[t]), len(npzs)
-        if t not in cache:   # one target's tables on the device at a time (the plan lists a rank's blocks target by target)
-            for old in cache.values():
-                for tb in old:
-                    tb.close()
-            cache = {t: [sampler.build_tables(ctx, z, seq, params, rule=rule) for z in npzs]}
-        tabs = cache[t]
-        starts = sampler.random_torsions(n_t, L, seed + 104729 * t)
-        model = np.minimum(np.arange(n_t) * nm // max(n_t, 1), nm - 1)
-        ids = np.arange(d0, d0 + cnt)
-        for m in range(nm):
-            sel = ids[model[ids] == m]
-            if len(sel) == 0:
-                continue
-            batch = capi.FoldBatch(ctx, [tabs[m]], [len(sel)], sampler.aa_index(seq), schedule_for(params))
-            out = batch.run(starts[sel])
-            batch.close()
-            for k, d in enumerate(sel):
-                results[(t, int(d))] = dict(xyz=out["xyz"][k], tors=out["tors"][k], terms=out["terms"][k], model=m)
-                if out_dir:
-                    p = os.path.join(out_dir, name, "initial%d.pdb" % d)
-                    os.makedirs(os.path.dirname(p), exist_ok=True)
-                    pdbio.write_pdb(p, seq, out["xyz"][k], ["target %s decoy %d model %d" % (name, d, m)])
-    for tabs in cache.values():
-        for tb in tabs:
-            tb.close()
+        c = free.get()
+        out_t = {}
+        try:
+            tabs = [sampler.build_tables(c, z, seq, params, rule=rule) for z in npzs]
+            starts = sampler.random_torsions(n_t, L, seed + 104729 * t)
+            model = np.minimum(np.arange(n_t) * nm // max(n_t, 1), nm - 1)
+            ids = np.concatenate([np.arange(d0, d0 + cnt) for d0, cnt in by_target[t]])
+            for m in range(nm):
+                sel = ids[model[ids] == m]
+                if len(sel) == 0:
+                    continue
+                batch = capi.FoldBatch(c, [tabs[m]], [len(sel)], sampler.aa_index(seq), schedule_for(params))
+                out = batch.run(starts[sel])
+                batch.close()
+                for k, d in enumerate(sel):
+                    out_t[(t, int(d))] = dict(xyz=out["xyz"][k], tors=out["tors"][k], terms=out["terms"][k], model=m)
+                    if out_dir:
+                        p = os.path.join(out_dir, name, "initial%d.pdb" % d)
+                        os.makedirs(os.path.dirname(p), exist_ok=True)
+                        pdbio.write_pdb(p, seq, out["xyz"][k], ["target %s decoy %d model %d" % (name, d, m)])
+            for tb in tabs:
+                tb.close()
+        finally:
+            free.put(c)
+        return out_t
+
+    results = {}
+    order = sorted(by_target, key=lambda t: -len(targets[t][1]))   # longest targets first: the tail is made of short ones
+    if len(ctxs) == 1:
+        for t in order:
+            results.update(fold_target(t))
+    else:
+        with ThreadPoolExecutor(max_workers=len(ctxs)) as ex:
+            for part in ex.map(fold_target, order):
+                results.update(part)
     return results
 
 

@@ -31,6 +31,25 @@ def read_wts(name, data_dir=None):
     return [w[t] for t in TERMS]
 
 
+def ignored_terms(data_dir=None, names=("scorefxn.wts", "scorefxn1.wts", "scorefxn_cart.wts", "scorefxn_vdw.wts")):
+    """[(file, term, weight)] of the weight-file entries this library does NOT score (Rosetta's database-driven
+    cen_hb / hbond_sr_bb / hbond_lr_bb: folding/data/scorefxn.wts:1, scorefxn1.wts:1, scorefxn_cart.wts:1-2).
+    The drop-in folding.py prints them and records them in the PDB REMARKs: its decoys come from an energy
+    function that differs from the reference's in these terms, and whose vdw / rama / omega / cart_bonded are
+    stated approximations (include/trx_centroid_model.h)."""
+    out = []
+    for name in names:
+        with open(os.path.join(data_dir or _DATA, name)) as fh:
+            for line in fh:
+                tok = line.split()
+                if len(tok) >= 2 and tok[0] not in TERMS and not tok[0].startswith("#"):
+                    try:
+                        out.append((name, tok[0], float(tok[1])))
+                    except ValueError:
+                        pass
+    return out
+
+
 def make_run(w, max_iter, tol=1e-4, clash_check=False, clash_thr=10.0, skip_to=0, cartesian=False):
     r = Run()
     for k in range(NTERM):
