@@ -1309,6 +1309,262 @@ __global__ void __launch_bounds__(LB_THREADS, 2) lbfgs_update_kernel(FoldState s
     }
 }
 
+// ---- L-BFGS sweeps through a bulk-async shared-memory ring (sm_90+/sm_100: cp.async.bulk + mbarrier) -----------
+// A group's history [ndof][m][32] is one sequential stream, and with register-staged loads a sweep holds only
+// what its registers can (one 255-register CTA per SM: ~40 KB in flight, ~55 % of the copy peak).  Here a
+// producer warp streams S and Y -- and in sweep A the four vectors x, xt, g, gt -- into a ring of shared-memory
+// stages with bulk copies (SASS UBLKCP) that complete on an mbarrier; eight consumer warps work out of shared
+// memory and hand the stage back through a second mbarrier.  Nothing is staged through registers, two CTAs fit an
+// SM, and ~170 KB per SM are in flight.
+// Sweep A splits the HISTORY SLOTS over the warps (slot j -> warp j % 8; 5 accumulators per slot), not the vector
+// elements: every warp owns complete sums over a chunk for its slots, formed in element order, so there is no
+// cross-warp reduction and the sums are the same bits in any batch.  Sweep B keeps one warp per vector element
+// and the order of its sum over the slots: its output is bit-identical to lbfgs_update_kernel.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE_%=;\n"
+        "bra LAB_WAIT_%=;\n"
+        "LAB_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+constexpr int RING_CONSUMERS = 8;                          // consumer warps
+constexpr int RING_THREADS = (RING_CONSUMERS + 1) * 32;    // + the producer warp
+constexpr int RING_A_E = 4, RING_A_STAGES = 4;             // sweep A: vector elements per stage, stages
+constexpr int RING_B_E = 8, RING_B_STAGES = 2;             // sweep B
+__host__ __device__ constexpr size_t ring_a_stage_floats(int m) { return (size_t)RING_A_E * (2 * m + 4) * LANES; }
+__host__ __device__ constexpr size_t ring_b_stage_floats(int m) { return (size_t)RING_B_E * 2 * m * LANES; }
+
+template <int M>
+__global__ void __launch_bounds__(RING_THREADS, 2) lbfgs_dots_ring_kernel(FoldState s)
+{
+    extern __shared__ __align__(128) unsigned char ring_raw[];
+    __shared__ __align__(8) unsigned long long full[RING_A_STAGES], empty[RING_A_STAGES];
+    constexpr int NRED = LbSmem<M>::NRED, SPW = (M + RING_CONSUMERS - 1) / RING_CONSUMERS;
+    const int g = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = g * LANES + lane;
+    if (!s.gactive[g]) return;
+    const int nd = s.ndof, m = s.m;
+    float *ring = reinterpret_cast<float *>(ring_raw);
+    const size_t stage_f = ring_a_stage_floats(m);
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < RING_A_STAGES; ++k) { mbar_init(&full[k], 1); mbar_init(&empty[k], RING_CONSUMERS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const size_t vb = (size_t)g * nd * LANES;
+    const float *__restrict__ gx = s.x + vb, *__restrict__ gxt = s.xt + vb, *__restrict__ gg = s.g + vb, *__restrict__ ggt = s.gt + vb;
+    const float *__restrict__ gS = s.S + (size_t)g * m * nd * LANES, *__restrict__ gY = s.Y + (size_t)g * m * nd * LANES;
+    const int per = (nd + LB_MAXCH - 1) / LB_MAXCH;
+    if (warp == RING_CONSUMERS) {
+        // ---- producer: one lane issues the bulk copies of every stage of every chunk of this CTA, in order
+        if (lane == 0) {
+            int it = 0;
+            for (int ch = blockIdx.y; ch < LB_MAXCH; ch += gridDim.y) {
+                const int k0 = ch * per, k1 = min(nd, k0 + per);
+                for (int k = k0; k < k1; k += RING_A_E, ++it) {
+                    const int st = it % RING_A_STAGES, ne = min(RING_A_E, k1 - k);
+                    if (it >= RING_A_STAGES) mbar_wait(&empty[st], ((it / RING_A_STAGES) - 1) & 1);
+                    float *dst = ring + (size_t)st * stage_f;
+                    const unsigned hb = (unsigned)(ne * m * LANES * sizeof(float)), vbz = (unsigned)(ne * LANES * sizeof(float));
+                    mbar_expect_tx(&full[st], 2 * hb + 4 * vbz);
+                    bulk_g2s(dst, gS + (size_t)k * m * LANES, hb, &full[st]);
+                    bulk_g2s(dst + (size_t)RING_A_E * m * LANES, gY + (size_t)k * m * LANES, hb, &full[st]);
+                    float *vec = dst + (size_t)2 * RING_A_E * m * LANES;
+                    bulk_g2s(vec, gx + (size_t)k * LANES, vbz, &full[st]);
+                    bulk_g2s(vec + RING_A_E * LANES, gxt + (size_t)k * LANES, vbz, &full[st]);
+                    bulk_g2s(vec + 2 * RING_A_E * LANES, gg + (size_t)k * LANES, vbz, &full[st]);
+                    bulk_g2s(vec + 3 * RING_A_E * LANES, ggt + (size_t)k * LANES, vbz, &full[st]);
+                }
+            }
+        }
+        return;
+    }
+    // ---- consumers
+    const int status = n < s.N ? s.status[n] : ST_DONE;
+    const int action = lb_action(s, n, status), head = s.head[n];
+    const bool is_acc = action == 2, is_new = action == 1 || action == 2;
+    float *__restrict__ wx = s.x + vb + lane, *__restrict__ wg = s.g + vb + lane;
+    float *__restrict__ wS = s.S + (size_t)g * m * nd * LANES + lane, *__restrict__ wY = s.Y + (size_t)g * m * nd * LANES + lane;
+    int it = 0;
+    for (int ch = blockIdx.y; ch < LB_MAXCH; ch += gridDim.y) {
+        const int k0 = ch * per, k1 = min(nd, k0 + per);
+        float aYG[SPW], aYY[SPW], aYS[SPW], aSG[SPW], aSY[SPW], sc[6];
+#pragma unroll
+        for (int q = 0; q < SPW; ++q) { aYG[q] = 0.f; aYY[q] = 0.f; aYS[q] = 0.f; aSG[q] = 0.f; aSY[q] = 0.f; }
+#pragma unroll
+        for (int q = 0; q < 6; ++q) sc[q] = 0.f;
+        for (int k = k0; k < k1; k += RING_A_E, ++it) {
+            const int st = it % RING_A_STAGES, ne = min(RING_A_E, k1 - k);
+            mbar_wait(&full[st], (it / RING_A_STAGES) & 1);
+            const float *src = ring + (size_t)st * stage_f;
+            const float *Ss = src + lane, *Ys = src + (size_t)RING_A_E * m * LANES + lane;
+            const float *vec = src + (size_t)2 * RING_A_E * m * LANES + lane;
+            for (int e = 0; e < ne; ++e) {
+                const float xk = vec[e * LANES], xtk = vec[(RING_A_E + e) * LANES], gk = vec[(2 * RING_A_E + e) * LANES], gtk = vec[(3 * RING_A_E + e) * LANES];
+                const float sn = xtk - xk, yn = gtk - gk, gn = is_new ? gtk : gk;
+#pragma unroll
+                for (int q = 0; q < SPW; ++q) {
+                    const int j = warp + RING_CONSUMERS * q;
+                    if (j < m) {
+                        const float yj = Ys[(e * m + j) * LANES], sj = Ss[(e * m + j) * LANES];
+                        aYG[q] += yj * gn; aYY[q] += yj * yn; aYS[q] += yj * sn;
+                        aSG[q] += sj * gn; aSY[q] += sj * yn;
+                    }
+                }
+                if (warp == 0) { sc[0] += sn * sn; sc[1] += sn * yn; sc[2] += yn * yn; sc[3] += gn * gn; sc[4] += sn * gn; sc[5] += yn * gn; }
+                if (warp == ((k + e) & (RING_CONSUMERS - 1))) {   // the element's write-back, spread over the warps
+                    if (is_acc) {
+                        wS[((size_t)(k + e) * m + head) * LANES] = sn;
+                        wY[((size_t)(k + e) * m + head) * LANES] = yn;
+                    }
+                    if (is_new) {
+                        wx[(size_t)(k + e) * LANES] = xtk;
+                        wg[(size_t)(k + e) * LANES] = gtk;
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);
+        }
+        float *__restrict__ part = s.lbpart + ((size_t)g * LB_MAXCH + ch) * NRED * LANES + lane;
+#pragma unroll
+        for (int q = 0; q < SPW; ++q) {
+            const int j = warp + RING_CONSUMERS * q;
+            if (j < M) {
+                part[(size_t)j * LANES] = aYG[q]; part[(size_t)(M + j) * LANES] = aYY[q]; part[(size_t)(2 * M + j) * LANES] = aYS[q];
+                part[(size_t)(3 * M + j) * LANES] = aSG[q]; part[(size_t)(4 * M + j) * LANES] = aSY[q];
+            }
+        }
+        if (warp == 0) {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) part[(size_t)(5 * M + q) * LANES] = sc[q];
+            part[(size_t)(5 * M + 6) * LANES] = 0.f; part[(size_t)(5 * M + 7) * LANES] = 0.f;
+        }
+    }
+}
+
+template <int M>
+__global__ void __launch_bounds__(RING_THREADS, 2) lbfgs_update_ring_kernel(FoldState s)
+{
+    extern __shared__ __align__(128) unsigned char ring_raw[];
+    __shared__ __align__(8) unsigned long long full[RING_B_STAGES], empty[RING_B_STAGES];
+    const int g = blockIdx.x, ch = blockIdx.y, nch = gridDim.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (!s.gactive[g]) return;
+    const int nd = s.ndof, m = s.m;
+    const int per = (nd + nch - 1) / nch, k0 = ch * per, k1 = min(nd, k0 + per);
+    const size_t vb = (size_t)g * nd * LANES + lane;
+    float *__restrict__ x = s.x + vb;
+    const float *__restrict__ gv = s.g + vb;
+    float *__restrict__ d = s.d + vb, *__restrict__ xt = s.xt + vb;
+    const float *__restrict__ coef = s.lbcoef + (size_t)g * LbSmem<M>::NCOEF * LANES + lane;
+    const int mode = __float_as_int(coef[(2 * M + 2) * LANES]);
+    float *ring = reinterpret_cast<float *>(ring_raw);
+    const size_t stage_f = ring_b_stage_floats(m);
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < RING_B_STAGES; ++k) { mbar_init(&full[k], 1); mbar_init(&empty[k], RING_CONSUMERS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const int anymc = __syncthreads_or(mode >= 4);
+    const int anydir = __syncthreads_or(mode == 1);
+    if (warp == RING_CONSUMERS) {
+        if (lane == 0 && anydir) {
+            const float *__restrict__ gS = s.S + (size_t)g * m * nd * LANES, *__restrict__ gY = s.Y + (size_t)g * m * nd * LANES;
+            int it = 0;
+            for (int k = k0; k < k1; k += RING_B_E, ++it) {
+                const int st = it % RING_B_STAGES, ne = min(RING_B_E, k1 - k);
+                if (it >= RING_B_STAGES) mbar_wait(&empty[st], ((it / RING_B_STAGES) - 1) & 1);
+                float *dst = ring + (size_t)st * stage_f;
+                const unsigned hb = (unsigned)(ne * m * LANES * sizeof(float));
+                mbar_expect_tx(&full[st], 2 * hb);
+                bulk_g2s(dst, gS + (size_t)k * m * LANES, hb, &full[st]);
+                bulk_g2s(dst + (size_t)RING_B_E * m * LANES, gY + (size_t)k * m * LANES, hb, &full[st]);
+            }
+        }
+        return;
+    }
+    if (anymc) {   // Monte-Carlo moves (rare rounds): revert and / or perturb, see lbfgs_step_kernel
+        const int n = g * LANES + lane;
+        if (mode >= 4) {
+            float *__restrict__ xs = s.xsave + vb;
+            const unsigned long long id = s.mc.id_offset + (unsigned long long)caller_index(s, s.orig[n]);
+            const int cycle = s.mccyc[n] - 1;
+            for (int k = k0 + warp; k < k1; k += RING_CONSUMERS) {
+                const float base = mode == 4 ? x[(size_t)k * LANES] : xs[(size_t)k * LANES];
+                if (mode == 4) xs[(size_t)k * LANES] = base;
+                const float nv = mode == 6 ? base : mc_perturb(s.mc, s.L, id, cycle, k, base);
+                x[(size_t)k * LANES] = nv;
+                xt[(size_t)k * LANES] = nv;
+            }
+        }
+    }
+    const float cgv = coef[(2 * M) * LANES], al = coef[(2 * M + 1) * LANES];
+    if (anydir) {
+        float cS[M], cY[M];
+#pragma unroll
+        for (int j = 0; j < M; ++j) { cS[j] = coef[j * LANES]; cY[j] = coef[(M + j) * LANES]; }
+        int it = 0;
+        for (int k = k0; k < k1; k += RING_B_E, ++it) {
+            const int st = it % RING_B_STAGES, ne = min(RING_B_E, k1 - k);
+            mbar_wait(&full[st], (it / RING_B_STAGES) & 1);
+            const float *src = ring + (size_t)st * stage_f;
+            if (warp < ne) {   // one element per consumer warp and stage
+                const int kk = k + warp;
+                const float *Ss = src + (size_t)warp * m * LANES + lane, *Ys = src + ((size_t)RING_B_E + warp) * m * LANES + lane;
+                const float xk = x[(size_t)kk * LANES];
+                float dk = cgv * gv[(size_t)kk * LANES];
+                float yj[M], sj[M];
+#pragma unroll
+                for (int j = 0; j < M; ++j) {
+                    yj[j] = j < m ? Ys[j * LANES] : 0.f;
+                    sj[j] = j < m ? Ss[j * LANES] : 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < M; ++j) dk += cS[j] * sj[j] + cY[j] * yj[j];
+                if (mode == 1) {
+                    d[(size_t)kk * LANES] = dk;
+                    xt[(size_t)kk * LANES] = xk + al * dk;
+                } else if (mode == 2) xt[(size_t)kk * LANES] = xk + al * d[(size_t)kk * LANES];
+                else if (mode == 3) xt[(size_t)kk * LANES] = xk;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);
+        }
+    } else {
+        for (int k = k0 + warp; k < k1; k += RING_CONSUMERS) {
+            const float xk = x[(size_t)k * LANES];
+            if (mode == 2) xt[(size_t)k * LANES] = xk + al * d[(size_t)k * LANES];
+            else if (mode == 3) xt[(size_t)k * LANES] = xk;
+        }
+    }
+}
+
 // group activity + number of unfinished decoys
 __global__ void activity_kernel(FoldState s)
 {
@@ -1698,6 +1954,7 @@ struct trx_fold_batch {
     struct Segment { int lo, hi, cart; };
     std::vector<Segment> segs;   // maximal stretches of torsion-space / Cartesian runs
     bool has_cart = false;
+    bool lb_ring = true;         // L-BFGS sweeps through the bulk-async shared-memory ring (TRX_NO_LB_RING=1: register-staged sweeps)
     bool migrate = true;         // TRX_NO_MIGRATE=1 disables the packing of unfinished decoys (same results, bit for bit)
     int mig_num = 3, mig_den = 4; // pack when unfinished <= mig_num/mig_den of the positions they are spread over (1/2: 1246, 3/4: 1257 decoys/s)
     long long k1_decoy_evals[16] = {0};   // restraint-kernel decoy evaluations of the last call, per table block
@@ -1856,17 +2113,22 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
         }
     }
     static_assert(LB_MAXCH == 16, "lbpart is carved for 16 chunks");
-    auto lb_attr = [&](auto dots, auto step, size_t bytes) -> int {
+    if (const char *ev = getenv("TRX_NO_LB_RING")) b->lb_ring = !(ev[0] && ev[0] != '0');
+    auto lb_attr = [&](auto dots, auto step, auto rdots, auto rupd, size_t bytes) -> int {
         b->lb_smem = bytes;
         TRX_CUDA(cudaFuncSetAttribute(dots, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         TRX_CUDA(cudaFuncSetAttribute(step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        // ring sizes for the largest history the template serves (the attribute is per device, batches differ in m)
+        const int mmax = lbM;
+        TRX_CUDA(cudaFuncSetAttribute(rdots, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RING_A_STAGES * ring_a_stage_floats(mmax) * sizeof(float))));
+        TRX_CUDA(cudaFuncSetAttribute(rupd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RING_B_STAGES * ring_b_stage_floats(mmax) * sizeof(float))));
         return TRX_OK;
     };
     int rc_attr;
-    if (lbM == 8) rc_attr = lb_attr(lbfgs_dots_kernel<8>, lbfgs_step_kernel<8>, sizeof(LbSmem<8>));
-    else if (lbM == 16) rc_attr = lb_attr(lbfgs_dots_kernel<16>, lbfgs_step_kernel<16>, sizeof(LbSmem<16>));
-    else if (lbM == 20) rc_attr = lb_attr(lbfgs_dots_kernel<20>, lbfgs_step_kernel<20>, sizeof(LbSmem<20>));
-    else rc_attr = lb_attr(lbfgs_dots_kernel<24>, lbfgs_step_kernel<24>, sizeof(LbSmem<24>));
+    if (lbM == 8) rc_attr = lb_attr(lbfgs_dots_kernel<8>, lbfgs_step_kernel<8>, lbfgs_dots_ring_kernel<8>, lbfgs_update_ring_kernel<8>, sizeof(LbSmem<8>));
+    else if (lbM == 16) rc_attr = lb_attr(lbfgs_dots_kernel<16>, lbfgs_step_kernel<16>, lbfgs_dots_ring_kernel<16>, lbfgs_update_ring_kernel<16>, sizeof(LbSmem<16>));
+    else if (lbM == 20) rc_attr = lb_attr(lbfgs_dots_kernel<20>, lbfgs_step_kernel<20>, lbfgs_dots_ring_kernel<20>, lbfgs_update_ring_kernel<20>, sizeof(LbSmem<20>));
+    else rc_attr = lb_attr(lbfgs_dots_kernel<24>, lbfgs_step_kernel<24>, lbfgs_dots_ring_kernel<24>, lbfgs_update_ring_kernel<24>, sizeof(LbSmem<24>));
     if (rc_attr) return rc_attr;
     guard.b = nullptr;
     *out = b;
@@ -1919,6 +2181,13 @@ static void lbfgs_launch(trx_fold_batch *b, const dim3 &grid)
 {
     trx_ctx *ctx = b->ctx;
     FoldState &s = b->s;
+    if (b->lb_ring) {
+        const size_t ra = RING_A_STAGES * ring_a_stage_floats(s.m) * sizeof(float), rb = RING_B_STAGES * ring_b_stage_floats(s.m) * sizeof(float);
+        lbfgs_dots_ring_kernel<M><<<grid, RING_THREADS, ra, ctx->stream>>>(s);
+        lbfgs_step_kernel<M><<<s.G, LB_STEP_THREADS, b->lb_smem, ctx->stream>>>(s, LB_MAXCH);
+        lbfgs_update_ring_kernel<M><<<grid, RING_THREADS, rb, ctx->stream>>>(s);
+        return;
+    }
     lbfgs_dots_kernel<M><<<grid, LB_THREADS, b->lb_smem, ctx->stream>>>(s);
     lbfgs_step_kernel<M><<<s.G, LB_STEP_THREADS, b->lb_smem, ctx->stream>>>(s, LB_MAXCH);
     lbfgs_update_kernel<M><<<grid, LB_THREADS, 0, ctx->stream>>>(s);
