@@ -162,6 +162,16 @@ int trx_fold_run_queue(trx_fold_batch *b, const int *nq, float *tors, float *xyz
  * evaluations the restraint kernel made per table block (evaluations of vdw-only runs skip it).  out: [ntab].
  * Measurement aid (roofline accounting of bench.py); no reference counterpart. */
 int trx_fold_k1_evals(trx_fold_batch *b, long long *out);
+/* Failure reporting.  The reference has no error convention on this path: a decoy whose child process failed is a
+ * missing PDB file that raises later in the parent (utils_trX2dy/utils.py:491-498).  Here every decoy of
+ * the last trx_fold_run / trx_fold_run_queue / trx_fold_mc* call reports, in the caller's order, 0 (clean) or a
+ * combination of the bits below; the host driver re-seeds decoys that report TRX_DECOY_NONFINITE. */
+enum {
+    TRX_DECOY_NONFINITE = 1,  /* a run started from, or the decoy ended with, a non-finite energy term */
+    TRX_DECOY_LINESEARCH = 2, /* a line search failed from steepest descent (the run was cut short there) */
+    TRX_DECOY_UNFINISHED = 4  /* the round budget (max_rounds) ran out before the decoy finished its schedule */
+};
+int trx_fold_status(trx_fold_batch *b, int *out, int n);
 /* Monte-Carlo sampling on top of the fold -- an EXTENSION with no reference behaviour
  * (BASELINE config 4; the reference's folding/ has no Metropolis step).
  * Minimises through the whole schedule, whose LAST run (index mc_run) defines the MC score;

@@ -378,6 +378,7 @@ def test_round_budget_closes_every_decoy(ctx):
     t0 = sampler.random_torsions(80, 40, seed=1)
     out = batch.run_queue(t0, [80], max_rounds=48)
     assert np.all(np.isfinite(out["xyz"])) and np.all(np.isfinite(out["terms"]))
+    assert np.all(batch.status() & 4) and not np.any(batch.status() & 1)    # TRX_DECOY_UNFINISHED for every decoy, none non-finite
     assert out["evals"][:32].min() > 0 and out["evals"][64:].max() == 0      # the tail of the queue never started
     np.testing.assert_array_equal(out["tors"][64:], t0[64:])
     chk = capi.FoldBatch(ctx, [tb], [80], sampler.aa_index(seq), runs)
@@ -386,6 +387,7 @@ def test_round_budget_closes_every_decoy(ctx):
     assert np.abs(xyz - out["xyz"]).max() < 1e-4
     assert np.allclose(terms, out["terms"], rtol=1e-6, atol=1e-6)
     full = batch.run_queue(t0, [80])
+    assert not np.any(batch.status() & (1 | 4))                             # finished, finite
     assert np.all((full["terms"] @ w) < (out["terms"] @ w)[:80] + 1e-6)
     chk.close(); batch.close(); tb.close()
 

@@ -38,7 +38,7 @@ def lib():
         L.trx_last_error.restype = C.c_char_p
         L.trx_ctx_launch_count.restype = C.c_longlong
         L.trx_ctx_launch_count.argtypes = [C.c_void_p]
-        for fn in (L.trx_fold_run_queue, L.trx_fold_mc_queue, L.trx_fold_k1_evals):
+        for fn in (L.trx_fold_run_queue, L.trx_fold_mc_queue, L.trx_fold_k1_evals, L.trx_fold_status):
             fn.restype = C.c_int
         _lib = L
     return _lib
@@ -223,6 +223,7 @@ class FoldBatch:
         terms = np.zeros((self.N, NTERM))
         stats = np.zeros((self.N, 2), dtype=np.int64)
         rounds = C.c_int()
+        self._last_n = self.N
         check(lib().trx_fold_run(self._h, _ptr(tors, C.c_float), _ptr(xyz, C.c_float) if want_xyz else None,
                                  _ptr(terms, C.c_double), _ptr(stats, C.c_longlong), C.c_int(max_rounds),
                                  C.c_int(check_every), C.byref(rounds)))
@@ -242,7 +243,7 @@ class FoldBatch:
         batch's positions, refilling a position as soon as its decoy has left the schedule segment in
         progress.  tors (sum nq, L, 3), the decoys of block 0 first.  Same dict as run()."""
         tors, nq, arr = self._nq(tors, nq)
-        n = sum(nq)
+        n = self._last_n = sum(nq)
         xyz = np.zeros((n, self.L, 5, 3), dtype=np.float32) if want_xyz else None
         terms = np.zeros((n, NTERM))
         stats = np.zeros((n, 2), dtype=np.int64)
@@ -251,6 +252,14 @@ class FoldBatch:
                                        _ptr(terms, C.c_double), _ptr(stats, C.c_longlong), C.c_int(max_rounds),
                                        C.c_int(check_every), C.byref(rounds)))
         return dict(tors=tors, xyz=xyz, terms=terms, evals=stats[:, 0], iters=stats[:, 1], rounds=rounds.value)
+
+    def status(self, n=None):
+        """TRX_DECOY_* bits of the decoys of the last run*/run_mc call (0 = clean; 1 non-finite energy,
+        2 line search failed, 4 round budget ran out)."""
+        n = self._last_n if n is None else n
+        out = np.zeros(n, dtype=np.int32)
+        check(lib().trx_fold_status(self._h, _ptr(out, C.c_int32), C.c_int(n)))
+        return out
 
     def k1_evals(self):
         """Decoy evaluations the restraint kernel made in the last run*/run_mc call, per table block."""
@@ -264,7 +273,7 @@ class FoldBatch:
         Metropolis) on device.  nq: decoys per table block (continuous batching), default one per position.
         Returns the dict of run() plus 'accepted' (N,)."""
         tors, nq, arr = self._nq(tors, nq)
-        n = sum(nq)
+        n = self._last_n = sum(nq)
         xyz = np.zeros((n, self.L, 5, 3), dtype=np.float32)
         terms = np.zeros((n, NTERM))
         stats = np.zeros((n, 3), dtype=np.int64)

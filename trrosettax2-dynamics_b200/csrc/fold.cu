@@ -99,6 +99,7 @@ struct FoldState {
     int lb_M;                // compile-time history bound of the L-BFGS kernel in use (8, 16, 20 or 24)
     int *nmem, *hist, *head, *iter, *run, *bt, *status, *restart;
     int *evals, *iters;
+    int *flags;              // [Npad] TRX_DECOY_* bits: what went wrong for the decoy, if anything (failure reporting)
     double *terms;           // [TRX_NTERM][Npad] unweighted terms of the last evaluation
     double *ft;              // [Npad] weighted total of the last evaluation
     float *wl;               // [TRX_NTERM][Npad] weights in force per decoy
@@ -145,11 +146,12 @@ struct FoldState {
     float *q_tors;           // [Nqpad/32][3L][32]
     float *q_X;              // [Nqpad/32][Lpad*15][32] (only with a Cartesian run)
     double *q_terms;         // [TRX_NTERM][Nqpad]
-    int *q_run, *q_held, *q_evals, *q_iters;   // [Nqpad]
+    int *q_run, *q_held, *q_evals, *q_iters, *q_flags;   // [Nqpad]
     // results in the caller's order
     float *o_tors, *o_xyz;   // [Nq][3L], [Nq][L][15] (o_xyz may be NULL)
     double *o_terms;         // [Nq][TRX_NTERM]
     long long *o_stats;      // [Nq][3] evaluations, accepted iterations, accepted MC moves
+    int *o_flags;            // [Nq] TRX_DECOY_* bits
     // Migration: the position of a decoy in the arrays above is not its identity.  When fewer than
     // half of a table block's positions hold unfinished decoys, the unfinished ones are moved to the
     // front of the block (swapped with finished ones), so the L-BFGS kernels -- which stream a whole
@@ -1139,13 +1141,13 @@ __global__ void __launch_bounds__(LB_STEP_THREADS, 1) lbfgs_step_kernel(FoldStat
             hist = 0; head = 0; iter = 0; bt = 0; restart = 1; nmem = 1;
             s.fmem[n] = f;
             if (!s.cart && n < s.N) s.held[n] = 0;   // a torsion-space run rebuilds the chain with ideal geometry
-            if (!fin) run_over = true;   // cannot start from a non-finite energy
+            if (!fin) { run_over = true; if (n < s.N) s.flags[n] |= TRX_DECOY_NONFINITE; }   // cannot start from a non-finite energy
             else need_dir = true;
         } else if (action == 3) {
             bt++;
             if (bt >= LS_MAXBACK) {
                 if (hist > 0) { hist = 0; head = 0; restart = 1; bt = 0; need_dir = true; }   // retry from steepest descent
-                else run_over = true;
+                else { run_over = true; if (n < s.N) s.flags[n] |= TRX_DECOY_LINESEARCH; }
             } else {
                 float q = fin ? -0.5f * slope * alpha * alpha / (float)(ft - f - (double)(slope * alpha)) : 0.1f * alpha;
                 if (!(q > 0.1f * alpha)) q = 0.1f * alpha;
@@ -1320,39 +1322,6 @@ __global__ void __launch_bounds__(LB_THREADS, 2) lbfgs_update_kernel(FoldState s
 // elements: every warp owns complete sums over a chunk for its slots, formed in element order, so there is no
 // cross-warp reduction and the sums are the same bits in any batch.  Sweep B keeps one warp per vector element
 // and the order of its sum over the slots: its output is bit-identical to lbfgs_update_kernel.
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "LAB_WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra LAB_DONE_%=;\n"
-        "bra LAB_WAIT_%=;\n"
-        "LAB_DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
-                 "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
 constexpr int RING_CONSUMERS = 8;                          // consumer warps
 constexpr int RING_THREADS = (RING_CONSUMERS + 1) * 32;    // + the producer warp
 constexpr int RING_A_E = 4, RING_A_STAGES = 4;             // sweep A: vector elements per stage, stages
@@ -1647,6 +1616,7 @@ __global__ void init_state_kernel(FoldState s, const float *__restrict__ tors_na
     s.held[n] = 0;
     s.orig[n] = -1;
     s.mccyc[n] = 0;
+    s.flags[n] = 0;
     s.status[n] = n < s.N ? ST_INIT : ST_DONE;
     s.run[n] = 0; s.hist[n] = 0; s.head[n] = 0; s.iter[n] = 0; s.bt[n] = 0; s.restart[n] = 1; s.nmem[n] = 0;
     s.f[n] = 0.0; s.alpha[n] = 0.f; s.slope[n] = 0.f; s.evals[n] = 0; s.iters[n] = 0;
@@ -1667,7 +1637,7 @@ __global__ void __launch_bounds__(256) queue_init_kernel(FoldState s, const floa
     float *__restrict__ qt = s.q_tors + (size_t)gq * s.ndof_t * LANES + lane;
     for (int k = warp; k < s.ndof_t; k += nw) qt[(size_t)k * LANES] = real ? tors_nat[(size_t)c * s.ndof_t + k] : (float)TRX_PI;
     if (warp == 0) {
-        s.q_run[q] = 0; s.q_held[q] = 0; s.q_evals[q] = 0; s.q_iters[q] = 0;
+        s.q_run[q] = 0; s.q_held[q] = 0; s.q_evals[q] = 0; s.q_iters[q] = 0; s.q_flags[q] = 0;
         for (int k = 0; k < TRX_NTERM; ++k) s.q_terms[(size_t)k * s.Nqpad + q] = 0.0;
     }
 }
@@ -1764,7 +1734,7 @@ __global__ void __launch_bounds__(128) turnover_move_kernel(FoldState s)
         }
         if (threadIdx.x == 0) {
             const bool keep_terms = !s.cart && held;   // still holding its Cartesian coordinates: their terms stand
-            s.q_run[old] = s.run[pos]; s.q_evals[old] = s.evals[pos]; s.q_iters[old] = s.iters[pos];
+            s.q_run[old] = s.run[pos]; s.q_evals[old] = s.evals[pos]; s.q_iters[old] = s.iters[pos]; s.q_flags[old] = s.flags[pos];
             s.q_held[old] = s.cart ? 1 : held;
             for (int k = 0; k < TRX_NTERM; ++k) {
                 const double v = keep_terms ? s.theld[(size_t)k * Npad + pos] : s.terms[(size_t)k * Npad + pos];
@@ -1775,6 +1745,11 @@ __global__ void __launch_bounds__(128) turnover_move_kernel(FoldState s)
                 s.o_stats[(size_t)c * 3] = s.evals[pos];
                 s.o_stats[(size_t)c * 3 + 1] = s.iters[pos];
                 s.o_stats[(size_t)c * 3 + 2] = s.naccept[pos];
+                int fl = s.flags[pos];
+                bool finite = true;
+                for (int k = 0; k < TRX_NTERM; ++k) finite = finite && isfinite(s.q_terms[(size_t)k * Nqpad + old]);
+                if (!finite) fl |= TRX_DECOY_NONFINITE;
+                s.o_flags[c] = fl;
             }
         }
     }
@@ -1808,6 +1783,7 @@ __global__ void __launch_bounds__(128) turnover_move_kernel(FoldState s)
             // a record beyond the segment passes through with one closing evaluation
             s.status[n] = (run >= s.seg_lo && run < s.seg_hi) ? ST_INIT : ST_FINAL;
             s.run[n] = run; s.evals[n] = s.q_evals[nid]; s.iters[n] = s.q_iters[nid]; s.held[n] = s.q_held[nid];
+            s.flags[n] = s.q_flags[nid];
             const Run &r = s.runs[min(run, s.nruns - 1)];
             for (int k = 0; k < TRX_NTERM; ++k) {
                 s.wl[(size_t)k * Npad + n] = r.w[k];
@@ -1815,7 +1791,7 @@ __global__ void __launch_bounds__(128) turnover_move_kernel(FoldState s)
                 s.theld[(size_t)k * Npad + n] = s.q_terms[(size_t)k * Nqpad + nid];
             }
         } else {
-            s.status[n] = ST_DONE; s.run[n] = s.nruns; s.held[n] = 0; s.evals[n] = 0; s.iters[n] = 0;
+            s.status[n] = ST_DONE; s.run[n] = s.nruns; s.held[n] = 0; s.evals[n] = 0; s.iters[n] = 0; s.flags[n] = 0;
         }
     }
 }
@@ -1830,12 +1806,12 @@ __global__ void __launch_bounds__(256) force_final_kernel(FoldState s)
     if (st != ST_INIT && st != ST_LS) return;
     const size_t vb = (size_t)g * s.ndof * LANES + lane;
     for (int k = warp; k < s.ndof; k += nw) s.xt[vb + (size_t)k * LANES] = s.x[vb + (size_t)k * LANES];
-    if (warp == 0) { s.status[n] = ST_FINAL; s.run[n] = s.nruns; }
+    if (warp == 0) { s.status[n] = ST_FINAL; s.run[n] = s.nruns; s.flags[n] |= TRX_DECOY_UNFINISHED; }
 }
 __global__ void force_final_queue_kernel(FoldState s)
 {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < s.Nqpad && s.q_run[q] < s.nruns) s.q_run[q] = s.nruns;
+    if (q < s.Nqpad && s.q_run[q] < s.nruns) { s.q_run[q] = s.nruns; s.q_flags[q] |= TRX_DECOY_UNFINISHED; }
 }
 
 // Which positions swap: in table block t, the k-th finished decoy among the first `nlive` positions
@@ -1917,7 +1893,7 @@ __global__ void __launch_bounds__(256) migrate_swap_kernel(FoldState s)
         swp_d(s.f, 0, 1); swp_d(s.fmem, Npad, 3); swp_d(s.fsave, 0, 1); swp_d(s.terms, Npad, TRX_NTERM); swp_d(s.ft, 0, 1); swp_d(s.theld, Npad, TRX_NTERM);
         swp_f(s.alpha, 0, 1); swp_f(s.slope, 0, 1); swp_f(s.wl, Npad, TRX_NTERM);
         swp_i(s.nmem); swp_i(s.hist); swp_i(s.head); swp_i(s.iter); swp_i(s.run); swp_i(s.bt); swp_i(s.status); swp_i(s.restart);
-        swp_i(s.evals); swp_i(s.iters); swp_i(s.naccept); swp_i(s.held); swp_i(s.orig); swp_i(s.mccyc); swp_i(s.slot_of);
+        swp_i(s.evals); swp_i(s.iters); swp_i(s.naccept); swp_i(s.held); swp_i(s.orig); swp_i(s.mccyc); swp_i(s.slot_of); swp_i(s.flags);
     }
 }
 
@@ -1958,6 +1934,7 @@ struct trx_fold_batch {
     bool migrate = true;         // TRX_NO_MIGRATE=1 disables the packing of unfinished decoys (same results, bit for bit)
     int mig_num = 3, mig_den = 4; // pack when unfinished <= mig_num/mig_den of the positions they are spread over (1/2: 1246, 3/4: 1257 decoys/s)
     long long k1_decoy_evals[16] = {0};   // restraint-kernel decoy evaluations of the last call, per table block
+    std::vector<int> status;              // TRX_DECOY_* bits of every decoy of the last call (caller order)
 };
 
 extern "C" {
@@ -2057,6 +2034,7 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     size_t o_orig = carve(np * 4), o_ma = carve(np * 4), o_mb = carve(np * 4), o_mn = carve(256);
     size_t o_held = carve(np * 4), o_th = carve(np * 8 * TRX_NTERM);
     size_t o_mcc = carve(np * 4), o_sof = carve(np * 4), o_nid = carve(np * 4), o_qc = carve(256), o_qo = carve(256), o_k1c = carve(256);
+    size_t o_flg = carve(np * 4);
     cudaError_t e = cudaMalloc(&b->arena, off);
     if (e != cudaSuccess) {
         set_error("trx_fold_create: cudaMalloc(%zu bytes) failed: %s", off, cudaGetErrorString(e));
@@ -2083,6 +2061,7 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     s.held = (int *)(A + o_held); s.theld = (double *)(A + o_th);
     s.mccyc = (int *)(A + o_mcc); s.slot_of = (int *)(A + o_sof); s.newid = (int *)(A + o_nid);
     s.qcursor = (int *)(A + o_qc); s.qocc = (int *)(A + o_qo); s.k1count = (long long *)(A + o_k1c);
+    s.flags = (int *)(A + o_flg);
     s.mc = McOpts{};
     TRX_CUDA(cudaMallocHost(&b->h_poll, 64 * sizeof(int)));
     s.ntab = ntab;
@@ -2351,16 +2330,20 @@ static int fold_queue(trx_fold_batch *b, const int *nq, float *tors, float *xyz,
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
     const size_t o_qt = carve(np * s.ndof_t * 4), o_qx = carve(b->has_cart ? np * s.ndof_c * 4 : 256);
     const size_t o_qe = carve(np * 8 * TRX_NTERM), o_qr = carve(np * 4), o_qh = carve(np * 4), o_qv = carve(np * 4), o_qi = carve(np * 4);
+    const size_t o_qf = carve(np * 4), o_of = carve((size_t)Nq * 4);
     if ((rc = ctx->get_scratch("fold_queue", off, &d_q))) return rc;
     char *Q = (char *)d_q;
     s.q_tors = (float *)(Q + o_qt); s.q_X = (float *)(Q + o_qx); s.q_terms = (double *)(Q + o_qe);
     s.q_run = (int *)(Q + o_qr); s.q_held = (int *)(Q + o_qh); s.q_evals = (int *)(Q + o_qv); s.q_iters = (int *)(Q + o_qi);
+    s.q_flags = (int *)(Q + o_qf); s.o_flags = (int *)(Q + o_of);
+    b->status.assign(Nq, 0);
     s.o_tors = (float *)d_ot; s.o_xyz = (float *)d_ox; s.o_terms = (double *)d_oe; s.o_stats = (long long *)d_os;
     TRX_CUDA(cudaMemcpyAsync(d_in, tors, tb, cudaMemcpyHostToDevice, ctx->stream));
     ctx->time_begin("fold_device");   // device time of the whole fold, inputs resident (H2D done, D2H not started)
     --ctx->launches;
     TRX_CUDA(cudaMemsetAsync(s.k1count, 0, 16 * sizeof(long long), ctx->stream));
     TRX_CUDA(cudaMemsetAsync(d_os, 0, (size_t)Nq * 3 * sizeof(long long), ctx->stream));
+    TRX_CUDA(cudaMemsetAsync(s.o_flags, 0xff, (size_t)Nq * sizeof(int), ctx->stream));   // -1 until the decoy's results are written
     ctx->time_begin("fold_init");
     queue_init_kernel<<<Gq, 256, 0, ctx->stream>>>(s, (const float *)d_in);
     ctx->time_end("fold_init");
@@ -2379,6 +2362,7 @@ static int fold_queue(trx_fold_batch *b, const int *nq, float *tors, float *xyz,
             TRX_CUDA(cudaMemcpyAsync(st3.data(), d_os, st3.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
         }
     }
+    TRX_CUDA(cudaMemcpyAsync(b->status.data(), s.o_flags, (size_t)Nq * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     TRX_CUDA(cudaMemcpyAsync(b->k1_decoy_evals, s.k1count, 16 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
     TRX_CUDA(cudaStreamSynchronize(ctx->stream));
     if (stats && stats_cols == 2)
@@ -2418,6 +2402,16 @@ int trx_fold_k1_evals(trx_fold_batch *b, long long *out)
 {
     TRX_REQUIRE(b && out, "trx_fold_k1_evals: NULL argument");
     for (int t = 0; t < b->s.ntab; ++t) out[t] = b->k1_decoy_evals[t];
+    return TRX_OK;
+}
+
+/* Failure reporting (the reference has none: a failed child process is a missing PDB file, utils_trX2dy/utils.py:491-498).
+ * Per decoy of the last trx_fold_run* / trx_fold_mc* call on this batch, caller order: 0 = clean, else TRX_DECOY_* bits.
+ * A caller re-seeds the decoys it does not accept (sampler.fold does).  out: [n], n <= decoys of the call. */
+int trx_fold_status(trx_fold_batch *b, int *out, int n)
+{
+    TRX_REQUIRE(b && out && n >= 0 && (size_t)n <= b->status.size(), "trx_fold_status: bad argument (the last call had %zu decoys)", b ? b->status.size() : (size_t)0);
+    for (int k = 0; k < n; ++k) out[k] = b->status[k];
     return TRX_OK;
 }
 

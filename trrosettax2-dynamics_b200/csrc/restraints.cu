@@ -90,6 +90,9 @@ struct KnotHead {
     int goff, K, urun0, pad;
 };
 constexpr int KX_TOTAL = MAXK + 3 * MAXK_ANG;
+constexpr int K1_MAXSTEPS = TILE * TILE;   // a tile has at most 256 pairs, hence at most 256 steps
+// dynamic shared memory of the restraint kernel: two gradient records, the tile's pair records, its schedule, one mbarrier
+__host__ __device__ constexpr size_t k1_dyn_bytes(size_t elem) { return 2 * REC_ELEMS * elem + TILE * TILE * 8 * sizeof(int) + K1_MAXSTEPS * K1_WARPS * sizeof(unsigned short) + 16; }
 __host__ __device__ constexpr int kx_off(int type) { return type == 0 ? 0 : MAXK + (type - 1) * MAXK_ANG; }
 
 template <typename T>
@@ -108,6 +111,7 @@ struct K1Params {
     int xstride;                                 // values per residue in X (9: N,CA,CB; 15: fold layout)
     int dist_ca;                                 // distance restraints on CA-CA (af2 variant, distance-only tables)
     int g0;                                      // first decoy group of this launch
+    int stage;                                   // pair records + step schedule of the tile staged in shared memory (bulk async copy)
     const int *gactive;                          // per-group flag or NULL (all active)
     const float *wl;                             // per-decoy weights [3][Npad] or NULL (use w0..w2)
     int Npad;
@@ -296,15 +300,18 @@ __device__ __forceinline__ void pair_eval(const K1Params<T> &p, const KnotHead<T
     }
 }
 
-// ---- packed fp32 path: TWO decoys per lane (sm_100 f32x2 arithmetic) ----------------------------------
+// ---- packed fp32 path (sm_100 f32x2 arithmetic) -------------------------------------------------------
 // Blackwell issues a two-wide fp32 FMA (SASS FFMA2 / FMUL2 / FADD2; PTX fma/mul/add.f32x2 on a 64-bit register
-// pair) in one slot, and the restraint kernel is bound by instruction issue, not by bytes.  A lane therefore
-// carries the same residue pair of two decoys -- the decoy groups 2h and 2h+1 -- and everything that is plain
-// arithmetic (the pair geometry: differences, cross and dot products; the whole gradient assembly; the
-// shared-memory accumulation) runs once for both.  What has no packed form stays per decoy: MUFU reciprocal /
-// rsqrt, min/max/selects of atan2, the interval search and the table gathers (each decoy its own interval).
-// The halves are independent IEEE operations, so a decoy's result does not depend on the half it sits in
-// nor on its partner.
+// pair) in one slot, and the restraint kernel is bound by instruction issue, not by bytes.  The restraints of a
+// residue pair are symmetric under exchange of the two residues: theta(j,i) and phi(j,i) are theta(i,j) and
+// phi(i,j) with the roles "self" and "other" swapped and D = CB_other - CB_self negated, and the omega
+// gradient has the same structure.  A lane therefore evaluates BOTH SIDES of its pair at once, side 0
+// (self = i) in the low half and side 1 (self = j) in the high half of every packed value: the geometry
+// (P|Q, U_i|U_j, the plane normals X|Y' and W_i|W_j, their norms and dot products), the atan2 polynomials of
+// the two thetas and the two phis, and the whole gradient assembly.  Registers and occupancy stay those of
+// the one-decoy-per-lane kernel (the packed value P|Q replaces the two scalars P and Q).
+// Measured alternative (profiles/r2_k1_variants.md): packing two DECOYS per lane needs 248 registers and twice
+// the shared memory, halves the resident warps and is 1.35x slower than the scalar kernel.
 struct F2 {
     unsigned long long v;
     __device__ __forceinline__ F2() {}
@@ -320,12 +327,11 @@ __device__ __forceinline__ F2 operator*(F2 a, F2 b) { F2 r; asm("mul.f32x2 %0, %
 __device__ __forceinline__ F2 operator-(F2 a) { return F2(0.f) - a; }   // one FADD2 with a negated operand
 __device__ __forceinline__ F2 &operator+=(F2 &a, F2 b) { a = a + b; return a; }
 __device__ __forceinline__ F2 &operator-=(F2 &a, F2 b) { a = a - b; return a; }
-__device__ __forceinline__ F2 t_rsqrt(F2 x) { return F2(t_rsqrt(lo(x)), t_rsqrt(hi(x))); }
-__device__ __forceinline__ F2 t_rcp(F2 x) { return F2(t_rcp(lo(x)), t_rcp(hi(x))); }
-__device__ __forceinline__ F2 fmax2(F2 a, F2 b) { return F2(fmaxf(lo(a), lo(b)), fmaxf(hi(a), hi(b))); }
-template <> __device__ __forceinline__ F2 t_tiny<F2>() { return F2(1e-12f); }
-// atan2 of both halves: the reduction to [0,1] and the final selects per decoy, the polynomial packed
-__device__ __forceinline__ void t_atan2(F2 y, F2 x, float &rl, float &rh)
+__device__ __forceinline__ F2 rsqrt2(F2 x) { return F2(t_rsqrt(lo(x)), t_rsqrt(hi(x))); }
+__device__ __forceinline__ F2 rcp2(F2 x) { return F2(t_rcp(lo(x)), t_rcp(hi(x))); }
+__device__ __forceinline__ F2 fmax2(F2 a, float m) { return F2(fmaxf(lo(a), m), fmaxf(hi(a), m)); }
+// atan2 of both halves: the reduction to [0,1] and the final selects per half, the polynomial packed
+__device__ __forceinline__ void atan2_2(F2 y, F2 x, float &rl, float &rh)
 {
     const float xl = lo(x), xh = hi(x), yl = lo(y), yh = hi(y);
     const float axl = fabsf(xl), ayl = fabsf(yl), axh = fabsf(xh), ayh = fabsf(yh);
@@ -345,286 +351,101 @@ __device__ __forceinline__ void t_atan2(F2 y, F2 x, float &rl, float &rh)
     rh = copysignf(rh, yh);
 }
 
-// One restraint of both decoys: intervals and the two table gathers (phase 1); value and slope (phase 2)
-struct Spl2 {
-    Coef<float> cl, ch;
-    float ul, uh;
-};
-template <bool HEAD>
-__device__ __forceinline__ void spl2_load(Spl2 &q, const Coef<float> *__restrict__ tab, int off, const KnotHead<float> &kn,
-                                          const float *__restrict__ kx, float vl, float vh)
-{
-    const int kl = spline_locate<HEAD>(kn, kx, vl, q.ul), kh = spline_locate<HEAD>(kn, kx, vh, q.uh);
-    q.cl = spline_load(tab, off, kl);
-    q.ch = spline_load(tab, off, kh);
-}
-__device__ __forceinline__ F2 spl2_f(const Spl2 &q)
+// All restraints of the residue pair (i = row, j = column), both sides at once.  self[k] = (row | column) value k of
+// N(0..2) CA(3..5) CB(6..8).  Packed conventions, half 0 / half 1:
+//   Dp = CB_other - CB_self = ( D | -D ),  Pp = CA_self - CB_self = ( P | Q ),  Up = N_self - CA_self,
+//   Xp = Dp x Pp = ( X | Y' = -Y ),  Wp = Up x Pp,  pdp = Pp.Dp = ( pd | -qd )
+// theta(self,other) = atan2(-|Pp| Up.Xp, Wp.Xp),  phi(self,other) = atan2(|Xp|, pdp),  omega = atan2(d P.Y', -X.Y').
+// Absent restraints of a pair get zero coefficients (value 0, slope 0): one straight-line path for every pair.
+// G[9]: gradient of (row | column) atoms; adds to `other` CB cross over at the end.
+__device__ __forceinline__ void pair_eval_sym(const K1Params<float> &p, const KnotHead<float> *geom, const float *__restrict__ kx, const int4 ia,
+                                              const int4 ib, const F2 *self, F2 *G, const float w0, const float w1, const float w2,
+                                              float &e0, float &e1, float &e2)
 {
     typedef float T;
-    return F2(SPLINE_F(q.cl, q.ul), SPLINE_F(q.ch, q.uh));
-}
-__device__ __forceinline__ F2 spl2_df(const Spl2 &q)
-{
-    typedef float T;
-    return F2(SPLINE_DF(q.cl, q.ul), SPLINE_DF(q.ch, q.uh));
-}
-
-// pair_eval for two decoys per lane; same formulas, same order of operations per decoy
-template <bool ALL>
-__device__ __forceinline__ void pair_eval2(const K1Params<float> &p, const KnotHead<float> *geom, const float *__restrict__ kx, const int4 ia,
-                                           const int4 ib, const F2 *row, const ColGeom<F2> &c, F2 *rg, F2 *cg, const F2 w0, const F2 w1,
-                                           const F2 w2, F2 &e0, F2 &e1, F2 &e2)
-{
-    typedef F2 T;
     const int mask = ia.x;
-    const T Dx = c.Bx - row[0], Dy = c.By - row[1], Dz = c.Bz - row[2];
-    const T Px = row[3], Py = row[4], Pz = row[5];
-    const T Qx = c.Qx, Qy = c.Qy, Qz = c.Qz;
-    const T dd = fmax2(DOT(D, D), t_tiny<T>());
-    const T rd = t_rsqrt(dd);
-    const T d = dd * rd;
-    T Xx, Xy, Xz, Yx, Yy, Yz;
-    CROSS(X, D, P);
-    CROSS(Y, D, Q);
-    const T xx = fmax2(DOT(X, X), t_tiny<T>()), yy = fmax2(DOT(Y, Y), t_tiny<T>());
-    const T pd = DOT(P, D), qd = DOT(Q, D);
-    const T pp = fmax2(DOT(P, P), t_tiny<T>());
-    const T rX = t_rsqrt(xx), rY = t_rsqrt(yy);
-    const T Ux = row[6], Uy = row[7], Uz = row[8];
-    T Wx, Wy, Wz;
-    CROSS(W, U, P);
-    const T ww = fmax2(DOT(W, W), t_tiny<T>());
-    const T rp = t_rsqrt(pp), np_ = pp * rp;
-    const T rq = t_rsqrt(c.qq), nq = c.qq * rq;
+    const Coef<float> czero = {0.f, 0.f, 0.f, 0.f};
+    const float Dx = hi(self[6]) - lo(self[6]), Dy = hi(self[7]) - lo(self[7]), Dz = hi(self[8]) - lo(self[8]);
+    const F2 Dpx = F2(Dx, -Dx), Dpy = F2(Dy, -Dy), Dpz = F2(Dz, -Dz);
+    const F2 Ppx = self[3] - self[6], Ppy = self[4] - self[7], Ppz = self[5] - self[8];
+    const F2 Upx = self[0] - self[3], Upy = self[1] - self[4], Upz = self[2] - self[5];
+    const float dd = fmaxf(DOT(D, D), 1e-12f), rd = t_rsqrt(dd), d = dd * rd;
+    F2 Xpx, Xpy, Xpz, Wpx, Wpy, Wpz;
+    CROSS(Xp, Dp, Pp);
+    CROSS(Wp, Up, Pp);
+    const F2 xxp = fmax2(DOT(Xp, Xp), 1e-12f), ppp = fmax2(DOT(Pp, Pp), 1e-12f), wwp = fmax2(DOT(Wp, Wp), 1e-12f);
+    const F2 pdp = DOT(Pp, Dp), upp = DOT(Up, Pp);
+    const F2 rXp = rsqrt2(xxp), rpp = rsqrt2(ppp), npp = ppp * rpp;
 
-    // ---- phase 1: values, intervals, loads (twelve independent gathers in flight)
-    Spl2 s0, s1, s2, s3, s4, s5;
-    float al, ah;
-    if (ALL || (mask & 1)) spl2_load<true>(s0, p.tab[0], ia.y, geom[0], kx + kx_off(0), lo(d), hi(d));
-    if (ALL || (mask & 2)) {
-        t_atan2(-(d * DOT(P, Y)), DOT(X, Y), al, ah);
-        spl2_load<false>(s1, p.tab[1], ia.z, geom[1], kx + kx_off(1), al, ah);
+    // ---- phase 1: values, intervals, loads (six independent gathers in flight)
+    float u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f, u4 = 0.f, u5 = 0.f;
+    Coef<float> c0 = czero, c1 = czero, c2 = czero, c3 = czero, c4 = czero, c5 = czero;
+    {
+        const int k = spline_locate<true>(geom[0], kx + kx_off(0), d, u0);
+        if (mask & 1) c0 = spline_load(p.tab[0], ia.y, k);
     }
-    if (ALL || (mask & 4)) {
-        t_atan2(-(np_ * DOT(U, X)), DOT(W, X), al, ah);
-        spl2_load<false>(s2, p.tab[2], ia.w, geom[2], kx + kx_off(2), al, ah);
+    {   // omega: F = P, G = -D, H = Q  =>  A = X, B = Y = -Y'
+        const float Px = lo(Ppx), Py = lo(Ppy), Pz = lo(Ppz), Xx = lo(Xpx), Xy = lo(Xpy), Xz = lo(Xpz);
+        const float Yx = hi(Xpx), Yy = hi(Xpy), Yz = hi(Xpz);   // Y'
+        const int k = spline_locate<false>(geom[1], kx + kx_off(1), t_atan2(d * DOT(P, Y), -DOT(X, Y)), u1);
+        if (mask & 2) c1 = spline_load(p.tab[1], ia.z, k);
     }
-    if (ALL || (mask & 8)) {
-        t_atan2(nq * (c.Ux * Yx + c.Uy * Yy + c.Uz * Yz), -(c.Wx * Yx + c.Wy * Yy + c.Wz * Yz), al, ah);
-        spl2_load<false>(s3, p.tab[2], ib.x, geom[2], kx + kx_off(2), al, ah);
+    {   // theta(i,j) | theta(j,i)
+        float al, ah;
+        atan2_2(-(npp * DOT(Up, Xp)), DOT(Wp, Xp), al, ah);
+        const int kl = spline_locate<false>(geom[2], kx + kx_off(2), al, u2), kh = spline_locate<false>(geom[2], kx + kx_off(2), ah, u3);
+        if (mask & 4) c2 = spline_load(p.tab[2], ia.w, kl);
+        if (mask & 8) c3 = spline_load(p.tab[2], ib.x, kh);
     }
-    if (ALL || (mask & 16)) {
-        t_atan2(xx * rX, pd, al, ah);
-        spl2_load<false>(s4, p.tab[3], ib.y, geom[3], kx + kx_off(3), al, ah);
-    }
-    if (ALL || (mask & 32)) {
-        t_atan2(yy * rY, -qd, al, ah);
-        spl2_load<false>(s5, p.tab[3], ib.z, geom[3], kx + kx_off(3), al, ah);
+    {   // phi(i,j) | phi(j,i): sin = |Xp| / (|Pp||D|)
+        float al, ah;
+        atan2_2(xxp * rXp, pdp, al, ah);
+        const int kl = spline_locate<false>(geom[3], kx + kx_off(3), al, u4), kh = spline_locate<false>(geom[3], kx + kx_off(3), ah, u5);
+        if (mask & 16) c4 = spline_load(p.tab[3], ib.y, kl);
+        if (mask & 32) c5 = spline_load(p.tab[3], ib.z, kh);
     }
 
     // ---- phase 2: energies and gradients
-    const T ixx = rX * rX, iyy = rY * rY;
-    if (ALL || (mask & 1)) {
-        e0 += spl2_f(s0);
-        const T s = w0 * spl2_df(s0) * rd;
-        cg[6] += s * Dx; cg[7] += s * Dy; cg[8] += s * Dz;
-        rg[6] -= s * Dx; rg[7] -= s * Dy; rg[8] -= s * Dz;
+    const F2 ixxp = rXp * rXp;
+    e0 += SPLINE_F(c0, u0);
+    e1 += SPLINE_F(c1, u1) + SPLINE_F(c2, u2) + SPLINE_F(c3, u3);
+    e2 += SPLINE_F(c4, u4) + SPLINE_F(c5, u5);
+    F2 Ox = F2(0.f), Oy = F2(0.f), Oz = F2(0.f);   // gradient on the OTHER residue's CB, per side
+    {   // dist: CB_self -= s Dp
+        const F2 s = F2(w0 * SPLINE_DF(c0, u0) * rd);
+        G[6] -= s * Dpx; G[7] -= s * Dpy; G[8] -= s * Dpz;
     }
-    if (ALL || (mask & 2)) {
-        e1 += spl2_f(s1);
-        const T s = w1 * spl2_df(s1);
-        const T sd = s * d, a1 = -(sd * ixx), a4 = sd * iyy, tA = -(s * pd * ixx * rd), tB = -(s * qd * iyy * rd);
-        const T tx = tA * Xx - tB * Yx, ty = tA * Xy - tB * Yy, tz = tA * Xz - tB * Yz;
-        rg[3] += a1 * Xx; rg[4] += a1 * Xy; rg[5] += a1 * Xz;                  // CA_i
-        cg[3] += a4 * Yx; cg[4] += a4 * Yy; cg[5] += a4 * Yz;                  // CA_j
-        rg[6] += tx - a1 * Xx; rg[7] += ty - a1 * Xy; rg[8] += tz - a1 * Xz;   // CB_i
-        cg[6] -= tx + a4 * Yx; cg[7] -= ty + a4 * Yy; cg[8] -= tz + a4 * Yz;   // CB_j
+    {   // omega: CA_self += a1 Xp;  CB_self += (tA - a1) Xp - tA_other X_other
+        const float s = w1 * SPLINE_DF(c1, u1);
+        const F2 sx = F2(s) * ixxp, a1 = -(F2(d) * sx), tA = -(pdp * sx * F2(rd)), za = tA - a1;
+        G[3] += a1 * Xpx; G[4] += a1 * Xpy; G[5] += a1 * Xpz;
+        G[6] += za * Xpx; G[7] += za * Xpy; G[8] += za * Xpz;
+        Ox -= tA * Xpx; Oy -= tA * Xpy; Oz -= tA * Xpz;
     }
-    if (ALL || (mask & 4)) {
-        e1 += spl2_f(s2);
-        const T s = w1 * spl2_df(s2), iww = t_rcp(ww), up = DOT(U, P);
-        const T a1 = -(s * np_ * iww), a4 = s * np_ * ixx, tA = s * up * iww * rp, tB = s * pd * ixx * rp;
-        const T tx = tA * Wx - tB * Xx, ty = tA * Wy - tB * Xy, tz = tA * Wz - tB * Xz;
-        rg[0] += a1 * Wx; rg[1] += a1 * Wy; rg[2] += a1 * Wz;                  // N_i
-        cg[6] += a4 * Xx; cg[7] += a4 * Xy; cg[8] += a4 * Xz;                  // CB_j
-        rg[3] += tx - a1 * Wx; rg[4] += ty - a1 * Wy; rg[5] += tz - a1 * Wz;   // CA_i
-        rg[6] -= tx + a4 * Xx; rg[7] -= ty + a4 * Xy; rg[8] -= tz + a4 * Xz;   // CB_i
+    {   // theta: N_self += a1 Wp;  CB_other += a4 Xp;  CA_self += t - a1 Wp;  CB_self -= t + a4 Xp,  t = tA Wp - tB Xp
+        const F2 s = F2(w1) * F2(SPLINE_DF(c2, u2), SPLINE_DF(c3, u3)), iww = rcp2(wwp);
+        const F2 sn = s * npp, a1 = -(sn * iww), a4 = sn * ixxp, tA = s * upp * iww * rpp, tB = s * pdp * ixxp * rpp;
+        const F2 tx = tA * Wpx - tB * Xpx, ty = tA * Wpy - tB * Xpy, tz = tA * Wpz - tB * Xpz;
+        G[0] += a1 * Wpx; G[1] += a1 * Wpy; G[2] += a1 * Wpz;
+        Ox += a4 * Xpx; Oy += a4 * Xpy; Oz += a4 * Xpz;
+        G[3] += tx - a1 * Wpx; G[4] += ty - a1 * Wpy; G[5] += tz - a1 * Wpz;
+        G[6] -= tx + a4 * Xpx; G[7] -= ty + a4 * Xpy; G[8] -= tz + a4 * Xpz;
     }
-    if (ALL || (mask & 8)) {
-        e1 += spl2_f(s3);
-        const T s = w1 * spl2_df(s3), iww = t_rcp(c.ww);
-        const T a1 = -(s * nq * iww), a4 = s * nq * iyy, tA = s * c.uq * iww * rq, tB = s * qd * iyy * rq;
-        const T tx = tA * c.Wx - tB * Yx, ty = tA * c.Wy - tB * Yy, tz = tA * c.Wz - tB * Yz;
-        cg[0] += a1 * c.Wx; cg[1] += a1 * c.Wy; cg[2] += a1 * c.Wz;                    // N_j
-        rg[6] -= a4 * Yx; rg[7] -= a4 * Yy; rg[8] -= a4 * Yz;                          // CB_i  (a4 * B, B = -Y)
-        cg[3] += tx - a1 * c.Wx; cg[4] += ty - a1 * c.Wy; cg[5] += tz - a1 * c.Wz;     // CA_j
-        cg[6] -= tx - a4 * Yx; cg[7] -= ty - a4 * Yy; cg[8] -= tz - a4 * Yz;           // CB_j
+    {   // phi: CA_self += u;  CB_other += v;  CB_self -= u + v
+        const F2 s = F2(w2) * F2(SPLINE_DF(c4, u4), SPLINE_DF(c5, u5)) * rXp, a = pdp * rpp * rpp, b = pdp * F2(rd * rd);
+        const F2 ux = s * (a * Ppx - Dpx), uy = s * (a * Ppy - Dpy), uz = s * (a * Ppz - Dpz);
+        const F2 vx = s * (b * Dpx - Ppx), vy = s * (b * Dpy - Ppy), vz = s * (b * Dpz - Ppz);
+        G[3] += ux; G[4] += uy; G[5] += uz;
+        Ox += vx; Oy += vy; Oz += vz;
+        G[6] -= ux + vx; G[7] -= uy + vy; G[8] -= uz + vz;
     }
-    if (ALL || (mask & 16)) {
-        e2 += spl2_f(s4);
-        const T s = w2 * spl2_df(s4) * rX, a = pd * rp * rp, b = pd * rd * rd;
-        const T ux = s * (a * Px - Dx), uy = s * (a * Py - Dy), uz = s * (a * Pz - Dz);   // d/dCA_i
-        const T vx = s * (b * Dx - Px), vy = s * (b * Dy - Py), vz = s * (b * Dz - Pz);   // d/dCB_j
-        rg[3] += ux; rg[4] += uy; rg[5] += uz;
-        cg[6] += vx; cg[7] += vy; cg[8] += vz;
-        rg[6] -= ux + vx; rg[7] -= uy + vy; rg[8] -= uz + vz;
-    }
-    if (ALL || (mask & 32)) {
-        e2 += spl2_f(s5);
-        const T s = w2 * spl2_df(s5) * rY, a = qd * rq * rq, b = qd * rd * rd;
-        const T ux = s * (Dx - a * Qx), uy = s * (Dy - a * Qy), uz = s * (Dz - a * Qz);      // d/dCA_j
-        const T vx = s * (b * Dx - Qx), vy = s * (b * Dy - Qy), vz = s * (b * Dz - Qz);      // d/dCB_i
-        cg[3] += ux; cg[4] += uy; cg[5] += uz;
-        rg[6] += vx; rg[7] += vy; rg[8] += vz;
-        cg[6] -= ux + vx; cg[7] -= uy + vy; cg[8] -= uz + vz;
-    }
+    // the `other` of side 0 is the column residue, of side 1 the row residue
+    G[6] += F2(hi(Ox), lo(Ox)); G[7] += F2(hi(Oy), lo(Oy)); G[8] += F2(hi(Oz), lo(Oz));
 }
 
-#ifndef TRX_K1X2_MINBLOCKS
-#define TRX_K1X2_MINBLOCKS 2
-#endif
-// The fp32 restraint kernel: a CTA of K1_WARPS warps evaluates one work item (tile) for the decoy groups
-// g0 = p.g0 + 2 blockIdx.x and g0 + 1 (the second may be absent: odd group count, or not active).
-__global__ void __launch_bounds__(K1_THREADS, TRX_K1X2_MINBLOCKS) restraints2_kernel(const K1Params<float> p, int ng)
-{
-    __shared__ KnotHead<float> geom[4];
-    __shared__ float kx[KX_TOTAL];
-    extern __shared__ __align__(16) unsigned char k1_dyn[];
-    F2 *colg = reinterpret_cast<F2 *>(k1_dyn);   // column-block gradient of the current tile, both decoys of a lane
-    F2 *rowg = colg + REC_ELEMS;                  // row-block gradient of the whole work item
-    double(*ered)[6][LANES] = reinterpret_cast<double(*)[6][LANES]>(colg);   // reused after the last flush
-    static_assert(sizeof(double) * K1_WARPS * 6 * LANES <= sizeof(F2) * REC_ELEMS, "energy scratch must fit");
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int q = blockIdx.y, ga = p.g0 + 2 * blockIdx.x;
-    const bool has_b = 2 * (int)blockIdx.x + 1 < ng;
-    const int gb = has_b ? ga + 1 : ga;           // an absent partner replays the first group (finite, never written)
-    const bool act_a = !p.gactive || p.gactive[ga], act_b = has_b && (!p.gactive || p.gactive[gb]);
-    if (!act_a && !act_b) return;
-    {
-        if (threadIdx.x < 4) {
-            const KnotGeom<float> &gs = p.geom[threadIdx.x];
-            KnotHead<float> h;
-            h.gx0 = gs.gx0; h.ginv = gs.ginv; h.goff = gs.goff; h.K = gs.K; h.urun0 = gs.urun0; h.pad = 0;
-            geom[threadIdx.x] = h;
-        }
-        for (int e = threadIdx.x; e < KX_TOTAL; e += K1_THREADS) {
-            const int t = e < MAXK ? 0 : 1 + (e - MAXK) / MAXK_ANG, k = e - kx_off(t);
-            kx[e] = p.geom[t].x[k];
-        }
-        const F2 z = F2(0.f);
-        for (int e = threadIdx.x; e < REC_ELEMS; e += K1_THREADS) { colg[e] = z; rowg[e] = z; }
-    }
-    const int I = p.work[q * 4 + 0], t0 = p.work[q * 4 + 1], nt = p.work[q * 4 + 2], rowrec = p.work[q * 4 + 3];
-    const int xs = p.xstride;
-    size_t basea = (size_t)ga * p.Lpad * xs * LANES + lane, baseb = (size_t)gb * p.Lpad * xs * LANES + lane;
-    asm volatile("" : "+l"(basea), "+l"(baseb));   // keep the group offsets in registers
-    const float *__restrict__ Xa = p.X + basea, *__restrict__ Xb = p.X + baseb;
-    const unsigned xrow = (unsigned)xs * LANES;
-    F2 w0 = F2(p.w0), w1 = F2(p.w1), w2 = F2(p.w2);
-    if (p.wl) {
-        const size_t na = (size_t)ga * LANES + lane, nb = (size_t)gb * LANES + lane;
-        w0 = F2(p.wl[na], p.wl[nb]);
-        w1 = F2(p.wl[(size_t)p.Npad + na], p.wl[(size_t)p.Npad + nb]);
-        w2 = F2(p.wl[2 * (size_t)p.Npad + na], p.wl[2 * (size_t)p.Npad + nb]);
-    }
-    double ea0 = 0.0, ea1 = 0.0, ea2 = 0.0, eb0 = 0.0, eb1 = 0.0, eb2 = 0.0;
-    __syncthreads();
-
-    for (int t = t0; t < t0 + nt; ++t) {
-        const int J = p.tileJ[t];
-        const int *__restrict__ rec_t = p.pairrec + (size_t)t * TILE * TILE * 8;
-        F2 f0 = F2(0.f), f1 = F2(0.f), f2 = F2(0.f);   // per-tile partial energies
-        const int s0 = p.nsteps[t], s1 = p.nsteps[t + 1];
-        for (int s = s0; s < s1; ++s) {
-            const int e = p.sched[(size_t)s * K1_WARPS + w];
-            if (e != 0xffff) {
-                const int r = e & 15, c = (e >> 4) & 15;
-                const int4 *rp = reinterpret_cast<const int4 *>(rec_t + (r * TILE + c) * 8);
-                const int4 ia = __ldg(rp), ib = __ldg(rp + 1);
-                F2 ri[9], cj[9], rg[9], cg[9];
-                const unsigned orow = (unsigned)(I * TILE + r) * xrow, ocol = (unsigned)(J * TILE + c) * xrow;
-#pragma unroll
-                for (int k = 0; k < 9; ++k) {
-                    ri[k] = F2(Xa[orow + k * LANES], Xb[orow + k * LANES]);
-                    cj[k] = F2(Xa[ocol + k * LANES], Xb[ocol + k * LANES]);
-                    rg[k] = F2(0.f);
-                    cg[k] = F2(0.f);
-                }
-                F2 row[9];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    row[k] = ri[6 + k];
-                    row[3 + k] = ri[3 + k] - ri[6 + k];
-                    row[6 + k] = ri[k] - ri[3 + k];
-                }
-                if (p.dist_ca) {   // 'AtomPair CA a CA b' (utils_ros.py:191): the only restraint of such a pair
-                    const F2 Dx = cj[3] - ri[3], Dy = cj[4] - ri[4], Dz = cj[5] - ri[5];
-                    const F2 dd = fmax2(DOT(D, D), t_tiny<F2>()), rd = t_rsqrt(dd), d = dd * rd;
-                    Spl2 sq;
-                    spl2_load<true>(sq, p.tab[0], ia.y, geom[0], kx + kx_off(0), lo(d), hi(d));
-                    f0 += spl2_f(sq);
-                    const F2 sg = w0 * spl2_df(sq) * rd;
-                    cg[3] += sg * Dx; cg[4] += sg * Dy; cg[5] += sg * Dz;
-                    rg[3] -= sg * Dx; rg[4] -= sg * Dy; rg[5] -= sg * Dz;
-                } else {
-                    ColGeom<F2> cgm;
-                    cgm.Bx = cj[6]; cgm.By = cj[7]; cgm.Bz = cj[8];
-                    cgm.Qx = cj[3] - cj[6]; cgm.Qy = cj[4] - cj[7]; cgm.Qz = cj[5] - cj[8];
-                    cgm.Ux = cj[0] - cj[3]; cgm.Uy = cj[1] - cj[4]; cgm.Uz = cj[2] - cj[5];
-                    cgm.Wx = cgm.Uy * cgm.Qz - cgm.Uz * cgm.Qy;
-                    cgm.Wy = cgm.Uz * cgm.Qx - cgm.Ux * cgm.Qz;
-                    cgm.Wz = cgm.Ux * cgm.Qy - cgm.Uy * cgm.Qx;
-                    cgm.qq = fmax2(cgm.Qx * cgm.Qx + cgm.Qy * cgm.Qy + cgm.Qz * cgm.Qz, t_tiny<F2>());
-                    cgm.ww = fmax2(cgm.Wx * cgm.Wx + cgm.Wy * cgm.Wy + cgm.Wz * cgm.Wz, t_tiny<F2>());
-                    cgm.uq = cgm.Ux * cgm.Qx + cgm.Uy * cgm.Qy + cgm.Uz * cgm.Qz;
-                    // pairs carrying all six restraints take a straight-line path (no per-restraint branches)
-                    if (ia.x == 63) pair_eval2<true>(p, geom, kx, ia, ib, row, cgm, rg, cg, w0, w1, w2, f0, f1, f2);
-                    else pair_eval2<false>(p, geom, kx, ia, ib, row, cgm, rg, cg, w0, w1, w2, f0, f1, f2);
-                }
-#pragma unroll
-                for (int k = 0; k < 9; ++k) {
-                    rowg[(r * 9 + k) * LANES + lane] += rg[k];
-                    colg[(c * 9 + k) * LANES + lane] += cg[k];
-                }
-            }
-            __syncthreads();
-        }
-        ea0 += (double)lo(f0); ea1 += (double)lo(f1); ea2 += (double)lo(f2);
-        eb0 += (double)hi(f0); eb1 += (double)hi(f1); eb2 += (double)hi(f2);
-        // column record of the tile, one per decoy group: four packed values -> one 16-byte store per group
-        float *__restrict__ dsta = p.recs + ((size_t)ga * p.nrec + t) * REC_ELEMS, *__restrict__ dstb = p.recs + ((size_t)gb * p.nrec + t) * REC_ELEMS;
-        for (int e = threadIdx.x * 4; e < REC_ELEMS; e += K1_THREADS * 4) {
-            const F2 v0 = colg[e], v1 = colg[e + 1], v2 = colg[e + 2], v3 = colg[e + 3];
-            if (act_a) *reinterpret_cast<float4 *>(dsta + e) = make_float4(lo(v0), lo(v1), lo(v2), lo(v3));
-            if (act_b) *reinterpret_cast<float4 *>(dstb + e) = make_float4(hi(v0), hi(v1), hi(v2), hi(v3));
-            const F2 z = F2(0.f);
-            colg[e] = z; colg[e + 1] = z; colg[e + 2] = z; colg[e + 3] = z;
-        }
-        __syncthreads();
-    }
-    {
-        float *__restrict__ dsta = p.recs + ((size_t)ga * p.nrec + rowrec) * REC_ELEMS, *__restrict__ dstb = p.recs + ((size_t)gb * p.nrec + rowrec) * REC_ELEMS;
-        for (int e = threadIdx.x * 4; e < REC_ELEMS; e += K1_THREADS * 4) {
-            const F2 v0 = rowg[e], v1 = rowg[e + 1], v2 = rowg[e + 2], v3 = rowg[e + 3];
-            if (act_a) *reinterpret_cast<float4 *>(dsta + e) = make_float4(lo(v0), lo(v1), lo(v2), lo(v3));
-            if (act_b) *reinterpret_cast<float4 *>(dstb + e) = make_float4(hi(v0), hi(v1), hi(v2), hi(v3));
-        }
-    }
-    __syncthreads();   // colg is about to be reused as energy scratch
-    ered[w][0][lane] = ea0; ered[w][1][lane] = ea1; ered[w][2][lane] = ea2;
-    ered[w][3][lane] = eb0; ered[w][4][lane] = eb1; ered[w][5][lane] = eb2;
-    __syncthreads();
-    for (int k = w; k < 6; k += K1_WARPS) {
-        double s = 0.0;
-#pragma unroll
-        for (int v = 0; v < K1_WARPS; ++v) s += ered[v][k][lane];
-        const bool second = k >= 3;
-        if (second ? act_b : act_a)
-            p.Epart[(((size_t)(second ? gb : ga) * p.nwork + q) * 3 + (k % 3)) * LANES + lane] = s;
-    }
-}
-
-template <typename T>
+// SYM (fp32 only): both sides of a pair packed in f32x2 (pair_eval_sym); otherwise the scalar formulas (fp64 parity
+// mode; fp32 with TRX_K1_SCALAR=1 for A/B measurements)
+template <typename T, bool SYM>
 __global__ void __launch_bounds__(K1_THREADS, (sizeof(T) == 4 ? TRX_K1_MINBLOCKS : 1)) restraints_kernel(const K1Params<T> p)
 {
     __shared__ KnotHead<T> geom[4];
@@ -639,10 +460,21 @@ __global__ void __launch_bounds__(K1_THREADS, (sizeof(T) == 4 ? TRX_K1_MINBLOCKS
     KVec kzero;
 #pragma unroll
     for (int k = 0; k < KV; ++k) kzero.v[k] = (T)0;
+    // The tile's pair records (8 KB, one contiguous block) arrive by ONE bulk asynchronous copy (cp.async.bulk ->
+    // UBLKCP, completion on an mbarrier) and its step schedule by one coalesced load per thread, while the CTA
+    // zeroes its accumulators: the per-step chain schedule entry -> pair record -> table gather, three dependent
+    // L2 round trips, becomes two shared-memory reads and one gather.
+    int *recs_s = reinterpret_cast<int *>(k1_dyn + 2 * REC_ELEMS * sizeof(T));
+    unsigned short *sched_s = reinterpret_cast<unsigned short *>(recs_s + TILE * TILE * 8);
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(sched_s + K1_MAXSTEPS * K1_WARPS);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int q = blockIdx.y, g = p.g0 + blockIdx.x;   // group is the fast grid index: co-resident CTAs share tiles
     if (p.gactive && !p.gactive[g]) return;
     {
+        if (p.stage && threadIdx.x == 0) {
+            mbar_init(bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
         if (threadIdx.x < 4) {
             const KnotGeom<T> &gs = p.geom[threadIdx.x];
             KnotHead<T> h;
@@ -677,12 +509,28 @@ __global__ void __launch_bounds__(K1_THREADS, (sizeof(T) == 4 ? TRX_K1_MINBLOCKS
         // host-built schedule: the (<= K1_WARPS) pairs of a step have distinct rows and distinct columns,
         // so one warp per pair can add its row and column gradients to shared memory without atomics
         const int s0 = p.nsteps[t], s1 = p.nsteps[t + 1];
+        if (p.stage) {
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(bar, TILE * TILE * 8 * sizeof(int));
+                bulk_g2s(recs_s, rec_t, TILE * TILE * 8 * sizeof(int), bar);
+            }
+            const uint2 *__restrict__ src = reinterpret_cast<const uint2 *>(p.sched + (size_t)s0 * K1_WARPS);   // 8 B per step
+            for (int e = threadIdx.x; e < s1 - s0; e += K1_THREADS) reinterpret_cast<uint2 *>(sched_s)[e] = src[e];
+            mbar_wait(bar, (t - t0) & 1);
+            __syncthreads();
+        }
         for (int s = s0; s < s1; ++s) {
-            const int e = p.sched[(size_t)s * K1_WARPS + w];
+            const int e = p.stage ? sched_s[(s - s0) * K1_WARPS + w] : p.sched[(size_t)s * K1_WARPS + w];
             if (e != 0xffff) {
                 const int r = e & 15, c = (e >> 4) & 15;
-                const int4 *rp = reinterpret_cast<const int4 *>(rec_t + (r * TILE + c) * 8);
-                const int4 ia = __ldg(rp), ib = __ldg(rp + 1);
+                int4 ia, ib;
+                if (p.stage) {
+                    const int4 *rp = reinterpret_cast<const int4 *>(recs_s + (r * TILE + c) * 8);
+                    ia = rp[0]; ib = rp[1];
+                } else {
+                    const int4 *rp = reinterpret_cast<const int4 *>(rec_t + (r * TILE + c) * 8);
+                    ia = __ldg(rp); ib = __ldg(rp + 1);
+                }
                 T ri[9], cj[9], rg[9], cg[9];
                 const T *__restrict__ xr = Xg + (unsigned)(I * TILE + r) * xrow, *__restrict__ xc = Xg + (unsigned)(J * TILE + c) * xrow;
 #pragma unroll
@@ -691,6 +539,21 @@ __global__ void __launch_bounds__(K1_THREADS, (sizeof(T) == 4 ? TRX_K1_MINBLOCKS
                     cj[k] = xc[k * LANES];
                     rg[k] = (T)0;
                     cg[k] = (T)0;
+                }
+                if constexpr (SYM) {
+                    if (!p.dist_ca) {
+                        F2 self[9], G[9];
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) { self[k] = F2(ri[k], cj[k]); G[k] = F2(0.f); }
+                        pair_eval_sym(p, geom, kx, ia, ib, self, G, w0, w1, w2, f0, f1, f2);
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) {
+                            rowg[(r * 9 + k) * LANES + lane] += lo(G[k]);
+                            colg[(c * 9 + k) * LANES + lane] += hi(G[k]);
+                        }
+                        __syncthreads();
+                        continue;
+                    }
                 }
                 T row[9];
 #pragma unroll
@@ -827,6 +690,8 @@ int k1_launch(trx_ctx *ctx, trx_tables *tb, int Gtot, int g0, int ng, const T *d
     p.xstride = xstride;
     p.dist_ca = tb->dist_ca;
     p.g0 = g0;
+    static const bool no_stage = [] { const char *ev = getenv("TRX_K1_NO_STAGE"); return ev && ev[0] && ev[0] != '0'; }();   // A/B
+    p.stage = no_stage ? 0 : 1;
     p.gactive = gactive;
     p.wl = wl;
     p.Npad = Gtot * LANES;
@@ -835,35 +700,24 @@ int k1_launch(trx_ctx *ctx, trx_tables *tb, int Gtot, int g0, int ng, const T *d
     p.w2 = (T)(w ? w[2] : 0.0);
     if (plan->nwork > 0) {
         ctx->time_begin("restraints");
-        const size_t dyn = 2 * REC_ELEMS * sizeof(T);
-        static bool attr_set_dev[64][2] = {};   // function attributes are per device
-        bool *attr_set = attr_set_dev[ctx->device & 63];
-        if (!attr_set[sizeof(T) == 8]) {
-            TRX_CUDA(cudaFuncSetAttribute(restraints_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-            int carve = TRX_K1_CARVEOUT;
-            if (const char *ev = getenv("TRX_K1_CARVEOUT")) carve = atoi(ev);   // development knob: percent of the L1/shared array
-            TRX_CUDA(cudaFuncSetAttribute(restraints_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-            attr_set[sizeof(T) == 8] = true;
-        }
-        static const bool scalar_f32 = [] { const char *ev = getenv("TRX_K1_SCALAR"); return ev && ev[0] && ev[0] != '0'; }();   // A/B: one decoy per lane
-        if constexpr (sizeof(T) == 4) {
-            if (!scalar_f32) {
-                const size_t dyn2 = 2 * REC_ELEMS * sizeof(F2);
-                static bool attr2_dev[64] = {};
-                if (!attr2_dev[ctx->device & 63]) {
-                    TRX_CUDA(cudaFuncSetAttribute(restraints2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn2));
-                    int carve = 70;   // 164 KB of shared memory: two CTAs resident, ~64 KB of L1 left for coordinate and table lines
-                    if (const char *ev = getenv("TRX_K1_CARVEOUT")) carve = atoi(ev);
-                    TRX_CUDA(cudaFuncSetAttribute(restraints2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-                    attr2_dev[ctx->device & 63] = true;
-                }
-                restraints2_kernel<<<dim3((ng + 1) / 2, plan->nwork), K1_THREADS, dyn2, ctx->stream>>>(p, ng);
-            } else {
-                restraints_kernel<T><<<dim3(ng, plan->nwork), K1_THREADS, dyn, ctx->stream>>>(p);
+        const size_t dyn = k1_dyn_bytes(sizeof(T));
+        static const bool scalar_f32 = [] { const char *ev = getenv("TRX_K1_SCALAR"); return ev && ev[0] && ev[0] != '0'; }();   // A/B: scalar formulas in fp32
+        auto launch = [&](auto kern) -> int {
+            static bool attr_set_dev[64] = {};   // function attributes are per device (one flag per instantiation of this lambda)
+            if (!attr_set_dev[ctx->device & 63]) {
+                TRX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+                int carve = TRX_K1_CARVEOUT;
+                if (const char *ev = getenv("TRX_K1_CARVEOUT")) carve = atoi(ev);   // development knob: percent of the L1/shared array
+                TRX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+                attr_set_dev[ctx->device & 63] = true;
             }
-        } else {
-            restraints_kernel<T><<<dim3(ng, plan->nwork), K1_THREADS, dyn, ctx->stream>>>(p);
-        }
+            kern<<<dim3(ng, plan->nwork), K1_THREADS, dyn, ctx->stream>>>(p);
+            return TRX_OK;
+        };
+        int rcl;
+        if constexpr (sizeof(T) == 4) rcl = scalar_f32 ? launch(restraints_kernel<float, false>) : launch(restraints_kernel<float, true>);
+        else rcl = launch(restraints_kernel<T, false>);
+        if (rcl) return rcl;
         ctx->time_end("restraints");
         TRX_CUDA(cudaGetLastError());
     }
@@ -890,10 +744,10 @@ extern "C" {
 /* Development aid (not part of include/trx2dyn.h): resident CTAs per SM of the fp32 restraint kernel. */
 int trx_debug_k1_occupancy(int *out)
 {
-    const size_t dyn = 2 * REC_ELEMS * sizeof(float);
-    TRX_CUDA(cudaFuncSetAttribute(restraints_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    TRX_CUDA(cudaFuncSetAttribute(restraints_kernel<float>, cudaFuncAttributePreferredSharedMemoryCarveout, TRX_K1_CARVEOUT));
-    TRX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, restraints_kernel<float>, K1_THREADS, dyn));
+    const size_t dyn = k1_dyn_bytes(sizeof(float));
+    TRX_CUDA(cudaFuncSetAttribute(restraints_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    TRX_CUDA(cudaFuncSetAttribute(restraints_kernel<float, true>, cudaFuncAttributePreferredSharedMemoryCarveout, TRX_K1_CARVEOUT));
+    TRX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, restraints_kernel<float, true>, K1_THREADS, dyn));
     return TRX_OK;
 }
 

@@ -29,36 +29,85 @@ def read_fasta(path):
     return seq
 
 
-def run_single_from_npz(name, fasta, npz_paths, save_dir, init_num=10, n_max=300, angle=True, device=0, seed=0,
-                        rule="H1", ctx=None):
-    """npz_paths: [NMR npz] or [NMR npz, X-ray npz] (--mult_two_models).  Returns the list of PDB paths."""
-    seq = read_fasta(fasta)
+def _run_chain(ctx, seq, npz_path, m, out_dir, init_num, n_max, angle, seed, rule, params):
+    """One model's chain of run_inference.generate_npz_and_pdb (run_inference.py:16-143): init_num decoys in one
+    batch, then one decoy per iteration on the decayed distograms.  Iterations depend on each other, so a chain
+    is sequential; parallel width comes from running many chains (models, targets) at once."""
     L = len(seq)
-    own = ctx is None
-    ctx = ctx or capi.Context(device)
-    out_dir = os.path.join(save_dir, name, "pred_pdb")
-    os.makedirs(out_dir, exist_ok=True)
-    params = tables.load_params()
-    params["USE_ORIENT"] = bool(angle)
+    npz0 = {k: np.asarray(v) for k, v in np.load(npz_path).items()}
+    counter = {"k": 0, "calls": 0}
     written = []
-    for m, path in enumerate(npz_paths, start=1):
-        npz0 = {k: np.asarray(v) for k, v in np.load(path).items()}
-        counter = {"k": 0, "calls": 0}
 
-        def fold_fn(npz, n):
-            counter["calls"] += 1
-            return sampler.fold(ctx, [npz], seq, [n], seed=seed + 7919 * m + counter["calls"], params=params, rule=rule)
+    def fold_fn(npz, n):
+        counter["calls"] += 1
+        return sampler.fold(ctx, [npz], seq, [n], seed=seed + 7919 * m + counter["calls"], params=params, rule=rule)
 
-        def on_decoy(tag, xyz):
-            counter["k"] += 1
-            p = os.path.join(out_dir, "conf_%d_%d.pdb" % (m, counter["k"]))
-            pdbio.write_pdb(p, seq, xyz, ["source %s model %d" % (tag, m)])
-            written.append(p)
+    def on_decoy(tag, xyz):
+        counter["k"] += 1
+        p = os.path.join(out_dir, "conf_%d_%d.pdb" % (m, counter["k"]))
+        pdbio.write_pdb(p, seq, xyz, ["source %s model %d" % (tag, m)])
+        written.append(p)
 
-        dynamics.generate(fold_fn, npz0, L, n_init=init_num, n_max=n_max, angle=angle, on_decoy=on_decoy, seq=seq)
-    if own:
-        ctx.close()
+    dynamics.generate(fold_fn, npz0, L, n_init=init_num, n_max=n_max, angle=angle, on_decoy=on_decoy, seq=seq)
     return written
+
+
+def run_many_from_npz(jobs, save_dir, init_num=10, n_max=300, angle=True, device=0, seed=0, rule="H1", ctx=None, streams=None):
+    """The dynamics loop for many chains at once.  jobs: [(name, fasta, [NMR npz] or [NMR npz, X-ray npz]), ...]
+    (the reference's name_lst loop over run_single, run_inference.py:339-354, with --mult_two_models).  Every
+    (target, model) pair is an independent chain; `streams` chains (default: all, at most 16) run concurrently,
+    one CUDA stream and one host thread each -- a chain folds ONE decoy per iteration and leaves a B200 almost
+    idle on its own.  A decoy's result depends only on (seed, model, iteration), not on what runs beside it.
+    ctx: None (contexts are created), one context (chains run one after the other on it) or a list of
+    contexts.  Returns {name: [PDB paths]}, conf_{model}_{k}.pdb in the order the reference numbers them."""
+    import queue
+    from concurrent.futures import ThreadPoolExecutor
+    chains = []
+    for name, fasta, npz_paths in jobs:
+        seq = read_fasta(fasta)
+        out_dir = os.path.join(save_dir, name, "pred_pdb")
+        os.makedirs(out_dir, exist_ok=True)
+        for m, path in enumerate(npz_paths, start=1):
+            chains.append((name, seq, path, m, out_dir))
+    own = ctx is None
+    if own:
+        n_ctx = max(1, min(streams or len(chains), len(chains), 16))
+        ctxs = [capi.Context(device) for _ in range(n_ctx)]
+    else:
+        ctxs = list(ctx) if isinstance(ctx, (list, tuple)) else [ctx]
+    free = queue.Queue()
+    for c in ctxs:
+        free.put(c)
+
+    def work(ch):
+        name, seq, path, m, out_dir = ch
+        params = tables.load_params()
+        params["USE_ORIENT"] = bool(angle)
+        c = free.get()
+        try:
+            return _run_chain(c, seq, path, m, out_dir, init_num, n_max, angle, seed, rule, params)
+        finally:
+            free.put(c)
+
+    if len(ctxs) == 1:
+        parts = [work(ch) for ch in chains]
+    else:
+        with ThreadPoolExecutor(max_workers=len(ctxs)) as ex:
+            parts = list(ex.map(work, chains))
+    out = {}
+    for ch, files in zip(chains, parts):
+        out.setdefault(ch[0], []).extend(files)
+    if own:
+        for c in ctxs:
+            c.close()
+    return out
+
+
+def run_single_from_npz(name, fasta, npz_paths, save_dir, init_num=10, n_max=300, angle=True, device=0, seed=0,
+                        rule="H1", ctx=None, streams=None):
+    """npz_paths: [NMR npz] or [NMR npz, X-ray npz] (--mult_two_models).  The models' chains run concurrently
+    (see run_many_from_npz).  Returns the list of PDB paths."""
+    return run_many_from_npz([(name, fasta, npz_paths)], save_dir, init_num, n_max, angle, device, seed, rule, ctx, streams)[name]
 
 
 def main(argv=None):
@@ -73,8 +122,9 @@ def main(argv=None):
     ap.add_argument("--no-angle", dest="angle", action="store_false")
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--streams", type=int, default=None, help="chains (models) in flight at once; default all")
     a = ap.parse_args(argv)
-    files = run_single_from_npz(a.name, a.fasta, a.npz, a.save_dir, a.init_num, a.Nmax, a.angle, a.device, a.seed)
+    files = run_single_from_npz(a.name, a.fasta, a.npz, a.save_dir, a.init_num, a.Nmax, a.angle, a.device, a.seed, streams=a.streams)
     print("wrote %d decoys under %s" % (len(files), os.path.join(a.save_dir, a.name, "pred_pdb")))
 
 

@@ -46,7 +46,7 @@ def build_tables(ctx, npz, seq, params, sep=(1, None), rule="H1", nogly=False, u
     return capi.Tables(ctx, L, tables.active_restraints(rst, masks, rule))
 
 
-def fold(ctx, npzs, seq, n_decoys, seed=0, params=None, runs=None, lbfgs_m=20, rule="H1", max_rounds=20000):
+def fold(ctx, npzs, seq, n_decoys, seed=0, params=None, runs=None, lbfgs_m=20, rule="H1", max_rounds=20000, reseed=2):
     """Folds n_decoys[t] decoys against npzs[t] (two-model mixing = two entries).
     Returns the dict of capi.FoldBatch.run plus 'model' (index of the npz per decoy)."""
     params = params or tables.load_params()
@@ -56,6 +56,21 @@ def fold(ctx, npzs, seq, n_decoys, seed=0, params=None, runs=None, lbfgs_m=20, r
     batch = capi.FoldBatch(ctx, tabs, n_decoys, aa_index(seq), runs, lbfgs_m)
     out = batch.run(random_torsions(sum(n_decoys), L, seed), max_rounds=max_rounds)
     out["model"] = np.repeat(np.arange(len(npzs)), n_decoys)
+    out["status"] = batch.status()
+    # failure handling: decoys that report a non-finite energy are folded again from a new random start
+    # (the reference has no such step: a failed child process is a missing PDB file)
+    for attempt in range(1, reseed + 1):
+        bad = np.nonzero(out["status"] & 1)[0]
+        if len(bad) == 0:
+            break
+        fresh = random_torsions(sum(n_decoys), L, seed + 1000003 * attempt)
+        start = out["tors"].copy()
+        start[bad] = fresh[bad]
+        again = batch.run(start, max_rounds=max_rounds)
+        st = batch.status()
+        for key in ("tors", "xyz", "terms", "evals", "iters"):
+            out[key][bad] = again[key][bad]
+        out["status"][bad] = st[bad] | 8          # 8: re-seeded
     batch.close()
     for t in tabs:
         t.close()
