@@ -464,7 +464,7 @@ def run_b200_fold(args):
     # pinned host buffers: torsions in, coordinates + terms out (the e2e path IS the product call)
     tors_h = torch.empty((N, L, 3), dtype=torch.float32).pin_memory()
     xyz_h = torch.empty((N, L, 5, 3), dtype=torch.float32).pin_memory()
-    terms_h = torch.empty((N, 7), dtype=torch.float64).pin_memory()
+    terms_h = torch.empty((N, 8), dtype=torch.float64).pin_memory()
     ncol = 3 if mc else 2
     stats_h = torch.empty((N, ncol), dtype=torch.int64).pin_memory()
     id0 = int(np.sum(parallel.shard_counts(total, world)[:rank])) if strong else rank * N

@@ -11,7 +11,7 @@ produce with N processes (folding_with_pred_npz(repeat=N)) come out of ONE launc
 
 The staged schedule includes the Cartesian min_mover_cart stage.  Not built: the
 full-atom FastRelax stage (--fastrelax is accepted and ignored; decoys are centroid backbone + CB) and
-Rosetta's database-driven cen_hb / hbond terms."""
+Rosetta's own database-driven potentials (vdw, rama, omega, cart_bonded, cen_hb / hbond are stated approximations)."""
 import os
 import sys
 import time
@@ -58,8 +58,9 @@ def main(argv=None):
         raise SystemExit("folding.py: --ndecoy %d needs a '{i}' placeholder in -OUT (every decoy would be written to %s)" % (n, args.OUT))
     # what differs from the reference's energy function, said where a user sees it (and in the PDB REMARKs)
     dropped = schedule.ignored_terms()
-    model_note = ["energy function: atom_pair/dihedral/angle constraints as the reference; vdw, rama, omega, cart_bonded are",
-                  "stated approximations of Rosetta's centroid terms (include/trx_centroid_model.h); no full-atom FastRelax"]
+    model_note = ["energy function: atom_pair/dihedral/angle constraints as the reference; vdw, rama, omega, cart_bonded and the",
+                  "backbone H-bond term (for cen_hb / hbond_sr_bb / hbond_lr_bb) are stated approximations of Rosetta's",
+                  "database-driven terms (include/trx_centroid_model.h); no full-atom FastRelax"]
     if dropped:
         model_note.append("weight-file terms NOT scored: " + ", ".join("%s %g (%s)" % (t, w, f) for f, t, w in dropped))
     for ln in model_note:

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TRX_ABI_VERSION 1
+#define TRX_ABI_VERSION 2
 
 typedef enum {
     TRX_OK = 0,
@@ -108,16 +108,19 @@ int trx_to_grouped(trx_ctx *ctx, int N, int L, int n_atoms, int precision, const
 int trx_from_grouped(trx_ctx *ctx, int N, int L, int n_atoms, int precision, const void *d_grouped, void *d_natural);
 
 /* ------------------------------------------------------------------ the centroid fold
- * Energy terms of the fold, order of every w[7] / terms[7]:
- * atom_pair_constraint, dihedral_constraint, angle_constraint, vdw, rama, omega, cart_bonded. */
-enum { TRX_TERM_APC = 0, TRX_TERM_DIH = 1, TRX_TERM_ANG = 2, TRX_TERM_VDW = 3, TRX_TERM_RAMA = 4, TRX_TERM_OMEGA = 5, TRX_TERM_CART = 6, TRX_NTERMS = 7 };
+ * Energy terms of the fold, order of every w[8] / terms[8]:
+ * atom_pair_constraint, dihedral_constraint, angle_constraint, vdw, rama, omega, cart_bonded, and the backbone
+ * hydrogen-bond term that stands in for cen_hb (centroid stages) and hbond_sr_bb + hbond_lr_bb (Cartesian stage).
+ * Only the three constraint terms carry a parity claim; the others are stated approximations of Rosetta's
+ * database-driven terms (include/trx_centroid_model.h). */
+enum { TRX_TERM_APC = 0, TRX_TERM_DIH = 1, TRX_TERM_ANG = 2, TRX_TERM_VDW = 3, TRX_TERM_RAMA = 4, TRX_TERM_OMEGA = 5, TRX_TERM_CART = 6, TRX_TERM_HB = 7, TRX_NTERMS = 8 };
 
 /* One MinMover.apply of the reference's schedule (folding/folding.py:91-104): score
  * weights (data/ *.wts), max_iter, tolerance.  clash_check = 1 restates remove_clash
  * (utils_ros.py:699-703): when rama+vdw (weights 1,1) < clash_thr at the start of the run,
  * execution continues at run skip_to instead. */
 typedef struct {
-    double w[7];
+    double w[8];
     int max_iter;
     double tol;
     int clash_check;
@@ -142,7 +145,7 @@ int trx_fold_destroy(trx_fold_batch *b);
 /* Minimises every decoy through the schedule, all on device (NeRF, restraint + centroid
  * terms, torsion gradient, L-BFGS / Armijo); the host only polls a counter every
  * check_every evaluation rounds.  tors: host [N][L][3] float (phi,psi,omega radians), in/out.
- * xyz (may be NULL): [N][L][5][3] float, atoms N,CA,CB,C,O.  terms (may be NULL): [N][7].
+ * xyz (may be NULL): [N][L][5][3] float, atoms N,CA,CB,C,O.  terms (may be NULL): [N][8].
  * stats (may be NULL): [N][2] = energy evaluations, accepted L-BFGS iterations.
  * Replaces: remove_clash + repeat_mover.apply + remove_clash (folding.py:119,164-171). */
 int trx_fold_run(trx_fold_batch *b, float *tors, float *xyz, double *terms, long long *stats, int max_rounds,
@@ -190,18 +193,38 @@ int trx_fold_mc_queue(trx_fold_batch *b, const int *nq, float *tors, float *xyz,
                       int cycles, double kT, int block_min, int block_max, double sigma_deg, unsigned long long seed,
                       unsigned long long id_offset, int max_rounds, int check_every, int *rounds_out);
 /* One evaluation at given torsions under uniform weights (parity entry for the NeRF /
- * vdw / rama / omega / torsion-gradient kernels): total[N], terms[N][7], gtors[N][L][3],
+ * vdw / rama / omega / torsion-gradient kernels): total[N], terms[N][8], gtors[N][L][3],
  * xyz[N][L][5][3] (any output may be NULL). */
-int trx_fold_eval(trx_fold_batch *b, const float *tors, const double w[7], double *total, double *terms, float *gtors,
+int trx_fold_eval(trx_fold_batch *b, const float *tors, const double w[8], double *total, double *terms, float *gtors,
                   float *xyz);
 
 /* One Cartesian-mode evaluation under uniform weights (parity entry for the Cartesian stage:
  * cart_bonded springs, rama / omega from coordinates, restraint + vdw gradients on xyz):
- * xyz[N][L][5][3] in; total[N], terms[N][7], grad[N][L][5][3], tors[N][L][3] (torsions read
+ * xyz[N][L][5][3] in; total[N], terms[N][8], grad[N][L][5][3], tors[N][L][3] (torsions read
  * back from the coordinates) out, any of which may be NULL.  The batch's schedule must
  * contain a Cartesian run. */
-int trx_fold_eval_cart(trx_fold_batch *b, const float *xyz, const double w[7], double *total, double *terms, float *grad,
+int trx_fold_eval_cart(trx_fold_batch *b, const float *xyz, const double w[8], double *total, double *terms, float *grad,
                        float *tors);
+
+/* ------------------------------------------------------------------ the outer dynamics loop
+ * Device-resident distograms of one chain of run_inference.generate_npz_and_pdb (run_inference.py:97-139).
+ * dist [L][L][37] float; omega, theta [L][L][25], phi [L][L][13] (all three or none: --no-angle).
+ * Replaces: the npz files the reference rewrites every iteration (run_inference.py:116-133). */
+typedef struct trx_dyn trx_dyn;
+int trx_dyn_create(trx_ctx *ctx, int L, const float *dist, const float *omega, const float *theta, const float *phi,
+                   trx_dyn **out);
+int trx_dyn_destroy(trx_dyn *d);
+/* One iteration: the decoy just folded (backbone n, ca, c and cb, [L][3] double each; cb is used where use_cb[i] != 0
+ * -- the reference takes the file's CB for non-Gly residues, utils_trX2dy/utils.py:145-150 -- and the virtual CB
+ * elsewhere) is turned into realised 6D bins, and the four maps and the un-normalised `tmp` map are decayed,
+ * renormalised and Gaussian-smoothed in place, bit-identically to the reference's numpy / scipy arithmetic.
+ * w9: the nine Gaussian taps (scipy.ndimage, sigma as chosen, truncate 4).  *max_tmp_change: the convergence signal.
+ * Replaces: get_neighbors + pros + process_distribution_with_pred_distribution
+ * (utils_trX2dy/utils.py:125-249,379-403) behind get_npz_from_pred_pdb (:406-476). */
+int trx_dyn_step(trx_dyn *d, const double *n, const double *ca, const double *c, const double *cb, const unsigned char *use_cb,
+                 const double *w9, double *max_tmp_change);
+/* Current maps to the host (any pointer may be NULL); bins: [4][L][L] realised bins of the last step. */
+int trx_dyn_get(trx_dyn *d, float *dist, float *omega, float *theta, float *phi, float *tmp, int *bins);
 
 /* ------------------------------------------------------------------ decoy-set metrics
  * GloCon matrix of M decoys of L residues: out[M][M], out[i][j] = mean over residue pairs a<b of

@@ -36,7 +36,7 @@
 enum { TRX_AT_N = 0, TRX_AT_CA = 1, TRX_AT_CB = 2, TRX_AT_C = 3, TRX_AT_O = 4, TRX_NAT = 5 };
 
 /* energy terms of the fold path, order of every terms[] / weights[] array */
-enum { TRX_T_APC = 0, TRX_T_DIH = 1, TRX_T_ANG = 2, TRX_T_VDW = 3, TRX_T_RAMA = 4, TRX_T_OMEGA = 5, TRX_T_CART = 6, TRX_NTERM = 7 };
+enum { TRX_T_APC = 0, TRX_T_DIH = 1, TRX_T_ANG = 2, TRX_T_VDW = 3, TRX_T_RAMA = 4, TRX_T_OMEGA = 5, TRX_T_CART = 6, TRX_T_HB = 7, TRX_NTERM = 8 };
 
 /* amino-acid index: position in "ARNDCQEGHILKMFPSTWYV" */
 #define TRX_AA_ORDER "ARNDCQEGHILKMFPSTWYV"
@@ -79,6 +79,20 @@ static const double TRX_RAMA_OFFSET[2] = {2.125029287790165, 1.956450144676099};
 /* omega tether: 0.01 * (deviation from 180 in degrees)^2 */
 #define TRX_OMEGA_K 0.01
 
+
+/* Backbone hydrogen-bond term.  Stands in for cen_hb (weight 5 in scorefxn.wts / scorefxn1.wts, with -hb_cen_soft,
+ * folding.py:48) in the centroid stages and for hbond_sr_bb + hbond_lr_bb (weight 3 each, scorefxn_cart.wts) in the
+ * Cartesian stage; Rosetta's own potentials are database-driven and not in the reference tree, so this is a stated
+ * approximation with the same role: a smooth, orientation-dependent attraction between backbone N-H and C=O.
+ *   donor residue i (i >= 1, not Pro), acceptor residue j, |i - j| >= TRX_HB_MINSEP
+ *   r = O_j - N_i, d = |r|;  v = 2 N_i - C_{i-1} - CA_i (direction of the N-H bond);  q = O_j - C_j
+ *   c1 = unit(v).unit(r)   (N-H...O linearity),   c2 = -unit(q).unit(r)   (C=O...N linearity)
+ *   E = -TRX_HB_EPS f(d) g(c1) g(c2),   f(d) = (1 - ((d - D0)/W)^2)^2 for |d - D0| < W else 0,   g(c) = max(c, 0)^2
+ * C1-continuous with compact support (N...O within D0 +- W = 2.0 .. 3.8 A). */
+#define TRX_HB_EPS 1.0
+#define TRX_HB_D0 2.9
+#define TRX_HB_W 0.9
+#define TRX_HB_MINSEP 3
 
 /* Cartesian stage (min_mover_cart, folding.py:100-102,170): a cart_bonded-like term keeps the
  * backbone near ideal geometry while xyz are the degrees of freedom.  Rosetta's cart_bonded

@@ -125,6 +125,56 @@ double trxo_vdw(int L, const int *aa, const double *xyz, double w, double *grad)
     return E;
 }
 
+/* Backbone hydrogen-bond term (include/trx_centroid_model.h): donors N_i (i >= 1, not Pro), acceptors O_j,
+ * |i-j| >= TRX_HB_MINSEP.  grad[L][5][3] is ACCUMULATED with w*dE/dx on N_i, CA_i, C_{i-1}, O_j, C_j. */
+double trxo_hbond(int L, const int *aa, const double *xyz, double w, double *grad)
+{
+    double E = 0.0;
+    const double dmax = TRX_HB_D0 + TRX_HB_W, dmin = TRX_HB_D0 - TRX_HB_W;
+    for (int i = 1; i < L; ++i) {
+        if (aa[i] == TRX_AA_PRO) continue;
+        const double *N = XYZ(i, TRX_AT_N), *CA = XYZ(i, TRX_AT_CA), *Cp = XYZ(i - 1, TRX_AT_C);
+        double v[3];
+        for (int k = 0; k < 3; ++k) v[k] = 2.0 * N[k] - Cp[k] - CA[k];
+        const double vn = sqrt(v_dot(v, v));
+        for (int j = 0; j < L; ++j) {
+            if (abs(i - j) < TRX_HB_MINSEP) continue;
+            const double *O = XYZ(j, TRX_AT_O), *C = XYZ(j, TRX_AT_C);
+            double r[3], q[3];
+            v_sub(O, N, r);
+            const double d2 = v_dot(r, r);
+            if (d2 >= dmax * dmax || d2 <= dmin * dmin) continue;
+            const double d = sqrt(d2);
+            v_sub(O, C, q);
+            const double qn = sqrt(v_dot(q, q));
+            const double c1 = v_dot(v, r) / (vn * d), c2 = -v_dot(q, r) / (qn * d);
+            if (c1 <= 0.0 || c2 <= 0.0) continue;
+            const double t = (d - TRX_HB_D0) / TRX_HB_W, u = 1.0 - t * t;
+            const double F = u * u, dF = -4.0 * u * t / TRX_HB_W;
+            const double G1 = c1 * c1, G2 = c2 * c2;
+            E += -TRX_HB_EPS * F * G1 * G2;
+            if (!grad) continue;
+            const double a = -TRX_HB_EPS * w;
+            const double kd = a * dF * G1 * G2, k1 = a * F * 2.0 * c1 * G2, k2 = a * F * G1 * 2.0 * c2;
+            double gr[3], gv[3], gq[3];
+            for (int k = 0; k < 3; ++k) {
+                const double rh = r[k] / d, vh = v[k] / vn, qh = q[k] / qn;
+                gr[k] = kd * rh + k1 * (vh - c1 * rh) / d - k2 * (qh + c2 * rh) / d;
+                gv[k] = k1 * (rh - c1 * vh) / vn;
+                gq[k] = -k2 * (rh + c2 * qh) / qn;
+            }
+            for (int k = 0; k < 3; ++k) {
+                grad[((size_t)j * TRX_NAT + TRX_AT_O) * 3 + k] += gr[k] + gq[k];
+                grad[((size_t)j * TRX_NAT + TRX_AT_C) * 3 + k] -= gq[k];
+                grad[((size_t)i * TRX_NAT + TRX_AT_N) * 3 + k] += -gr[k] + 2.0 * gv[k];
+                grad[((size_t)i * TRX_NAT + TRX_AT_CA) * 3 + k] -= gv[k];
+                grad[((size_t)(i - 1) * TRX_NAT + TRX_AT_C) * 3 + k] -= gv[k];
+            }
+        }
+    }
+    return E;
+}
+
 /* Ramachandran (von-Mises mixture, residues 1..L-2 as Rosetta skips termini) and omega
  * tether (residues 0..L-2).  gtors[L][3] is ACCUMULATED with the weighted derivatives. */
 void trxo_rama_omega(int L, const int *aa, const double *tors, double w_rama, double w_omega,
@@ -212,6 +262,7 @@ double trxo_eval(const trxo_target *T, const double *w, const double *tors, doub
     trxo_energy_grad(L, x9, T->sets[0], T->sets[1], T->sets[2], T->sets[3], w, terms, g9, NULL, NULL);
     for (int i = 0; i < L; ++i) memcpy(g + (size_t)i * TRX_NAT * 3, g9 + (size_t)i * 9, 9 * sizeof(double));
     terms[TRX_T_VDW] = trxo_vdw(L, T->aa, xyz, w[TRX_T_VDW], g);
+    terms[TRX_T_HB] = trxo_hbond(L, T->aa, xyz, w[TRX_T_HB], g);
     terms[TRX_T_CART] = 0.0;   /* ideal internal geometry in torsion space */
     memset(gt, 0, sizeof(double) * (size_t)L * 3);
     trxo_rama_omega(L, T->aa, tors, w[TRX_T_RAMA], w[TRX_T_OMEGA], &terms[TRX_T_RAMA], &terms[TRX_T_OMEGA], gt);
@@ -380,6 +431,7 @@ double trxo_eval_cart(const trxo_target *T, const double *w, const double *xyz, 
     trxo_energy_grad(L, x9, T->sets[0], T->sets[1], T->sets[2], T->sets[3], w, terms, g9, NULL, NULL);
     for (int i = 0; i < L; ++i) memcpy(g + (size_t)i * TRX_NAT * 3, g9 + (size_t)i * 9, 9 * sizeof(double));
     terms[TRX_T_VDW] = trxo_vdw(L, T->aa, xyz, w[TRX_T_VDW], g);
+    terms[TRX_T_HB] = trxo_hbond(L, T->aa, xyz, w[TRX_T_HB], g);
     double E[3];
     trxo_cart_terms(L, T->aa, xyz, w[TRX_T_CART], w[TRX_T_RAMA], w[TRX_T_OMEGA], E, g);
     terms[TRX_T_CART] = E[0]; terms[TRX_T_RAMA] = E[1]; terms[TRX_T_OMEGA] = E[2];
@@ -535,7 +587,7 @@ double trxo_fold(const trxo_target *T, const trx_run *runs, int nruns, int m, do
             double e;
             if (held) e = terms[TRX_T_VDW] + terms[TRX_T_RAMA];
             else {
-                double wv[TRX_NTERM] = {0, 0, 0, 1.0, 1.0, 0, 0};
+                double wv[TRX_NTERM] = {0, 0, 0, 1.0, 1.0, 0, 0, 0};
                 e = trxo_eval(T, wv, tors, terms, gt, xyz);
                 st->evals++;
             }
@@ -623,4 +675,4 @@ void trxo_fold_batch(int nthreads, int N, int L, const int *aa, const int *n, co
     for (int k = 0; k < nthreads; ++k) pthread_join(th[k], NULL);
 }
 
-int trxo_fold_abi_version(void) { return 2; }
+int trxo_fold_abi_version(void) { return 3; }

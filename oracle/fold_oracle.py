@@ -8,13 +8,22 @@ import numpy as np
 
 from .restraints_oracle import lib, TYPES
 
-NTERM = 7
+NTERM = 8
 AA_ORDER = "ARNDCQEGHILKMFPSTWYV"
 
 
 class Run(C.Structure):
     _fields_ = [("w", C.c_double * NTERM), ("max_iter", C.c_int), ("tol", C.c_double),
                 ("clash_check", C.c_int), ("clash_thr", C.c_double), ("skip_to", C.c_int), ("cartesian", C.c_int)]
+
+
+def _weights(w):
+    """NTERM weights; the 7-term form of earlier callers (no H-bond weight) is padded with 0."""
+    w = np.asarray(w, dtype=np.float64)
+    if w.shape == (NTERM - 1,):
+        w = np.concatenate([w, [0.0]])
+    assert w.shape == (NTERM,)
+    return np.ascontiguousarray(w)
 
 
 def aa_index(seq, gly_to_ala=True):
@@ -26,18 +35,19 @@ def aa_index(seq, gly_to_ala=True):
 
 
 def reference_schedule(cartesian=True):
-    """folding.py:74-104,118-119,164-171 (mode 2) with data/*.wts (hbond_* / cen_hb have no
-    restatement and are dropped).  Term order: apc, dih, ang, vdw, rama, omega, cart_bonded."""
+    """folding.py:74-104,118-119,164-171 (mode 2) with data/*.wts.  Term order: apc, dih, ang, vdw, rama,
+    omega, cart_bonded, backbone H-bond (cen_hb in the centroid stages, hbond_sr_bb / hbond_lr_bb in the
+    Cartesian one: a stated approximation, include/trx_centroid_model.h)."""
     def run(w, it, clash=False, skip_to=0, cart=False):
         r = Run()
         r.w[:] = w
         r.max_iter, r.tol = it, 1e-4
         r.clash_check, r.clash_thr, r.skip_to, r.cartesian = int(clash), 10.0, skip_to, int(cart)
         return r
-    sf = [5, 4, 4, 1, 1, 0.5, 0]
-    sf1 = [3, 1, 1, 3, 1, 0.5, 0]
-    sf_vdw = [0, 0, 0, 1, 1, 0, 0]
-    sf_cart = [5, 4, 4, 0.5, 1, 0.5, 0.1]
+    sf = [5, 4, 4, 1, 1, 0.5, 0, 5]              # ... cen_hb 5
+    sf1 = [3, 1, 1, 3, 1, 0.5, 0, 5]
+    sf_vdw = [0, 0, 0, 1, 1, 0, 0, 0]
+    sf_cart = [5, 4, 4, 0.5, 1, 0.5, 0.1, 3]     # ... hbond_sr_bb 3, hbond_lr_bb 3 (one function here, one weight)
     runs = [run(sf_vdw, 500, True, 5) for _ in range(5)]          # remove_clash(sf_vdw, min_mover_vdw)
     runs += [run(sf, 1000) for _ in range(3)]                     # RepeatMover(min_mover, 3)
     if cartesian:
@@ -78,9 +88,9 @@ class FoldOracle:
         return xyz
 
     def eval(self, tors, w):
-        """-> (total, terms[7], gtors (L,3), xyz (L,5,3))"""
+        """-> (total, terms[8], gtors (L,3), xyz (L,5,3))"""
         tors = np.ascontiguousarray(tors, dtype=np.float64)
-        w = np.ascontiguousarray(w, dtype=np.float64)
+        w = _weights(w)
         terms, gt, xyz = np.zeros(NTERM), np.zeros((self.L, 3)), np.zeros((self.L, 5, 3))
         P = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
         tot = lib().trxo_eval_flat(C.c_int(self.L), self.aa.ctypes.data_as(C.POINTER(C.c_int)), *self._args, P(w), P(tors),
@@ -88,9 +98,9 @@ class FoldOracle:
         return tot, terms, gt, xyz
 
     def eval_cart(self, xyz, w):
-        """Cartesian-mode evaluation -> (total, terms[7], grad (L,5,3))."""
+        """Cartesian-mode evaluation -> (total, terms[8], grad (L,5,3))."""
         xyz = np.ascontiguousarray(xyz, dtype=np.float64)
-        w = np.ascontiguousarray(w, dtype=np.float64)
+        w = _weights(w)
         terms, g = np.zeros(NTERM), np.zeros((self.L, 5, 3))
         P = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
         lib().trxo_eval_cart_flat.restype = C.c_double

@@ -24,7 +24,7 @@ def test_every_declared_symbol_is_exported():
     assert len(names) >= 15
     for n in names:
         assert hasattr(lib, n), n
-    assert lib.trx_abi_version() == 1
+    assert lib.trx_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_gpu():

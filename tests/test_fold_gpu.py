@@ -47,7 +47,7 @@ def test_single_evaluation_matches_oracle(ctx, example):
     tors[N // 2:] += np.random.default_rng(0).normal(size=(N - N // 2, L, 3)).astype(np.float32) * 0.3
     runs = schedule.reference_schedule()
     batch = capi.FoldBatch(ctx, [tb], [N], sampler.aa_index(seq), runs)
-    w = np.array([5.0, 4.0, 4.0, 1.0, 1.0, 0.5, 0.0])
+    w = np.array([5.0, 4.0, 4.0, 1.0, 1.0, 0.5, 0.0, 5.0])
     total, terms, gt, xyz = batch.eval(tors, w)
     for n in (0, 7, 20, 33, 39):
         to, termo, gto, xyzo = F.eval(tors[n].astype(np.float64), w)
@@ -71,7 +71,7 @@ def test_vdw_only_on_clashing_start(ctx):
     N = 33
     tors = np.random.default_rng(2).uniform(-np.pi, np.pi, size=(N, 64, 3)).astype(np.float32)
     batch = capi.FoldBatch(ctx, [tb], [N], sampler.aa_index(seq), schedule.reference_schedule())
-    w = np.array([0.0, 0.0, 0.0, 1.0, 1.0, 0.5, 0.0])
+    w = np.array([0.0, 0.0, 0.0, 1.0, 1.0, 0.5, 0.0, 0.0])
     total, terms, gt, xyz = batch.eval(tors, w)
     assert terms[:, 3].max() > 10.0
     for n in (0, 16, 32):
@@ -129,7 +129,7 @@ def test_cartesian_evaluation_matches_oracle(ctx, example):
     xyz[N // 2:] += rng.normal(size=(N - N // 2, L, 5, 3)) * 0.04      # half ideal, half strained
     xyz = xyz.astype(np.float32)
     batch = capi.FoldBatch(ctx, [tb], [N], sampler.aa_index(seq), schedule.reference_schedule())
-    for w in (np.array([5.0, 4.0, 4.0, 0.5, 1.0, 0.5, 0.1]), np.array([0.0, 0.0, 0.0, 0.0, 1.0, 0.5, 1.0])):
+    for w in (np.array([5.0, 4.0, 4.0, 0.5, 1.0, 0.5, 0.1, 3.0]), np.array([0.0, 0.0, 0.0, 0.0, 1.0, 0.5, 1.0, 1.0])):
         total, terms, grad, back = batch.eval_cart(xyz, w)
         for n in (0, 7, 19, 20, 33, 39):
             to, termo, go = F.eval_cart(xyz[n].astype(np.float64), w)
@@ -221,7 +221,7 @@ def test_decoy_distributions_match_the_oracle(ctx, example):
         return tm, rm
     tm_d, rm_d = quality(out["xyz"][:, :, 1].astype(np.float64))
     tm_o, rm_o = quality(o["xyz"][:, :, 1])
-    w = np.array([5.0, 4.0, 4.0, 1.0, 1.0, 0.5, 0.0])
+    w = np.array([5.0, 4.0, 4.0, 1.0, 1.0, 0.5, 0.0, 5.0])
     for name, a, b in (("TM", tm_d, tm_o), ("RMSD", rm_d, rm_o), ("score", out["terms"] @ w, o["terms"] @ w)):
         p = ks_2samp(a, b).pvalue
         assert p > 0.01, (name, p, np.median(a), np.median(b))

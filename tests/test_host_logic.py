@@ -18,10 +18,12 @@ def test_schedule_matches_reference_weights_and_caps():
     # remove_clash with sf1 (<=5 x, 1000)            folding.py:86-104,118-119,164-171
     assert len(runs) == 14
     assert [r.max_iter for r in runs] == [500] * 5 + [1000] * 9
-    assert list(runs[0].w) == [0, 0, 0, 1, 1, 0, 0]                 # scorefxn_vdw.wts
-    assert list(runs[5].w) == [5, 4, 4, 1, 1, 0.5, 0]               # scorefxn.wts
-    assert list(runs[8].w) == [5, 4, 4, 0.5, 1, 0.5, 0.1]           # scorefxn_cart.wts (hbond_* dropped)
-    assert list(runs[9].w) == [3, 1, 1, 3, 1, 0.5, 0]               # scorefxn1.wts
+    # last entry: the backbone hydrogen-bond term that stands in for cen_hb / hbond_sr_bb / hbond_lr_bb
+    assert list(runs[0].w) == [0, 0, 0, 1, 1, 0, 0, 0]              # scorefxn_vdw.wts
+    assert list(runs[5].w) == [5, 4, 4, 1, 1, 0.5, 0, 5]            # scorefxn.wts (cen_hb 5)
+    assert list(runs[8].w) == [5, 4, 4, 0.5, 1, 0.5, 0.1, 3]        # scorefxn_cart.wts (hbond_sr_bb 3, hbond_lr_bb 3)
+    assert list(runs[9].w) == [3, 1, 1, 3, 1, 0.5, 0, 5]            # scorefxn1.wts (cen_hb 5)
+    assert schedule.ignored_terms() == []                           # every weight-file term is scored (as a stated approximation or exactly)
     assert all(r.tol == 1e-4 for r in runs)
     assert [r.cartesian for r in runs] == [0] * 8 + [1] + [0] * 5
     assert [r.clash_check for r in runs] == [1] * 5 + [0] * 4 + [1] * 5

@@ -41,7 +41,7 @@ def test_nerf_ideal_geometry_and_torsions(small):
     np.testing.assert_allclose(CB, -0.58273431 * np.cross(b, c) + 0.56802827 * b - 0.54067466 * c + CA, atol=1e-12)
 
 
-@pytest.mark.parametrize("w", [(5, 4, 4, 1, 1, 0.5, 0), (0, 0, 0, 1, 1, 0, 0), (3, 1, 1, 3, 1, 0.5, 0)])
+@pytest.mark.parametrize("w", [(5, 4, 4, 1, 1, 0.5, 0, 5), (0, 0, 0, 1, 1, 0, 0, 0), (3, 1, 1, 3, 1, 0.5, 0, 5)])
 def test_torsion_gradient_matches_central_differences(small, w):
     seq, nat, F = small
     L = len(seq)
@@ -65,7 +65,7 @@ def test_schedule_folds_a_small_target(small):
     L = len(seq)
     t0 = fo.random_torsions(6, L, 5)
     out = F.fold(t0, fo.reference_schedule(), m=20, nthreads=6)
-    w = np.array([5, 4, 4, 1, 1, 0.5, 0.0])
+    w = np.array([5, 4, 4, 1, 1, 0.5, 0.0, 5.0])
     e_start = np.array([F.eval(t, w)[0] for t in t0])
     assert np.all(out["terms"] @ w < e_start)
     assert np.all(out["evals"] > out["iters"]) and np.all(out["iters"] > 20)
@@ -80,14 +80,14 @@ def test_cartesian_terms_match_autograd_and_vanish_on_ideal_geometry(small):
     seq, nat, F = small
     L = len(seq)
     tors = fo.random_torsions(1, L, 0)[0] + np.random.default_rng(0).normal(size=(L, 3)) * 0.2
-    w = np.array([5, 4, 4, 0.5, 1, 0.5, 0.1])
+    w = np.array([5, 4, 4, 0.5, 1, 0.5, 0.1, 3.0])
     xyz = F.nerf(tors)
     tot, terms, g = F.eval_cart(xyz, w)
     tot_t, terms_t, _, _ = F.eval(tors, w)
     assert terms[6] < 1e-20                                          # NeRF builds exactly the springs' rest geometry
     np.testing.assert_allclose(terms[:6], terms_t[:6], rtol=1e-10)   # rama / omega from coordinates == from torsions
     xyz2 = xyz + np.random.default_rng(1).normal(size=xyz.shape) * 0.05
-    w0 = np.array([0, 0, 0, 0, 1, 0.5, 0.1])
+    w0 = np.array([0, 0, 0, 0, 1, 0.5, 0.1, 0.0])
     tot, terms, g = F.eval_cart(xyz2, w0)
     ref, gref = co.cart_energy_grad(xyz2, F.aa, 0.1, 1.0, 0.5)
     np.testing.assert_allclose([terms[6], terms[4], terms[5]], [ref["cart"], ref["rama"], ref["omega"]], rtol=1e-12)
@@ -166,3 +166,41 @@ def test_ideal_geometry_constants_match_rosetta_written_structures(golden_dir, s
     for k in ("N-CA-C", "CA-C-N", "C-N-CA", "CA-C-O", "O-C-N"):
         assert abs(ours[k] - stat[k]) < 1.0, (k, ours[k], stat[k])
     assert stat["abs_omega"] > 175.0      # trans peptides: the omega tether's minimum
+
+
+def test_backbone_hbond_term(small):
+    """The stated approximation of cen_hb / hbond_sr_bb / hbond_lr_bb (include/trx_centroid_model.h): an ideal helix
+    is hydrogen-bonded i -> i-4 along its whole length, an extended chain not at all; the analytic gradient
+    matches central differences in torsion space and in Cartesian space (where it acts on N, CA, C(-1), O, C)."""
+    seq, nat, F = small
+    L = len(seq)
+    w = np.zeros(8)
+    w[7] = 1.0
+    helix = np.tile(np.deg2rad([-57.8, -47.0, 180.0]), (L, 1))
+    ext = np.tile(np.deg2rad([-140.0, 135.0, 180.0]), (L, 1))
+    e_h = F.eval(helix, w)[1][7]
+    e_x = F.eval(ext, w)[1][7]
+    n_pro = sum(1 for c in seq[4:] if c == "P")
+    assert e_h < -0.45 * (L - 4 - n_pro) and e_h >= -1.0 * (L - 4)      # close to one well-formed bond per residue
+    assert e_x == 0.0
+    rng = np.random.default_rng(3)
+    tors = helix + rng.normal(size=(L, 3)) * 0.08
+    tot, terms, gt, xyz = F.eval(tors, w)
+    assert terms[7] < 0 and tot == pytest.approx(terms[7])
+    for _ in range(10):
+        i, k = rng.integers(1, L - 1), rng.integers(3)
+        h = 1e-6
+        tp, tm = tors.copy(), tors.copy()
+        tp[i, k] += h; tm[i, k] -= h
+        fd = (F.eval(tp, w)[0] - F.eval(tm, w)[0]) / (2 * h)
+        assert abs(fd - gt[i, k]) < 1e-5 * max(1.0, abs(fd)), (i, k, fd, gt[i, k])
+    x2 = xyz + rng.normal(size=xyz.shape) * 0.03
+    tot, terms, g = F.eval_cart(x2, w)
+    assert np.abs(g[:, 2]).max() == 0.0                                   # CB carries no hydrogen-bond gradient
+    for _ in range(16):
+        i, a, k = rng.integers(L), rng.choice([0, 1, 3, 4]), rng.integers(3)
+        h = 1e-6
+        xp, xm = x2.copy(), x2.copy()
+        xp[i, a, k] += h; xm[i, a, k] -= h
+        fd = (F.eval_cart(xp, w)[0] - F.eval_cart(xm, w)[0]) / (2 * h)
+        assert abs(fd - g[i, a, k]) < 1e-5 * max(1.0, abs(g[i, a, k])), (i, a, k, fd, g[i, a, k])

@@ -99,7 +99,7 @@ def test_full_size_fold_is_reproducible_and_batch_independent(ctx, full):
     np.testing.assert_array_equal(c["tors"], a["tors"][128:192])
     np.testing.assert_array_equal(c["terms"], a["terms"][128:192])
     small.close()
-    w = np.array([5.0, 4.0, 4.0, 1.0, 1.0, 0.5, 0.0])
+    w = np.array([5.0, 4.0, 4.0, 1.0, 1.0, 0.5, 0.0, 5.0])
     assert np.median(a["terms"] @ w) < -100000 and np.all(a["iters"] > 50)
     # ... also inside a bench-sized batch (2048 decoys on this table: many more decoy groups per launch, decoys packed
     # and re-packed as they finish); the restraint kernel's summation order must not follow the live-decoy count

@@ -38,7 +38,7 @@ def lib():
         L.trx_last_error.restype = C.c_char_p
         L.trx_ctx_launch_count.restype = C.c_longlong
         L.trx_ctx_launch_count.argtypes = [C.c_void_p]
-        for fn in (L.trx_fold_run_queue, L.trx_fold_mc_queue, L.trx_fold_k1_evals, L.trx_fold_status):
+        for fn in (L.trx_fold_run_queue, L.trx_fold_mc_queue, L.trx_fold_k1_evals, L.trx_fold_status, L.trx_dyn_create, L.trx_dyn_step, L.trx_dyn_get, L.trx_dyn_destroy):
             fn.restype = C.c_int
         _lib = L
     return _lib
@@ -178,7 +178,17 @@ def from_grouped(ctx, N, L, n_atoms, precision, d_grp, d_nat):
     check(lib().trx_from_grouped(ctx._h, C.c_int(N), C.c_int(L), C.c_int(n_atoms), C.c_int(precision), C.c_void_p(d_grp), C.c_void_p(d_nat)))
 
 
-NTERM = 7
+NTERM = 8
+
+
+def _weights(w):
+    """NTERM weights; the 7-term form (no H-bond weight) is padded with 0."""
+    w = np.asarray(w, dtype=np.float64)
+    if w.shape == (NTERM - 1,):
+        w = np.concatenate([w, [0.0]])
+    if w.shape != (NTERM,):
+        raise ValueError("weights must have %d entries" % NTERM)
+    return np.ascontiguousarray(w)
 
 
 class Run(C.Structure):
@@ -215,7 +225,7 @@ class FoldBatch:
             pass
 
     def run(self, tors, max_rounds=20000, check_every=16, want_xyz=True):
-        """tors (N,L,3) float32 radians -> dict(tors, xyz (N,L,5,3) [N,CA,CB,C,O], terms (N,7), evals, iters, rounds)."""
+        """tors (N,L,3) float32 radians -> dict(tors, xyz (N,L,5,3) [N,CA,CB,C,O], terms (N,8), evals, iters, rounds)."""
         tors = np.ascontiguousarray(tors, dtype=np.float32).copy()
         if tors.shape != (self.N, self.L, 3):
             raise ValueError("tors must be (%d, %d, 3)" % (self.N, self.L))
@@ -286,9 +296,9 @@ class FoldBatch:
                     rounds=rounds.value)
 
     def eval(self, tors, w):
-        """Single evaluation -> (total (N,), terms (N,7), gtors (N,L,3), xyz (N,L,5,3))."""
+        """Single evaluation -> (total (N,), terms (N,8), gtors (N,L,3), xyz (N,L,5,3))."""
         tors = np.ascontiguousarray(tors, dtype=np.float32)
-        w = np.ascontiguousarray(w, dtype=np.float64)
+        w = _weights(w)
         total, terms = np.zeros(self.N), np.zeros((self.N, NTERM))
         gt = np.zeros((self.N, self.L, 3), dtype=np.float32)
         xyz = np.zeros((self.N, self.L, 5, 3), dtype=np.float32)
@@ -297,14 +307,82 @@ class FoldBatch:
         return total, terms, gt, xyz
 
     def eval_cart(self, xyz, w):
-        """Single Cartesian-mode evaluation: xyz (N,L,5,3) -> (total (N,), terms (N,7), grad (N,L,5,3), tors (N,L,3))."""
+        """Single Cartesian-mode evaluation: xyz (N,L,5,3) -> (total (N,), terms (N,8), grad (N,L,5,3), tors (N,L,3))."""
         xyz = np.ascontiguousarray(xyz, dtype=np.float32)
         if xyz.shape != (self.N, self.L, 5, 3):
             raise ValueError("xyz must be (%d, %d, 5, 3)" % (self.N, self.L))
-        w = np.ascontiguousarray(w, dtype=np.float64)
+        w = _weights(w)
         total, terms = np.zeros(self.N), np.zeros((self.N, NTERM))
         grad = np.zeros((self.N, self.L, 5, 3), dtype=np.float32)
         tors = np.zeros((self.N, self.L, 3), dtype=np.float32)
         check(lib().trx_fold_eval_cart(self._h, _ptr(xyz, C.c_float), _ptr(w, C.c_double), _ptr(total, C.c_double),
                                        _ptr(terms, C.c_double), _ptr(grad, C.c_float), _ptr(tors, C.c_float)))
         return total, terms, grad, tors
+
+
+class DynState:
+    """Device-resident distograms of one chain of the outer dynamics loop (trx_dyn_*): step() applies one decoy."""
+
+    def __init__(self, ctx, npz, angle=True):
+        self.ctx = ctx
+        self.L = int(np.asarray(npz["dist"]).shape[0])
+        self.angle = bool(angle) and all(k in npz for k in ("omega", "theta", "phi"))
+        arrs = [np.ascontiguousarray(npz["dist"], dtype=np.float32)]
+        if self.angle:
+            arrs += [np.ascontiguousarray(npz[k], dtype=np.float32) for k in ("omega", "theta", "phi")]
+        ptrs = [_ptr(a, C.c_float) for a in arrs] + [None] * (4 - len(arrs))
+        self._h = C.c_void_p()
+        check(lib().trx_dyn_create(ctx._h, C.c_int(self.L), *ptrs, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().trx_dyn_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def gaussian_taps(sigma=1.0, truncate=4.0):
+        """The kernel scipy.ndimage.gaussian_filter1d builds (_gaussian_kernel1d, order 0)."""
+        lw = int(truncate * float(sigma) + 0.5)
+        if lw != 4:
+            raise ValueError("the device filter has 9 taps (sigma 1)")
+        x = np.arange(-lw, lw + 1)
+        p = np.exp(-0.5 / (sigma * sigma) * x ** 2)
+        return np.ascontiguousarray(p / p.sum(), dtype=np.float64)
+
+    def step(self, n, ca, c, cb=None, seq=None, sigma=1.0):
+        """One decoy: updates the maps in place, returns max |tmp_new - tmp_old|."""
+        n, ca, c = (np.ascontiguousarray(a, dtype=np.float64) for a in (n, ca, c))
+        use = np.zeros(self.L, dtype=np.uint8)
+        cbv = np.zeros((self.L, 3))
+        if cb is not None and seq is not None:
+            cb = np.asarray(cb, dtype=np.float64)
+            use = (np.array([s != "G" for s in seq]) & ~np.isnan(cb).any(axis=1)).astype(np.uint8)
+            cbv = np.ascontiguousarray(np.nan_to_num(cb))
+        w = self.gaussian_taps(sigma)
+        chg = C.c_double()
+        check(lib().trx_dyn_step(self._h, _ptr(n, C.c_double), _ptr(ca, C.c_double), _ptr(c, C.c_double), _ptr(cbv, C.c_double),
+                                 _ptr(use, C.c_ubyte), _ptr(w, C.c_double), C.byref(chg)))
+        return chg.value
+
+    def get(self, want_bins=False):
+        """Current maps as a dict like the reference's npz (dist, [omega, theta, phi,] tmp[, bins])."""
+        L = self.L
+        out = {"dist": np.empty((L, L, 37), dtype=np.float32), "tmp": np.empty((L, L, 37), dtype=np.float32)}
+        if self.angle:
+            out.update(omega=np.empty((L, L, 25), dtype=np.float32), theta=np.empty((L, L, 25), dtype=np.float32),
+                       phi=np.empty((L, L, 13), dtype=np.float32))
+        bins = np.empty((4, L, L), dtype=np.int32) if want_bins else None
+        check(lib().trx_dyn_get(self._h, _ptr(out["dist"], C.c_float),
+                                _ptr(out["omega"], C.c_float) if self.angle else None,
+                                _ptr(out["theta"], C.c_float) if self.angle else None,
+                                _ptr(out["phi"], C.c_float) if self.angle else None,
+                                _ptr(out["tmp"], C.c_float), _ptr(bins, C.c_int32) if want_bins else None))
+        if want_bins:
+            out["bins"] = bins
+        return out

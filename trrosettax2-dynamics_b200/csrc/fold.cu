@@ -109,6 +109,7 @@ struct FoldState {
     float *gk1;              // [G][Lpad][9][32]
     double *E3;              // [3][Npad]
     double *Evdw;            // [Npad]
+    double *Ehb;             // [Npad] backbone hydrogen-bond term (slot order, like Evdw)
     int *gactive;            // [G] decoy group has an unfinished decoy (L-BFGS kernel)
     int *nactive;            // [1]
     // slot space: the unfinished decoys of each table block, compacted to the front of the
@@ -297,6 +298,9 @@ __global__ void __launch_bounds__(SEG_THREADS) nerf_kernel(FoldState s)
 // ATOMS.ADD, no CAS loop): integer sums are order-independent => bit-reproducible.
 constexpr int VDW_THREADS = 256;
 constexpr float VDW_FIX = 65536.0f;   // 2^16: gradients as 32-bit fixed point (range +-32768, step 1.5e-5)
+// two residues whose bounding spheres are farther apart than this beyond touching cannot hold a hydrogen bond:
+// the spheres contain the N and O spheres, so |N - O| >= gap + r_N + r_O
+constexpr float HB_MARGIN = (float)(TRX_HB_D0 + TRX_HB_W - 1.40 - 1.35) + 1e-3f;
 
 __global__ void __launch_bounds__(VDW_THREADS) vdw_kernel(FoldState s)
 {
@@ -307,7 +311,7 @@ __global__ void __launch_bounds__(VDW_THREADS) vdw_kernel(FoldState s)
     float4 *at = reinterpret_cast<float4 *>(smem_raw);                                   // [L][6]
     int *acc = reinterpret_cast<int *>(smem_raw + sizeof(float4) * 6 * L);               // [L][6][3]
     float4 *bsph = reinterpret_cast<float4 *>(smem_raw + sizeof(float4) * 6 * L + ((sizeof(int) * 18 * L + 15) / 16) * 16);   // [L] bounding spheres
-    __shared__ double ered[VDW_THREADS / 32];
+    __shared__ double ered[2 * (VDW_THREADS / 32)];
     const float *__restrict__ xn = s.xnat + (size_t)n * L * NATP;
     for (int i = threadIdx.x; i < L; i += VDW_THREADS) {
         const int aa = s.aa[i];
@@ -335,7 +339,45 @@ __global__ void __launch_bounds__(VDW_THREADS) vdw_kernel(FoldState s)
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double e_thread = 0.0;
+    // gradients are accumulated already weighted (vdw and the hydrogen-bond term have their own weights)
+    const float w_vdw = s.wslot[(size_t)TRX_T_VDW * s.Npad + n], w_hb = s.wslot[(size_t)TRX_T_HB * s.Npad + n];
+    double e_thread = 0.0, e_hb = 0.0;
+    // Backbone hydrogen bond donor residue i (N-H) -> acceptor residue j (C=O), include/trx_centroid_model.h.
+    // Atoms: N_i, CA_i, C_{i-1}, O_j, C_j.  Called by one lane per queued residue pair and direction.
+    auto hbond = [&](int i, int j) {
+        if (i < 1 || abs(i - j) < TRX_HB_MINSEP || s.aa[i] == TRX_AA_PRO) return;
+        const float4 N = at[i * 6 + TRX_AT_N], O = at[j * 6 + TRX_AT_O];
+        const float rx = O.x - N.x, ry = O.y - N.y, rz = O.z - N.z, d2 = rx * rx + ry * ry + rz * rz;
+        const float dmax = (float)(TRX_HB_D0 + TRX_HB_W), dmin = (float)(TRX_HB_D0 - TRX_HB_W);
+        if (d2 >= dmax * dmax || d2 <= dmin * dmin) return;
+        const float4 CA = at[i * 6 + TRX_AT_CA], Cp = at[(i - 1) * 6 + TRX_AT_C], C = at[j * 6 + TRX_AT_C];
+        const float vx = 2.f * N.x - Cp.x - CA.x, vy = 2.f * N.y - Cp.y - CA.y, vz = 2.f * N.z - Cp.z - CA.z;
+        const float qx = O.x - C.x, qy = O.y - C.y, qz = O.z - C.z;
+        const float id = rsqrtf(d2), iv = rsqrtf(vx * vx + vy * vy + vz * vz), iq = rsqrtf(qx * qx + qy * qy + qz * qz);
+        const float rhx = rx * id, rhy = ry * id, rhz = rz * id, vhx = vx * iv, vhy = vy * iv, vhz = vz * iv;
+        const float qhx = qx * iq, qhy = qy * iq, qhz = qz * iq;
+        const float c1 = vhx * rhx + vhy * rhy + vhz * rhz, c2 = -(qhx * rhx + qhy * rhy + qhz * rhz);
+        if (c1 <= 0.f || c2 <= 0.f) return;
+        const float d = d2 * id, t = (d - (float)TRX_HB_D0) * (float)(1.0 / TRX_HB_W), u = 1.f - t * t;
+        const float F = u * u, dF = -4.f * u * t * (float)(1.0 / TRX_HB_W), G1 = c1 * c1, G2 = c2 * c2;
+        e_hb += (double)(-(float)TRX_HB_EPS * F * G1 * G2);
+        const float a = -(float)TRX_HB_EPS * w_hb;
+        const float kd = a * dF * G1 * G2, k1 = a * F * 2.f * c1 * G2, k2 = a * F * G1 * 2.f * c2;
+        const float grx = kd * rhx + (k1 * (vhx - c1 * rhx) - k2 * (qhx + c2 * rhx)) * id;
+        const float gry = kd * rhy + (k1 * (vhy - c1 * rhy) - k2 * (qhy + c2 * rhy)) * id;
+        const float grz = kd * rhz + (k1 * (vhz - c1 * rhz) - k2 * (qhz + c2 * rhz)) * id;
+        const float gvx = k1 * (rhx - c1 * vhx) * iv, gvy = k1 * (rhy - c1 * vhy) * iv, gvz = k1 * (rhz - c1 * vhz) * iv;
+        const float gqx = -k2 * (rhx + c2 * qhx) * iq, gqy = -k2 * (rhy + c2 * qhy) * iq, gqz = -k2 * (rhz + c2 * qhz) * iq;
+        auto add3 = [&](int res, int atom, float x, float y, float z) {
+            int *pa = acc + (res * 6 + atom) * 3;
+            atomicAdd(pa + 0, __float2int_rn(x * VDW_FIX)); atomicAdd(pa + 1, __float2int_rn(y * VDW_FIX)); atomicAdd(pa + 2, __float2int_rn(z * VDW_FIX));
+        };
+        add3(j, TRX_AT_O, grx + gqx, gry + gqy, grz + gqz);
+        add3(j, TRX_AT_C, -gqx, -gqy, -gqz);
+        add3(i, TRX_AT_N, 2.f * gvx - grx, 2.f * gvy - gry, 2.f * gvz - grz);
+        add3(i, TRX_AT_CA, -gvx, -gvy, -gvz);
+        add3(i - 1, TRX_AT_C, -gvx, -gvy, -gvz);
+    };
     // per-warp queue of close residue pairs
     __shared__ int queue[VDW_THREADS / 32][64];
     int qn = 0;
@@ -359,13 +401,15 @@ __global__ void __launch_bounds__(VDW_THREADS) vdw_kernel(FoldState s)
                     if (d2 < r2) {
                         const float c = r2 - d2, ir2 = 1.0f / r2;
                         e_thread += (double)((float)TRX_VDW_SCALE * c * c * ir2);
-                        const float f = -4.0f * (float)TRX_VDW_SCALE * c * ir2;
+                        const float f = -4.0f * (float)TRX_VDW_SCALE * c * ir2 * w_vdw;
                         const int gx = __float2int_rn(f * dx * VDW_FIX), gy = __float2int_rn(f * dy * VDW_FIX), gz = __float2int_rn(f * dz * VDW_FIX);
                         int *pj = acc + (j * 6 + b) * 3;
                         atomicAdd(pi + 0, gx); atomicAdd(pi + 1, gy); atomicAdd(pi + 2, gz);
                         atomicAdd(pj + 0, -gx); atomicAdd(pj + 1, -gy); atomicAdd(pj + 2, -gz);
                     }
                 }
+                if (fa == 0) hbond(i, j);        // the pair's two hydrogen-bond directions, one lane each
+                else if (fa == 1) hbond(j, i);
             }
         }
     };
@@ -376,7 +420,8 @@ __global__ void __launch_bounds__(VDW_THREADS) vdw_kernel(FoldState s)
             bool close = false;
             if (j < L) {
                 const float4 cj = bsph[j];
-                const float dx = ci.x - cj.x, dy = ci.y - cj.y, dz = ci.z - cj.z, cut = ci.w + cj.w;
+                // + the reach of a hydrogen bond beyond touching N and O spheres (N...O up to D0 + W)
+                const float dx = ci.x - cj.x, dy = ci.y - cj.y, dz = ci.z - cj.z, cut = ci.w + cj.w + HB_MARGIN;
                 close = dx * dx + dy * dy + dz * dz < cut * cut;
             }
             unsigned m = __ballot_sync(0xffffffffu, close);
@@ -400,16 +445,17 @@ __global__ void __launch_bounds__(VDW_THREADS) vdw_kernel(FoldState s)
     }
     flush(qn);
     // energy: fixed-shape reduction
-    for (int o = 16; o > 0; o >>= 1) e_thread += __shfl_down_sync(0xffffffffu, e_thread, o);
-    if (lane == 0) ered[warp] = e_thread;
+    for (int o = 16; o > 0; o >>= 1) { e_thread += __shfl_down_sync(0xffffffffu, e_thread, o); e_hb += __shfl_down_sync(0xffffffffu, e_hb, o); }
+    if (lane == 0) { ered[warp] = e_thread; ered[VDW_THREADS / 32 + warp] = e_hb; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        double e = 0.0;
-        for (int k = 0; k < VDW_THREADS / 32; ++k) e += ered[k];
+        double e = 0.0, eh = 0.0;
+        for (int k = 0; k < VDW_THREADS / 32; ++k) { e += ered[k]; eh += ered[VDW_THREADS / 32 + k]; }
         s.Evdw[n] = e;
+        s.Ehb[n] = eh;
     }
-    // gradient out (weighted), CEN folded into CA and CB
-    const float w = s.wslot[(size_t)TRX_T_VDW * s.Npad + n];
+    // gradient out (already weighted), CEN folded into CA and CB
+    const float w = 1.0f;
     float *__restrict__ gn = s.gnat + (size_t)n * L * NATP;
     for (int i = threadIdx.x; i < L; i += VDW_THREADS) {
         const float cs = c_model.cen_s[s.aa[i]];
@@ -550,6 +596,7 @@ __global__ void __launch_bounds__(SEG_THREADS) torsion_grad_kernel(FoldState s)
         term[TRX_T_RAMA] = er;
         term[TRX_T_OMEGA] = eo;
         term[TRX_T_CART] = 0.0;   // ideal internal geometry in torsion space
+        term[TRX_T_HB] = s.Ehb[n];
         double total = 0.0;
 #pragma unroll
         for (int k = 0; k < TRX_NTERM; ++k) {
@@ -787,6 +834,7 @@ __global__ void __launch_bounds__(CART_THREADS) cart_grad_kernel(FoldState s)
         term[TRX_T_RAMA] = er;
         term[TRX_T_OMEGA] = eo;
         term[TRX_T_CART] = ec;
+        term[TRX_T_HB] = s.Ehb[n];
         double total = 0.0;
 #pragma unroll
         for (int k = 0; k < TRX_NTERM; ++k) {
@@ -1620,7 +1668,7 @@ __global__ void init_state_kernel(FoldState s, const float *__restrict__ tors_na
     s.status[n] = n < s.N ? ST_INIT : ST_DONE;
     s.run[n] = 0; s.hist[n] = 0; s.head[n] = 0; s.iter[n] = 0; s.bt[n] = 0; s.restart[n] = 1; s.nmem[n] = 0;
     s.f[n] = 0.0; s.alpha[n] = 0.f; s.slope[n] = 0.f; s.evals[n] = 0; s.iters[n] = 0;
-    s.ft[n] = 0.0; s.Evdw[n] = 0.0;
+    s.ft[n] = 0.0; s.Evdw[n] = 0.0; s.Ehb[n] = 0.0;
     for (int k = 0; k < TRX_NTERM; ++k) { s.wl[(size_t)k * s.Npad + n] = s.runs[0].w[k]; s.terms[(size_t)k * s.Npad + n] = 0.0; }
     for (int k = 0; k < 3; ++k) { s.fmem[(size_t)k * s.Npad + n] = 0.0; s.E3[(size_t)k * s.Npad + n] = 0.0; }
 }
@@ -2034,7 +2082,7 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     size_t o_orig = carve(np * 4), o_ma = carve(np * 4), o_mb = carve(np * 4), o_mn = carve(256);
     size_t o_held = carve(np * 4), o_th = carve(np * 8 * TRX_NTERM);
     size_t o_mcc = carve(np * 4), o_sof = carve(np * 4), o_nid = carve(np * 4), o_qc = carve(256), o_qo = carve(256), o_k1c = carve(256);
-    size_t o_flg = carve(np * 4);
+    size_t o_flg = carve(np * 4), o_Eh = carve(np * 8);
     cudaError_t e = cudaMalloc(&b->arena, off);
     if (e != cudaSuccess) {
         set_error("trx_fold_create: cudaMalloc(%zu bytes) failed: %s", off, cudaGetErrorString(e));
@@ -2061,7 +2109,7 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     s.held = (int *)(A + o_held); s.theld = (double *)(A + o_th);
     s.mccyc = (int *)(A + o_mcc); s.slot_of = (int *)(A + o_sof); s.newid = (int *)(A + o_nid);
     s.qcursor = (int *)(A + o_qc); s.qocc = (int *)(A + o_qo); s.k1count = (long long *)(A + o_k1c);
-    s.flags = (int *)(A + o_flg);
+    s.flags = (int *)(A + o_flg); s.Ehb = (double *)(A + o_Eh);
     s.mc = McOpts{};
     TRX_CUDA(cudaMallocHost(&b->h_poll, 64 * sizeof(int)));
     s.ntab = ntab;
@@ -2373,7 +2421,7 @@ static int fold_queue(trx_fold_batch *b, const int *nq, float *tors, float *xyz,
 
 /* Runs the schedule to completion (or max_rounds evaluation rounds) for as many decoys as the batch has
  * positions.  tors: host [N][L][3] float, in: start torsions, out: final torsions.  xyz (may be NULL):
- * host [N][L][5][3] float, atoms N,CA,CB,C,O.  terms (may be NULL): [N][7] double.  stats (may be NULL):
+ * host [N][L][5][3] float, atoms N,CA,CB,C,O.  terms (may be NULL): [N][8] double.  stats (may be NULL):
  * [N][2] evaluations, accepted iterations.  *rounds_out (may be NULL): evaluation rounds executed. */
 int trx_fold_run(trx_fold_batch *b, float *tors, float *xyz, double *terms, long long *stats, int max_rounds,
                  int check_every, int *rounds_out)
@@ -2449,7 +2497,7 @@ int trx_fold_mc(trx_fold_batch *b, float *tors, float *xyz, double *terms, long 
 }
 
 /* Single evaluation at given torsions under uniform weights (parity tests of K2-K4):
- * tors host [N][L][3] float -> total [N], terms [N][7], gtors [N][L][3] float, xyz [N][L][5][3] float. */
+ * tors host [N][L][3] float -> total [N], terms [N][8], gtors [N][L][3] float, xyz [N][L][5][3] float. */
 int trx_fold_eval(trx_fold_batch *b, const float *tors, const double w[TRX_NTERM], double *total, double *terms, float *gtors, float *xyz)
 {
     TRX_REQUIRE(b && tors && w, "trx_fold_eval: NULL argument");
@@ -2484,7 +2532,7 @@ int trx_fold_eval(trx_fold_batch *b, const float *tors, const double w[TRX_NTERM
 }
 
 /* Single Cartesian-mode evaluation (parity entry of the Cartesian stage): xyz host
- * [N][L][5][3] float are the degrees of freedom -> total [N], terms [N][7], grad [N][L][5][3]
+ * [N][L][5][3] float are the degrees of freedom -> total [N], terms [N][8], grad [N][L][5][3]
  * float (gradient of the weighted total w.r.t. every coordinate), tors [N][L][3] float (the
  * torsions read back from the coordinates).  Any output may be NULL.  The batch must have
  * been created with a schedule that contains a Cartesian run. */

@@ -15,6 +15,7 @@
 // gradients are accumulated in shared memory with plain read-modify-writes: no
 // atomics, bit-reproducible sums.  Per-tile column gradients and per-CTA row
 // gradients are written as partial records that the reduce kernel sums in a fixed order.
+#include <algorithm>
 #include <cstdlib>
 
 #include "internal.cuh"
@@ -92,7 +93,8 @@ struct KnotHead {
 constexpr int KX_TOTAL = MAXK + 3 * MAXK_ANG;
 constexpr int K1_MAXSTEPS = TILE * TILE;   // a tile has at most 256 pairs, hence at most 256 steps
 // dynamic shared memory of the restraint kernel: two gradient records, the tile's pair records, its schedule, one mbarrier
-__host__ __device__ constexpr size_t k1_dyn_bytes(size_t elem) { return 2 * REC_ELEMS * elem + TILE * TILE * 8 * sizeof(int) + K1_MAXSTEPS * K1_WARPS * sizeof(unsigned short) + 16; }
+// (with the coordinate stage only what stage 2 asks for: shared memory decides how many CTAs are resident)
+__host__ __device__ constexpr size_t k1_dyn_bytes(size_t elem, int stage) { return 2 * REC_ELEMS * elem + (stage > 0 ? TILE * TILE * 8 * sizeof(int) + K1_MAXSTEPS * K1_WARPS * sizeof(unsigned short) + 16 : 0) + (stage > 1 ? 2 * REC_ELEMS * elem : 0); }
 __host__ __device__ constexpr int kx_off(int type) { return type == 0 ? 0 : MAXK + (type - 1) * MAXK_ANG; }
 
 template <typename T>
@@ -111,7 +113,7 @@ struct K1Params {
     int xstride;                                 // values per residue in X (9: N,CA,CB; 15: fold layout)
     int dist_ca;                                 // distance restraints on CA-CA (af2 variant, distance-only tables)
     int g0;                                      // first decoy group of this launch
-    int stage;                                   // pair records + step schedule of the tile staged in shared memory (bulk async copy)
+    int stage;                                   // staged in shared memory by bulk async copies: 1 pair records + schedule of the tile, 2 + its coordinates
     const int *gactive;                          // per-group flag or NULL (all active)
     const float *wl;                             // per-decoy weights [3][Npad] or NULL (use w0..w2)
     int Npad;
@@ -171,6 +173,16 @@ __device__ __forceinline__ int spline_locate(const KnotHead<double> &kn, const d
 // 32-bit add and one widening multiply-add instead of 64-bit pointer arithmetic per load
 template <typename T>
 __device__ __forceinline__ Coef<T> spline_load(const Coef<T> *__restrict__ tab, int off, int k) { return tab[(unsigned)(off + k)]; }
+#ifdef TRX_K1_TAB_NOALLOC
+// experiment: table gathers bypass L1 allocation, leaving L1 to the coordinate lines a tile re-reads
+template <>
+__device__ __forceinline__ Coef<float> spline_load<float>(const Coef<float> *__restrict__ tab, int off, int k)
+{
+    Coef<float> c;
+    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c.c0), "=f"(c.c1), "=f"(c.c2), "=f"(c.c3) : "l"(tab + (unsigned)(off + k)));
+    return c;
+}
+#endif
 
 #define SPLINE_F(c, u) ((c).c0 + (u) * ((c).c1 + (u) * ((c).c2 + (u) * (c).c3)))
 #define SPLINE_DF(c, u) ((c).c1 + (u) * ((T)2 * (c).c2 + (T)3 * (c).c3 * (u)))
@@ -443,6 +455,210 @@ __device__ __forceinline__ void pair_eval_sym(const K1Params<float> &p, const Kn
     G[6] += F2(hi(Ox), lo(Ox)); G[7] += F2(hi(Oy), lo(Oy)); G[8] += F2(hi(Oz), lo(Oz));
 }
 
+// One residue pair of one decoy per lane: coordinates in, gradients of the row residue (rg) and of the column
+// residue (cg) out -- N(0..2) CA(3..5) CB(6..8) -- and the pair's energies added to e0..e2.
+template <typename T, bool SYM>
+__device__ __forceinline__ void eval_pair(const K1Params<T> &p, const KnotHead<T> *geom, const T *__restrict__ kx, const int4 ia, const int4 ib,
+                                          const T *__restrict__ xr, const T *__restrict__ xc, T *rg, T *cg, const T w0, const T w1, const T w2,
+                                          T &f0, T &f1, T &f2)
+{
+    T ri[9], cj[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        ri[k] = xr[k * LANES];
+        cj[k] = xc[k * LANES];
+        rg[k] = (T)0;
+        cg[k] = (T)0;
+    }
+    if constexpr (SYM) {
+        if (!p.dist_ca) {
+            F2 self[9], G[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { self[k] = F2(ri[k], cj[k]); G[k] = F2(0.f); }
+            pair_eval_sym(p, geom, kx, ia, ib, self, G, w0, w1, w2, f0, f1, f2);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { rg[k] = lo(G[k]); cg[k] = hi(G[k]); }
+            return;
+        }
+    }
+    T row[9];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        row[k] = ri[6 + k];
+        row[3 + k] = ri[3 + k] - ri[6 + k];
+        row[6 + k] = ri[k] - ri[3 + k];
+    }
+    ColGeom<T> cgm;
+    cgm.Bx = cj[6]; cgm.By = cj[7]; cgm.Bz = cj[8];
+    cgm.Qx = cj[3] - cj[6]; cgm.Qy = cj[4] - cj[7]; cgm.Qz = cj[5] - cj[8];
+    cgm.Ux = cj[0] - cj[3]; cgm.Uy = cj[1] - cj[4]; cgm.Uz = cj[2] - cj[5];
+    cgm.Wx = cgm.Uy * cgm.Qz - cgm.Uz * cgm.Qy;
+    cgm.Wy = cgm.Uz * cgm.Qx - cgm.Ux * cgm.Qz;
+    cgm.Wz = cgm.Ux * cgm.Qy - cgm.Uy * cgm.Qx;
+    cgm.qq = max(cgm.Qx * cgm.Qx + cgm.Qy * cgm.Qy + cgm.Qz * cgm.Qz, t_tiny<T>());
+    cgm.ww = max(cgm.Wx * cgm.Wx + cgm.Wy * cgm.Wy + cgm.Wz * cgm.Wz, t_tiny<T>());
+    cgm.uq = cgm.Ux * cgm.Qx + cgm.Uy * cgm.Qy + cgm.Uz * cgm.Qz;
+    if (p.dist_ca) {   // 'AtomPair CA a CA b' (utils_ros.py:191): the only restraint of such a pair
+        const T Dx = cj[3] - ri[3], Dy = cj[4] - ri[4], Dz = cj[5] - ri[5];
+        const T dd = max(DOT(D, D), t_tiny<T>()), rd = t_rsqrt(dd);
+        T u0;
+        const Coef<T> c0 = spline_load(p.tab[0], ia.y, spline_locate<true>(geom[0], kx + kx_off(0), dd * rd, u0));
+        f0 += SPLINE_F(c0, u0);
+        const T sg = w0 * SPLINE_DF(c0, u0) * rd;
+        cg[3] += sg * Dx; cg[4] += sg * Dy; cg[5] += sg * Dz;
+        rg[3] -= sg * Dx; rg[4] -= sg * Dy; rg[5] -= sg * Dz;
+    } else
+    // pairs carrying all six restraints take a straight-line path (no per-restraint branches)
+    if (ia.x == 63) pair_eval<T, true>(p, geom, kx, ia, ib, row, cgm, rg, cg, w0, w1, w2, f0, f1, f2);
+    else pair_eval<T, false>(p, geom, kx, ia, ib, row, cgm, rg, cg, w0, w1, w2, f0, f1, f2);
+}
+
+// ---- the barrier-free fp32 kernel ------------------------------------------------------------------------
+// The step schedule above exists so that plain shared-memory read-modify-writes never collide -- at the price of a
+// block-wide barrier per step, which is the kernel's top stall (ncu, round 1) and couples the latencies of the
+// four warps of a tile.  Here the row and column gradients of a tile are accumulated with native 32-bit
+// SHARED-MEMORY INTEGER ATOMICS ON TWO-LEVEL FIXED POINT: a value v is split exactly into h = rint(v 2^10) and
+// l = rint((v - h 2^-10) 2^34), added to an int32 `hi` and an int32 `lo` accumulator (range +-2^21, resolution
+// 5.8e-11; at most 16 contributions per accumulator and tile, so `lo` cannot overflow).  Integer sums do not depend
+// on the order of the additions: the result is bit-reproducible with no ordering at all between the warps.  The
+// pairs of a tile are dealt round-robin to K1F_WARPS warps that never wait for each other: no per-step barrier,
+// no idle slots from imperfect matchings, twice the warps per tile for the same shared memory per warp.
+// (A 64-bit fixed-point atomicAdd on shared memory is a compare-and-swap loop in SASS -- ATOMS.CAST.SPIN.64.)
+constexpr int K1F_WARPS = 8;
+constexpr int K1F_THREADS = K1F_WARPS * 32;
+constexpr float K1F_HI = 1024.0f, K1F_LO = 17179869184.0f;   // 2^10, 2^34
+__host__ __device__ constexpr size_t k1f_dyn_bytes() { return 4 * REC_ELEMS * sizeof(int) + TILE * TILE * 8 * sizeof(int) + K1_MAXSTEPS * K1_WARPS * sizeof(unsigned short) + 16 + 2 * REC_ELEMS * sizeof(float); }
+#ifndef TRX_K1F_MINBLOCKS
+#define TRX_K1F_MINBLOCKS 2
+#endif
+
+__device__ __forceinline__ float fx_value(int h, int l) { return (float)((double)h * (1.0 / 1024.0) + (double)l * (1.0 / 17179869184.0)); }
+
+template <bool SYM>
+__global__ void __launch_bounds__(K1F_THREADS, TRX_K1F_MINBLOCKS) restraints_free_kernel(const K1Params<float> p)
+{
+    typedef float T;
+    __shared__ KnotHead<T> geom[4];
+    __shared__ T kx[KX_TOTAL];
+    extern __shared__ __align__(16) unsigned char k1_dyn[];
+    int *colhi = reinterpret_cast<int *>(k1_dyn), *collo = colhi + REC_ELEMS;   // column-block gradient of the current tile
+    int *rowhi = collo + REC_ELEMS, *rowlo = rowhi + REC_ELEMS;                 // row-block gradient of the whole work item
+    double(*ered)[3][LANES] = reinterpret_cast<double(*)[3][LANES]>(colhi);     // reused after the last flush
+    int *recs_s = reinterpret_cast<int *>(k1_dyn + 4 * REC_ELEMS * sizeof(int));
+    unsigned short *sched_s = reinterpret_cast<unsigned short *>(recs_s + TILE * TILE * 8);
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(sched_s + K1_MAXSTEPS * K1_WARPS);
+    T *xrow_s = reinterpret_cast<T *>(reinterpret_cast<unsigned char *>(bar) + 16), *xcol_s = xrow_s + REC_ELEMS;   // staged coordinates
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int q = blockIdx.y, g = p.g0 + blockIdx.x;
+    if (p.gactive && !p.gactive[g]) return;
+    {
+        if (threadIdx.x == 0) {
+            mbar_init(bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        if (threadIdx.x < 4) {
+            const KnotGeom<T> &gs = p.geom[threadIdx.x];
+            KnotHead<T> h;
+            h.gx0 = gs.gx0; h.ginv = gs.ginv; h.goff = gs.goff; h.K = gs.K; h.urun0 = gs.urun0; h.pad = 0;
+            geom[threadIdx.x] = h;
+        }
+        for (int e = threadIdx.x; e < KX_TOTAL; e += K1F_THREADS) {
+            const int t = e < MAXK ? 0 : 1 + (e - MAXK) / MAXK_ANG, k = e - kx_off(t);
+            kx[e] = p.geom[t].x[k];
+        }
+        for (int e = threadIdx.x; e < 4 * REC_ELEMS; e += K1F_THREADS) colhi[e] = 0;
+    }
+    const int I = p.work[q * 4 + 0], t0 = p.work[q * 4 + 1], nt = p.work[q * 4 + 2], rowrec = p.work[q * 4 + 3];
+    const int xs = p.xstride;
+    size_t gbase = (size_t)g * p.Lpad * xs * LANES + lane;
+    asm volatile("" : "+l"(gbase));
+    const T *__restrict__ Xg = p.X + gbase;
+    const unsigned xrow = (unsigned)xs * LANES;
+    T w0 = p.w0, w1 = p.w1, w2 = p.w2;
+    if (p.wl) {
+        w0 = p.wl[0 * (size_t)p.Npad + g * LANES + lane];
+        w1 = p.wl[1 * (size_t)p.Npad + g * LANES + lane];
+        w2 = p.wl[2 * (size_t)p.Npad + g * LANES + lane];
+    }
+    double e0 = 0.0, e1 = 0.0, e2 = 0.0;
+    __syncthreads();
+
+    for (int t = t0; t < t0 + nt; ++t) {
+        const int J = p.tileJ[t];
+        const int *__restrict__ rec_t = p.pairrec + (size_t)t * TILE * TILE * 8;
+        T f0 = 0.f, f1 = 0.f, f2 = 0.f;   // this warp's partial energies of the tile
+        const int s0 = p.nsteps[t], s1 = p.nsteps[t + 1];
+        {   // the tile's pair records by one bulk asynchronous copy, its pair list by one coalesced load per thread
+            const unsigned cb = 9 * LANES * sizeof(T);
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(bar, TILE * TILE * 8 * sizeof(int) + (t == t0 ? 2 : 1) * TILE * cb);
+                bulk_g2s(recs_s, rec_t, TILE * TILE * 8 * sizeof(int), bar);
+            }
+            if (w == 0) {
+                __syncwarp();
+                const T *__restrict__ Xgrp = p.X + (size_t)g * p.Lpad * xs * LANES;
+                if (lane < TILE) {
+                    if (t == t0) bulk_g2s(xrow_s + lane * 9 * LANES, Xgrp + (size_t)(I * TILE + lane) * xrow, cb, bar);
+                } else {
+                    bulk_g2s(xcol_s + (lane - TILE) * 9 * LANES, Xgrp + (size_t)(J * TILE + lane - TILE) * xrow, cb, bar);
+                }
+            }
+            const uint2 *__restrict__ src = reinterpret_cast<const uint2 *>(p.sched + (size_t)s0 * K1_WARPS);
+            for (int e = threadIdx.x; e < s1 - s0; e += K1F_THREADS) reinterpret_cast<uint2 *>(sched_s)[e] = src[e];
+            mbar_wait(bar, (t - t0) & 1);
+            __syncthreads();
+        }
+        // pair list of the tile = the entries of its step schedule (idle entries skipped), dealt round-robin to the warps
+        const int nent = (s1 - s0) * K1_WARPS;
+        for (int idx = w; idx < nent; idx += K1F_WARPS) {
+            const int e = sched_s[idx];
+            if (e == 0xffff) continue;
+            const int r = e & 15, c = (e >> 4) & 15;
+            const int4 *rp = reinterpret_cast<const int4 *>(recs_s + (r * TILE + c) * 8);
+            const int4 ia = rp[0], ib = rp[1];
+            T rg[9], cg[9];
+            eval_pair<T, SYM>(p, geom, kx, ia, ib, xrow_s + r * 9 * LANES + lane, xcol_s + c * 9 * LANES + lane, rg, cg, w0, w1, w2, f0, f1, f2);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const float hr = rintf(rg[k] * K1F_HI), hc = rintf(cg[k] * K1F_HI);
+                const float lr = fmaf(hr, -1.0f / K1F_HI, rg[k]), lc = fmaf(hc, -1.0f / K1F_HI, cg[k]);   // exact remainders
+                atomicAdd(&rowhi[(r * 9 + k) * LANES + lane], __float2int_rn(hr));
+                atomicAdd(&rowlo[(r * 9 + k) * LANES + lane], __float2int_rn(lr * K1F_LO));
+                atomicAdd(&colhi[(c * 9 + k) * LANES + lane], __float2int_rn(hc));
+                atomicAdd(&collo[(c * 9 + k) * LANES + lane], __float2int_rn(lc * K1F_LO));
+            }
+        }
+        e0 += (double)f0; e1 += (double)f1; e2 += (double)f2;
+        __syncthreads();   // every pair of the tile is in
+        T *__restrict__ dst = p.recs + ((size_t)g * p.nrec + t) * REC_ELEMS;
+        for (int e = threadIdx.x * 4; e < REC_ELEMS; e += K1F_THREADS * 4) {   // 16-byte stores
+            const int4 h = *reinterpret_cast<const int4 *>(colhi + e), l = *reinterpret_cast<const int4 *>(collo + e);
+            *reinterpret_cast<float4 *>(dst + e) = make_float4(fx_value(h.x, l.x), fx_value(h.y, l.y), fx_value(h.z, l.z), fx_value(h.w, l.w));
+            *reinterpret_cast<int4 *>(colhi + e) = make_int4(0, 0, 0, 0);
+            *reinterpret_cast<int4 *>(collo + e) = make_int4(0, 0, 0, 0);
+        }
+        __syncthreads();
+    }
+    {
+        T *__restrict__ dst = p.recs + ((size_t)g * p.nrec + rowrec) * REC_ELEMS;
+        for (int e = threadIdx.x * 4; e < REC_ELEMS; e += K1F_THREADS * 4) {
+            const int4 h = *reinterpret_cast<const int4 *>(rowhi + e), l = *reinterpret_cast<const int4 *>(rowlo + e);
+            *reinterpret_cast<float4 *>(dst + e) = make_float4(fx_value(h.x, l.x), fx_value(h.y, l.y), fx_value(h.z, l.z), fx_value(h.w, l.w));
+        }
+    }
+    __syncthreads();
+    ered[w][0][lane] = e0;
+    ered[w][1][lane] = e1;
+    ered[w][2][lane] = e2;
+    __syncthreads();
+    if (w < 3) {
+        double sum = 0.0;
+#pragma unroll
+        for (int k = 0; k < K1F_WARPS; ++k) sum += ered[k][w][lane];
+        p.Epart[(((size_t)g * p.nwork + q) * 3 + w) * LANES + lane] = sum;
+    }
+}
+
 // SYM (fp32 only): both sides of a pair packed in f32x2 (pair_eval_sym); otherwise the scalar formulas (fp64 parity
 // mode; fp32 with TRX_K1_SCALAR=1 for A/B measurements)
 template <typename T, bool SYM>
@@ -467,6 +683,11 @@ __global__ void __launch_bounds__(K1_THREADS, (sizeof(T) == 4 ? TRX_K1_MINBLOCKS
     int *recs_s = reinterpret_cast<int *>(k1_dyn + 2 * REC_ELEMS * sizeof(T));
     unsigned short *sched_s = reinterpret_cast<unsigned short *>(recs_s + TILE * TILE * 8);
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(sched_s + K1_MAXSTEPS * K1_WARPS);
+    // The coordinates of the tile's 16 row and 16 column residues (N, CA, CB of 32 decoys: 1152 B per residue in
+    // fp32) are staged the same way, 32 bulk copies issued by one warp: a pair then reads its 18 coordinate lines
+    // from shared memory instead of L1/L2 -- each line is fetched once per tile instead of once per pair of its row
+    // or column (8x on protein-like contact maps; L1 held only 12 % of these re-reads, ncu round 1).
+    T *xrow_s = reinterpret_cast<T *>(reinterpret_cast<unsigned char *>(bar) + 16), *xcol_s = xrow_s + REC_ELEMS;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int q = blockIdx.y, g = p.g0 + blockIdx.x;   // group is the fast grid index: co-resident CTAs share tiles
     if (p.gactive && !p.gactive[g]) return;
@@ -511,8 +732,19 @@ __global__ void __launch_bounds__(K1_THREADS, (sizeof(T) == 4 ? TRX_K1_MINBLOCKS
         const int s0 = p.nsteps[t], s1 = p.nsteps[t + 1];
         if (p.stage) {
             if (threadIdx.x == 0) {
-                mbar_expect_tx(bar, TILE * TILE * 8 * sizeof(int));
+                const unsigned cb = 9 * LANES * sizeof(T);
+                mbar_expect_tx(bar, TILE * TILE * 8 * sizeof(int) + (p.stage > 1 ? (t == t0 ? 2 : 1) * TILE * cb : 0u));
                 bulk_g2s(recs_s, rec_t, TILE * TILE * 8 * sizeof(int), bar);
+            }
+            if (p.stage > 1 && w == 0) {
+                __syncwarp();   // the expect_tx above precedes every copy of this warp
+                const unsigned cb = 9 * LANES * sizeof(T);
+                const T *__restrict__ Xgrp = p.X + (size_t)g * p.Lpad * xs * LANES;
+                if (lane < TILE) {
+                    if (t == t0) bulk_g2s(xrow_s + lane * 9 * LANES, Xgrp + (size_t)(I * TILE + lane) * xrow, cb, bar);
+                } else {
+                    bulk_g2s(xcol_s + (lane - TILE) * 9 * LANES, Xgrp + (size_t)(J * TILE + lane - TILE) * xrow, cb, bar);
+                }
             }
             const uint2 *__restrict__ src = reinterpret_cast<const uint2 *>(p.sched + (size_t)s0 * K1_WARPS);   // 8 B per step
             for (int e = threadIdx.x; e < s1 - s0; e += K1_THREADS) reinterpret_cast<uint2 *>(sched_s)[e] = src[e];
@@ -531,60 +763,9 @@ __global__ void __launch_bounds__(K1_THREADS, (sizeof(T) == 4 ? TRX_K1_MINBLOCKS
                     const int4 *rp = reinterpret_cast<const int4 *>(rec_t + (r * TILE + c) * 8);
                     ia = __ldg(rp); ib = __ldg(rp + 1);
                 }
-                T ri[9], cj[9], rg[9], cg[9];
-                const T *__restrict__ xr = Xg + (unsigned)(I * TILE + r) * xrow, *__restrict__ xc = Xg + (unsigned)(J * TILE + c) * xrow;
-#pragma unroll
-                for (int k = 0; k < 9; ++k) {
-                    ri[k] = xr[k * LANES];
-                    cj[k] = xc[k * LANES];
-                    rg[k] = (T)0;
-                    cg[k] = (T)0;
-                }
-                if constexpr (SYM) {
-                    if (!p.dist_ca) {
-                        F2 self[9], G[9];
-#pragma unroll
-                        for (int k = 0; k < 9; ++k) { self[k] = F2(ri[k], cj[k]); G[k] = F2(0.f); }
-                        pair_eval_sym(p, geom, kx, ia, ib, self, G, w0, w1, w2, f0, f1, f2);
-#pragma unroll
-                        for (int k = 0; k < 9; ++k) {
-                            rowg[(r * 9 + k) * LANES + lane] += lo(G[k]);
-                            colg[(c * 9 + k) * LANES + lane] += hi(G[k]);
-                        }
-                        __syncthreads();
-                        continue;
-                    }
-                }
-                T row[9];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    row[k] = ri[6 + k];
-                    row[3 + k] = ri[3 + k] - ri[6 + k];
-                    row[6 + k] = ri[k] - ri[3 + k];
-                }
-                ColGeom<T> cgm;
-                cgm.Bx = cj[6]; cgm.By = cj[7]; cgm.Bz = cj[8];
-                cgm.Qx = cj[3] - cj[6]; cgm.Qy = cj[4] - cj[7]; cgm.Qz = cj[5] - cj[8];
-                cgm.Ux = cj[0] - cj[3]; cgm.Uy = cj[1] - cj[4]; cgm.Uz = cj[2] - cj[5];
-                cgm.Wx = cgm.Uy * cgm.Qz - cgm.Uz * cgm.Qy;
-                cgm.Wy = cgm.Uz * cgm.Qx - cgm.Ux * cgm.Qz;
-                cgm.Wz = cgm.Ux * cgm.Qy - cgm.Uy * cgm.Qx;
-                cgm.qq = max(cgm.Qx * cgm.Qx + cgm.Qy * cgm.Qy + cgm.Qz * cgm.Qz, t_tiny<T>());
-                cgm.ww = max(cgm.Wx * cgm.Wx + cgm.Wy * cgm.Wy + cgm.Wz * cgm.Wz, t_tiny<T>());
-                cgm.uq = cgm.Ux * cgm.Qx + cgm.Uy * cgm.Qy + cgm.Uz * cgm.Qz;
-                if (p.dist_ca) {   // 'AtomPair CA a CA b' (utils_ros.py:191): the only restraint of such a pair
-                    const T Dx = cj[3] - ri[3], Dy = cj[4] - ri[4], Dz = cj[5] - ri[5];
-                    const T dd = max(DOT(D, D), t_tiny<T>()), rd = t_rsqrt(dd);
-                    T u0;
-                    const Coef<T> c0 = spline_load(p.tab[0], ia.y, spline_locate<true>(geom[0], kx + kx_off(0), dd * rd, u0));
-                    f0 += SPLINE_F(c0, u0);
-                    const T sg = w0 * SPLINE_DF(c0, u0) * rd;
-                    cg[3] += sg * Dx; cg[4] += sg * Dy; cg[5] += sg * Dz;
-                    rg[3] -= sg * Dx; rg[4] -= sg * Dy; rg[5] -= sg * Dz;
-                } else
-                // pairs carrying all six restraints take a straight-line path (no per-restraint branches)
-                if (ia.x == 63) pair_eval<T, true>(p, geom, kx, ia, ib, row, cgm, rg, cg, w0, w1, w2, f0, f1, f2);
-                else pair_eval<T, false>(p, geom, kx, ia, ib, row, cgm, rg, cg, w0, w1, w2, f0, f1, f2);
+                T rg[9], cg[9];
+                if (p.stage > 1) eval_pair<T, SYM>(p, geom, kx, ia, ib, xrow_s + r * 9 * LANES + lane, xcol_s + c * 9 * LANES + lane, rg, cg, w0, w1, w2, f0, f1, f2);
+                else eval_pair<T, SYM>(p, geom, kx, ia, ib, Xg + (unsigned)(I * TILE + r) * xrow, Xg + (unsigned)(J * TILE + c) * xrow, rg, cg, w0, w1, w2, f0, f1, f2);
 #pragma unroll
                 for (int k = 0; k < 9; ++k) {
                     rowg[(r * 9 + k) * LANES + lane] += rg[k];
@@ -690,8 +871,8 @@ int k1_launch(trx_ctx *ctx, trx_tables *tb, int Gtot, int g0, int ng, const T *d
     p.xstride = xstride;
     p.dist_ca = tb->dist_ca;
     p.g0 = g0;
-    static const bool no_stage = [] { const char *ev = getenv("TRX_K1_NO_STAGE"); return ev && ev[0] && ev[0] != '0'; }();   // A/B
-    p.stage = no_stage ? 0 : 1;
+    static const int stage = [] { const char *ev = getenv("TRX_K1_STAGE"); return ev && ev[0] ? atoi(ev) : 1; }();   // 0 none, 1 pair records (default), 2 + coordinates
+    p.stage = sizeof(T) == 8 ? std::min(stage, 1) : stage;
     p.gactive = gactive;
     p.wl = wl;
     p.Npad = Gtot * LANES;
@@ -700,13 +881,16 @@ int k1_launch(trx_ctx *ctx, trx_tables *tb, int Gtot, int g0, int ng, const T *d
     p.w2 = (T)(w ? w[2] : 0.0);
     if (plan->nwork > 0) {
         ctx->time_begin("restraints");
-        const size_t dyn = k1_dyn_bytes(sizeof(T));
-        static const bool scalar_f32 = [] { const char *ev = getenv("TRX_K1_SCALAR"); return ev && ev[0] && ev[0] != '0'; }();   // A/B: scalar formulas in fp32
+        const size_t dyn = k1_dyn_bytes(sizeof(T), p.stage);
+        // Default fp32 kernel: step schedule, scalar formulas, pair records staged by a bulk copy.  The measured
+        // alternatives stay selectable (profiles/r2_k1_variants.md): TRX_K1_SYM=1 both sides of a pair packed in f32x2,
+        // TRX_K1_FREE=1 barrier-free fixed-point accumulation, TRX_K1_STAGE=0|1|2.
+        static const bool scalar_f32 = [] { const char *ev = getenv("TRX_K1_SYM"); return !(ev && ev[0] && ev[0] != '0'); }();
         auto launch = [&](auto kern) -> int {
             static bool attr_set_dev[64] = {};   // function attributes are per device (one flag per instantiation of this lambda)
             if (!attr_set_dev[ctx->device & 63]) {
-                TRX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-                int carve = TRX_K1_CARVEOUT;
+                TRX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_dyn_bytes(sizeof(T), sizeof(T) == 4 ? 2 : 1)));
+                int carve = p.stage > 1 ? 86 : TRX_K1_CARVEOUT;   // with staged coordinates: 196 KB of shared memory, two 84 KB CTAs resident
                 if (const char *ev = getenv("TRX_K1_CARVEOUT")) carve = atoi(ev);   // development knob: percent of the L1/shared array
                 TRX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
                 attr_set_dev[ctx->device & 63] = true;
@@ -714,9 +898,24 @@ int k1_launch(trx_ctx *ctx, trx_tables *tb, int Gtot, int g0, int ng, const T *d
             kern<<<dim3(ng, plan->nwork), K1_THREADS, dyn, ctx->stream>>>(p);
             return TRX_OK;
         };
+        static const bool stepped_f32 = [] { const char *ev = getenv("TRX_K1_FREE"); return !(ev && ev[0] && ev[0] != '0'); }();
+        auto launch_free = [&](auto kern) -> int {
+            static bool attr_set_dev[64] = {};
+            if (!attr_set_dev[ctx->device & 63]) {
+                TRX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1f_dyn_bytes()));
+                int carve = 86;   // 196 KB of shared memory: two 8-warp CTAs resident
+                if (const char *ev = getenv("TRX_K1_CARVEOUT")) carve = atoi(ev);
+                TRX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+                attr_set_dev[ctx->device & 63] = true;
+            }
+            kern<<<dim3(ng, plan->nwork), K1F_THREADS, k1f_dyn_bytes(), ctx->stream>>>(p);
+            return TRX_OK;
+        };
         int rcl;
-        if constexpr (sizeof(T) == 4) rcl = scalar_f32 ? launch(restraints_kernel<float, false>) : launch(restraints_kernel<float, true>);
-        else rcl = launch(restraints_kernel<T, false>);
+        if constexpr (sizeof(T) == 4) {
+            if (stepped_f32) rcl = scalar_f32 ? launch(restraints_kernel<float, false>) : launch(restraints_kernel<float, true>);
+            else rcl = scalar_f32 ? launch_free(restraints_free_kernel<false>) : launch_free(restraints_free_kernel<true>);
+        } else rcl = launch(restraints_kernel<T, false>);
         if (rcl) return rcl;
         ctx->time_end("restraints");
         TRX_CUDA(cudaGetLastError());
@@ -744,7 +943,7 @@ extern "C" {
 /* Development aid (not part of include/trx2dyn.h): resident CTAs per SM of the fp32 restraint kernel. */
 int trx_debug_k1_occupancy(int *out)
 {
-    const size_t dyn = k1_dyn_bytes(sizeof(float));
+    const size_t dyn = k1_dyn_bytes(sizeof(float), 1);
     TRX_CUDA(cudaFuncSetAttribute(restraints_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     TRX_CUDA(cudaFuncSetAttribute(restraints_kernel<float, true>, cudaFuncAttributePreferredSharedMemoryCarveout, TRX_K1_CARVEOUT));
     TRX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, restraints_kernel<float, true>, K1_THREADS, dyn));

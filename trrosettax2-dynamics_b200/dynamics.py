@@ -111,12 +111,14 @@ def reliability_score(tors):
     return np.mean((phi >= -180.0) & (phi <= 0.0), axis=-1)
 
 
-def generate(fold_fn, initial_npz, L, n_init=10, n_max=300, sigma=1.0, angle=True, on_decoy=None, seq=None):
+def generate(fold_fn, initial_npz, L, n_init=10, n_max=300, sigma=1.0, angle=True, on_decoy=None, seq=None, ctx=None):
     """generate_npz_and_pdb (run_inference.py:16-143) in memory.  fold_fn(npz, n) -> dict with
     'xyz' (n,L,5,3) [N,CA,CB,C,O] and 'tors' (n,L,3): folds n decoys on the given distograms.
     seq: the target's sequence.  The reference re-reads every decoy from its PDB file and takes the
     file's CB for every non-Gly residue (utils.py:145-150), the virtual CB only for Gly; with seq
     given the decoy's own CB is used the same way (without it every CB is the virtual one).
+    ctx: a capi.Context -- the distograms then live on the device and the update (6D geometry, binning, decay,
+    renormalisation, smoothing) runs there (trx_dyn_step; bit-identical maps); without it the numpy path below.
     Returns the list of decoys [(xyz, tors), ...]: the n_init initial ones, then one per iteration."""
     decoys = []
     out = fold_fn(initial_npz, n_init)
@@ -126,12 +128,24 @@ def generate(fold_fn, initial_npz, L, n_init=10, n_max=300, sigma=1.0, angle=Tru
             on_decoy("initial%d" % k, out["xyz"][k])
     best = int(np.argmax(reliability_score(out["tors"])))     # first maximum, as the reference's loop
     xyz = out["xyz"][best].astype(np.float64)
-    cur = next_npz(initial_npz, xyz[:, 0], xyz[:, 1], xyz[:, 3], cb=xyz[:, 2] if seq else None, seq=seq, sigma=sigma, angle=angle)
-    old_tmp = np.asarray(initial_npz["dist"])
+    state = None
+    if ctx is not None:
+        from . import capi
+        state = capi.DynState(ctx, initial_npz, angle=angle)
+
+    def advance(cur_npz, xyz):
+        """-> (next distograms, max change of 'tmp')"""
+        if state is not None:
+            chg = state.step(xyz[:, 0], xyz[:, 1], xyz[:, 3], cb=xyz[:, 2] if seq else None, seq=seq, sigma=sigma)
+            return state.get(), chg
+        nxt = next_npz(cur_npz, xyz[:, 0], xyz[:, 1], xyz[:, 3], cb=xyz[:, 2] if seq else None, seq=seq, sigma=sigma, angle=angle)
+        base = cur_npz["tmp"] if "tmp" in cur_npz else cur_npz["dist"]
+        return nxt, float(np.max(np.abs(np.asarray(base) - nxt["tmp"])))
+
+    cur, _ = advance(initial_npz, xyz)
     it = 0
     while True:
         it += 1
-        old_tmp = cur["tmp"]
         o = fold_fn(cur, 1)
         decoys.append((o["xyz"][0], o["tors"][0]))
         if on_decoy:
@@ -139,7 +153,9 @@ def generate(fold_fn, initial_npz, L, n_init=10, n_max=300, sigma=1.0, angle=Tru
         if it >= n_max:
             break
         xyz = o["xyz"][0].astype(np.float64)
-        cur = next_npz(cur, xyz[:, 0], xyz[:, 1], xyz[:, 3], cb=xyz[:, 2] if seq else None, seq=seq, sigma=sigma, angle=angle)
-        if np.max(np.abs(old_tmp - cur["tmp"])) < 0.01:
+        cur, chg = advance(cur, xyz)
+        if chg < 0.01:
             break
+    if state is not None:
+        state.close()
     return decoys

@@ -48,7 +48,7 @@ def _run_chain(ctx, seq, npz_path, m, out_dir, init_num, n_max, angle, seed, rul
         pdbio.write_pdb(p, seq, xyz, ["source %s model %d" % (tag, m)])
         written.append(p)
 
-    dynamics.generate(fold_fn, npz0, L, n_init=init_num, n_max=n_max, angle=angle, on_decoy=on_decoy, seq=seq)
+    dynamics.generate(fold_fn, npz0, L, n_init=init_num, n_max=n_max, angle=angle, on_decoy=on_decoy, seq=seq, ctx=ctx)
     return written
 
 

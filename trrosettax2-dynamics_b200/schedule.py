@@ -8,15 +8,19 @@ folding/folding.py:74-104 builds four ScoreFunctions from data/*.wts and four Mi
     min_mover_cart                             Cartesian stage: xyz are the degrees of freedom (scorefxn_cart.wts)
     remove_clash(sf_vdw, min_mover1)           <= 5 x { ...; minimise under scorefxn1.wts }
 Terms the library implements: atom_pair_constraint, dihedral_constraint, angle_constraint,
-vdw, rama, omega, cart_bonded (the non-restraint ones as stated approximations).  cen_hb /
-hbond_* weights are read and ignored (database-driven terms, not in the reference tree)."""
+vdw, rama, omega, cart_bonded and one backbone hydrogen-bond term for cen_hb / hbond_sr_bb / hbond_lr_bb
+(the non-restraint ones as stated approximations: Rosetta's are database-driven and not in the reference tree)."""
 from __future__ import annotations
 
 import os
 
 from .capi import Run, NTERM
 
-TERMS = ("atom_pair_constraint", "dihedral_constraint", "angle_constraint", "vdw", "rama", "omega", "cart_bonded")
+TERMS = ("atom_pair_constraint", "dihedral_constraint", "angle_constraint", "vdw", "rama", "omega", "cart_bonded", "backbone_hbond")
+# Rosetta's backbone hydrogen-bond terms all map onto the one stated approximation of include/trx_centroid_model.h:
+# cen_hb in the centroid stages; hbond_sr_bb / hbond_lr_bb (the same potential on complementary sequence
+# separations, the same weight in scorefxn_cart.wts) in the Cartesian stage
+_HB_ALIASES = ("cen_hb", "hbond_sr_bb", "hbond_lr_bb")
 _DATA = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "folding", "data")
 
 
@@ -28,6 +32,8 @@ def read_wts(name, data_dir=None):
             tok = line.split()
             if len(tok) >= 2 and tok[0] in w:
                 w[tok[0]] = float(tok[1])
+            elif len(tok) >= 2 and tok[0] in _HB_ALIASES:
+                w["backbone_hbond"] = max(w["backbone_hbond"], float(tok[1]))
     return [w[t] for t in TERMS]
 
 
@@ -42,7 +48,7 @@ def ignored_terms(data_dir=None, names=("scorefxn.wts", "scorefxn1.wts", "scoref
         with open(os.path.join(data_dir or _DATA, name)) as fh:
             for line in fh:
                 tok = line.split()
-                if len(tok) >= 2 and tok[0] not in TERMS and not tok[0].startswith("#"):
+                if len(tok) >= 2 and tok[0] not in TERMS and tok[0] not in _HB_ALIASES and not tok[0].startswith("#"):
                     try:
                         out.append((name, tok[0], float(tok[1])))
                     except ValueError:
