@@ -16,6 +16,7 @@ Outputs
   example_tmscore.npz                          bin/TMscore (TM-score, RMSD) + GloCon on the 8 example decoys and 2 natives
   example_backbone_stats.npz                   bond / angle statistics of the reference's 8 example decoys (Rosetta-written)
   dynamics_example48.npz                       outer-loop arithmetic (get_neighbors, pros, process_distribution...)
+  example_reliability.npz                      backbones of the 8 example decoys + the reference's ramachandran_score of each
 """
 import hashlib, os, shutil, sys, tempfile, types
 import numpy as np
@@ -299,6 +300,34 @@ def make_tmscore_golden():
     np.savez_compressed(f"{HERE}/example_tmscore.npz", names=np.array(names), ca=np.stack(ca), cb=np.stack(cb), n=np.stack(nn),
                         tm=tm, rmsd=rm, glocon=glocon)
     print("TMscore golden written:", tm[2, 0], rm[2, 0])
+
+
+def make_reliability_golden():
+    """calculate_reliability_score (utils_trX2dy/utils.py:337-372) on the reference's own example decoys.  Bio.PDB is
+    absent here, so the phi/psi list PPBuilder would give (every residue with both angles defined, radians, IUPAC
+    sign) is computed from the backbone with a plain dihedral; the SCORE is the reference's own ramachandran_score
+    function applied to that list (note its degree bounds on radian angles: it counts phi <= 0)."""
+    U = load_reference_geometry()
+    import glob
+    bbs, scores, names = [], [], []
+    for pdb in sorted(glob.glob(os.path.join(REF, "example/output/seq/pred_pdb/conf_*.pdb"))):
+        res = {}
+        for ln in open(pdb):
+            if ln.startswith("ATOM") and ln[12:16].strip() in ("N", "CA", "C"):
+                res.setdefault(int(ln[22:26]), {})[ln[12:16].strip()] = [float(ln[30:38]), float(ln[38:46]), float(ln[46:54])]
+        keys = sorted(res)
+        bb = np.array([[res[k]["N"], res[k]["CA"], res[k]["C"]] for k in keys])
+
+        def dih(p0, p1, p2, p3):
+            b0, b1, b2 = p0 - p1, p2 - p1, p3 - p2
+            b1 = b1 / np.linalg.norm(b1)
+            v, w = b0 - np.dot(b0, b1) * b1, b2 - np.dot(b2, b1) * b1
+            return float(np.arctan2(np.dot(np.cross(b1, v), w), np.dot(v, w)))
+        L = len(bb)
+        lst = [(dih(bb[i - 1, 2], bb[i, 0], bb[i, 1], bb[i, 2]), dih(bb[i, 0], bb[i, 1], bb[i, 2], bb[i + 1, 0])) for i in range(1, L - 1)]
+        bbs.append(bb); scores.append(U.ramachandran_score(lst)); names.append(os.path.basename(pdb))
+    np.savez_compressed(os.path.join(HERE, "example_reliability.npz"), bb=np.array(bbs), score=np.array(scores), names=np.array(names))
+    print("example_reliability.npz", dict(zip(names, scores)))
 
 
 def make_backbone_stats_golden():

@@ -123,3 +123,16 @@ def test_device_dynamics_step_is_bit_identical(gold):
     st0.step(gold["n"], gold["ca"], gold["c"], gold["cb"], seq)
     np.testing.assert_array_equal(st0.get()["dist"], gold["proc_dist"])
     st0.close(); st.close(); ctx.close()
+
+
+def test_reliability_score_on_the_reference_example_decoys(golden_dir):
+    """calculate_reliability_score (utils_trX2dy/utils.py:337-372) on the reference's own 8 example decoys: the
+    reference's ramachandran_score of each (tests/golden/make_golden.py: make_reliability_golden) equals
+    reliability_score of the backbone torsions, and the best-decoy pick (first maximum, run_inference.py:61-69)
+    is the same."""
+    g = np.load(f"{golden_dir}/example_reliability.npz")
+    bb = g["bb"]
+    tors = dynamics.backbone_torsions(bb[:, :, 0], bb[:, :, 1], bb[:, :, 2])
+    got = dynamics.reliability_score(tors)
+    np.testing.assert_allclose(got, g["score"], rtol=0, atol=1e-15)
+    assert int(np.argmax(got)) == int(np.argmax(g["score"])) and 0.9 < got.min() <= got.max() < 1.0

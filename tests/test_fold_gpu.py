@@ -392,6 +392,35 @@ def test_round_budget_closes_every_decoy(ctx):
     chk.close(); batch.close(); tb.close()
 
 
+def test_pair_list_changes_nothing(ctx, monkeypatch):
+    """The vdw / hydrogen-bond pair search keeps a Verlet list per position (partners within reach + a 2 A skin,
+    rebuilt when a residue has used up half the skin).  Energies are summed as 64-bit and gradients as 32-bit
+    fixed point, so an evaluation through the list is the same bits as one through the full scan: the whole fold
+    (two table blocks, Cartesian segment, Monte-Carlo cycles, migration) is bit-identical with and without the list
+    (opt-in, TRX_NBL=1: measured slower than the full scan)."""
+    seq, npzs, nat = synth.target(56, seed=21, two_model=True)
+    params = tables.load_params()
+    tabs = [sampler.build_tables(ctx, z, seq, params) for z in npzs]
+    aa = sampler.aa_index(seq)
+    nd = [96, 45]
+    t0 = sampler.random_torsions(sum(nd), 56, seed=8)
+    res = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("TRX_NBL", flag)
+        batch = capi.FoldBatch(ctx, tabs, nd, aa, schedule.reference_schedule())
+        res["fold" + flag] = batch.run(t0)
+        batch.close()
+        batch = capi.FoldBatch(ctx, tabs, nd, aa, schedule.mc_schedule(mc_max_iter=60))
+        res["mc" + flag] = batch.run_mc(t0, cycles=2, kT=2.0, sigma_deg=25.0, seed=5)
+        batch.close()
+    for kind in ("fold", "mc"):
+        a, b = res[kind + "1"], res[kind + "0"]
+        for key in a:
+            np.testing.assert_array_equal(a[key], b[key], err_msg="%s %s" % (kind, key))
+    for t in tabs:
+        t.close()
+
+
 def test_monte_carlo_extension(ctx):
     """Extension with no reference behaviour: checks the invariants it can have --
     Metropolis never loses the best state at kT -> 0, counters are sane, trajectories are

@@ -86,5 +86,22 @@ def launches(path, header):
     print("```")
 
 
+def traffic(rep, decoys):
+    """profiles/k1_traffic.json: DRAM bytes per decoy evaluation of the restraint kernel, from one ncu --set full capture of
+    the full-batch standalone launch (bench.py multiplies it by the decoy evaluations per launch of the fold)."""
+    import json
+    rows = ncu_csv(rep, "raw")
+    d = dict(zip(rows[0], zip(rows[2], rows[1])))
+
+    def to_bytes(key):
+        v, unit = d[key]
+        mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+        return float(v.replace(",", "")) * mult
+    rd, wr = to_bytes("dram__bytes_read.sum"), to_bytes("dram__bytes_write.sum")
+    print(json.dumps({"dram_bytes_read_per_launch": rd, "dram_bytes_write_per_launch": wr, "decoys_per_launch": int(decoys),
+                      "dram_bytes_per_decoy_eval": (rd + wr) / float(decoys), "kernel": d["Kernel Name"][0],
+                      "source": "ncu --set full capture %s (tools/k1_bench.py, L=300 protein-like table, %s decoys): dram__bytes_read.sum + dram__bytes_write.sum" % (rep, decoys)}, indent=1))
+
+
 if __name__ == "__main__":
-    {"full": full, "launches": launches}[sys.argv[1]](sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "")
+    {"full": full, "launches": launches, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "")

@@ -871,7 +871,7 @@ int k1_launch(trx_ctx *ctx, trx_tables *tb, int Gtot, int g0, int ng, const T *d
     p.xstride = xstride;
     p.dist_ca = tb->dist_ca;
     p.g0 = g0;
-    static const int stage = [] { const char *ev = getenv("TRX_K1_STAGE"); return ev && ev[0] ? atoi(ev) : 1; }();   // 0 none, 1 pair records (default), 2 + coordinates
+    static const int stage = [] { const char *ev = getenv("TRX_K1_STAGE"); return ev && ev[0] ? atoi(ev) : 0; }();   // 0 nothing staged (default: the smallest footprint wins, profiles/r2_k1_variants.md), 1 pair records, 2 + coordinates
     p.stage = sizeof(T) == 8 ? std::min(stage, 1) : stage;
     p.gactive = gactive;
     p.wl = wl;
@@ -882,7 +882,7 @@ int k1_launch(trx_ctx *ctx, trx_tables *tb, int Gtot, int g0, int ng, const T *d
     if (plan->nwork > 0) {
         ctx->time_begin("restraints");
         const size_t dyn = k1_dyn_bytes(sizeof(T), p.stage);
-        // Default fp32 kernel: step schedule, scalar formulas, pair records staged by a bulk copy.  The measured
+        // Default fp32 kernel: step schedule, scalar formulas, nothing staged (the smallest footprint).  The measured
         // alternatives stay selectable (profiles/r2_k1_variants.md): TRX_K1_SYM=1 both sides of a pair packed in f32x2,
         // TRX_K1_FREE=1 barrier-free fixed-point accumulation, TRX_K1_STAGE=0|1|2.
         static const bool scalar_f32 = [] { const char *ev = getenv("TRX_K1_SYM"); return !(ev && ev[0] && ev[0] != '0'); }();

@@ -111,6 +111,18 @@ def reliability_score(tors):
     return np.mean((phi >= -180.0) & (phi <= 0.0), axis=-1)
 
 
+def backbone_torsions(n, ca, c):
+    """phi, psi, omega (L,3) radians from backbone coordinates (..., L, 3) each; undefined ones (phi of the first,
+    psi / omega of the last residue) are pi.  What PPBuilder.get_phi_psi_list gives the reference
+    (utils_trX2dy/utils.py:337-349), for decoys that exist as coordinates rather than torsions."""
+    n, ca, c = (np.asarray(a, dtype=np.float64) for a in (n, ca, c))
+    t = np.full(n.shape[:-1] + (3,), np.pi)
+    t[..., 1:, 0] = _dihedrals(c[..., :-1, :], n[..., 1:, :], ca[..., 1:, :], c[..., 1:, :])
+    t[..., :-1, 1] = _dihedrals(n[..., :-1, :], ca[..., :-1, :], c[..., :-1, :], n[..., 1:, :])
+    t[..., :-1, 2] = _dihedrals(ca[..., :-1, :], c[..., :-1, :], n[..., 1:, :], ca[..., 1:, :])
+    return t
+
+
 def generate(fold_fn, initial_npz, L, n_init=10, n_max=300, sigma=1.0, angle=True, on_decoy=None, seq=None, ctx=None):
     """generate_npz_and_pdb (run_inference.py:16-143) in memory.  fold_fn(npz, n) -> dict with
     'xyz' (n,L,5,3) [N,CA,CB,C,O] and 'tors' (n,L,3): folds n decoys on the given distograms.
