@@ -21,4 +21,5 @@ ncu --set full --clock-control none --import-source on -k regex:restraints_kerne
 for k in vdw_kernel lbfgs_dots_ring lbfgs_update_ring lbfgs_step nerf_kernel torsion_grad; do
   ncu --set full --clock-control none --import-source on -k regex:$k -s 400 -c 1 -o gpurun_out/r2_$k $CMD > gpurun_out/r2_ncu_$k.log 2>&1
 done
+python tools/dynamics_example.py --n-max 40 > gpurun_out/r2_dynamics_example.log 2>&1; cat gpurun_out/r2_dynamics_example.log
 ls -la gpurun_out/*.ncu-rep

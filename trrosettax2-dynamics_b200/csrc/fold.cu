@@ -401,12 +401,16 @@ __global__ void __launch_bounds__(VDW_THREADS) vdw_kernel(FoldState s)
             const int q = base + fq;
             if (fq < 5 && q < count) {
                 const int pr = queue[warp][q];
-                const int i = (pr >> 16) & 0x7fff, j = pr & 0xffff;
-                const bool touching = pr >= 0;   // bit 31: the spheres do not touch, only a hydrogen bond is in reach
+                const int i = pr >> 16, j = pr & 0xffff;
                 const float4 pa = at[i * 6 + fa];
                 int *pi = acc + (i * 6 + fa) * 3;
+                // second-level filter: this atom against the other residue's bounding sphere (most atoms of two residues
+                // whose spheres touch are still out of each other's reach)
+                const float4 sj = bsph[j];
+                const float ex = pa.x - sj.x, ey = pa.y - sj.y, ez = pa.z - sj.z, er = pa.w + sj.w;
+                const bool near = ex * ex + ey * ey + ez * ez < er * er;
 #pragma unroll
-                for (int b = 0; touching && b < 6; ++b) {
+                for (int b = 0; near && b < 6; ++b) {
                     const float4 pb = at[j * 6 + b];
                     const float dx = pa.x - pb.x, dy = pa.y - pb.y, dz = pa.z - pb.z;
                     const float r = pa.w + pb.w, r2 = r * r, d2 = dx * dx + dy * dy + dz * dz;
@@ -420,17 +424,50 @@ __global__ void __launch_bounds__(VDW_THREADS) vdw_kernel(FoldState s)
                         atomicAdd(pj + 0, -gx); atomicAdd(pj + 1, -gy); atomicAdd(pj + 2, -gz);
                     }
                 }
-                if (fa == 0) hbond(i, j);        // the pair's two hydrogen-bond directions, one lane each
-                else if (fa == 1) hbond(j, i);
             }
+        }
+    };
+    // residue pairs in reach of a hydrogen bond have their own per-warp queue: one lane per pair, both directions
+    __shared__ int hqueue[VDW_THREADS / 32][64];
+    int hn = 0;
+    auto flush_hb = [&](int count) {
+        if (lane < count) {
+            const int pr = hqueue[warp][lane];
+            const int i = pr >> 16, j = pr & 0xffff;
+            hbond(i, j);
+            hbond(j, i);
         }
     };
     // a candidate pair (i, j) of this warp's row goes to the queue when its spheres are within reach now
     auto push = [&](bool close, bool touching, int i, int j) {
-        const unsigned m = __ballot_sync(0xffffffffu, close);
+        // a hydrogen bond between the two residues needs N...O < D0 + W, hence CA...CA < D0 + W + |CA-N| + |CA-O| (1.5 + 2.5 A)
+        bool hb = close && j - i >= TRX_HB_MINSEP;
+        if (hb) {
+            const float4 a = at[i * 6 + TRX_AT_CA], b = at[j * 6 + TRX_AT_CA];
+            const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z, reach = (float)(TRX_HB_D0 + TRX_HB_W) + 4.0f;
+            hb = dx * dx + dy * dy + dz * dz < reach * reach;
+        }
+        const unsigned mh = __ballot_sync(0xffffffffu, hb);
+        if (mh) {
+            const int pos = hn + __popc(mh & ((1u << lane) - 1));
+            if (hb) hqueue[warp][pos] = (i << 16) | j;
+            hn += __popc(mh);
+            __syncwarp();
+            if (hn >= 32) {
+                flush_hb(32);
+                __syncwarp();
+                const int rest = hn - 32;
+                const int v = lane < rest ? hqueue[warp][32 + lane] : 0;
+                __syncwarp();
+                if (lane < rest) hqueue[warp][lane] = v;
+                hn = rest;
+                __syncwarp();
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, close && touching);
         if (m) {
             const int pos = qn + __popc(m & ((1u << lane) - 1));
-            if (close) queue[warp][pos] = (touching ? 0 : (int)0x80000000) | (i << 16) | j;
+            if (close && touching) queue[warp][pos] = (i << 16) | j;
             qn += __popc(m);
             __syncwarp();
             if (qn >= 30) {   // 30 pairs = 6 full passes of 5 pairs
@@ -529,6 +566,7 @@ __global__ void __launch_bounds__(VDW_THREADS) vdw_kernel(FoldState s)
         }
     }
     flush(qn);
+    flush_hb(hn);
     // energy: fixed-shape reduction
     for (int o = 16; o > 0; o >>= 1) { e_thread += __shfl_down_sync(0xffffffffu, e_thread, o); e_hb += __shfl_down_sync(0xffffffffu, e_hb, o); }
     if (lane == 0) { ered[warp] = e_thread; ered[VDW_THREADS / 32 + warp] = e_hb; }
