@@ -55,12 +55,19 @@ def _ptr(arr, ctype):
 
 class Context:
     def __init__(self, device=0, stream=None):
+        import weakref
         self._h = C.c_void_p()
         check(lib().trx_ctx_create(C.c_int(device), C.c_void_p(stream or 0), C.byref(self._h)))
         self.device = device
+        self._children = weakref.WeakSet()   # tables, fold batches, dynamics states: they hold pointers into the context
+
+    def _adopt(self, child):
+        self._children.add(child)
 
     def close(self):
         if self._h:
+            for child in list(self._children):   # a handle that outlives its context would dangle (its destroy reads the context)
+                child.close()
             lib().trx_ctx_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -114,6 +121,7 @@ class Tables:
                 sets[t] = RstSet(0, None, None, 0, None, None)
         self._h = C.c_void_p()
         check(lib().trx_tables_create(ctx._h, C.c_int(L), sets, C.byref(self._h)))
+        ctx._adopt(self)
         self.counts = [int(s.n) for s in sets]
         self.K = [int(s.K) for s in sets]
         if dist_atom not in ("CA", "CB"):
@@ -212,6 +220,7 @@ class FoldBatch:
         self._h = C.c_void_p()
         check(lib().trx_fold_create(ctx._h, C.c_int(len(self.tabs)), arr_t, arr_n, _ptr(aa, C.c_int32), arr_r,
                                     C.c_int(len(runs)), C.c_int(lbfgs_m), C.byref(self._h)))
+        ctx._adopt(self)
 
     def close(self):
         if self._h:
@@ -333,6 +342,7 @@ class DynState:
         ptrs = [_ptr(a, C.c_float) for a in arrs] + [None] * (4 - len(arrs))
         self._h = C.c_void_p()
         check(lib().trx_dyn_create(ctx._h, C.c_int(self.L), *ptrs, C.byref(self._h)))
+        ctx._adopt(self)
 
     def close(self):
         if self._h:

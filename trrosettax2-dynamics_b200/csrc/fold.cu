@@ -322,6 +322,7 @@ __global__ void __launch_bounds__(VDW_THREADS) vdw_kernel(FoldState s)
     float4 *at = reinterpret_cast<float4 *>(smem_raw);                                   // [L][6]
     int *acc = reinterpret_cast<int *>(smem_raw + sizeof(float4) * 6 * L);               // [L][6][3]
     float4 *bsph = reinterpret_cast<float4 *>(smem_raw + sizeof(float4) * 6 * L + ((sizeof(int) * 18 * L + 15) / 16) * 16);   // [L] bounding spheres
+    float2 *hreach = reinterpret_cast<float2 *>(bsph + L);   // [L] |CA - N|, |CA - O|: how far a residue's donor / acceptor atom is from its CA
     __shared__ long long ered[2 * (VDW_THREADS / 32)];
     const float *__restrict__ xn = s.xnat + (size_t)n * L * NATP;
     for (int i = threadIdx.x; i < L; i += VDW_THREADS) {
@@ -345,6 +346,8 @@ __global__ void __launch_bounds__(VDW_THREADS) vdw_kernel(FoldState s)
             rb = fmaxf(rb, sqrtf((q.x - cx) * (q.x - cx) + (q.y - cy) * (q.y - cy) + (q.z - cz) * (q.z - cz)) + q.w);
         }
         bsph[i] = make_float4(cx, cy, cz, rb + 1e-3f);
+        hreach[i] = make_float2(sqrtf((v[0] - v[3]) * (v[0] - v[3]) + (v[1] - v[4]) * (v[1] - v[4]) + (v[2] - v[5]) * (v[2] - v[5])) + 1e-3f,
+                                sqrtf((v[12] - v[3]) * (v[12] - v[3]) + (v[13] - v[4]) * (v[13] - v[4]) + (v[14] - v[5]) * (v[14] - v[5])) + 1e-3f);
     }
     for (int e = threadIdx.x; e < L * 18; e += VDW_THREADS) acc[e] = 0;
     __syncthreads();
@@ -440,11 +443,14 @@ __global__ void __launch_bounds__(VDW_THREADS) vdw_kernel(FoldState s)
     };
     // a candidate pair (i, j) of this warp's row goes to the queue when its spheres are within reach now
     auto push = [&](bool close, bool touching, int i, int j) {
-        // a hydrogen bond between the two residues needs N...O < D0 + W, hence CA...CA < D0 + W + |CA-N| + |CA-O| (1.5 + 2.5 A)
+        // a hydrogen bond between the two residues needs N...O < D0 + W, hence CA...CA < D0 + W + |CA-N| + |CA-O| of the
+        // donor / acceptor (the residues' own distances, so the filter is exact for any geometry)
         bool hb = close && j - i >= TRX_HB_MINSEP;
         if (hb) {
             const float4 a = at[i * 6 + TRX_AT_CA], b = at[j * 6 + TRX_AT_CA];
-            const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z, reach = (float)(TRX_HB_D0 + TRX_HB_W) + 4.0f;
+            const float2 ri = hreach[i], rj = hreach[j];
+            const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+            const float reach = (float)(TRX_HB_D0 + TRX_HB_W) + fmaxf(ri.x + rj.y, rj.x + ri.y);
             hb = dx * dx + dy * dy + dz * dz < reach * reach;
         }
         const unsigned mh = __ballot_sync(0xffffffffu, hb);
@@ -2184,7 +2190,7 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     s.has_cart = b->has_cart ? 1 : 0;
     s.k1skip = 1;
     if (const char *ev = getenv("TRX_NO_K1SKIP")) s.k1skip = !(ev[0] && ev[0] != '0');   // A/B and tests: same results, bit for bit
-    b->vdw_smem = sizeof(float4) * 6 * L + ((sizeof(int) * 18 * L + 15) / 16) * 16 + sizeof(float4) * L;
+    b->vdw_smem = sizeof(float4) * 6 * L + ((sizeof(int) * 18 * L + 15) / 16) * 16 + sizeof(float4) * L + sizeof(float2) * L;
     TRX_REQUIRE(b->vdw_smem <= 220 * 1024, "trx_fold_create: L=%d exceeds the shared-memory budget of the vdw kernel", L);
     TRX_REQUIRE(L < 65536, "trx_fold_create: L too large");
     // one arena, carved into aligned pieces
