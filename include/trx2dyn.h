@@ -66,8 +66,10 @@ const char *trx_last_error(void);
 int trx_ctx_create(int device, void *stream, trx_ctx **out);
 int trx_ctx_destroy(trx_ctx *ctx);
 int trx_ctx_sync(trx_ctx *ctx);
-/* Per-kernel device timing (CUDA events on the context's stream around each launch).
- * name: "restraints", "reduce", "nerf", "centroid", "torsion_grad", "lbfgs". */
+/* Per-kernel device timing (CUDA events on the context's stream around each launch).  enabled: 0 off, 1 every kernel,
+ * 2 only the restraint kernel ("restraints") and the whole fold ("fold_device") -- two event records per launch are
+ * not free when a round is a dozen launches of a few microseconds.
+ * name: "restraints", "reduce", "nerf", "centroid", "torsion_grad", "lbfgs", "turnover", "fold_device", ... */
 int trx_ctx_set_timing(trx_ctx *ctx, int enabled);
 int trx_ctx_get_timing(trx_ctx *ctx, const char *name, double *total_ms, long long *launches);
 int trx_ctx_reset_timing(trx_ctx *ctx);

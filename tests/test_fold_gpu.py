@@ -200,7 +200,11 @@ def test_cartesian_stage_in_the_schedule(ctx):
     sub = half.run(t0[32:])
     np.testing.assert_array_equal(sub["tors"], held["tors"][32:])
     np.testing.assert_array_equal(sub["xyz"], held["xyz"][32:])
-    half.close(); batch.close(); tb.close()
+    half.close(); batch.close()
+    # a Cartesian segment starts from what the torsion-space segment before it parked: a schedule may not open with one
+    with pytest.raises(capi.TrxError, match="may not open with a Cartesian run"):
+        capi.FoldBatch(ctx, [tb], [32], aa, runs[8:])
+    tb.close()
 
 
 def test_decoy_distributions_match_the_oracle(ctx, example):
@@ -396,8 +400,7 @@ def test_pair_list_changes_nothing(ctx, monkeypatch):
     """The vdw / hydrogen-bond pair search keeps a Verlet list per position (partners within reach + a 2 A skin,
     rebuilt when a residue has used up half the skin).  Energies are summed as 64-bit and gradients as 32-bit
     fixed point, so an evaluation through the list is the same bits as one through the full scan: the whole fold
-    (two table blocks, Cartesian segment, Monte-Carlo cycles, migration) is bit-identical with and without the list
-    (opt-in, TRX_NBL=1: measured slower than the full scan)."""
+    (two table blocks, Cartesian segment, Monte-Carlo cycles, migration) is bit-identical with TRX_NO_NBL=1."""
     seq, npzs, nat = synth.target(56, seed=21, two_model=True)
     params = tables.load_params()
     tabs = [sampler.build_tables(ctx, z, seq, params) for z in npzs]
@@ -406,7 +409,7 @@ def test_pair_list_changes_nothing(ctx, monkeypatch):
     t0 = sampler.random_torsions(sum(nd), 56, seed=8)
     res = {}
     for flag in ("1", "0"):
-        monkeypatch.setenv("TRX_NBL", flag)
+        monkeypatch.setenv("TRX_NO_NBL", flag)
         batch = capi.FoldBatch(ctx, tabs, nd, aa, schedule.reference_schedule())
         res["fold" + flag] = batch.run(t0)
         batch.close()

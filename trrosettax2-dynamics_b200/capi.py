@@ -81,7 +81,8 @@ class Context:
         check(lib().trx_ctx_sync(self._h))
 
     def set_timing(self, on=True):
-        check(lib().trx_ctx_set_timing(self._h, C.c_int(1 if on else 0)))
+        """on: False / True (every kernel) / 2 (only the restraint kernel and the whole fold)."""
+        check(lib().trx_ctx_set_timing(self._h, C.c_int(int(on))))
 
     def reset_timing(self):
         check(lib().trx_ctx_reset_timing(self._h))

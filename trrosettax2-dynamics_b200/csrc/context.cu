@@ -74,10 +74,17 @@ int trx_ctx::get_scratch(const char *tag, size_t bytes, void **out)
     return TRX_OK;
 }
 
+// timing == 2: only the dominant kernel and the whole fold are bracketed with events (two event records per launch are
+// not free when a round is a dozen launches of a few microseconds each)
+static inline bool timed(int mode, const char *name)
+{
+    return mode == 1 || (mode == 2 && (!strcmp(name, "restraints") || !strcmp(name, "fold_device")));
+}
+
 void trx_ctx::time_begin(const char *name)
 {
     ++launches;
-    if (!timing) return;
+    if (!timed(timing, name)) return;
     cudaEvent_t a, b;
     cudaEventCreate(&a);
     cudaEventCreate(&b);
@@ -87,7 +94,7 @@ void trx_ctx::time_begin(const char *name)
 
 void trx_ctx::time_end(const char *name)
 {
-    if (!timing) return;
+    if (!timed(timing, name)) return;
     auto &t = timers[name];
     cudaEventRecord(t.pending.back().second, stream);
 }
@@ -163,7 +170,7 @@ int trx_ctx_sync(trx_ctx *ctx)
 int trx_ctx_set_timing(trx_ctx *ctx, int enabled)
 {
     TRX_REQUIRE(ctx, "trx_ctx_set_timing: ctx is NULL");
-    ctx->timing = enabled != 0;
+    ctx->timing = enabled < 0 ? 0 : (enabled > 2 ? 1 : enabled);
     return TRX_OK;
 }
 

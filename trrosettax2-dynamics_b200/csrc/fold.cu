@@ -1711,17 +1711,6 @@ __global__ void __launch_bounds__(RING_THREADS, 2) lbfgs_update_ring_kernel(Fold
     }
 }
 
-// group activity + number of unfinished decoys
-__global__ void activity_kernel(FoldState s)
-{
-    const int g = blockIdx.x * blockDim.y + threadIdx.y, lane = threadIdx.x;
-    if (g >= s.G) return;
-    const int n = g * LANES + lane;
-    const bool active = n < s.N && s.status[n] != ST_DONE;
-    const unsigned m = __ballot_sync(0xffffffffu, active);
-    if (lane == 0) s.gactive[g] = m != 0;
-}
-
 // Slot assignment: the unfinished decoys of table block t fill the slots from the start of the
 // block (one CTA per block, chunked block-wide exclusive scans): first, in decoy order, those
 // whose run in force scores the restraints, then those whose run does not (the vdw-only runs of
@@ -1742,6 +1731,10 @@ __global__ void __launch_bounds__(1024) compact_kernel(FoldState s, int identity
         for (int c0 = 0; c0 < span; c0 += 1024) {
             const int i = c0 + threadIdx.x;
             bool pick = false;
+            if (pass == 0) {   // which position groups the L-BFGS kernels stream (a warp of this scan is one position group)
+                const unsigned ma = __ballot_sync(0xffffffffu, i < nt && s.status[d0 + i] != ST_DONE);
+                if (lane == 0 && i < span) s.gactive[(d0 + i) / LANES] = ma != 0;
+            }
             if (i < nt) {
                 const int n = d0 + i;
                 if (identity) pick = true;
@@ -1863,16 +1856,25 @@ __global__ void __launch_bounds__(1024) turnover_plan_kernel(FoldState s)
     }
 }
 
-// Turnover, step 2 (one CTA per position that changes hands).  PARK: the decoy's record goes back to the
+__device__ void turnover_move_one(const FoldState &s, const int pos);
+
+// Turnover, step 2 (one CTA per position group; a position that changes hands is handled by the whole CTA).  PARK: the decoy's record goes back to the
 // queue store -- torsions (read back from the coordinates after a Cartesian segment), the coordinates it
 // holds or that the next (Cartesian) segment starts from, the terms of its closing evaluation, counters --
 // and, when it has left the LAST segment, its results go to the output arrays in the caller's order.
 // LOAD: the next waiting decoy starts the segment from its record.
 __global__ void __launch_bounds__(128) turnover_move_kernel(FoldState s)
 {
-    const int pos = blockIdx.x;
+    // one CTA per position group: in most rounds none of its 32 positions changes hands
+    const int nid_mine = s.newid[blockIdx.x * LANES + (threadIdx.x & 31)];
+    if (!__syncthreads_or(nid_mine != -2)) return;
+    for (int lanepos = 0; lanepos < LANES; ++lanepos) turnover_move_one(s, blockIdx.x * LANES + lanepos);
+}
+
+__device__ void turnover_move_one(const FoldState &s, const int pos)
+{
     const int nid = s.newid[pos];
-    if (nid == -2) return;
+    if (nid == -2) return;   // uniform over the CTA
     const int L = s.L, Npad = s.Npad, Nqpad = s.Nqpad;
     const int old = s.orig[pos];
     const size_t vb = (size_t)(pos / LANES) * s.ndof * LANES + pos % LANES;
@@ -2175,6 +2177,8 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
         else b->segs.back().hi = r + 1;
         b->has_cart = b->has_cart || runs[r].cartesian;
     }
+    // a Cartesian segment starts from the coordinates the torsion-space segment before it parked
+    TRX_REQUIRE(!runs[0].cartesian, "trx_fold_create: the schedule may not open with a Cartesian run (put a torsion-space run with max_iter 0 in front)");
     for (int r = 0; r < nruns; ++r)   // a clash check may not jump over a Cartesian run
         if (runs[r].clash_check)
             for (int q = r + 1; q < runs[r].skip_to; ++q)
@@ -2372,19 +2376,15 @@ static int run_rounds(trx_fold_batch *b, int max_rounds, int check_every, int *r
     std::vector<int> ng(b->tab_ng);   // live slot groups per table block: an upper bound between polls
     std::vector<int> cap(s.ntab);     // positions of each block its unfinished decoys are spread over (all, until a migration)
     for (int t = 0; t < s.ntab; ++t) cap[t] = s.tab_n[t];
-    dim3 ablk(32, 8), agrd((s.G + 7) / 8);
     while (busy && *rounds_io + rounds < max_rounds) {
         for (int k = 0; k < check_every && *rounds_io + rounds < max_rounds; ++k, ++rounds) {
             ctx->time_begin("turnover");
             turnover_plan_kernel<<<s.ntab, 1024, 0, ctx->stream>>>(s);
             ctx->time_end("turnover");
             ctx->time_begin("turnover");
-            turnover_move_kernel<<<s.Npad, 128, 0, ctx->stream>>>(s);
+            turnover_move_kernel<<<s.G, 128, 0, ctx->stream>>>(s);
             ctx->time_end("turnover");
-            ctx->time_begin("activity");
-            activity_kernel<<<agrd, ablk, 0, ctx->stream>>>(s);
-            ctx->time_end("activity");
-            if ((rc = fold_eval(b, ng.data(), false))) return rc;
+            if ((rc = fold_eval(b, ng.data(), false))) return rc;   // (compact_kernel also flags the position groups that are live)
             ctx->time_begin("lbfgs");
             {   // enough CTAs for ~3 per SM, at least 4 vector elements per warp and chunk
                 int nch = std::max(1, (3 * 148 + s.G - 1) / s.G);   // CTAs that share a group's LB_MAXCH chunks

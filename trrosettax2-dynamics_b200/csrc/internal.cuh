@@ -56,7 +56,7 @@ struct trx_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool owns_stream = false;
-    bool timing = false;
+    int timing = 0;              // 0 off, 1 every kernel, 2 only the restraint kernel and the whole fold
     long long launches = 0;
     std::map<std::string, trx::KernelTimer> timers;
     // scratch device buffers reused across calls, keyed by a tag
