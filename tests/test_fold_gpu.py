@@ -203,7 +203,7 @@ def test_cartesian_stage_in_the_schedule(ctx):
     half.close(); batch.close()
     # a Cartesian segment starts from what the torsion-space segment before it parked: a schedule may not open with one
     with pytest.raises(capi.TrxError, match="may not open with a Cartesian run"):
-        capi.FoldBatch(ctx, [tb], [32], aa, runs[8:])
+        capi.FoldBatch(ctx, [tb], [32], aa, [runs[8]])
     tb.close()
 
 

@@ -5,13 +5,17 @@ import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-runs = [("r2_bench_default", "python bench.py  (default: configs[2], 16384 decoys per step through 4096 resident positions)"),
+runs = [("r2_bench_default", "python bench.py --decoys 32768  (configs[2], 32768 decoys per step through 4096 resident positions; the default is 24576)"),
+        ("r2_bench_default24k", "python bench.py  (default: configs[2], 24576 decoys per step through 4096 resident positions)"),
+        ("r2_bench_65536", "python bench.py --decoys 65536 --steps 1 --warmup 1  (queue of 16 resident batches)"),
+        ("r2_bench_s2", "python bench.py --streams 2 --steps 1 --warmup 1  (two fold lanes on two streams)"),
         ("r2_bench_4096", "python bench.py --decoys 4096 --resident 4096  (configs[2], one resident batch: no refill)"),
         ("r2_bench_reference", "python bench.py --impl reference"),
+        ("r2_bench_512", "python bench.py --decoys 512 --resident 512  (configs[2], the per-GPU share of the strong-scaling run at 8 GPUs)"),
         ("r2_bench_c1", "python bench.py --config 1  (configs[1]: L=150 distance-only, 256 decoys)"),
         ("r2_bench_c3", "python bench.py --config 3  (configs[3]: L=800, 2048 decoys, 4 MC cycles, 1 GPU)"),
         ("r2_bench_c4", "python bench.py --config 4 --streams 8  (configs[4]: 64 targets x 100 decoys, 1 GPU)"),
-        ("r2_8gpu_c2_weak", "torchrun x8 bench.py --gpus 8  (configs[2], weak: 16384 decoys per GPU and step)"),
+        ("r2_8gpu_c2_weak", "torchrun x8 bench.py --gpus 8 --decoys 16384  (configs[2], weak: 16384 decoys per GPU and step; the build before the default became 32768)"),
         ("r2_8gpu_c2_strong", "torchrun x8 bench.py --gpus 8 --scaling strong --decoys 4096  (configs[2] as written: 4096 decoys sharded over 8 GPUs)"),
         ("r2_4gpu_c2_strong", "torchrun x4 ... --scaling strong --decoys 4096"),
         ("r2_2gpu_c2_strong", "torchrun x2 ... --scaling strong --decoys 4096"),
