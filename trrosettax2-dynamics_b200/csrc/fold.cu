@@ -14,10 +14,12 @@
 // (include/trx_centroid_model.h).
 //
 // The schedule is cut into segments of torsion-space runs and Cartesian runs
-// (min_mover_cart, folding.py:100-102,170).  Within a segment the decoys run free; a
-// segment boundary is a batch-wide barrier at which the degrees of freedom change
-// (torsions -> coordinates by NeRF, coordinates -> torsions by reading the dihedrals back).
-// The same L-BFGS kernel serves both: it only sees a vector of ndof floats per decoy.
+// (min_mover_cart, folding.py:100-102,170); a segment changes the degrees of freedom
+// (torsions -> coordinates by NeRF, coordinates -> torsions by reading the dihedrals back),
+// and the same L-BFGS kernels serve both: they only see a vector of ndof floats per decoy.
+// A call folds any number of decoys through the batch's resident positions (continuous
+// batching): within a segment a position whose decoy has left it is parked into a queue
+// store and refilled in the same round; the queue is walked segment by segment.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -118,7 +120,6 @@ struct FoldState {
     unsigned short *nbl_j;   // [Npad][L][NBL_W] partners j > i of residue i, ascending
     unsigned short *nbl_cnt; // [Npad][L]
     int *gactive;            // [G] decoy group has an unfinished decoy (L-BFGS kernel)
-    int *nactive;            // [1]
     // slot space: the unfinished decoys of each table block, compacted to the front of the
     // block every round, so the evaluation kernels only touch live lanes
     int *perm;               // [Npad] slot -> position, -1 for an empty slot
@@ -542,24 +543,30 @@ __global__ void __launch_bounds__(VDW_THREADS) vdw_kernel(FoldState s)
         for (int i = warp; i < L - TRX_VDW_MINSEP; i += VDW_THREADS / 32) {
             const float4 ci = bsph[i];
             int cnt = 0;
-            for (int j0 = i + TRX_VDW_MINSEP; j0 < L; j0 += 32) {
-                const int j = j0 + lane;
-                bool close = false, inl = false, tch = false;
-                if (j < L) {
-                    float cut;
-                    const float4 cj = bsph[j];
-                    const float d2 = gap2(ci, cj, 0.f, cut);
-                    close = d2 < cut * cut;
-                    tch = touch(ci, cj, d2);
-                    inl = d2 < (cut + NBL_SKIN) * (cut + NBL_SKIN);
-                }
+            // One candidate j per lane and half-step, two half-steps per iteration; most iterations find nothing in
+            // reach, so the common path is two sphere tests and ONE vote.
+            auto handle = [&](int j, const float4 cj, float d2, float cut) {
+                const bool close = d2 < cut * cut, tch = touch(ci, cj, d2);
                 if (lj) {
+                    const bool inl = d2 < (cut + NBL_SKIN) * (cut + NBL_SKIN);
                     const unsigned ml = __ballot_sync(0xffffffffu, inl);
                     const int at_ = cnt + __popc(ml & ((1u << lane) - 1));
                     if (inl && at_ < NBL_W) lj[(size_t)i * NBL_W + at_] = (unsigned short)j;
                     cnt += __popc(ml);
                 }
                 push(close, tch, i, j);
+            };
+            const float extra = lj ? NBL_SKIN : 0.f;
+            for (int j0 = i + TRX_VDW_MINSEP; j0 < L; j0 += 64) {
+                const int ja = j0 + lane, jb = ja + 32;
+                float4 cja = ci, cjb = ci;
+                float d2a = 1e30f, d2b = 1e30f, cuta = 0.f, cutb = 0.f;
+                if (ja < L) { cja = bsph[ja]; d2a = gap2(ci, cja, 0.f, cuta); }
+                if (jb < L) { cjb = bsph[jb]; d2b = gap2(ci, cjb, 0.f, cutb); }
+                const bool hit = d2a < (cuta + extra) * (cuta + extra) || d2b < (cutb + extra) * (cutb + extra);
+                if (!__any_sync(0xffffffffu, hit)) continue;
+                handle(ja, cja, d2a, cuta);
+                handle(jb, cjb, d2b, cutb);
             }
             if (lj) {
                 if (cnt > NBL_W) overflow = 1;
@@ -2242,7 +2249,7 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     s.evals = (int *)(A + o_i[8]); s.iters = (int *)(A + o_i[9]);
     s.terms = (double *)(A + o_terms); s.ft = (double *)(A + o_ft); s.wl = (float *)(A + o_wl);
     s.X = (float *)(A + o_X); s.xnat = (float *)(A + o_xn); s.gnat = (float *)(A + o_gn); s.gk1 = (float *)(A + o_gk);
-    s.E3 = (double *)(A + o_E3); s.Evdw = (double *)(A + o_Ev); s.gactive = (int *)(A + o_ga); s.nactive = (int *)(A + o_na);
+    s.E3 = (double *)(A + o_E3); s.Evdw = (double *)(A + o_Ev); s.gactive = (int *)(A + o_ga);
     s.xsave = (float *)(A + o_xs); s.fsave = (double *)(A + o_fs); s.naccept = (int *)(A + o_nacc);
     s.perm = (int *)(A + o_perm); s.gslot = (int *)(A + o_gs); s.nslot = (int *)(A + o_ns); s.wslot = (float *)(A + o_ws);
     s.gneedk1 = (int *)(A + o_gk1f);
