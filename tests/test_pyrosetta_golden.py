@@ -47,6 +47,33 @@ def test_kit_is_present_and_self_contained():
     assert "import pyrosetta" in src and "/root/reference" not in src.replace("/path/to/reference", "")
 
 
+def test_kit_writes_the_references_restraint_files(tmp_path):
+    """What the kit feeds PyRosetta is what the reference feeds it: constraint lines and spline files byte-identical to
+    a run of the reference's own gen_rst on the example npz (hashes in tests/golden/gen_rst_example_NMR.npz)."""
+    import hashlib
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("pyrosetta_golden", os.path.join(os.path.dirname(GOLD), "..", "tools", "pyrosetta_golden.py"))
+    kit = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(kit)                      # importing the kit does not import pyrosetta (only main() does)
+    g = np.load(os.path.join(GOLD, "gen_rst_example_NMR.npz"))
+    rst, _ = _sets()
+    every = {name: np.ones(len(rst[name]["a"]), dtype=bool) for name in rst}
+    cst, n = kit.write_restraints(rst, every, str(tmp_path))
+    lines = open(cst).read().splitlines()
+    assert n == len(lines) == sum(len(rst[k]["a"]) for k in rst)
+    pos = 0
+    for name in ("dist", "omega", "theta", "phi"):
+        cnt = len(rst[name]["a"])
+        hl, ht = hashlib.sha256(), hashlib.sha256()
+        for ln in lines[pos:pos + cnt]:
+            hl.update(ln.replace(str(tmp_path), "TMP").encode())
+            path = [tok for tok in ln.split() if tok.startswith(str(tmp_path))][0]
+            ht.update(open(path).read().encode())
+        assert hl.hexdigest() == str(g[f"{name}_lines_sha256"]), name
+        assert ht.hexdigest() == str(g[f"{name}_sha256"]), name
+        pos += cnt
+
+
 @needs_vectors
 def test_oracle_matches_pyrosetta_and_settles_the_end_knot_rule():
     rst, sel = _sets()

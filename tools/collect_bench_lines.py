@@ -25,18 +25,17 @@ out = ["# Round 2 bench lines (B200, gpurun; one JSON line per run, copied verba
        "| run | command | value | e2e | ms/step | steps | roofline.frac (K1) | notes |", "|---|---|---|---|---|---|---|---|"]
 for tag, cmd in runs:
     p = os.path.join(ROOT, "gpurun_out", tag + ".log")
-    if not os.path.exists(p):
-        continue
+    kept = os.path.join(ROOT, "profiles", "r2_line_%s.json" % tag.replace("r2_", ""))
     line = None
-    for ln in open(p):
-        ln = ln.strip()
-        if ln.startswith("{") and '"metric"' in ln:
-            line = ln
-    if line is None:
-        out.append("| %s | `%s` | no JSON line (see gpurun_out) | | | | | |" % (tag, cmd))
+    if os.path.exists(p):
+        for ln in open(p):
+            ln = ln.strip()
+            if ln.startswith("{") and '"metric"' in ln:
+                line = ln
+    if line is None and not os.path.exists(kept):
         continue
-    d = json.loads(line)
-    json.dump(d, open(os.path.join(ROOT, "profiles", "r2_line_%s.json" % tag.replace("r2_", "")), "w"), indent=1)
+    d = json.loads(line) if line else json.load(open(kept))   # a line whose log is gone stays as committed
+    json.dump(d, open(kept, "w"), indent=1)
     rf = d.get("roofline") or {}
     notes = []
     if "mean_evals_per_decoy" in d:

@@ -37,9 +37,25 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+_SUFFIX = {"dist": "", "omega": "_omega", "theta": "_theta", "phi": "_phi"}
+
+
+def constraint_line(name, a, b, path):
+    """The line gen_rst builds for one record (utils_ros.py:73,95,114,138), 1-based residue numbers."""
+    if name == "dist":
+        return "AtomPair %s %d %s %d SPLINE TAG %s 1.0 %.3f %.5f" % ("CB", a, "CB", b, path, 1.0, 0.5)
+    if name == "omega":
+        return "Dihedral CA %d CB %d CB %d CA %d SPLINE TAG %s 1.0 %.3f %.5f" % (a, a, b, b, path, 1.0, np.deg2rad(15.0))
+    if name == "theta":
+        return "Dihedral N %d CA %d CB %d CB %d SPLINE TAG %s 1.0 %.3f %.5f" % (a, a, a, b, path, 1.0, np.deg2rad(15.0))
+    return "Angle CA %d CB %d CB %d SPLINE TAG %s 1.0 %.3f %.5f" % (a, a, b, path, 1.0, np.deg2rad(15.0))
+
+
 def write_restraints(rst, masks, tmpdir):
-    """The reference's on-disk form of the selected restraints (utils_ros.py:62-75,88-97,108-119,132-144 and
-    add_rst :731-735): one two-line spline file per restraint and one constraint line each."""
+    """The reference's on-disk form of the selected restraints: one two-line spline file per restraint
+    (utils_ros.py:62-72,88-94,108-113,132-137: 'x_axis ...' / 'y_axis ...', named a.b.txt, a.b_omega.txt, ...) and one
+    constraint line each in minimize.cst (add_rst, utils_ros.py:731-735).  Files and lines are byte-identical to what
+    the reference writes (tests/test_pyrosetta_golden.py checks both against hashes of a reference run)."""
     from oracle.tables_oracle import text_lines
     lines = []
     for name in ("dist", "omega", "theta", "phi"):
@@ -47,18 +63,11 @@ def write_restraints(rst, masks, tmpdir):
             continue
         rec = rst[name]
         for k in np.nonzero(masks[name])[0]:
-            a, b = int(rec["a"][k]), int(rec["b"][k])
-            path = os.path.join(tmpdir, "%s.%d.%d.txt" % (name, a + 1, b + 1))
+            a, b = int(rec["a"][k]) + 1, int(rec["b"][k]) + 1
+            path = os.path.join(tmpdir, "%d.%d%s.txt" % (a, b, _SUFFIX[name]))
             with open(path, "w") as fh:
                 fh.writelines(text_lines(rec, k))
-            if name == "dist":
-                lines.append("AtomPair %s %d %s %d SPLINE TAG %s 1.0 %.3f %.5f\n" % ("CB", a + 1, "CB", b + 1, path, 1.0, 0.5))
-            elif name == "omega":
-                lines.append("Dihedral CA %d CB %d CB %d CA %d SPLINE TAG %s 1.0 %.3f %.5f\n" % (a + 1, a + 1, b + 1, b + 1, path, 1.0, np.deg2rad(15.0)))
-            elif name == "theta":
-                lines.append("Dihedral N %d CA %d CB %d CB %d SPLINE TAG %s 1.0 %.3f %.5f\n" % (a + 1, a + 1, a + 1, b + 1, path, 1.0, np.deg2rad(15.0)))
-            else:
-                lines.append("Angle CA %d CB %d CB %d SPLINE TAG %s 1.0 %.3f %.5f\n" % (a + 1, a + 1, b + 1, path, 1.0, np.deg2rad(15.0)))
+            lines.append(constraint_line(name, a, b, path) + "\n")
     cst = os.path.join(tmpdir, "minimize.cst")
     with open(cst, "w") as fh:
         fh.writelines(lines)
