@@ -64,6 +64,10 @@ const char *trx_last_error(void);
 /* device: CUDA ordinal.  stream: a cudaStream_t (e.g. torch's current stream) or NULL
  * for a stream the context creates and owns. */
 int trx_ctx_create(int device, void *stream, trx_ctx **out);
+/* Tables, fold batches and dynamics states keep their context alive: the context is released with the last of them,
+ * whichever order the caller (or its garbage collector) destroys them in; the handle itself is dead after this call.
+ * Device blocks of destroyed tables / batches stay with the context for the next create (a dynamics loop rebuilds
+ * both every iteration) and go back to the driver with the context. */
 int trx_ctx_destroy(trx_ctx *ctx);
 int trx_ctx_sync(trx_ctx *ctx);
 /* Per-kernel device timing (CUDA events on the context's stream around each launch).  enabled: 0 off, 1 every kernel,

@@ -473,3 +473,63 @@ def test_dynamics_pipeline_on_example(tmp_path, golden_dir, example, ctx):
         tms.append((metrics.tm_score(at["CA"], nat["apo"]), metrics.tm_score(at["CA"], nat["holo"])))
     tms = np.array(tms)
     assert tms.max(axis=0).min() > 0.5, tms
+
+
+def test_recycled_device_blocks_change_nothing(example):
+    """Tables, fold batches and their scratch come from the context's block pool (csrc/context.cu): a dynamics loop
+    rebuilds them every iteration.  A fold on recycled blocks -- of a DIFFERENT, larger earlier owner -- returns the
+    same bits as the same fold on a fresh context."""
+    seq, npzs, _ = example
+    L = len(seq)
+    params = tables.load_params()
+    runs = schedule.reference_schedule()
+    tors = sampler.random_torsions(24, L, seed=11)
+
+    def fold(c, npz, n):
+        tb = sampler.build_tables(c, npz, seq, params)
+        batch = capi.FoldBatch(c, [tb], [n], sampler.aa_index(seq), runs)
+        out = batch.run(tors[:n])
+        batch.close()
+        tb.close()
+        return out
+
+    fresh = capi.Context(0)
+    ref = fold(fresh, npzs[0], 24)
+    fresh.close()
+    c = capi.Context(0)
+    fold(c, npzs[1], 24)          # other restraints, same sizes: its blocks are what the next fold gets
+    again = fold(c, npzs[0], 24)
+    small = fold(c, npzs[0], 7)   # smaller request served from larger released blocks
+    c.close()
+    for k in ("tors", "xyz", "terms", "evals"):
+        assert np.array_equal(ref[k], again[k]), k
+        assert np.array_equal(ref[k][:7], small[k]), k
+
+
+def test_context_may_be_destroyed_before_its_children(golden_dir):
+    """A garbage collector picks its own order (Python at interpreter exit destroys the context first): tables, fold
+    batches and dynamics states hold a reference on their context (csrc/context.cu: ctx_release), so either order works.
+    Run in a child process: the failure mode is a crash."""
+    import subprocess
+    import sys
+    code = f"""
+import numpy as np, ctypes as C
+import trx2dyn
+from trx2dyn import capi, sampler, schedule, tables
+seq = open(r"{golden_dir}/example_seq.fasta").read().split("\\n")[1]
+npz = dict(np.load(r"{golden_dir}/example_NMR.npz"))
+ctx = capi.Context(0)
+tb = sampler.build_tables(ctx, npz, seq, tables.load_params())
+batch = capi.FoldBatch(ctx, [tb], [4], sampler.aa_index(seq), schedule.reference_schedule())
+state = capi.DynState(ctx, npz)
+out = batch.run(sampler.random_torsions(4, len(seq), 0))
+capi.lib().trx_ctx_destroy(ctx._h); ctx._h = C.c_void_p()      # the context handle goes first
+batch.close(); state.close(); tb.close()                        # ... and its children after it
+ctx2 = capi.Context(0)                                           # and: nothing closed at all, left to interpreter exit
+tb2 = sampler.build_tables(ctx2, npz, seq, tables.load_params())
+state2 = capi.DynState(ctx2, npz)
+print("ok", float(out["terms"].sum()))
+"""
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.returncode, r.stdout[-2000:], r.stderr[-2000:])
+    assert r.stdout.strip().startswith("ok")

@@ -1,4 +1,5 @@
 // Context, error reporting, per-kernel timing and the natural <-> grouped layout kernels.
+#include <algorithm>
 #include <cstdarg>
 #include <cstring>
 
@@ -50,6 +51,103 @@ __global__ void from_grouped_kernel(int N, int L, int Lpad, int A3, const T *__r
 }
 
 }  // namespace trx
+
+namespace trx {
+void ctx_release(trx_ctx *ctx)
+{
+    if (ctx->refs.fetch_sub(1) != 1) return;   // tables / fold batches / dynamics states of this context are still alive
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->collect_timers();
+    for (auto &kv : ctx->scratch)
+        if (kv.second.first) cudaFree(kv.second.first);
+    ctx->pool_trim();
+    for (void *h : ctx->pinned_free) cudaFreeHost(h);
+    if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+}  // namespace trx
+
+// ---- the per-context block pool (see internal.cuh)
+static constexpr size_t POOL_BLOCK_MAX = (size_t)512 << 20;   // larger blocks go straight back to the driver
+static constexpr size_t POOL_TOTAL_MAX = (size_t)4 << 30;
+
+cudaError_t trx_ctx::dev_alloc_bytes(void **p, size_t bytes)
+{
+    size_t want = (std::max<size_t>(bytes, 1) + 511) & ~(size_t)511;
+    {
+        std::lock_guard<std::mutex> lk(pool_mu);
+        auto it = pool_free.lower_bound(want);
+        if (it != pool_free.end() && it->first <= 2 * want + (64 << 10)) {
+            *p = it->second;
+            pool_bytes -= it->first;
+            pool_cap[*p] = it->first;
+            pool_free.erase(it);
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMalloc(p, want);
+    if (e != cudaSuccess) {   // give the pooled blocks back and try once more
+        (void)cudaGetLastError();
+        pool_trim();
+        e = cudaMalloc(p, want);
+    }
+    if (e != cudaSuccess) {
+        *p = nullptr;
+        return e;
+    }
+    std::lock_guard<std::mutex> lk(pool_mu);
+    pool_cap[*p] = want;
+    return cudaSuccess;
+}
+
+void trx_ctx::dev_free(void *p)
+{
+    if (!p) return;
+    size_t cap = 0;
+    {
+        std::lock_guard<std::mutex> lk(pool_mu);
+        auto it = pool_cap.find(p);
+        if (it != pool_cap.end()) {
+            cap = it->second;
+            pool_cap.erase(it);
+            if (cap <= POOL_BLOCK_MAX && pool_bytes + cap <= POOL_TOTAL_MAX) {
+                pool_free.emplace(cap, p);
+                pool_bytes += cap;
+                return;
+            }
+        }
+    }
+    cudaFree(p);
+}
+
+void trx_ctx::pool_trim()
+{
+    std::lock_guard<std::mutex> lk(pool_mu);
+    for (auto &kv : pool_free) cudaFree(kv.second);
+    pool_free.clear();
+    pool_bytes = 0;
+}
+
+cudaError_t trx_ctx::pinned_alloc(void **p)
+{
+    {
+        std::lock_guard<std::mutex> lk(pool_mu);
+        if (!pinned_free.empty()) {
+            *p = pinned_free.back();
+            pinned_free.pop_back();
+            return cudaSuccess;
+        }
+    }
+    return cudaMallocHost(p, PINNED_BLOCK);
+}
+
+void trx_ctx::pinned_release(void *p)
+{
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(pool_mu);
+    pinned_free.push_back(p);
+}
 
 int trx_ctx::get_scratch(const char *tag, size_t bytes, void **out)
 {
@@ -150,13 +248,7 @@ int trx_ctx_create(int device, void *stream, trx_ctx **out)
 int trx_ctx_destroy(trx_ctx *ctx)
 {
     if (!ctx) return TRX_OK;
-    cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
-    ctx->collect_timers();
-    for (auto &kv : ctx->scratch)
-        if (kv.second.first) cudaFree(kv.second.first);
-    if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
-    delete ctx;
+    trx::ctx_release(ctx);
     return TRX_OK;
 }
 

@@ -191,15 +191,17 @@ int trx_dyn_destroy(trx_dyn *d)
     if (!d) return TRX_OK;
     cudaSetDevice(d->ctx->device);
     cudaStreamSynchronize(d->ctx->stream);
-    for (int t = 0; t < 4; ++t) if (d->map[t]) cudaFree(d->map[t]);
-    if (d->tmp) cudaFree(d->tmp);
-    if (d->scratch) cudaFree(d->scratch);
-    if (d->bins) cudaFree(d->bins);
-    if (d->xyz) cudaFree(d->xyz);
-    if (d->use_cb) cudaFree(d->use_cb);
-    if (d->w) cudaFree(d->w);
-    if (d->maxchg) cudaFree(d->maxchg);
+    for (int t = 0; t < 4; ++t) d->ctx->dev_free(d->map[t]);
+    d->ctx->dev_free(d->tmp);
+    d->ctx->dev_free(d->scratch);
+    d->ctx->dev_free(d->bins);
+    d->ctx->dev_free(d->xyz);
+    d->ctx->dev_free(d->use_cb);
+    d->ctx->dev_free(d->w);
+    d->ctx->dev_free(d->maxchg);
+    trx_ctx *ctx = d->ctx;
     delete d;
+    ctx_release(ctx);
     return TRX_OK;
 }
 
@@ -210,23 +212,24 @@ int trx_dyn_create(trx_ctx *ctx, int L, const float *dist, const float *omega, c
     TRX_CUDA(cudaSetDevice(ctx->device));
     trx_dyn *d = new trx_dyn();
     d->ctx = ctx; d->L = L; d->angle = omega ? 1 : 0;
+    ctx->retain();   // given back by trx_dyn_destroy (the failure path below goes through it too)
     const size_t np = (size_t)L * L;
     const int nb[4] = {NB_D, NB_A, NB_A, NB_P};
     const float *src[4] = {dist, omega, theta, phi};
     cudaError_t e = cudaSuccess;
     for (int t = 0; t < 4 && e == cudaSuccess; ++t)
         if (src[t]) {
-            e = cudaMalloc(&d->map[t], np * nb[t] * sizeof(float));
+            e = ctx->dev_alloc(&d->map[t], np * nb[t] * sizeof(float));
             if (e == cudaSuccess) e = cudaMemcpyAsync(d->map[t], src[t], np * nb[t] * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
         }
-    if (e == cudaSuccess) e = cudaMalloc(&d->tmp, np * NB_D * sizeof(float));
+    if (e == cudaSuccess) e = ctx->dev_alloc(&d->tmp, np * NB_D * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpyAsync(d->tmp, dist, np * NB_D * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);   // 'tmp' starts as dist (run_inference.py:116-133)
-    if (e == cudaSuccess) e = cudaMalloc(&d->scratch, np * NB_MAX * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(&d->bins, 4 * np * sizeof(int));
-    if (e == cudaSuccess) e = cudaMalloc(&d->xyz, (size_t)5 * L * 3 * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&d->use_cb, L);
-    if (e == cudaSuccess) e = cudaMalloc(&d->w, 9 * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&d->maxchg, sizeof(unsigned int));
+    if (e == cudaSuccess) e = ctx->dev_alloc(&d->scratch, np * NB_MAX * sizeof(float));
+    if (e == cudaSuccess) e = ctx->dev_alloc(&d->bins, 4 * np * sizeof(int));
+    if (e == cudaSuccess) e = ctx->dev_alloc(&d->xyz, (size_t)5 * L * 3 * sizeof(double));
+    if (e == cudaSuccess) e = ctx->dev_alloc(&d->use_cb, L);
+    if (e == cudaSuccess) e = ctx->dev_alloc(&d->w, 9 * sizeof(double));
+    if (e == cudaSuccess) e = ctx->dev_alloc(&d->maxchg, sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
         set_error("trx_dyn_create: %s", cudaGetErrorString(e));

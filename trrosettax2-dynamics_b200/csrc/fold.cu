@@ -2133,11 +2133,13 @@ int trx_fold_destroy(trx_fold_batch *b)
     if (!b) return TRX_OK;
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
-    if (b->arena) cudaFree(b->arena);
-    if (b->d_aa) cudaFree(b->d_aa);
-    if (b->d_runs) cudaFree(b->d_runs);
-    if (b->h_poll) cudaFreeHost(b->h_poll);
+    b->ctx->dev_free(b->arena);
+    b->ctx->dev_free(b->d_aa);
+    b->ctx->dev_free(b->d_runs);
+    b->ctx->pinned_release(b->h_poll);
+    trx_ctx *ctx = b->ctx;
     delete b;
+    ctx_release(ctx);
     return TRX_OK;
 }
 
@@ -2157,10 +2159,12 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
         ~Guard()
         {
             if (!b) return;
-            if (b->arena) cudaFree(b->arena);
-            if (b->d_aa) cudaFree(b->d_aa);
-            if (b->d_runs) cudaFree(b->d_runs);
-            if (b->h_poll) cudaFreeHost(b->h_poll);
+            if (!b->ctx) { delete b; return; }
+            cudaStreamSynchronize(b->ctx->stream);
+            b->ctx->dev_free(b->arena);
+            b->ctx->dev_free(b->d_aa);
+            b->ctx->dev_free(b->d_runs);
+            b->ctx->pinned_release(b->h_poll);
             delete b;
         }
     } guard{b};
@@ -2231,7 +2235,7 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     // L=800), so it is opt-in (TRX_NBL=1); results are the same bits either way.
     const bool nbl = getenv("TRX_NBL") && getenv("TRX_NBL")[0] && getenv("TRX_NBL")[0] != '0';
     size_t o_nok = carve(np * 4), o_nref = carve(nbl ? np * L * sizeof(float4) : 256), o_nj = carve(nbl ? np * L * NBL_W * 2 : 256), o_nc = carve(nbl ? np * L * 2 : 256);
-    cudaError_t e = cudaMalloc(&b->arena, off);
+    cudaError_t e = ctx->dev_alloc(&b->arena, off);
     if (e != cudaSuccess) {
         set_error("trx_fold_create: cudaMalloc(%zu bytes) failed: %s", off, cudaGetErrorString(e));
         b->arena = nullptr;
@@ -2260,19 +2264,20 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     s.flags = (int *)(A + o_flg); s.Ehb = (double *)(A + o_Eh);
     s.nbl_ok = (int *)(A + o_nok); s.nbl_ref = (float4 *)(A + o_nref); s.nbl_j = nbl ? (unsigned short *)(A + o_nj) : nullptr; s.nbl_cnt = (unsigned short *)(A + o_nc);
     s.mc = McOpts{};
-    TRX_CUDA(cudaMallocHost(&b->h_poll, 64 * sizeof(int)));
+    static_assert(64 * sizeof(int) <= trx_ctx::PINNED_BLOCK, "h_poll");
+    TRX_CUDA(ctx->pinned_alloc((void **)&b->h_poll));
     s.ntab = ntab;
     for (int t = 0; t < ntab; ++t) { s.tab_d0[t] = b->tab_g0[t] * LANES; s.tab_n[t] = ndecoys[t]; }
-    TRX_CUDA(cudaMalloc(&b->d_aa, L * sizeof(int)));
-    TRX_CUDA(cudaMemcpy(b->d_aa, aa, L * sizeof(int), cudaMemcpyHostToDevice));
+    TRX_CUDA(ctx->dev_alloc(&b->d_aa, L * sizeof(int)));
+    TRX_CUDA(cudaMemcpyAsync(b->d_aa, aa, L * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     std::vector<Run> hr(nruns);
     for (int r = 0; r < nruns; ++r) {
         for (int k = 0; k < TRX_NTERM; ++k) hr[r].w[k] = (float)runs[r].w[k];
         hr[r].max_iter = runs[r].max_iter; hr[r].tol = (float)runs[r].tol; hr[r].clash_check = runs[r].clash_check;
         hr[r].clash_thr = (float)runs[r].clash_thr; hr[r].skip_to = runs[r].skip_to; hr[r].cartesian = runs[r].cartesian ? 1 : 0;
     }
-    TRX_CUDA(cudaMalloc(&b->d_runs, nruns * sizeof(Run)));
-    TRX_CUDA(cudaMemcpy(b->d_runs, hr.data(), nruns * sizeof(Run), cudaMemcpyHostToDevice));
+    TRX_CUDA(ctx->dev_alloc(&b->d_runs, nruns * sizeof(Run)));
+    TRX_CUDA(cudaMemcpyAsync(b->d_runs, hr.data(), nruns * sizeof(Run), cudaMemcpyHostToDevice, ctx->stream));
     s.aa = b->d_aa;
     s.runs = b->d_runs;
     upload_model();
@@ -2306,7 +2311,9 @@ int trx_fold_create(trx_ctx *ctx, int ntab, trx_tables *const *tabs, const int *
     else if (lbM == 20) rc_attr = lb_attr(lbfgs_dots_kernel<20>, lbfgs_step_kernel<20>, lbfgs_dots_ring_kernel<20>, lbfgs_update_ring_kernel<20>, sizeof(LbSmem<20>));
     else rc_attr = lb_attr(lbfgs_dots_kernel<24>, lbfgs_step_kernel<24>, lbfgs_dots_ring_kernel<24>, lbfgs_update_ring_kernel<24>, sizeof(LbSmem<24>));
     if (rc_attr) return rc_attr;
+    TRX_CUDA(cudaStreamSynchronize(ctx->stream));   // aa may be pinned memory of the caller: done with it on return
     guard.b = nullptr;
+    ctx->retain();
     *out = b;
     return TRX_OK;
 }

@@ -1,10 +1,13 @@
 // Internal declarations shared by the translation units of libtrx2dyn.so.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <map>
+#include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/trx2dyn.h"
@@ -23,6 +26,7 @@ constexpr int K1_WARPS = 4;
 constexpr int K1_THREADS = K1_WARPS * 32;
 
 void set_error(const char *fmt, ...);
+void ctx_release(trx_ctx *ctx);   // drops one reference (context.cu)
 
 #define TRX_CUDA(call)                                                                   \
     do {                                                                                 \
@@ -53,6 +57,11 @@ struct KernelTimer {
 }  // namespace trx
 
 struct trx_ctx {
+    // The creator's reference plus one per live tables / fold batch / dynamics state: those read the context when they
+    // are destroyed, and a garbage collector (Python at interpreter exit) may destroy the context first.
+    // trx_ctx_destroy drops the creator's reference; the context goes with the last one.
+    std::atomic<int> refs{1};
+    void retain() { refs.fetch_add(1); }
     int device = 0;
     cudaStream_t stream = nullptr;
     bool owns_stream = false;
@@ -61,6 +70,24 @@ struct trx_ctx {
     std::map<std::string, trx::KernelTimer> timers;
     // scratch device buffers reused across calls, keyed by a tag
     std::map<std::string, std::pair<void *, size_t>> scratch;
+
+    // Device blocks released by destroyed tables / fold batches / dynamics states, kept for the next create on this
+    // context: a dynamics loop rebuilds all three every iteration, and ~30 cudaMalloc + ~30 cudaFree (each a device-wide
+    // synchronisation) cost more than the fold they bracket.  Every user of a block works on ctx->stream and every
+    // destroy synchronises that stream before releasing, so a reused block has no reader left.
+    std::mutex pool_mu;
+    std::multimap<size_t, void *> pool_free;       // capacity -> released block
+    std::unordered_map<void *, size_t> pool_cap;   // every block dev_alloc handed out -> its capacity
+    size_t pool_bytes = 0;                         // sum over pool_free
+    std::vector<void *> pinned_free;               // released PINNED_BLOCK-byte host blocks
+    static constexpr size_t PINNED_BLOCK = 256;
+    cudaError_t dev_alloc_bytes(void **p, size_t bytes);
+    template <typename T>
+    cudaError_t dev_alloc(T **p, size_t bytes) { return dev_alloc_bytes((void **)p, bytes); }
+    void dev_free(void *p);
+    cudaError_t pinned_alloc(void **p);            // one PINNED_BLOCK-byte pinned host block
+    void pinned_release(void *p);
+    void pool_trim();                              // cudaFree everything the pool holds
 
     int get_scratch(const char *tag, size_t bytes, void **out);
     void time_begin(const char *name);

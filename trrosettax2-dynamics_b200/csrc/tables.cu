@@ -135,12 +135,12 @@ int trx_tables::get_plan(int groups, Plan **out)
     if (recs.empty()) recs.push_back(0);
     if (sorted.empty()) sorted.assign(4, 0);
     // tile -> col record id is the identity by construction (tile_rec[t] == t)
-    TRX_CUDA(cudaMalloc(&p.d_work, sorted.size() * sizeof(int)));
-    TRX_CUDA(cudaMalloc(&p.d_blk_ptr, ptr.size() * sizeof(int)));
-    TRX_CUDA(cudaMalloc(&p.d_blk_rec, recs.size() * sizeof(int)));
-    TRX_CUDA(cudaMemcpy(p.d_work, sorted.data(), sorted.size() * sizeof(int), cudaMemcpyHostToDevice));
-    TRX_CUDA(cudaMemcpy(p.d_blk_ptr, ptr.data(), ptr.size() * sizeof(int), cudaMemcpyHostToDevice));
-    TRX_CUDA(cudaMemcpy(p.d_blk_rec, recs.data(), recs.size() * sizeof(int), cudaMemcpyHostToDevice));
+    TRX_CUDA(ctx->dev_alloc(&p.d_work, sorted.size() * sizeof(int)));
+    TRX_CUDA(ctx->dev_alloc(&p.d_blk_ptr, ptr.size() * sizeof(int)));
+    TRX_CUDA(ctx->dev_alloc(&p.d_blk_rec, recs.size() * sizeof(int)));
+    TRX_CUDA(cudaMemcpyAsync(p.d_work, sorted.data(), sorted.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    TRX_CUDA(cudaMemcpyAsync(p.d_blk_ptr, ptr.data(), ptr.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    TRX_CUDA(cudaMemcpyAsync(p.d_blk_rec, recs.data(), recs.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     plans[(int)chunk] = p;
     *out = &plans[(int)chunk];
     return TRX_OK;
@@ -199,11 +199,11 @@ int trx_tables_create(trx_ctx *ctx, int L, const trx_rst_set sets[4], trx_tables
         if (s.n == 0) continue;
         double *d_x = nullptr, *d_y = nullptr;
         size_t ny = (size_t)s.n * s.K;
-        TRX_CUDA(cudaMalloc(&d_x, s.K * sizeof(double)));
-        TRX_CUDA(cudaMalloc(&d_y, ny * sizeof(double)));
-        TRX_CUDA(cudaMalloc(&T->d_tab64[t], ny * sizeof(Coef<double>)));
-        TRX_CUDA(cudaMalloc(&T->d_tab32[t], ny * sizeof(Coef<float>)));
-        TRX_CUDA(cudaMalloc(&T->d_y2[t], ny * sizeof(double)));
+        TRX_CUDA(ctx->dev_alloc(&d_x, s.K * sizeof(double)));
+        TRX_CUDA(ctx->dev_alloc(&d_y, ny * sizeof(double)));
+        TRX_CUDA(ctx->dev_alloc(&T->d_tab64[t], ny * sizeof(Coef<double>)));
+        TRX_CUDA(ctx->dev_alloc(&T->d_tab32[t], ny * sizeof(Coef<float>)));
+        TRX_CUDA(ctx->dev_alloc(&T->d_y2[t], ny * sizeof(double)));
         TRX_CUDA(cudaMemcpyAsync(d_x, s.x, s.K * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         TRX_CUDA(cudaMemcpyAsync(d_y, s.y, ny * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         ctx->time_begin("spline_fit");
@@ -211,14 +211,13 @@ int trx_tables_create(trx_ctx *ctx, int L, const trx_rst_set sets[4], trx_tables
                                                                      (Coef<float> *)T->d_tab32[t]);
         ctx->time_end("spline_fit");
         TRX_CUDA(cudaGetLastError());
-        TRX_CUDA(cudaStreamSynchronize(ctx->stream));
-        TRX_CUDA(cudaFree(d_x));
-        TRX_CUDA(cudaFree(d_y));
+        ctx->dev_free(d_x);   // reuse is ordered on ctx->stream, no synchronisation needed
+        ctx->dev_free(d_y);
     }
-    TRX_CUDA(cudaMalloc(&T->d_geom64, sizeof(g64)));
-    TRX_CUDA(cudaMalloc(&T->d_geom32, sizeof(g32)));
-    TRX_CUDA(cudaMemcpy(T->d_geom64, g64, sizeof(g64), cudaMemcpyHostToDevice));
-    TRX_CUDA(cudaMemcpy(T->d_geom32, g32, sizeof(g32), cudaMemcpyHostToDevice));
+    TRX_CUDA(ctx->dev_alloc(&T->d_geom64, sizeof(g64)));
+    TRX_CUDA(ctx->dev_alloc(&T->d_geom32, sizeof(g32)));
+    TRX_CUDA(cudaMemcpyAsync(T->d_geom64, g64, sizeof(g64), cudaMemcpyHostToDevice, ctx->stream));
+    TRX_CUDA(cudaMemcpyAsync(T->d_geom32, g32, sizeof(g32), cudaMemcpyHostToDevice, ctx->stream));
 
     // ---- pair slots: for the unordered pair i<j the six restraints
     //   0 dist(i,j) 1 omega(i,j) 2 theta(i,j) 3 theta(j,i) 4 phi(i,j) 5 phi(j,i)
@@ -298,17 +297,19 @@ int trx_tables_create(trx_ctx *ctx, int L, const trx_rst_set sets[4], trx_tables
     }
     if (sched.empty()) sched.assign(K1_WARPS, 0xffff);
     T->total_steps = step_ptr[std::max(1, T->ntiles)];
-    TRX_CUDA(cudaMalloc(&T->d_sched, sched.size() * sizeof(unsigned short)));
-    TRX_CUDA(cudaMalloc(&T->d_nsteps, step_ptr.size() * sizeof(int)));
-    TRX_CUDA(cudaMemcpy(T->d_sched, sched.data(), sched.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
-    TRX_CUDA(cudaMemcpy(T->d_nsteps, step_ptr.data(), step_ptr.size() * sizeof(int), cudaMemcpyHostToDevice));
+    TRX_CUDA(ctx->dev_alloc(&T->d_sched, sched.size() * sizeof(unsigned short)));
+    TRX_CUDA(ctx->dev_alloc(&T->d_nsteps, step_ptr.size() * sizeof(int)));
+    TRX_CUDA(cudaMemcpyAsync(T->d_sched, sched.data(), sched.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, ctx->stream));
+    TRX_CUDA(cudaMemcpyAsync(T->d_nsteps, step_ptr.data(), step_ptr.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     std::vector<int> tj = T->tileJ;
     if (tj.empty()) tj.push_back(0);
-    TRX_CUDA(cudaMalloc(&T->d_tileJ, tj.size() * sizeof(int)));
-    TRX_CUDA(cudaMalloc(&T->d_pairrec, rec.size() * sizeof(int)));
-    TRX_CUDA(cudaMemcpy(T->d_tileJ, tj.data(), tj.size() * sizeof(int), cudaMemcpyHostToDevice));
-    TRX_CUDA(cudaMemcpy(T->d_pairrec, rec.data(), rec.size() * sizeof(int), cudaMemcpyHostToDevice));
+    TRX_CUDA(ctx->dev_alloc(&T->d_tileJ, tj.size() * sizeof(int)));
+    TRX_CUDA(ctx->dev_alloc(&T->d_pairrec, rec.size() * sizeof(int)));
+    TRX_CUDA(cudaMemcpyAsync(T->d_tileJ, tj.data(), tj.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    TRX_CUDA(cudaMemcpyAsync(T->d_pairrec, rec.data(), rec.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    TRX_CUDA(cudaStreamSynchronize(ctx->stream));   // the caller's knot arrays may be pinned: done with them on return
     guard.T = nullptr;
+    ctx->retain();
     *out = T;
     return TRX_OK;
 }
@@ -319,22 +320,24 @@ int trx_tables_destroy(trx_tables *T)
     cudaSetDevice(T->ctx->device);
     cudaStreamSynchronize(T->ctx->stream);
     for (int t = 0; t < 4; ++t) {
-        if (T->d_tab64[t]) cudaFree(T->d_tab64[t]);
-        if (T->d_tab32[t]) cudaFree(T->d_tab32[t]);
-        if (T->d_y2[t]) cudaFree(T->d_y2[t]);
+        T->ctx->dev_free(T->d_tab64[t]);
+        T->ctx->dev_free(T->d_tab32[t]);
+        T->ctx->dev_free(T->d_y2[t]);
     }
-    if (T->d_geom64) cudaFree(T->d_geom64);
-    if (T->d_geom32) cudaFree(T->d_geom32);
-    if (T->d_tileJ) cudaFree(T->d_tileJ);
-    if (T->d_pairrec) cudaFree(T->d_pairrec);
-    if (T->d_sched) cudaFree(T->d_sched);
-    if (T->d_nsteps) cudaFree(T->d_nsteps);
+    T->ctx->dev_free(T->d_geom64);
+    T->ctx->dev_free(T->d_geom32);
+    T->ctx->dev_free(T->d_tileJ);
+    T->ctx->dev_free(T->d_pairrec);
+    T->ctx->dev_free(T->d_sched);
+    T->ctx->dev_free(T->d_nsteps);
     for (auto &kv : T->plans) {
-        cudaFree(kv.second.d_work);
-        cudaFree(kv.second.d_blk_ptr);
-        cudaFree(kv.second.d_blk_rec);
+        T->ctx->dev_free(kv.second.d_work);
+        T->ctx->dev_free(kv.second.d_blk_ptr);
+        T->ctx->dev_free(kv.second.d_blk_rec);
     }
+    trx_ctx *ctx = T->ctx;
     delete T;
+    trx::ctx_release(ctx);
     return TRX_OK;
 }
 
@@ -362,7 +365,8 @@ int trx_tables_get_y2(trx_tables *T, int type, double *y2)
     TRX_REQUIRE(T && y2 && type >= 0 && type < 4, "trx_tables_get_y2: bad argument");
     size_t n = (size_t)T->n[type] * T->K[type];
     if (n == 0) return TRX_OK;
-    TRX_CUDA(cudaMemcpy(y2, T->d_y2[type], n * sizeof(double), cudaMemcpyDeviceToHost));
+    TRX_CUDA(cudaMemcpyAsync(y2, T->d_y2[type], n * sizeof(double), cudaMemcpyDeviceToHost, T->ctx->stream));
+    TRX_CUDA(cudaStreamSynchronize(T->ctx->stream));
     return TRX_OK;
 }
 
