@@ -6,7 +6,8 @@ two-model mixing (half the decoys scored against each model's tables), full mode
 decoys sharded across GPUs with no data-path collective.  A "step" is one call of the public fold entry
 point (trx_fold_run_queue) over one batch of random starts: `--decoys` decoys per GPU folded through
 `--resident` positions (continuous batching: a position is refilled as soon as its decoy leaves the
-schedule segment in progress).  Defaults for configs[2]: 24576 decoys per GPU and step through 4096 positions (six resident batches;
+schedule segment in progress).  Defaults for configs[2]: 24576 decoys per GPU and step through 12288 positions (measured on one B200 with
+4096 / 8192 / 12288 / 16384 positions: 1563 / 1625 / 1658 / 1630 decoys/s; 12 GB of decoy state; the step is
 sized so that the driver's --steps 20 --warmup 5 stays well inside its per-run limit).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
@@ -39,7 +40,7 @@ WEIGHTS = (5.0, 4.0, 4.0)  # folding/data/scorefxn.wts: atom_pair 5, dihedral 4,
 CONFIGS = {
     1: dict(tag="configs[1]", L=150, seed=150, two_model=False, dist_only=True, decoys=256, resident=256, mc=None,
             metric="decoys_per_sec_L150_dist_only", desc="synthetic L=150 distance-only restraints (--no-angle)"),
-    2: dict(tag="configs[2]", L=300, seed=300, two_model=True, dist_only=False, decoys=24576, resident=4096, mc=None,
+    2: dict(tag="configs[2]", L=300, seed=300, two_model=True, dist_only=False, decoys=24576, resident=12288, mc=None,
             metric="decoys_per_sec_L300", desc="synthetic L=300 dist+omega+theta+phi, two-model mixing"),
     3: dict(tag="configs[3]", L=800, seed=800, two_model=False, dist_only=False, decoys=2048, resident=2048,
             mc=dict(cycles=4, kT=2.0, block=(3, 9), sigma_deg=20.0, mc_max_iter=200),
