@@ -172,6 +172,7 @@ int trx_tables_create(trx_ctx *ctx, int L, const trx_rst_set sets[4], trx_tables
         ~Guard() { if (T) trx_tables_destroy(T); }
     } guard{T};
     T->ctx = ctx;
+    ctx->retain();   // given back by trx_tables_destroy (the guard goes through it too)
     T->L = L;
     T->Lpad = padded_length(L);
     T->nb = T->Lpad / TILE;
@@ -309,7 +310,6 @@ int trx_tables_create(trx_ctx *ctx, int L, const trx_rst_set sets[4], trx_tables
     TRX_CUDA(cudaMemcpyAsync(T->d_pairrec, rec.data(), rec.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     TRX_CUDA(cudaStreamSynchronize(ctx->stream));   // the caller's knot arrays may be pinned: done with them on return
     guard.T = nullptr;
-    ctx->retain();
     *out = T;
     return TRX_OK;
 }
