@@ -20,6 +20,7 @@ runs = [("r2_bench_default", "python bench.py --decoys 32768  (configs[2], 32768
         ("r2_bench_c1", "python bench.py --config 1  (configs[1]: L=150 distance-only, 256 decoys)"),
         ("r2_bench_c3", "python bench.py --config 3  (configs[3]: L=800, 2048 decoys, 4 MC cycles, 1 GPU)"),
         ("r2_bench_c4", "python bench.py --config 4 --streams 8  (configs[4]: 64 targets x 100 decoys, 1 GPU)"),
+        ("r2_bench_c4_pool", "python bench.py --config 4 --streams 8 --steps 2 --warmup 1  (configs[4], final build: the 64 targets' tables and fold batches come from the contexts' block pools)"),
         ("r2_2gpu_c2_weak_final", "torchrun x2 bench.py --gpus 2 --steps 1 --warmup 1 --no-k1-standalone  (final build, default workload on 2 GPUs: weak scaling)"),
         ("r2_8gpu_c2_weak", "torchrun x8 bench.py --gpus 8 --decoys 16384  (configs[2], weak: 16384 decoys per GPU and step; the build before the default became 32768)"),
         ("r2_8gpu_c2_strong", "torchrun x8 bench.py --gpus 8 --scaling strong --decoys 4096  (configs[2] as written: 4096 decoys sharded over 8 GPUs)"),
