@@ -530,6 +530,9 @@ tb2 = sampler.build_tables(ctx2, npz, seq, tables.load_params())
 state2 = capi.DynState(ctx2, npz)
 print("ok", float(out["terms"].sum()))
 """
-    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(golden_dir)))   # the repository root, whatever the cwd
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=root,
+                       env=dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", "")))
     assert r.returncode == 0, (r.returncode, r.stdout[-2000:], r.stderr[-2000:])
     assert r.stdout.strip().startswith("ok")
