@@ -12,6 +12,7 @@ runs = [("r2_bench_default", "python bench.py --decoys 32768  (configs[2], 32768
         ("r2_bench_r12288", "python bench.py --resident 12288 --steps 2 --warmup 1 --no-k1-standalone"),
         ("r2_bench_r16384", "python bench.py --resident 16384 --steps 2 --warmup 1 --no-k1-standalone"),
         ("r2_bench_s2_final", "python bench.py --resident 4096 --streams 2 --steps 2 --warmup 1 --no-k1-standalone  (two lanes of 2048 positions; K1 launches of the two streams overlap, so its event-timed duration and roofline.frac are not those of a kernel running alone)"),
+        ("r2_bench_s2_12k", "python bench.py --streams 2 --steps 2 --warmup 1 --no-k1-standalone --no-cpu-baseline  (final build, default workload as two lanes of 6144 positions on two streams; the lanes' K1 launches overlap, so roofline.frac is not that of a kernel alone)"),
         ("r2_bench_65536", "python bench.py --decoys 65536 --steps 1 --warmup 1  (queue of 16 resident batches)"),
         ("r2_bench_s2", "python bench.py --streams 2 --steps 1 --warmup 1  (two fold lanes on two streams)"),
         ("r2_bench_4096", "python bench.py --decoys 4096 --resident 4096  (configs[2], one resident batch: no refill)"),
